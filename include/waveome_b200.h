@@ -1,0 +1,122 @@
+/* waveome_b200 — C ABI of the B200 batched GP model-fitting engine.
+ *
+ * The reference (omicsEye/waveome v0.1.3) has no FFI/plugin interface: its boundary on this path is the
+ * Python closure handed to SciPy, f(x: float64[P]) -> (loss, grad), created at
+ *   waveome/model_fitting.py:276-281   gpflow.optimizers.Scipy().minimize(m.training_loss, ...)
+ *   waveome/model_classes.py:325-334   optimizer.minimize(closure=self.training_loss_closure(data), ...)
+ * and the per-outcome fan-out around it (waveome/model_search.py:250-393, 474-489).
+ * The entry points below are what a ctypes binding of that path binds:
+ *
+ *   wv_batch_create      <- model construction: gpflow.models.GPR(data=(X, Y), kernel=k)
+ *                           (waveome/model_fitting.py:150-155) for B models that share X
+ *   wv_batch_eval        <- m.training_loss + gradients, i.e. -(GPR.log_marginal_likelihood + log prior)
+ *                           (mirror: waveome/model_types_DEPR.py:49-56)
+ *   wv_batch_fit_lbfgs   <- gpflow.optimizers.Scipy().minimize(..., method="L-BFGS-B", options=...)
+ *                           (waveome/model_fitting.py:276-281, waveome/model_classes.py:309-334)
+ *
+ * Plain pointers and sizes only; no torch types.  All floating point data is IEEE fp64.
+ * Return codes: 0 ok, <0 API misuse or CUDA failure (wv_last_error() explains).  Numerical trouble is
+ * reported per model in `status` bits, never as an error code.
+ * Threading: an engine and its batches belong to one host thread / one GPU.
+ */
+#ifndef WAVEOME_B200_H
+#define WAVEOME_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wv_engine wv_engine;
+typedef struct wv_batch wv_batch;
+
+/* leaf kernel types (GPflow names: squared_exponential, matern12/32/52, periodic[SE base], linear|lin,
+ * constant, categorical (waveome/kernels.py:86-124), polynomial|poly (waveome/kernels.py:42-83), empty) */
+enum { WVK_SE = 0, WVK_M12 = 1, WVK_M32 = 2, WVK_M52 = 3, WVK_PERIODIC = 4, WVK_LINEAR = 5, WVK_CONST = 6,
+       WVK_CAT = 7, WVK_POLY = 8, WVK_EMPTY = 9 };
+/* parameter bijectors: identity, softplus (gpflow positive()), softplus + lower bound, exp */
+enum { WVT_IDENTITY = 0, WVT_SOFTPLUS = 1, WVT_SOFTPLUS_SHIFT = 2, WVT_EXP = 3 };
+/* priors on the constrained value (tfd.Horseshoe / tfd.Laplace / tfd.Uniform) */
+enum { WVP_NONE = 0, WVP_HORSESHOE = 1, WVP_LAPLACE = 2, WVP_UNIFORM = 3 };
+/* per-model status bits */
+enum { WVS_OK = 0, WVS_CHOL_FAIL = 1, WVS_NONFINITE = 2, WVS_MAXITER = 4, WVS_LINESEARCH = 8 };
+
+/* One kernel program = sum over components of products of leaves, plus the parameter slot table.
+ * Arrays are flat; a batch passes `n_programs` of these back to back. */
+typedef struct wv_program_desc {
+  int32_t n_comp;              /* additive components */
+  int32_t n_leaves;            /* leaves over all components */
+  int32_t n_slots;             /* parameter slots (trainable + fixed), including noise variance and mean */
+  int32_t noise_slot;          /* slot of the Gaussian likelihood variance */
+  int32_t mean_slot;           /* slot of the constant mean, or -1 for a zero mean */
+  const int32_t* comp_start;   /* [n_comp + 1] leaf ranges of the components */
+  const int32_t* leaf_type;    /* [n_leaves] WVK_* */
+  const int32_t* leaf_dim;     /* [n_leaves] covariate column (active_dims[0]) */
+  const int32_t* leaf_s_var;   /* [n_leaves] slot of the variance, -1 if none */
+  const int32_t* leaf_s_ls;    /* [n_leaves] slot of lengthscales (or polynomial offset), -1 if none */
+  const int32_t* leaf_s_aux;   /* [n_leaves] slot of the period, -1 if none */
+  const int32_t* leaf_degree;  /* [n_leaves] polynomial degree */
+  const int32_t* slot_transform; /* [n_slots] WVT_* */
+  const int32_t* slot_xindex;    /* [n_slots] index into the packed unconstrained vector, -1 = not trainable */
+  const int32_t* slot_prior;     /* [n_slots] WVP_* */
+  const double* slot_fixed;      /* [n_slots] constrained value used when not trainable */
+  const double* slot_shift;      /* [n_slots] lower bound of WVT_SOFTPLUS_SHIFT */
+  const double* slot_pa;         /* [n_slots] prior parameter a (scale | loc | low) */
+  const double* slot_pb;         /* [n_slots] prior parameter b (  -   | scale | high) */
+} wv_program_desc;
+
+typedef struct wv_batch_desc {
+  int32_t n;                 /* observations */
+  int32_t D;                 /* covariate columns */
+  int32_t B;                 /* models in the batch (all share X) */
+  int32_t P;                 /* stride of the packed parameter vectors (>= max trainable count) */
+  const double* X;           /* HOST [n, D] row-major */
+  const double* Y;           /* HOST [B, n] row-major: outcome of each model */
+  int32_t n_programs;
+  const wv_program_desc* programs; /* HOST [n_programs] */
+  const int32_t* prog_id;    /* HOST [B] program of each model */
+} wv_batch_desc;
+
+typedef struct wv_lbfgs_opts {
+  int32_t maxcor;    /* SciPy default 10 */
+  int32_t maxiter;   /* SciPy default 15000 (waveome passes 50000) */
+  int32_t maxfun;    /* SciPy default 15000 */
+  int32_t maxls;     /* SciPy default 20 */
+  double ftol;       /* SciPy default 2.220446049250313e-09 (= factr * epsmch) */
+  double gtol;       /* SciPy default 1e-5 (pgtol) */
+} wv_lbfgs_opts;
+
+int wv_engine_create(int device, wv_engine** out);
+void wv_engine_destroy(wv_engine* e);
+/* CUDA stream the engine launches on (cudaStream_t as void*), for event timing by the caller */
+void* wv_engine_stream(wv_engine* e);
+
+int wv_batch_create(wv_engine* e, const wv_batch_desc* desc, wv_batch** out);
+void wv_batch_destroy(wv_batch* b);
+/* bytes of device workspace held by the batch */
+int64_t wv_batch_workspace_bytes(const wv_batch* b);
+/* replace the outcomes (HOST [B, n]) without rebuilding programs / workspaces */
+int wv_batch_set_y(wv_batch* b, const double* Y);
+
+/* One LML+gradient evaluation of every model.  HOST buffers:
+ *   x [B, P] unconstrained parameters; f [B] = -(lml + log prior); grad [B, P] = df/dx; lml [B]; status [B]. */
+int wv_batch_eval(wv_batch* b, const double* x, double* f, double* grad, double* lml, int32_t* status);
+
+/* Same, with DEVICE buffers, enqueued on the engine stream without host synchronisation. */
+int wv_batch_eval_device(wv_batch* b, const double* d_x, double* d_f, double* d_grad, double* d_lml,
+                         int32_t* d_status);
+
+/* L-BFGS-B MAP fit of every model, starting from x (HOST [B, P], overwritten with the optimum).
+ * f, lml [B] are evaluated at the returned x; n_iter, n_eval, status [B]. */
+int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* opts, double* f, double* lml,
+                       int32_t* n_iter, int32_t* n_eval, int32_t* status);
+
+/* counters since batch creation: kernels launched, batched evaluation rounds, model evaluations */
+void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t* rounds, int64_t* model_evals);
+
+const char* wv_last_error(void);
+const char* wv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

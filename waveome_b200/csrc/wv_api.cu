@@ -1,0 +1,415 @@
+// waveome_b200 — C ABI (include/waveome_b200.h): engine / batch lifecycle, batched evaluation and the
+// device-resident L-BFGS-B fit loop.  No CPU fallback: every entry point needs a CUDA device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/waveome_b200.h"
+#include "wv_kernels.cuh"
+#include "wv_lbfgsb.h"
+
+int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
+                    double* d_g, double* d_lml, int* d_status, cudaStream_t st);
+
+static thread_local std::string g_err;
+static int wv_fail(const std::string& m) { g_err = m; return -1; }
+#define WV_CUDA(x)                                                                                   \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess) return wv_fail(std::string(#x) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+struct wv_engine {
+  int device;
+  cudaStream_t stream;
+};
+
+struct wv_batch {
+  wv_engine* eng;
+  WvBatchDev bd;
+  std::vector<void*> allocs;
+  // device buffers
+  double *d_x, *d_f, *d_g, *d_lml;
+  int *d_status, *d_active, *d_active2, *d_count, *d_task, *d_nx, *d_iter, *d_neval, *d_st2;
+  WvLbScalars* d_lbs;
+  double* d_lbw;
+  int lb_m_alloc;
+  int* h_count;   // pinned
+  int64_t bytes, launches, rounds, model_evals;
+};
+
+template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
+  void* q = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return wv_fail(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+  b->allocs.push_back(q);
+  b->bytes += (int64_t)bytes;
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
+extern "C" const char* wv_last_error(void) { return g_err.c_str(); }
+extern "C" const char* wv_version(void) { return "waveome_b200 0.1 (sm_100a, fp64 DMMA)"; }
+
+extern "C" int wv_engine_create(int device, wv_engine** out) {
+  if (!out) return wv_fail("wv_engine_create: out is null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return wv_fail(std::string("wv_engine_create: no CUDA device (") + cudaGetErrorString(e) +
+                   "); waveome_b200 has no CPU fallback");
+  if (device < 0 || device >= count) return wv_fail("wv_engine_create: bad device index");
+  WV_CUDA(cudaSetDevice(device));
+  wv_engine* eng = new wv_engine();
+  eng->device = device;
+  WV_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+  *out = eng;
+  return 0;
+}
+
+extern "C" void wv_engine_destroy(wv_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" void* wv_engine_stream(wv_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+static int wv_build_program(const wv_program_desc& d, int D, WvProgram* p) {
+  memset(p, 0, sizeof(WvProgram));
+  if (d.n_comp < 0 || d.n_comp > WV_MAX_COMP) return wv_fail("program: too many components (max 32)");
+  if (d.n_leaves < 0 || d.n_leaves > WV_MAX_LEAVES) return wv_fail("program: too many leaves (max 64)");
+  if (d.n_slots <= 0 || d.n_slots > WV_MAX_SLOTS) return wv_fail("program: too many parameter slots (max 64)");
+  if (d.noise_slot < 0 || d.noise_slot >= d.n_slots) return wv_fail("program: bad noise_slot");
+  if (d.mean_slot >= d.n_slots) return wv_fail("program: bad mean_slot");
+  p->n_comp = d.n_comp; p->n_leaves = d.n_leaves; p->n_slots = d.n_slots;
+  p->noise_slot = d.noise_slot; p->mean_slot = d.mean_slot;
+  for (int c = 0; c <= d.n_comp; ++c) {
+    p->comp_start[c] = d.comp_start[c];
+    if (c > 0 && (d.comp_start[c] < d.comp_start[c - 1] || d.comp_start[c] > d.n_leaves))
+      return wv_fail("program: comp_start not monotone");
+  }
+  int nd = 0;
+  auto chk = [&](int s) { return s >= -1 && s < d.n_slots; };
+  for (int l = 0; l < d.n_leaves; ++l) {
+    int dim = d.leaf_dim[l];
+    if (dim < 0 || dim >= D) return wv_fail("program: leaf dim out of range");
+    int k = 0;
+    while (k < nd && p->dims[k] != dim) ++k;
+    if (k == nd) {
+      if (nd == WV_MAX_DIMS) return wv_fail("program: more than 16 distinct covariate columns");
+      p->dims[nd++] = dim;
+    }
+    WvLeaf& lf = p->leaves[l];
+    lf.type = d.leaf_type[l]; lf.dim = k;
+    lf.s_var = d.leaf_s_var[l]; lf.s_ls = d.leaf_s_ls[l]; lf.s_aux = d.leaf_s_aux[l];
+    lf.degree = d.leaf_degree ? d.leaf_degree[l] : 0;
+    if (lf.type < 0 || lf.type > WV_LEAF_EMPTY) return wv_fail("program: unknown leaf type");
+    if (!chk(lf.s_var) || !chk(lf.s_ls) || !chk(lf.s_aux)) return wv_fail("program: leaf slot out of range");
+    bool need_ls = lf.type <= WV_LEAF_PERIODIC || lf.type == WV_LEAF_POLY;
+    if (need_ls && lf.s_ls < 0) return wv_fail("program: leaf needs a lengthscale/offset slot");
+    if (lf.type == WV_LEAF_PERIODIC && lf.s_aux < 0) return wv_fail("program: periodic leaf needs a period slot");
+    if (lf.type != WV_LEAF_EMPTY && lf.s_var < 0) return wv_fail("program: leaf needs a variance slot");
+  }
+  p->n_dims = nd;
+  int nx = 0;
+  for (int s = 0; s < d.n_slots; ++s) {
+    WvSlot& sl = p->slots[s];
+    sl.transform = d.slot_transform[s]; sl.xindex = d.slot_xindex[s]; sl.prior = d.slot_prior[s];
+    sl.fixed = d.slot_fixed[s]; sl.shift = d.slot_shift[s]; sl.pa = d.slot_pa[s]; sl.pb = d.slot_pb[s];
+    if (sl.xindex >= 0) nx = sl.xindex + 1 > nx ? sl.xindex + 1 : nx;
+  }
+  p->n_x = nx;
+  return 0;
+}
+
+extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** out) {
+  if (!e || !d || !out) return wv_fail("wv_batch_create: null argument");
+  if (d->n <= 0 || d->B <= 0 || d->D <= 0 || d->P <= 0 || d->n_programs <= 0)
+    return wv_fail("wv_batch_create: n, D, B, P, n_programs must be positive");
+  WV_CUDA(cudaSetDevice(e->device));
+  wv_batch* b = new wv_batch();
+  b->eng = e; b->bytes = 0; b->launches = b->rounds = b->model_evals = 0;
+  b->d_lbs = nullptr; b->d_lbw = nullptr; b->lb_m_alloc = 0; b->h_count = nullptr;
+  WvBatchDev& bd = b->bd;
+  bd.n = d->n; bd.D = d->D; bd.B = d->B; bd.P = d->P;
+  bd.n8 = (d->n + 1 + 7) / 8 * 8;
+  bd.nt = (bd.n8 + WV_NB - 1) / WV_NB;
+  bd.npad = bd.nt * WV_NB;
+  std::vector<WvProgram> progs(d->n_programs);
+  int smax = 1;
+  for (int i = 0; i < d->n_programs; ++i) {
+    if (wv_build_program(d->programs[i], d->D, &progs[i]) != 0) { delete b; return -1; }
+    if (progs[i].n_x > d->P) { delete b; return wv_fail("wv_batch_create: program has more trainable params than P"); }
+    smax = progs[i].n_slots > smax ? progs[i].n_slots : smax;
+  }
+  bd.n_slots_max = smax;
+  for (int i = 0; i < d->B; ++i)
+    if (d->prog_id[i] < 0 || d->prog_id[i] >= d->n_programs) { delete b; return wv_fail("wv_batch_create: bad prog_id"); }
+  const size_t np = bd.npad, B = d->B;
+  const int ntiles = bd.nt * (bd.nt + 1) / 2;
+  double *dXt, *dY;
+  WvProgram* dprog;
+  int* dpid;
+#define WV_TRY(x) if ((x) != 0) { wv_batch_destroy(b); return -1; }
+  WV_TRY(wv_alloc(b, &dXt, (size_t)d->D * np));
+  WV_TRY(wv_alloc(b, &dY, B * np));
+  WV_TRY(wv_alloc(b, &dprog, (size_t)d->n_programs));
+  WV_TRY(wv_alloc(b, &dpid, B));
+  WV_TRY(wv_alloc(b, &bd.A, B * np * np));
+  WV_TRY(wv_alloc(b, &bd.Mt, B * np * np));
+  WV_TRY(wv_alloc(b, &bd.Dinv, B * bd.nt * WV_NB * WV_NB));
+  WV_TRY(wv_alloc(b, &bd.alpha, B * np));
+  WV_TRY(wv_alloc(b, &bd.logdet_part, B * bd.nt));
+  WV_TRY(wv_alloc(b, &bd.quad, B));
+  WV_TRY(wv_alloc(b, &bd.partial, B * ntiles * smax));
+  WV_TRY(wv_alloc(b, &bd.chol_fail, B));
+  WV_TRY(wv_alloc(b, &b->d_x, B * d->P));
+  WV_TRY(wv_alloc(b, &b->d_g, B * d->P));
+  WV_TRY(wv_alloc(b, &b->d_f, B));
+  WV_TRY(wv_alloc(b, &b->d_lml, B));
+  WV_TRY(wv_alloc(b, &b->d_status, B));
+  WV_TRY(wv_alloc(b, &b->d_active, B));
+  WV_TRY(wv_alloc(b, &b->d_active2, B));
+  WV_TRY(wv_alloc(b, &b->d_count, 4));
+  WV_TRY(wv_alloc(b, &b->d_task, B));
+  WV_TRY(wv_alloc(b, &b->d_nx, B));
+  WV_TRY(wv_alloc(b, &b->d_iter, B));
+  WV_TRY(wv_alloc(b, &b->d_neval, B));
+  WV_TRY(wv_alloc(b, &b->d_st2, B));
+#undef WV_TRY
+  bd.Xt = dXt; bd.Y = dY; bd.programs = dprog; bd.prog_id = dpid;
+  cudaStream_t st = e->stream;
+  // X -> column-major, zero padded
+  std::vector<double> xt((size_t)d->D * np, 0.0);
+  for (int i = 0; i < d->n; ++i)
+    for (int k = 0; k < d->D; ++k) xt[(size_t)k * np + i] = d->X[(size_t)i * d->D + k];
+  std::vector<int> ident(B);
+  for (size_t i = 0; i < B; ++i) ident[i] = (int)i;
+  cudaError_t ce = cudaSuccess;
+  auto step = [&](cudaError_t r) { if (ce == cudaSuccess) ce = r; };
+  step(cudaMemcpyAsync(dXt, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  step(cudaMemcpyAsync(dprog, progs.data(), progs.size() * sizeof(WvProgram), cudaMemcpyHostToDevice, st));
+  step(cudaMemcpyAsync(dpid, d->prog_id, B * sizeof(int), cudaMemcpyHostToDevice, st));
+  step(cudaMemcpyAsync(b->d_active, ident.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+  step(cudaMemsetAsync(bd.A, 0, B * np * np * sizeof(double), st));
+  step(cudaMemsetAsync(bd.Mt, 0, B * np * np * sizeof(double), st));
+  step(cudaMemsetAsync(dY, 0, B * np * sizeof(double), st));
+  step(cudaMemcpy2DAsync(dY, np * sizeof(double), d->Y, (size_t)d->n * sizeof(double), (size_t)d->n * sizeof(double), B,
+                         cudaMemcpyHostToDevice, st));
+  step(cudaMallocHost((void**)&b->h_count, 4 * sizeof(int)));
+  step(cudaStreamSynchronize(st));
+  if (ce != cudaSuccess) {
+    wv_batch_destroy(b);
+    return wv_fail(std::string("wv_batch_create: ") + cudaGetErrorString(ce));
+  }
+  *out = b;
+  return 0;
+}
+
+extern "C" void wv_batch_destroy(wv_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->eng->device);
+  cudaStreamSynchronize(b->eng->stream);
+  for (void* p : b->allocs) cudaFree(p);
+  if (b->h_count) cudaFreeHost(b->h_count);
+  delete b;
+}
+
+extern "C" int64_t wv_batch_workspace_bytes(const wv_batch* b) { return b ? b->bytes : 0; }
+
+extern "C" int wv_batch_set_y(wv_batch* b, const double* Y) {
+  if (!b || !Y) return wv_fail("wv_batch_set_y: null argument");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const WvBatchDev& bd = b->bd;
+  WV_CUDA(cudaMemcpy2DAsync((void*)bd.Y, (size_t)bd.npad * sizeof(double), Y, (size_t)bd.n * sizeof(double),
+                            (size_t)bd.n * sizeof(double), bd.B, cudaMemcpyHostToDevice, b->eng->stream));
+  WV_CUDA(cudaStreamSynchronize(b->eng->stream));
+  return 0;
+}
+
+extern "C" void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t* rounds, int64_t* model_evals) {
+  if (!b) return;
+  if (launches) *launches = b->launches;
+  if (rounds) *rounds = b->rounds;
+  if (model_evals) *model_evals = b->model_evals;
+}
+
+static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g, double* d_lml, int* d_status,
+                       const int* d_active, int n_active) {
+  int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, b->eng->stream);
+  if (l < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  b->launches += l; b->rounds += 1; b->model_evals += n_active;
+  return 0;
+}
+
+__global__ void wv_iota_kernel(int* a, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+
+extern "C" int wv_batch_eval_device(wv_batch* b, const double* d_x, double* d_f, double* d_grad, double* d_lml,
+                                    int32_t* d_status) {
+  if (!b || !d_x || !d_f || !d_grad || !d_lml || !d_status) return wv_fail("wv_batch_eval_device: null argument");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const int B = b->bd.B;
+  wv_iota_kernel<<<(B + 255) / 256, 256, 0, b->eng->stream>>>(b->d_active, B);
+  b->launches += 1;
+  return wv_eval_all(b, d_x, d_f, d_grad, d_lml, d_status, b->d_active, B);
+}
+
+extern "C" int wv_batch_eval(wv_batch* b, const double* x, double* f, double* grad, double* lml, int32_t* status) {
+  if (!b || !x || !f || !grad || !lml || !status) return wv_fail("wv_batch_eval: null argument");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const size_t B = b->bd.B, P = b->bd.P;
+  cudaStream_t st = b->eng->stream;
+  WV_CUDA(cudaMemcpyAsync(b->d_x, x, B * P * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (wv_batch_eval_device(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status) != 0) return -1;
+  WV_CUDA(cudaMemcpyAsync(f, b->d_f, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(grad, b->d_g, B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(lml, b->d_lml, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(status, b->d_status, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident L-BFGS-B: one thread per model
+// ---------------------------------------------------------------------------------------------
+#define WV_LB_CHOLFAIL 7
+
+__global__ void wv_lb_init_kernel(int B, int P, int m, WvLbScalars* sc, double* work, size_t wstride, double* x,
+                                  double* g, int* task) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  WvLbState L;
+  L.bind(sc + b, x + (size_t)b * P, g + (size_t)b * P, work + (size_t)b * wstride, P, m);
+  wv_lb_start(L);
+  task[b] = WV_LB_FG;
+}
+
+__global__ void wv_lb_step_kernel(const int* __restrict__ active, int n_active, const int* __restrict__ nx_of_model,
+                                  int Pstride, int m, WvLbOpts opts, WvLbScalars* sc, double* work, size_t wstride,
+                                  double* x, double* g, const double* __restrict__ f, const int* __restrict__ status,
+                                  int* task) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_active) return;
+  const int b = active[i];
+  WvLbState L;
+  // the optimiser sees only the model's own trainable parameters (n_x <= Pstride)
+  L.bind(sc + b, x + (size_t)b * Pstride, g + (size_t)b * Pstride, work + (size_t)b * wstride, nx_of_model[b], m);
+  if (status[b] & WV_STATUS_CHOL_FAIL) {   // TF raises InvalidArgumentError here and the fit is abandoned
+    task[b] = WV_LB_CHOLFAIL;
+    return;
+  }
+  task[b] = wv_lb_step(L, opts, f[b]);
+}
+
+// ordered compaction of the models that still need an evaluation (single CTA, warp ballots)
+__global__ void wv_compact_kernel(const int* __restrict__ task, int B, int* out, int* count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int start = 0; start < B; start += blockDim.x) {
+    int b = start + threadIdx.x;
+    bool act = b < B && task[b] == WV_LB_FG;
+    unsigned bal = __ballot_sync(0xffffffffu, act);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (act) out[off + __popc(bal & ((1u << lane) - 1))] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < nw; ++w) t += warp_tot[w];
+      base += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base;
+}
+
+__global__ void wv_nx_kernel(const WvProgram* progs, const int* prog_id, int B, int* nx) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) nx[b] = progs[prog_id[b]].n_x;
+}
+
+__global__ void wv_lb_report_kernel(int B, const WvLbScalars* sc, const int* task, const int* eval_status,
+                                    int* n_iter, int* n_eval, int* status) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  n_iter[b] = sc[b].nit;
+  n_eval[b] = sc[b].neval;
+  int st = eval_status[b];
+  int t = task[b];
+  if (t == WV_LB_MAXITER || t == WV_LB_MAXFUN) st |= WV_STATUS_MAXITER;
+  if (t == WV_LB_ABNORMAL) st |= WV_STATUS_LINESEARCH;
+  if (t == WV_LB_CHOLFAIL) st |= WV_STATUS_CHOL_FAIL;
+  status[b] = st;
+}
+
+extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o, double* f, double* lml,
+                                  int32_t* n_iter, int32_t* n_eval, int32_t* status) {
+  if (!b || !x || !o || !f || !lml || !n_iter || !n_eval || !status) return wv_fail("wv_batch_fit_lbfgs: null argument");
+  if (o->maxcor < 1 || o->maxcor > WV_LB_MAXCOR) return wv_fail("wv_batch_fit_lbfgs: maxcor must be in [1, 20]");
+  if (o->maxls < 1) return wv_fail("wv_batch_fit_lbfgs: maxls must be positive");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const int B = b->bd.B, P = b->bd.P, m = o->maxcor;
+  cudaStream_t st = b->eng->stream;
+  const size_t wstride = wv_lb_work_doubles(P, m);
+  if (b->lb_m_alloc < m) {
+    if (wv_alloc(b, &b->d_lbs, (size_t)B) != 0) return -1;
+    if (wv_alloc(b, &b->d_lbw, (size_t)B * wstride) != 0) return -1;
+    b->lb_m_alloc = m;
+  }
+  int *d_nx = b->d_nx, *d_iter = b->d_iter, *d_neval = b->d_neval, *d_st2 = b->d_st2;
+  WvLbOpts opts;
+  opts.m = m; opts.maxiter = o->maxiter; opts.maxfun = o->maxfun; opts.maxls = o->maxls;
+  opts.ftol = o->ftol; opts.pgtol = o->gtol;
+  const int tb = 64, gb = (B + tb - 1) / tb;
+  WV_CUDA(cudaMemcpyAsync(b->d_x, x, (size_t)B * P * sizeof(double), cudaMemcpyHostToDevice, st));
+  wv_nx_kernel<<<gb, tb, 0, st>>>(b->bd.programs, b->bd.prog_id, B, d_nx);
+  wv_lb_init_kernel<<<gb, tb, 0, st>>>(B, P, m, b->d_lbs, b->d_lbw, wstride, b->d_x, b->d_g, b->d_task);
+  wv_iota_kernel<<<(B + 255) / 256, 256, 0, st>>>(b->d_active, B);
+  b->launches += 3;
+  int n_active = B;
+  int* cur = b->d_active;
+  int* nxt = b->d_active2;
+  long guard = 0;
+  const long guard_max = (long)o->maxfun + (long)o->maxiter + 1000;
+  while (n_active > 0) {
+    if (wv_eval_all(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status, cur, n_active) != 0) return -1;
+    wv_lb_step_kernel<<<(n_active + tb - 1) / tb, tb, 0, st>>>(cur, n_active, d_nx, P, m, opts, b->d_lbs, b->d_lbw,
+                                                              wstride, b->d_x, b->d_g, b->d_f, b->d_status, b->d_task);
+    wv_compact_kernel<<<1, 1024, 0, st>>>(b->d_task, B, nxt, b->d_count);
+    b->launches += 2;
+    WV_CUDA(cudaMemcpyAsync(b->h_count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    WV_CUDA(cudaStreamSynchronize(st));
+    n_active = b->h_count[0];
+    int* tmp = cur; cur = nxt; nxt = tmp;
+    if (++guard > guard_max) return wv_fail("wv_batch_fit_lbfgs: iteration guard tripped");
+  }
+  // objective, LML and status at the returned optimum (waveome/model_fitting.py:316 log_posterior_density)
+  wv_iota_kernel<<<(B + 255) / 256, 256, 0, st>>>(b->d_active, B);
+  b->launches += 1;
+  if (wv_eval_all(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status, b->d_active, B) != 0) return -1;
+  wv_lb_report_kernel<<<gb, tb, 0, st>>>(B, b->d_lbs, b->d_task, b->d_status, d_iter, d_neval, d_st2);
+  b->launches += 1;
+  WV_CUDA(cudaMemcpyAsync(x, b->d_x, (size_t)B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(f, b->d_f, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(lml, b->d_lml, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(n_iter, d_iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(n_eval, d_neval, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(status, d_st2, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaStreamSynchronize(st));
+  WV_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,131 @@
+// waveome_b200 — common device/host definitions for the batched GP fitting engine (sm_100a).
+//
+// Replaces, on the model-fitting hot path, what the reference delegates to GPflow/TensorFlow:
+//   kernel tree evaluation   waveome/kernels.py:19-31,56-73,95-117,136-139 + gpflow.kernels.* [3P]
+//   GPR log marginal lik.    waveome/model_types_DEPR.py:49-56 (mirror of gpflow.models.GPR)
+//   priors / transforms      waveome/model_classes.py:837-864, waveome/model_fitting.py:198-242
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+#ifdef __CUDACC__
+#define WV_HD __host__ __device__ __forceinline__
+#else
+#define WV_HD inline
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// limits of the flat "kernel program" (sum of products of leaves)
+// ---------------------------------------------------------------------------------------------
+#define WV_MAX_COMP 32     // additive components
+#define WV_MAX_LEAVES 64   // leaves over all components
+#define WV_MAX_FACT 4      // leaves per product component
+#define WV_MAX_SLOTS 64    // parameter slots (trainable + fixed), incl. noise variance and mean
+#define WV_MAX_DIMS 16     // covariate columns staged per tile
+
+enum WvLeafType : int32_t {
+  WV_LEAF_SE = 0, WV_LEAF_M12 = 1, WV_LEAF_M32 = 2, WV_LEAF_M52 = 3, WV_LEAF_PERIODIC = 4,
+  WV_LEAF_LINEAR = 5, WV_LEAF_CONST = 6, WV_LEAF_CAT = 7, WV_LEAF_POLY = 8, WV_LEAF_EMPTY = 9
+};
+enum WvTransform : int32_t { WV_TR_IDENTITY = 0, WV_TR_SOFTPLUS = 1, WV_TR_SOFTPLUS_SHIFT = 2, WV_TR_EXP = 3 };
+enum WvPrior : int32_t { WV_PRIOR_NONE = 0, WV_PRIOR_HORSESHOE = 1, WV_PRIOR_LAPLACE = 2, WV_PRIOR_UNIFORM = 3 };
+
+// per-model status bits (replace TF exceptions, SURVEY §5 "failure detection")
+#define WV_STATUS_CHOL_FAIL 1
+#define WV_STATUS_NONFINITE 2
+#define WV_STATUS_MAXITER 4
+#define WV_STATUS_LINESEARCH 8
+
+struct WvLeaf {
+  int32_t type;    // WvLeafType
+  int32_t dim;     // covariate column (active_dims[0])
+  int32_t s_var;   // slot of variance (-1: none)
+  int32_t s_ls;    // slot of lengthscales / poly offset (-1: none)
+  int32_t s_aux;   // slot of period (-1: none)
+  int32_t degree;  // polynomial degree
+};
+
+struct WvSlot {
+  int32_t transform;  // WvTransform
+  int32_t xindex;     // index into the unconstrained vector, -1 if not trainable
+  int32_t prior;      // WvPrior (only applied when trainable)
+  int32_t pad;
+  double fixed;       // constrained value when not trainable
+  double shift;       // softplus_shift lower bound
+  double pa, pb;      // prior params: horseshoe(scale=pa), laplace(loc=pa, scale=pb), uniform(lo=pa, hi=pb)
+};
+
+struct WvProgram {
+  int32_t n_comp, n_leaves, n_slots, n_x;   // n_x = number of trainable (packed) parameters
+  int32_t noise_slot, mean_slot;            // mean_slot = -1 for a zero mean function
+  int32_t n_dims, pad;                      // number of distinct covariate columns used
+  int32_t comp_start[WV_MAX_COMP + 1];      // leaves of component c are [comp_start[c], comp_start[c+1])
+  int32_t dims[WV_MAX_DIMS];                // distinct covariate columns; WvLeaf.dim indexes THIS table
+  WvLeaf leaves[WV_MAX_LEAVES];
+  WvSlot slots[WV_MAX_SLOTS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// scalar math shared by host (tests) and device
+// ---------------------------------------------------------------------------------------------
+WV_HD double wv_softplus(double u) { return fmax(u, 0.0) + log1p(exp(-fabs(u))); }
+WV_HD double wv_sigmoid(double u) {
+  double e = exp(-fabs(u));
+  return u >= 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e);
+}
+WV_HD double wv_transform(int tr, double u, double shift) {
+  switch (tr) {
+    case WV_TR_SOFTPLUS: return wv_softplus(u);
+    case WV_TR_SOFTPLUS_SHIFT: return wv_softplus(u) + shift;
+    case WV_TR_EXP: return exp(u);
+    default: return u;
+  }
+}
+WV_HD double wv_transform_grad(int tr, double u) {
+  switch (tr) {
+    case WV_TR_SOFTPLUS:
+    case WV_TR_SOFTPLUS_SHIFT: return wv_sigmoid(u);
+    case WV_TR_EXP: return exp(u);
+    default: return 1.0;
+  }
+}
+
+// tfd.Horseshoe(scale).log_prob(x) (TFP closed-form approximation) and d/dx.
+WV_HD void wv_horseshoe(double x, double s, double* logp, double* dlogp) {
+  const double g = 0.5614594835668851, b = 1.0420764938351215, h_inf = 1.0801359952503342;
+  const double pw = 1.0919284281983377;
+  double xs = x / s;
+  double xx = xs * xs / 2.0;
+  double q = 20.0 / 47.0 * pow(xx, pw);
+  double x15 = pow(xx, 1.5);
+  double h = 1.0 / (1.0 + x15) + h_inf * q / (1.0 + q);
+  double c = -0.5 * log(2.0 * 3.141592653589793 * 3.141592653589793 * 3.141592653589793) - log(g * s);
+  double z = log1p(-g) - log(g);
+  double t = z - xx / (1.0 - g);
+  double hb = h + b * xx;
+  double u = g / xx - (1.0 - g) / (hb * hb);
+  double l1 = log1p(u);
+  *logp = -wv_softplus(t) + log(l1) + c;
+  double dA = wv_sigmoid(t) / (1.0 - g);
+  double dq = pw * q / xx;
+  double dh = -1.5 * sqrt(xx) / ((1.0 + x15) * (1.0 + x15)) + h_inf * dq / ((1.0 + q) * (1.0 + q));
+  double du = -g / (xx * xx) + 2.0 * (1.0 - g) * (dh + b) / (hb * hb * hb);
+  double dB = du / ((1.0 + u) * l1);
+  *dlogp = (dA + dB) * x / (s * s);
+}
+
+WV_HD void wv_prior(const WvSlot& sl, double v, double* logp, double* dlogp) {
+  *logp = 0.0; *dlogp = 0.0;
+  switch (sl.prior) {
+    case WV_PRIOR_HORSESHOE: wv_horseshoe(v, sl.pa, logp, dlogp); break;
+    case WV_PRIOR_LAPLACE: {
+      double dv = v - sl.pa;
+      *logp = -fabs(dv) / sl.pb - log(2.0 * sl.pb);
+      *dlogp = dv == 0.0 ? 0.0 : (dv > 0.0 ? -1.0 / sl.pb : 1.0 / sl.pb);
+    } break;
+    case WV_PRIOR_UNIFORM:
+      *logp = (v >= sl.pa && v <= sl.pb) ? -log(sl.pb - sl.pa) : -INFINITY;
+      break;
+    default: break;
+  }
+}

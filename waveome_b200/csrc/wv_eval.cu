@@ -1,0 +1,538 @@
+// waveome_b200 — kernels of one batched LML+gradient evaluation.  See wv_kernels.cuh for the plan.
+#include "wv_kernels.cuh"
+
+// dynamic shared memory is carved by hand; the GEMM pipeline and the epilogue tiles alias each other.
+extern __shared__ __align__(16) unsigned char wv_smem_raw[];
+
+// =============================================================================================
+// gram: lower tiles of K + sigma^2 I, RHS row, identity padding.
+// grid (n_lower_tiles, n_active), 256 threads, each thread a 4x4 micro-tile.
+// Algorithmic traffic: 8 n^2 bytes written (lower half + diagonal tiles actually written: ~4 n^2).
+// =============================================================================================
+struct WvElemSmem {
+  WvProgram pg;
+  double theta[WV_MAX_SLOTS];
+  double xr[WV_MAX_DIMS][WV_NB];
+  double xc[WV_MAX_DIMS][WV_NB];
+  double red[WV_MAX_SLOTS][8];   // per-warp partial sums (grad only)
+};
+
+__device__ __forceinline__ void wv_elem_prologue(const WvBatchDev& bd, int b, int ti, int tj, const double* xall,
+                                                 WvElemSmem& sm) {
+  const WvProgram* gp = bd.programs + bd.prog_id[b];
+  const int nwords = sizeof(WvProgram) / 4;
+  const int32_t* src = reinterpret_cast<const int32_t*>(gp);
+  int32_t* dst = reinterpret_cast<int32_t*>(&sm.pg);
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  wv_load_theta(&sm.pg, xall + (size_t)b * bd.P, sm.theta);
+  for (int i = threadIdx.x; i < sm.pg.n_dims * WV_NB; i += blockDim.x) {
+    int d = i / WV_NB, r = i % WV_NB;
+    const double* col = bd.Xt + (size_t)sm.pg.dims[d] * bd.npad;
+    sm.xr[d][r] = col[ti * WV_NB + r];
+    sm.xc[d][r] = col[tj * WV_NB + r];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(WV_ELEM_THREADS) wv_gram_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                                  const double* __restrict__ xall) {
+  WvElemSmem& sm = *reinterpret_cast<WvElemSmem*>(wv_smem_raw);
+  const int b = active[blockIdx.y];
+  int ti, tj;
+  wv_tile_from_linear(blockIdx.x, ti, tj);
+  wv_elem_prologue(bd, b, ti, tj, xall, sm);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int n = bd.n;
+  double acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  for (int c = 0; c < sm.pg.n_comp; ++c) {
+    double prod[16];
+    const int l0 = sm.pg.comp_start[c], l1 = sm.pg.comp_start[c + 1];
+    for (int l = l0; l < l1; ++l) {
+      const WvLeaf lf = sm.pg.leaves[l];
+      double xi[4], xj[4], val[16];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lf.dim][ty * 4 + a]; xj[a] = sm.xc[lf.dim][tx * 4 + a]; }
+      wv_leaf_vals(lf, sm.theta, xi, xj, val);
+      if (l == l0) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) prod[e] = val[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) prod[e] *= val[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] += prod[e];
+  }
+  const double s2 = sm.theta[sm.pg.noise_slot];
+  const double cmean = sm.pg.mean_slot >= 0 ? sm.theta[sm.pg.mean_slot] : 0.0;
+  double* Ab = bd.A + (size_t)b * bd.npad * bd.npad;
+  const double* yb = bd.Y + (size_t)b * bd.npad;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int gi = ti * WV_NB + ty * 4 + a;
+    double out[4];
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const int gj = tj * WV_NB + tx * 4 + bb;
+      double v;
+      if (gi < n && gj < n) v = acc[a * 4 + bb] + (gi == gj ? s2 : 0.0);
+      else if (gi == n && gj < n) v = yb[gj] - cmean;     // RHS row d^T
+      else v = (gi == gj) ? 1.0 : 0.0;                     // identity padding (incl. A[n][n] = 1)
+      out[bb] = v;
+    }
+    double2* dst = reinterpret_cast<double2*>(Ab + (size_t)gi * bd.npad + tj * WV_NB + tx * 4);
+    dst[0] = make_double2(out[0], out[1]);
+    dst[1] = make_double2(out[2], out[3]);
+  }
+}
+
+// =============================================================================================
+// chol_diag(j): T = A[j,j] - sum_{k<j} L[j,k] L[j,k]^T ; L_jj = chol(T) ; Linv_jj = L_jj^{-1}
+// grid (n_active), 128 threads.  Row n (the RHS row) takes part as an ordinary row but is never a pivot.
+// =============================================================================================
+struct WvDiagSmem {
+  union {
+    WvGemmSmem g;
+    struct {
+      double T[WV_NB * WV_LDP];
+      double Li[WV_NB * WV_LDP];
+    } e;
+  };
+  double diag[WV_NB];
+  int fail;
+};
+
+__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_chol_diag_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                                       int j) {
+  WvDiagSmem& sm = *reinterpret_cast<WvDiagSmem*>(wv_smem_raw);
+  const int b = active[blockIdx.x];
+  const int ld = bd.npad;
+  double* Ab = bd.A + (size_t)b * ld * ld;
+  const double* Lrow = Ab + (size_t)j * WV_NB * ld;
+  double acc[4][4][2];
+  wv_zero_acc(acc);
+  if (threadIdx.x == 0) sm.fail = 0;
+  if (j > 0) wv_gemm_nt_64(sm.g, Lrow, Lrow, ld, 0, j * WV_NB, acc);
+  else __syncthreads();
+  int r0, c0;
+  wv_frag_origin(r0, c0);
+  double* Tg = Ab + (size_t)j * WV_NB * ld + j * WV_NB;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      int r = r0 + mi * 8, c = c0 + ni * 8;
+      double2 a = *reinterpret_cast<const double2*>(Tg + (size_t)r * ld + c);
+      sm.e.T[r * WV_LDP + c] = a.x - acc[mi][ni][0];
+      sm.e.T[r * WV_LDP + c + 1] = a.y - acc[mi][ni][1];
+    }
+  for (int i = threadIdx.x; i < WV_NB * WV_LDP; i += WV_GEMM_THREADS) sm.e.Li[i] = 0.0;
+  __syncthreads();
+
+  // ---- unblocked right-looking Cholesky in shared memory; thread pair (r, h) owns row r, columns == h mod 2
+  const int rhs_local = bd.n - j * WV_NB;   // local index of the RHS row if inside this block
+  const int r = threadIdx.x >> 1, h = threadIdx.x & 1;
+  double* T = sm.e.T;
+  for (int c = 0; c < WV_NB; ++c) {
+    const double d = T[c * WV_LDP + c];
+    if (c == rhs_local) {   // not a pivot: unit diagonal, nothing below depends on it
+      if (threadIdx.x == 0) sm.diag[c] = 1.0;
+      continue;
+    }
+    if (d <= 0.0) { if (threadIdx.x == 0) sm.fail = 1; }   // NaN pivots flow through, as in TF's Eigen LLT
+    const double sd = sqrt(d);
+    const double lrc = r > c ? T[r * WV_LDP + c] / sd : 0.0;
+    __syncwarp();
+    if (r > c && h == 0) T[r * WV_LDP + c] = lrc;
+    if (threadIdx.x == 0) sm.diag[c] = sd;
+    __syncthreads();
+    if (r > c) {
+      for (int cc = c + 1 + h; cc <= r; cc += 2) T[r * WV_LDP + cc] -= lrc * T[cc * WV_LDP + c];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < WV_NB) T[threadIdx.x * WV_LDP + threadIdx.x] = sm.diag[threadIdx.x];
+  __syncthreads();
+
+  // ---- inverse of the 64x64 lower-triangular block: thread pair (jc, h) owns column jc
+  {
+    const int jc = threadIdx.x >> 1;
+    double* Li = sm.e.Li;
+    if (h == 0) Li[jc * WV_LDP + jc] = 1.0 / T[jc * WV_LDP + jc];
+    __syncwarp();
+    for (int rr = 1; rr < WV_NB; ++rr) {   // uniform trip count: the pair shuffle needs the full warp
+      double s = 0.0;
+      if (rr > jc)
+        for (int k = jc + h; k < rr; k += 2) s += T[rr * WV_LDP + k] * Li[k * WV_LDP + jc];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (rr > jc && h == 0) Li[rr * WV_LDP + jc] = -s / T[rr * WV_LDP + rr];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- write L_jj (lower, zeros above), Linv_jj (row-major) and Linv_jj^T into Mt[j,j]
+  double* Mg = bd.Mt + (size_t)b * ld * ld + (size_t)j * WV_NB * ld + j * WV_NB;
+  double* Dg = bd.Dinv + ((size_t)b * bd.nt + j) * WV_NB * WV_NB;
+  for (int i = threadIdx.x; i < WV_NB * WV_NB; i += WV_GEMM_THREADS) {
+    int rr = i >> 6, cc = i & 63;
+    Tg[(size_t)rr * ld + cc] = cc <= rr ? T[rr * WV_LDP + cc] : 0.0;
+    Dg[i] = sm.e.Li[rr * WV_LDP + cc];
+    Mg[(size_t)rr * ld + cc] = sm.e.Li[cc * WV_LDP + rr];
+  }
+  if (threadIdx.x == 0) {
+    int nreal = min(WV_NB, bd.n - j * WV_NB);
+    double s = 0.0;
+    for (int c = 0; c < nreal; ++c) s += log(sm.diag[c]);
+    bd.logdet_part[(size_t)b * bd.nt + j] = s;
+    if (sm.fail) bd.chol_fail[b] = 1;
+  }
+}
+
+// =============================================================================================
+// generic tile step:  out = sign * (C_in - sum_{k in [k0,k1)} Arow[.,k] Brow[.,k]^T) * Dinv^T
+//   chol_panel(j): tile (i,j), i>j   : L[i,j]  = (A[i,j] - sum_{k<j} L[i,k] L[j,k]^T) Linv_jj^T
+//   trtri(i)     : tile (j,i), j<i   : Mt[j,i] = -( sum_{k=j..i-1} Mt[j,k] L[i,k]^T ) Linv_ii^T
+// grid (n_tiles_in_step, n_active), 128 threads.
+// =============================================================================================
+struct WvPanelSmem {
+  union {
+    WvGemmSmem g;
+    struct {
+      double T[WV_NB * WV_LDT];
+      double D[WV_NB * WV_LDT];
+    } e;
+  };
+};
+
+template <int MODE>   // 0 = chol_panel, 1 = trtri
+__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_panel_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                                   int step) {
+  WvPanelSmem& sm = *reinterpret_cast<WvPanelSmem*>(wv_smem_raw);
+  const int b = active[blockIdx.y];
+  const int ld = bd.npad;
+  double* Ab = bd.A + (size_t)b * ld * ld;
+  double* Mb = bd.Mt + (size_t)b * ld * ld;
+  const double *Ag, *Bg;
+  double* Out;
+  const double* Cin;
+  int k0, k1;
+  if (MODE == 0) {
+    const int i = step + 1 + blockIdx.x, j = step;
+    Ag = Ab + (size_t)i * WV_NB * ld;
+    Bg = Ab + (size_t)j * WV_NB * ld;
+    k0 = 0; k1 = j * WV_NB;
+    Out = Ab + (size_t)i * WV_NB * ld + j * WV_NB;
+    Cin = Out;
+  } else {
+    const int i = step, j = blockIdx.x;
+    Ag = Mb + (size_t)j * WV_NB * ld;
+    Bg = Ab + (size_t)i * WV_NB * ld;
+    k0 = j * WV_NB; k1 = i * WV_NB;
+    Out = Mb + (size_t)j * WV_NB * ld + i * WV_NB;
+    Cin = nullptr;
+  }
+  double acc[4][4][2];
+  wv_zero_acc(acc);
+  if (k1 > k0) wv_gemm_nt_64(sm.g, Ag, Bg, ld, k0, k1, acc);
+  int r0, c0;
+  wv_frag_origin(r0, c0);
+  // T = C_in - acc  (or -acc ... the sign is applied at the end for trtri) -> smem as the A operand of the 2nd product
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      int r = r0 + mi * 8, c = c0 + ni * 8;
+      double2 v;
+      if (MODE == 0) {
+        double2 a = *reinterpret_cast<const double2*>(Cin + (size_t)r * ld + c);
+        v = make_double2(a.x - acc[mi][ni][0], a.y - acc[mi][ni][1]);
+      } else {
+        v = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+      }
+      *reinterpret_cast<double2*>(&sm.e.T[r * WV_LDT + c]) = v;
+    }
+  // D = Linv of the step's diagonal block (row-major)
+  const double2* Dg = reinterpret_cast<const double2*>(bd.Dinv + ((size_t)b * bd.nt + step) * WV_NB * WV_NB);
+  for (int i = threadIdx.x; i < WV_NB * WV_NB / 2; i += WV_GEMM_THREADS) {
+    int rr = i >> 5, c2 = (i & 31) * 2;
+    *reinterpret_cast<double2*>(&sm.e.D[rr * WV_LDT + c2]) = Dg[i];
+  }
+  __syncthreads();
+  wv_zero_acc(acc);
+  wv_gemm_nt_smem64(sm.e.T, sm.e.D, acc);
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      int r = r0 + mi * 8, c = c0 + ni * 8;
+      *reinterpret_cast<double2*>(Out + (size_t)r * ld + c) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+    }
+}
+
+// =============================================================================================
+// extract: alpha_j = -Mt[j][n], quad = |L[n][0:n]|^2 = |L^{-1} d|^2 ; then clear column n of Mt so that
+// kinv = Mt Mt^T excludes the augmented row.  grid (n_active), 256 threads.
+// =============================================================================================
+__global__ void __launch_bounds__(256) wv_extract_kernel(WvBatchDev bd, const int* __restrict__ active) {
+  __shared__ double red[8];
+  const int b = active[blockIdx.x];
+  const int ld = bd.npad, n = bd.n;
+  double* Mb = bd.Mt + (size_t)b * ld * ld;
+  const double* zrow = bd.A + (size_t)b * ld * ld + (size_t)n * ld;
+  double q = 0.0;
+  for (int jx = threadIdx.x; jx < ld; jx += blockDim.x) {
+    double a = 0.0;
+    if (jx < n) {
+      a = -Mb[(size_t)jx * ld + n];
+      double z = zrow[jx];
+      q += z * z;
+    }
+    bd.alpha[(size_t)b * ld + jx] = a;
+    if (jx <= n) Mb[(size_t)jx * ld + n] = 0.0;
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    bd.quad[b] = s;
+  }
+}
+
+// =============================================================================================
+// kinv: A[i,j] (j<=i) = sum_{k >= i*64}^{n8} Mt[i][k] Mt[j][k]^T.   grid (n_lower_tiles, n_active), 128 threads.
+// =============================================================================================
+__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_kinv_kernel(WvBatchDev bd, const int* __restrict__ active) {
+  WvGemmSmem& sm = *reinterpret_cast<WvGemmSmem*>(wv_smem_raw);
+  const int b = active[blockIdx.y];
+  const int ld = bd.npad;
+  int ti, tj;
+  wv_tile_from_linear(blockIdx.x, ti, tj);
+  const double* Mb = bd.Mt + (size_t)b * ld * ld;
+  double acc[4][4][2];
+  wv_zero_acc(acc);
+  wv_gemm_nt_64(sm, Mb + (size_t)ti * WV_NB * ld, Mb + (size_t)tj * WV_NB * ld, ld, ti * WV_NB, bd.n8, acc);
+  int r0, c0;
+  wv_frag_origin(r0, c0);
+  double* Out = bd.A + (size_t)b * ld * ld + (size_t)ti * WV_NB * ld + tj * WV_NB;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      int r = r0 + mi * 8, c = c0 + ni * 8;
+      *reinterpret_cast<double2*>(Out + (size_t)r * ld + c) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+    }
+}
+
+// =============================================================================================
+// grad: partial[b][tile][slot] = sum over the tile of wgt_ij * W_ij * dK_ij/dtheta_slot,
+//   W = alpha alpha^T - K^{-1};  wgt = 2 below the diagonal, 1 on it, 0 above / outside [0,n).
+// dK/dtheta is regenerated from the kernel program; nothing of size n^2 is materialised.
+// grid (n_lower_tiles, n_active), 256 threads.  Algorithmic traffic: 8 n^2 bytes read.
+// =============================================================================================
+__global__ void __launch_bounds__(WV_ELEM_THREADS) wv_grad_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                                  const double* __restrict__ xall) {
+  WvElemSmem& sm = *reinterpret_cast<WvElemSmem*>(wv_smem_raw);
+  const int b = active[blockIdx.y];
+  int ti, tj;
+  wv_tile_from_linear(blockIdx.x, ti, tj);
+  wv_elem_prologue(bd, b, ti, tj, xall, sm);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = bd.n, ld = bd.npad;
+  for (int i = threadIdx.x; i < WV_MAX_SLOTS * 8; i += blockDim.x) (&sm.red[0][0])[i] = 0.0;
+  const double* Kb = bd.A + (size_t)b * ld * ld;
+  const double* al = bd.alpha + (size_t)b * ld;
+  double w[16];
+  double trw = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int gi = ti * WV_NB + ty * 4 + a;
+    const double2* src = reinterpret_cast<const double2*>(Kb + (size_t)gi * ld + tj * WV_NB + tx * 4);
+    double2 k01 = src[0], k23 = src[1];
+    double kin[4] = {k01.x, k01.y, k23.x, k23.y};
+    const double ai = al[gi];
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const int gj = tj * WV_NB + tx * 4 + bb;
+      double wv = ai * al[gj] - kin[bb];
+      double wgt = (gi < n && gj < n) ? (gi > gj ? 2.0 : (gi == gj ? 1.0 : 0.0)) : 0.0;
+      w[a * 4 + bb] = wgt * wv;
+      if (gi == gj && gi < n) trw += wv;
+    }
+  }
+  __syncthreads();
+  for (int c = 0; c < sm.pg.n_comp; ++c) {
+    const int l0 = sm.pg.comp_start[c], l1 = sm.pg.comp_start[c + 1];
+    for (int l = l0; l < l1; ++l) {
+      const WvLeaf lf = sm.pg.leaves[l];
+      const bool tv = lf.s_var >= 0 && sm.pg.slots[lf.s_var].xindex >= 0;
+      const bool tl = lf.s_ls >= 0 && sm.pg.slots[lf.s_ls].xindex >= 0;
+      const bool ta = lf.s_aux >= 0 && sm.pg.slots[lf.s_aux].xindex >= 0;
+      if (!(tv || tl || ta)) continue;
+      double wo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) wo[e] = w[e];
+      for (int l2 = l0; l2 < l1; ++l2) {
+        if (l2 == l) continue;
+        const WvLeaf lo = sm.pg.leaves[l2];
+        double xi[4], xj[4], val[16];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lo.dim][ty * 4 + a]; xj[a] = sm.xc[lo.dim][tx * 4 + a]; }
+        wv_leaf_vals(lo, sm.theta, xi, xj, val);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) wo[e] *= val[e];
+      }
+      double xi[4], xj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lf.dim][ty * 4 + a]; xj[a] = sm.xc[lf.dim][tx * 4 + a]; }
+      double sv, sl, sa;
+      wv_leaf_grad_sums(lf, sm.theta, xi, xj, wo, sv, sl, sa);
+      for (int o = 16; o > 0; o >>= 1) {
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        sl += __shfl_xor_sync(0xffffffffu, sl, o);
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      }
+      if (lane == 0) {   // several leaves may share a slot: accumulate (warp-private column, no race)
+        if (tv) sm.red[lf.s_var][warp] += sv;
+        if (tl) sm.red[lf.s_ls][warp] += sl;
+        if (ta) sm.red[lf.s_aux][warp] += sa;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) trw += __shfl_xor_sync(0xffffffffu, trw, o);
+  if (lane == 0) sm.red[sm.pg.noise_slot][warp] += trw;
+  __syncthreads();
+  const int ntiles = gridDim.x;
+  double* dst = bd.partial + ((size_t)b * ntiles + blockIdx.x) * bd.n_slots_max;
+  for (int s = threadIdx.x; s < sm.pg.n_slots; s += blockDim.x) {
+    double t = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) t += sm.red[s][wq];
+    dst[s] = t;
+  }
+}
+
+// =============================================================================================
+// finalize: f = -(LML + log prior), df/dx; status bits.  grid (n_active), 64 threads (one per slot).
+// =============================================================================================
+__global__ void __launch_bounds__(64) wv_finalize_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                         const double* __restrict__ xall, int ntiles,
+                                                         double* __restrict__ f_out, double* __restrict__ g_out,
+                                                         double* __restrict__ lml_out, int* __restrict__ status_out) {
+  __shared__ double s_lp[64];
+  __shared__ double s_sum_alpha;
+  __shared__ int s_bad;
+  const int b = active[blockIdx.x];
+  const WvProgram* pg = bd.programs + bd.prog_id[b];
+  const double* x = xall + (size_t)b * bd.P;
+  const int s = threadIdx.x;
+  if (s == 0) s_bad = 0;
+  // sum(alpha) for the mean gradient (fixed order: lane-strided then tree)
+  {
+    double t = 0.0;
+    const double* al = bd.alpha + (size_t)b * bd.npad;
+    if (s < 32) {
+      for (int i = s; i < bd.n; i += 32) t += al[i];
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (s == 0) s_sum_alpha = t;
+    }
+  }
+  __syncthreads();
+  double lp = 0.0;
+  if (s < pg->n_slots) {
+    const WvSlot sl = pg->slots[s];
+    if (sl.xindex >= 0) {
+      const double u = x[sl.xindex];
+      const double v = wv_transform(sl.transform, u, sl.shift);
+      double dlp;
+      wv_prior(sl, v, &lp, &dlp);
+      double dl = 0.0;
+      const double* part = bd.partial + (size_t)b * ntiles * bd.n_slots_max + s;
+      for (int t = 0; t < ntiles; ++t) dl += part[(size_t)t * bd.n_slots_max];
+      dl *= 0.5;
+      if (s == pg->mean_slot) dl = s_sum_alpha;
+      const double g = -(dl + dlp) * wv_transform_grad(sl.transform, u);
+      g_out[(size_t)b * bd.P + sl.xindex] = g;
+      if (!isfinite(g)) atomicOr(&s_bad, 1);
+    }
+  }
+  s_lp[s] = lp;
+  __syncthreads();
+  if (s == 0) {
+    double lps = 0.0;
+    for (int i = 0; i < pg->n_slots; ++i) lps += s_lp[i];
+    double logdet = 0.0;
+    for (int jb = 0; jb < bd.nt; ++jb) logdet += bd.logdet_part[(size_t)b * bd.nt + jb];
+    const double lml = -0.5 * bd.quad[b] - 0.5 * bd.n * 1.8378770664093453 - logdet;
+    const double f = -(lml + lps);
+    f_out[b] = f;
+    lml_out[b] = lml;
+    int st = 0;
+    if (bd.chol_fail[b]) st |= WV_STATUS_CHOL_FAIL;
+    if (!isfinite(f) || s_bad) st |= WV_STATUS_NONFINITE;
+    status_out[b] = st;
+    for (int i = pg->n_x; i < bd.P; ++i) g_out[(size_t)b * bd.P + i] = 0.0;
+  }
+}
+
+// =============================================================================================
+// host-side launch sequence of one evaluation (enqueued on `stream`, no host sync)
+// =============================================================================================
+size_t wv_smem_gemm_bytes() { return sizeof(WvPanelSmem) > sizeof(WvDiagSmem) ? sizeof(WvPanelSmem) : sizeof(WvDiagSmem); }
+
+static bool g_attr_done = false;
+static cudaError_t wv_set_attrs() {
+  if (g_attr_done) return cudaSuccess;
+  cudaError_t e;
+#define WV_ATTR(k, bytes) \
+  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+  if (e != cudaSuccess) return e;
+  WV_ATTR(wv_gram_kernel, sizeof(WvElemSmem));
+  WV_ATTR(wv_grad_kernel, sizeof(WvElemSmem));
+  WV_ATTR(wv_chol_diag_kernel, sizeof(WvDiagSmem));
+  WV_ATTR(wv_panel_kernel<0>, sizeof(WvPanelSmem));
+  WV_ATTR(wv_panel_kernel<1>, sizeof(WvPanelSmem));
+  WV_ATTR(wv_kinv_kernel, sizeof(WvGemmSmem));
+#undef WV_ATTR
+  g_attr_done = true;
+  return cudaSuccess;
+}
+
+// Returns the number of kernel launches enqueued (for bench.py's gpu_launches), or -1 on error.
+int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
+                    double* d_g, double* d_lml, int* d_status, cudaStream_t st) {
+  if (n_active <= 0) return 0;
+  if (wv_set_attrs() != cudaSuccess) return -1;
+  int launches = 0;
+  const int nt = bd.nt;
+  const int ntiles = nt * (nt + 1) / 2;
+  cudaMemsetAsync(bd.chol_fail, 0, sizeof(int) * bd.B, st);
+  wv_gram_kernel<<<dim3(ntiles, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(bd, d_active, d_x);
+  ++launches;
+  for (int j = 0; j < nt; ++j) {
+    wv_chol_diag_kernel<<<dim3(n_active), WV_GEMM_THREADS, sizeof(WvDiagSmem), st>>>(bd, d_active, j);
+    ++launches;
+    if (j + 1 < nt) {
+      wv_panel_kernel<0><<<dim3(nt - j - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, j);
+      ++launches;
+    }
+  }
+  for (int i = 1; i < nt; ++i) {
+    wv_panel_kernel<1><<<dim3(i, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, i);
+    ++launches;
+  }
+  wv_extract_kernel<<<dim3(n_active), 256, 0, st>>>(bd, d_active);
+  wv_kinv_kernel<<<dim3(ntiles, n_active), WV_GEMM_THREADS, sizeof(WvGemmSmem), st>>>(bd, d_active);
+  wv_grad_kernel<<<dim3(ntiles, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(bd, d_active, d_x);
+  wv_finalize_kernel<<<dim3(n_active), 64, 0, st>>>(bd, d_active, d_x, ntiles, d_f, d_g, d_lml, d_status);
+  launches += 4;
+  if (cudaGetLastError() != cudaSuccess) return -1;
+  return launches;
+}

@@ -1,0 +1,389 @@
+// waveome_b200 — sm_100a kernels for one batched LML+gradient evaluation (objective A, exact GPR).
+//
+// Per evaluation of a batch of models that share X [n, D]:
+//   gram      K = sum_c prod_f k_f(X[:,d_f]; theta) + sigma^2 I       (+ RHS row d^T = (y - c)^T at row n)
+//   chol      blocked left-looking Cholesky, 64x64 tiles, FP64 DMMA (mma.sync.m8n8k4.f64) trailing updates
+//   trtri     Mt = L^{-T} (upper) by block rows; the augmented RHS row yields z = L^{-1} d and -alpha for free
+//   kinv      K^{-1} = Mt Mt^T  (lower tiles, DMMA)
+//   grad      0.5 * sum_ij (alpha_i alpha_j - K^{-1}_ij) dK_ij/dtheta_p, dK regenerated on the fly
+//   finalize  LML, priors, chain rule through the bijectors -> f = -(LML + log prior), df/dx
+//
+// Layout in HBM, per model b (npad = 64 * ceil((n + 1) / 64), ld = npad):
+//   A [npad x npad]  lower tiles: K + sigma^2 I  ->  L  ->  K^{-1};  row n holds d^T -> z^T
+//   Mt[npad x npad]  upper tiles: L^{-T};  column n holds -alpha before `extract` zeroes it
+//   Dinv[nt][64x64]  row-major inverses of the diagonal Cholesky blocks
+// Rows/cols in (n, npad) carry an identity so that no kernel needs ragged-edge special cases.
+#pragma once
+#include <cuda_runtime.h>
+#include "wv_common.cuh"
+
+#define WV_NB 64
+#define WV_BK 16
+#define WV_LDS (WV_BK + 4)   // smem row stride (doubles) of a pipeline stage: (row*20 + k) mod 16 distinct -> conflict-free DMMA fragment loads
+#define WV_LDT 68            // smem row stride of a 64x64 DMMA operand tile (68 mod 16 == 4)
+#define WV_LDP 65            // smem row stride of a 64x64 scalar-access tile (potrf / trtri of a diagonal block)
+#define WV_STAGES 3
+#define WV_GEMM_THREADS 128
+#define WV_ELEM_THREADS 256
+
+struct WvBatchDev {
+  int n, D, B, npad, nt, n8, P;     // P = stride of x / grad (max packed params)
+  int n_slots_max;                  // stride of theta / partial sums
+  const double* Xt;                 // [D][npad] covariates, column-major, zero padded
+  const double* Y;                  // [B][npad] outcomes, zero padded
+  const WvProgram* programs;        // [n_programs]
+  const int* prog_id;               // [B]
+  double* A;                        // [B][npad][npad]
+  double* Mt;                       // [B][npad][npad]
+  double* Dinv;                     // [B][nt][64][64]
+  double* alpha;                    // [B][npad]
+  double* logdet_part;              // [B][nt]
+  double* quad;                     // [B]
+  double* partial;                  // [B][n_tiles][n_slots_max]
+  int* chol_fail;                   // [B]
+};
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wv_cp_async16(void* smem, const void* gmem, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void wv_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void wv_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void wv_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// lower-triangular tile index -> (ti, tj), tj <= ti
+__device__ __forceinline__ void wv_tile_from_linear(int t, int& ti, int& tj) {
+  int i = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((i + 1) * (i + 2) / 2 <= t) ++i;
+  while (i * (i + 1) / 2 > t) --i;
+  ti = i;
+  tj = t - i * (i + 1) / 2;
+}
+
+// theta (constrained values of every slot) of one model into shared memory
+__device__ __forceinline__ void wv_load_theta(const WvProgram* __restrict__ pg, const double* __restrict__ x,
+                                              double* theta_s) {
+  for (int s = threadIdx.x; s < pg->n_slots; s += blockDim.x) {
+    const WvSlot& sl = pg->slots[s];
+    theta_s[s] = sl.xindex >= 0 ? wv_transform(sl.transform, x[sl.xindex], sl.shift) : sl.fixed;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel-tree leaves on a 4x4 micro-tile  (waveome/kernels.py)
+// ---------------------------------------------------------------------------------------------
+// squared distance exactly as gpflow.utilities.ops.square_distance on a = x / ell:
+//   (-2 a_i a_j) + (a_i^2 + a_j^2), no FMA contraction, so that the diagonal is exactly 0.
+__device__ __forceinline__ double wv_r2(double ai, double aj) {
+  return __dadd_rn(__dmul_rn(-2.0, __dmul_rn(ai, aj)), __dadd_rn(__dmul_rn(ai, ai), __dmul_rn(aj, aj)));
+}
+
+__device__ __forceinline__ double wv_powi(double b, int d) {
+  double r = 1.0;
+  for (int i = 0; i < d; ++i) r *= b;
+  return r;
+}
+
+// values only: val[a*4+b] = k(x_i[a], x_j[b])
+__device__ __forceinline__ void wv_leaf_vals(const WvLeaf& lf, const double* theta, const double (&xi)[4],
+                                             const double (&xj)[4], double (&val)[16]) {
+  const double var = lf.s_var >= 0 ? theta[lf.s_var] : 1.0;
+  switch (lf.type) {
+    case WV_LEAF_SE: {
+      const double ell = theta[lf.s_ls];
+      double ai[4], aj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { ai[a] = xi[a] / ell; aj[a] = xj[a] / ell; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) val[a * 4 + b] = var * exp(-0.5 * wv_r2(ai[a], aj[b]));
+    } break;
+    case WV_LEAF_M12:
+    case WV_LEAF_M32:
+    case WV_LEAF_M52: {
+      const double ell = theta[lf.s_ls];
+      double ai[4], aj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { ai[a] = xi[a] / ell; aj[a] = xj[a] / ell; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          double r = sqrt(fmax(wv_r2(ai[a], aj[b]), 1e-36));
+          double e;
+          if (lf.type == WV_LEAF_M12) e = exp(-r);
+          else if (lf.type == WV_LEAF_M32) { double s = 1.7320508075688772 * r; e = (1.0 + s) * exp(-s); }
+          else { double s = 2.23606797749979 * r; e = (1.0 + s + 5.0 / 3.0 * r * r) * exp(-s); }
+          val[a * 4 + b] = var * e;
+        }
+    } break;
+    case WV_LEAF_PERIODIC: {
+      const double ell = theta[lf.s_ls], per = theta[lf.s_aux];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          double arg = 3.141592653589793 * (xi[a] - xj[b]) / per;
+          double ss = sin(arg) / ell;
+          val[a * 4 + b] = var * exp(-0.5 * (ss * ss));
+        }
+    } break;
+    case WV_LEAF_LINEAR:
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) val[a * 4 + b] = var * (xi[a] * xj[b]);
+      break;
+    case WV_LEAF_CONST:
+#pragma unroll
+      for (int e = 0; e < 16; ++e) val[e] = var;
+      break;
+    case WV_LEAF_CAT: {
+      double ci[4], cj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { ci[a] = rint(xi[a]); cj[a] = rint(xj[a]); }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) val[a * 4 + b] = ci[a] == cj[b] ? var : 0.0;
+    } break;
+    case WV_LEAF_POLY: {
+      const double off = theta[lf.s_ls];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) val[a * 4 + b] = wv_powi(var * (xi[a] * xj[b]) + off, lf.degree);
+    } break;
+    default:
+#pragma unroll
+      for (int e = 0; e < 16; ++e) val[e] = 0.0;
+      break;
+  }
+}
+
+// gradient sums of one leaf over the micro-tile: s_* = sum_e wo[e] * d k_e / d theta_*
+// (wo = W weight times the product of the other leaves of the component)
+__device__ __forceinline__ void wv_leaf_grad_sums(const WvLeaf& lf, const double* theta, const double (&xi)[4],
+                                                  const double (&xj)[4], const double (&wo)[16], double& s_var,
+                                                  double& s_ls, double& s_aux) {
+  s_var = 0.0; s_ls = 0.0; s_aux = 0.0;
+  const double var = lf.s_var >= 0 ? theta[lf.s_var] : 1.0;
+  switch (lf.type) {
+    case WV_LEAF_SE: {
+      const double ell = theta[lf.s_ls];
+      double ai[4], aj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { ai[a] = xi[a] / ell; aj[a] = xj[a] / ell; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          double w = wo[a * 4 + b];
+          if (w != 0.0) {
+            double r2 = wv_r2(ai[a], aj[b]);
+            double e = exp(-0.5 * r2);
+            s_var += w * e;
+            s_ls += w * (var * e) * r2;
+          }
+        }
+      s_ls /= ell;
+    } break;
+    case WV_LEAF_M12:
+    case WV_LEAF_M32:
+    case WV_LEAF_M52: {
+      const double ell = theta[lf.s_ls];
+      double ai[4], aj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { ai[a] = xi[a] / ell; aj[a] = xj[a] / ell; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          double w = wo[a * 4 + b];
+          if (w != 0.0) {
+            double r2 = wv_r2(ai[a], aj[b]);
+            double r = sqrt(fmax(r2, 1e-36));
+            double e, de;  // de = dE/dr
+            if (lf.type == WV_LEAF_M12) { e = exp(-r); de = -e; }
+            else if (lf.type == WV_LEAF_M32) {
+              double s = 1.7320508075688772 * r, ex = exp(-s);
+              e = (1.0 + s) * ex; de = -3.0 * r * ex;
+            } else {
+              double s = 2.23606797749979 * r, ex = exp(-s);
+              e = (1.0 + s + 5.0 / 3.0 * r * r) * ex; de = -(5.0 / 3.0) * r * (1.0 + s) * ex;
+            }
+            s_var += w * e;
+            if (r2 > 1e-36) s_ls += w * (var * de) * (-r);
+          }
+        }
+      s_ls /= ell;
+    } break;
+    case WV_LEAF_PERIODIC: {
+      const double ell = theta[lf.s_ls], per = theta[lf.s_aux];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          double w = wo[a * 4 + b];
+          if (w != 0.0) {
+            double arg = 3.141592653589793 * (xi[a] - xj[b]) / per;
+            double sn, cs;
+            sincos(arg, &sn, &cs);
+            double ss = sn / ell;
+            double r2 = ss * ss;
+            double e = exp(-0.5 * r2);
+            double k = var * e;
+            s_var += w * e;
+            s_ls += w * k * r2;
+            s_aux += w * k * (ss * cs / ell) * (arg / per);
+          }
+        }
+      s_ls /= ell;
+    } break;
+    case WV_LEAF_LINEAR:
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s_var += wo[a * 4 + b] * (xi[a] * xj[b]);
+      break;
+    case WV_LEAF_CONST:
+#pragma unroll
+      for (int e = 0; e < 16; ++e) s_var += wo[e];
+      break;
+    case WV_LEAF_CAT: {
+      double ci[4], cj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { ci[a] = rint(xi[a]); cj[a] = rint(xj[a]); }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s_var += ci[a] == cj[b] ? wo[a * 4 + b] : 0.0;
+    } break;
+    case WV_LEAF_POLY: {
+      const double off = theta[lf.s_ls];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          double xx = xi[a] * xj[b];
+          double db = lf.degree * wv_powi(var * xx + off, lf.degree - 1);
+          s_var += wo[a * 4 + b] * db * xx;
+          s_ls += wo[a * 4 + b] * db;
+        }
+    } break;
+    default: break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 64x64 NT tile GEMM on the FP64 tensor pipe:
+//   acc[m][n] = sum_{k in [k0,k1)} Ag[m*ld + k] * Bg[n*ld + k],  k0 % 16 == 0, k1 % 8 == 0
+// 128 threads = 4 warps (2x2), each warp owns a 32x32 sub-tile = 4x4 DMMA.8x8x4 accumulators.
+// Operands are staged with a 3-deep cp.async ring (16B chunks, zero-fill beyond k1).
+// ---------------------------------------------------------------------------------------------
+struct WvGemmSmem {
+  double a[WV_STAGES][WV_NB * WV_LDS];
+  double b[WV_STAGES][WV_NB * WV_LDS];
+};
+
+__device__ __forceinline__ void wv_gemm_issue(WvGemmSmem& sm, int stage, const double* __restrict__ Ag,
+                                              const double* __restrict__ Bg, int ld, int kc, int k1) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int q = t + WV_GEMM_THREADS * r;
+    int row = q >> 3, ch = q & 7;
+    int k = kc + ch * 2;
+    bool ok = k < k1;
+    int ks = ok ? k : kc;
+    wv_cp_async16(&sm.a[stage][row * WV_LDS + ch * 2], Ag + (size_t)row * ld + ks, ok);
+    wv_cp_async16(&sm.b[stage][row * WV_LDS + ch * 2], Bg + (size_t)row * ld + ks, ok);
+  }
+}
+
+__device__ __forceinline__ void wv_gemm_nt_64(WvGemmSmem& sm, const double* __restrict__ Ag,
+                                              const double* __restrict__ Bg, int ld, int k0, int k1,
+                                              double (&acc)[4][4][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int nchunks = (k1 - k0 + WV_BK - 1) / WV_BK;
+#pragma unroll
+  for (int s = 0; s < WV_STAGES - 1; ++s) {
+    if (s < nchunks) wv_gemm_issue(sm, s, Ag, Bg, ld, k0 + s * WV_BK, k1);
+    wv_cp_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    wv_cp_wait<WV_STAGES - 2>();
+    __syncthreads();
+    {
+      int cn = c + WV_STAGES - 1;
+      if (cn < nchunks) wv_gemm_issue(sm, cn % WV_STAGES, Ag, Bg, ld, k0 + cn * WV_BK, k1);
+      wv_cp_commit();
+    }
+    const double* as = sm.a[c % WV_STAGES] + (wm * 32 + fr) * WV_LDS + fk;
+    const double* bs = sm.b[c % WV_STAGES] + (wn * 32 + fr) * WV_LDS + fk;
+#pragma unroll
+    for (int kk = 0; kk < WV_BK; kk += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        af[i] = as[i * 8 * WV_LDS + kk];
+        bf[i] = bs[i * 8 * WV_LDS + kk];
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) wv_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+  }
+  wv_cp_wait<0>();
+  __syncthreads();
+}
+
+// second-stage product from shared memory operands (64x64x64): acc[m][n] = sum_k Ts[m][k] * Bs[n][k]
+__device__ __forceinline__ void wv_gemm_nt_smem64(const double* __restrict__ Ts, const double* __restrict__ Bs,
+                                                  double (&acc)[4][4][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int fr = lane >> 2, fk = lane & 3;
+  const double* as = Ts + (wm * 32 + fr) * WV_LDT + fk;
+  const double* bs = Bs + (wn * 32 + fr) * WV_LDT + fk;
+#pragma unroll 4
+  for (int kk = 0; kk < WV_NB; kk += 4) {
+    double af[4], bf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      af[i] = as[i * 8 * WV_LDT + kk];
+      bf[i] = bs[i * 8 * WV_LDT + kk];
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) wv_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+  }
+}
+
+// accumulator fragment coordinates of this thread: row = r0 + mi*8, col = c0 + ni*8 (+0,+1)
+__device__ __forceinline__ void wv_frag_origin(int& r0, int& c0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  r0 = (warp >> 1) * 32 + (lane >> 2);
+  c0 = (warp & 1) * 32 + (lane & 3) * 2;
+}
+
+__device__ __forceinline__ void wv_zero_acc(double (&acc)[4][4][2]) {
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+}

@@ -1,0 +1,237 @@
+"""ctypes binding of the C ABI in include/waveome_b200.h (libwaveome_b200.so, built in-tree by
+``__graft_entry__.build()``).
+
+There is deliberately no CPU fallback: importing this module without the built library, or creating
+an ``Engine`` without a CUDA device, raises.  PyTorch is used only as plumbing (device tensors for the
+DLPack / device-pointer entry point, ``torch.distributed`` for sharding in ``model_search``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .program import Program
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libwaveome_b200.so")
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+class _ProgramDesc(C.Structure):
+    _fields_ = [
+        ("n_comp", C.c_int32), ("n_leaves", C.c_int32), ("n_slots", C.c_int32), ("noise_slot", C.c_int32),
+        ("mean_slot", C.c_int32),
+        ("comp_start", _i32p), ("leaf_type", _i32p), ("leaf_dim", _i32p), ("leaf_s_var", _i32p),
+        ("leaf_s_ls", _i32p), ("leaf_s_aux", _i32p), ("leaf_degree", _i32p),
+        ("slot_transform", _i32p), ("slot_xindex", _i32p), ("slot_prior", _i32p),
+        ("slot_fixed", _f64p), ("slot_shift", _f64p), ("slot_pa", _f64p), ("slot_pb", _f64p),
+    ]
+
+
+class _BatchDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("D", C.c_int32), ("B", C.c_int32), ("P", C.c_int32),
+        ("X", _f64p), ("Y", _f64p), ("n_programs", C.c_int32), ("programs", C.POINTER(_ProgramDesc)),
+        ("prog_id", _i32p),
+    ]
+
+
+class _LbfgsOpts(C.Structure):
+    _fields_ = [("maxcor", C.c_int32), ("maxiter", C.c_int32), ("maxfun", C.c_int32), ("maxls", C.c_int32),
+                ("ftol", C.c_double), ("gtol", C.c_double)]
+
+
+EXPORTED_SYMBOLS = [
+    "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_batch_create", "wv_batch_destroy",
+    "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
+    "wv_batch_counters", "wv_last_error", "wv_version",
+]
+
+_lib = None
+
+
+def load_library():
+    """Load libwaveome_b200.so or raise — never falls back to a CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"waveome_b200: CUDA extension not built ({_LIB_PATH} missing). Run `python -c 'import "
+            "__graft_entry__ as g; g.build()'` from the repository root. There is no CPU fallback.")
+    lib = C.CDLL(_LIB_PATH)
+    vp = C.c_void_p
+    lib.wv_engine_create.argtypes = [C.c_int, C.POINTER(vp)]; lib.wv_engine_create.restype = C.c_int
+    lib.wv_engine_destroy.argtypes = [vp]; lib.wv_engine_destroy.restype = None
+    lib.wv_engine_stream.argtypes = [vp]; lib.wv_engine_stream.restype = vp
+    lib.wv_batch_create.argtypes = [vp, C.POINTER(_BatchDesc), C.POINTER(vp)]; lib.wv_batch_create.restype = C.c_int
+    lib.wv_batch_destroy.argtypes = [vp]; lib.wv_batch_destroy.restype = None
+    lib.wv_batch_workspace_bytes.argtypes = [vp]; lib.wv_batch_workspace_bytes.restype = C.c_int64
+    lib.wv_batch_set_y.argtypes = [vp, _f64p]; lib.wv_batch_set_y.restype = C.c_int
+    lib.wv_batch_eval.argtypes = [vp, _f64p, _f64p, _f64p, _f64p, _i32p]; lib.wv_batch_eval.restype = C.c_int
+    lib.wv_batch_eval_device.argtypes = [vp, vp, vp, vp, vp, vp]; lib.wv_batch_eval_device.restype = C.c_int
+    lib.wv_batch_fit_lbfgs.argtypes = [vp, _f64p, C.POINTER(_LbfgsOpts), _f64p, _f64p, _i32p, _i32p, _i32p]
+    lib.wv_batch_fit_lbfgs.restype = C.c_int
+    lib.wv_batch_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.wv_batch_counters.restype = None
+    lib.wv_last_error.argtypes = []; lib.wv_last_error.restype = C.c_char_p
+    lib.wv_version.argtypes = []; lib.wv_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise EngineError(f"{what} failed: {load_library().wv_last_error().decode()}")
+
+
+def _f64(a):
+    return a.ctypes.data_as(_f64p)
+
+
+def _i32(a):
+    return a.ctypes.data_as(_i32p)
+
+
+#: SciPy L-BFGS-B defaults (scipy.optimize._lbfgsb_py._minimize_lbfgsb); waveome overrides maxiter/maxfun
+#: with 50000 at waveome/model_classes.py:310-315 and maxiter at waveome/model_fitting.py:280.
+DEFAULT_LBFGS = dict(maxcor=10, maxiter=15000, maxfun=15000, maxls=20, ftol=2.220446049250313e-09, gtol=1e-05)
+
+
+class Engine:
+    """One per GPU / host thread; owns the CUDA stream the batches launch on."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib.wv_engine_create(int(device), C.byref(h)), "wv_engine_create")
+        self.handle = h
+        self.device = int(device)
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.wv_engine_stream(self.handle) or 0)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.wv_engine_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """B independent GP models on shared covariates X: y_b ~ GP(mean_b, k_b) + noise."""
+
+    def __init__(self, engine: Engine, X: np.ndarray, Y: np.ndarray, programs: Sequence[Program],
+                 prog_id: Optional[Sequence[int]] = None, P: Optional[int] = None):
+        self.engine = engine
+        self.lib = engine.lib
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        if X.ndim != 2 or Y.ndim != 2 or Y.shape[1] != X.shape[0]:
+            raise ValueError("X must be [n, D] and Y must be [B, n]")
+        self.n, self.D = X.shape
+        self.B = Y.shape[0]
+        self.programs: List[Program] = list(programs)
+        pid = np.zeros(self.B, np.int32) if prog_id is None else np.ascontiguousarray(prog_id, dtype=np.int32)
+        if pid.shape != (self.B,):
+            raise ValueError("prog_id must have one entry per model")
+        self.prog_id = pid
+        self.P = int(P) if P is not None else max(1, max(p.n_x for p in self.programs))
+        descs = (_ProgramDesc * len(self.programs))()
+        for d, p in zip(descs, self.programs):
+            d.n_comp, d.n_leaves, d.n_slots = p.n_comp, p.n_leaves, p.n_slots
+            d.noise_slot, d.mean_slot = p.noise_slot, p.mean_slot
+            d.comp_start, d.leaf_type, d.leaf_dim = _i32(p.comp_start), _i32(p.leaf_type), _i32(p.leaf_dim)
+            d.leaf_s_var, d.leaf_s_ls, d.leaf_s_aux = _i32(p.leaf_s_var), _i32(p.leaf_s_ls), _i32(p.leaf_s_aux)
+            d.leaf_degree = _i32(p.leaf_degree)
+            d.slot_transform, d.slot_xindex, d.slot_prior = _i32(p.slot_transform), _i32(p.slot_xindex), _i32(p.slot_prior)
+            d.slot_fixed, d.slot_shift, d.slot_pa, d.slot_pb = _f64(p.slot_fixed), _f64(p.slot_shift), _f64(p.slot_pa), _f64(p.slot_pb)
+        bd = _BatchDesc(self.n, self.D, self.B, self.P, _f64(X), _f64(Y), len(self.programs), descs, _i32(pid))
+        h = C.c_void_p()
+        _check(self.lib.wv_batch_create(engine.handle, C.byref(bd), C.byref(h)), "wv_batch_create")
+        self.handle = h
+
+    # ------------------------------------------------------------------------------------------
+    def x0(self) -> np.ndarray:
+        """[B, P] unconstrained start vectors from the programs' current parameter values."""
+        x = np.zeros((self.B, self.P))
+        starts = [p.x0() for p in self.programs]
+        for b in range(self.B):
+            s = starts[self.prog_id[b]]
+            x[b, : s.size] = s
+        return x
+
+    def set_y(self, Y: np.ndarray):
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        if Y.shape != (self.B, self.n):
+            raise ValueError("Y must be [B, n]")
+        _check(self.lib.wv_batch_set_y(self.handle, _f64(Y)), "wv_batch_set_y")
+
+    def eval(self, x: np.ndarray):
+        """One LML+gradient evaluation from HOST buffers.  Returns (f, grad, lml, status)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.shape != (self.B, self.P):
+            raise ValueError(f"x must be [{self.B}, {self.P}]")
+        f = np.empty(self.B); g = np.empty((self.B, self.P)); lml = np.empty(self.B)
+        st = np.empty(self.B, np.int32)
+        _check(self.lib.wv_batch_eval(self.handle, _f64(x), _f64(f), _f64(g), _f64(lml), _i32(st)), "wv_batch_eval")
+        return f, g, lml, st
+
+    def eval_device(self, x, f, grad, lml, status):
+        """Same with DEVICE buffers (torch CUDA tensors or anything exposing ``data_ptr()`` /
+        ``__dlpack__``), enqueued on the engine stream without host synchronisation."""
+        ptrs = []
+        for t in (x, f, grad, lml, status):
+            if not hasattr(t, "data_ptr"):
+                import torch
+                t = torch.from_dlpack(t)
+            ptrs.append(C.c_void_p(t.data_ptr()))
+        _check(self.lib.wv_batch_eval_device(self.handle, *ptrs), "wv_batch_eval_device")
+
+    def fit(self, x0: Optional[np.ndarray] = None, **opts):
+        """Batched L-BFGS-B MAP fit.  Returns dict(x, f, lml, n_iter, n_eval, status)."""
+        o = dict(DEFAULT_LBFGS); o.update(opts)
+        x = self.x0() if x0 is None else np.array(x0, dtype=np.float64, order="C", copy=True)
+        if x.shape != (self.B, self.P):
+            raise ValueError(f"x0 must be [{self.B}, {self.P}]")
+        co = _LbfgsOpts(int(o["maxcor"]), int(o["maxiter"]), int(o["maxfun"]), int(o["maxls"]), float(o["ftol"]),
+                        float(o["gtol"]))
+        f = np.empty(self.B); lml = np.empty(self.B)
+        nit = np.empty(self.B, np.int32); nev = np.empty(self.B, np.int32); st = np.empty(self.B, np.int32)
+        _check(self.lib.wv_batch_fit_lbfgs(self.handle, _f64(x), C.byref(co), _f64(f), _f64(lml), _i32(nit), _i32(nev),
+                                           _i32(st)), "wv_batch_fit_lbfgs")
+        return dict(x=x, f=f, lml=lml, n_iter=nit, n_eval=nev, status=st)
+
+    def counters(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.lib.wv_batch_counters(self.handle, C.byref(a), C.byref(b), C.byref(c))
+        return dict(launches=a.value, rounds=b.value, model_evals=c.value)
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.wv_batch_workspace_bytes(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.wv_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,100 @@
+"""Model objects of the exact-GPR path: what ``gpflow.models.GPR(data=(X, Y), kernel=k)`` is to the
+reference (waveome/model_fitting.py:150-155), reduced to a description the CUDA engine consumes.
+
+A fitted ``GPR`` exposes what the reference's downstream code reads from a model:
+``.kernel``, ``.likelihood.variance``, ``.mean_function.c``, ``.kernel_name``, ``.trainable_parameters``,
+``.log_marginal_likelihood_value``, ``.log_posterior_density_value``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+from . import kernels as K
+from .program import Program, build_program
+
+
+class Gaussian:
+    """gpflow.likelihoods.Gaussian: variance = 1e-6 + softplus(u), default 1.0."""
+    name = "gaussian"
+
+    def __init__(self, variance=1.0, variance_lower_bound=1e-6):
+        self.variance = K.Parameter(variance, transform=("softplus_shift", variance_lower_bound))
+
+    @property
+    def parameters(self):
+        return [self.variance]
+
+
+class ConstantMean:
+    """gpflow.mean_functions.Constant: trainable scalar ``c`` (identity bijector), default 0."""
+    name = "constant"
+
+    def __init__(self, c=0.0):
+        self.c = K.Parameter(c, transform="identity")
+
+    @property
+    def parameters(self):
+        return [self.c]
+
+
+class ZeroMean:
+    """gpflow.mean_functions.Zero (the GPR default in waveome/model_fitting.py:151-155)."""
+    name = "zero"
+    parameters: list = []
+
+
+class GPR:
+    def __init__(self, kernel: K.Kernel, mean_function=None, noise_variance: float = 1.0, likelihood: Optional[Gaussian] = None):
+        self.kernel = kernel
+        self.mean_function = mean_function if mean_function is not None else ZeroMean()
+        self.likelihood = likelihood if likelihood is not None else Gaussian(noise_variance)
+        self.name = "gpr"
+        self.kernel_name = ""
+        self.data = None
+        self.log_marginal_likelihood_value = None
+        self.log_posterior_density_value = None
+        self.fit_info = None
+
+    # GPflow-like surface ---------------------------------------------------------------------
+    @property
+    def parameters(self) -> List[K.Parameter]:
+        return list(self.kernel.parameters) + list(self.likelihood.parameters) + list(self.mean_function.parameters)
+
+    @property
+    def trainable_parameters(self) -> List[K.Parameter]:
+        seen, out = set(), []
+        for p in self.parameters:
+            if p.trainable and id(p) not in seen:
+                seen.add(id(p))
+                out.append(p)
+        return out
+
+    def parameter_dict(self):
+        """gpflow.utilities.parameter_dict(model)-style {path: Parameter}."""
+        d = dict(self.kernel.named_parameters("kernel"))
+        d[".likelihood.variance"] = self.likelihood.variance
+        if isinstance(self.mean_function, ConstantMean):
+            d[".mean_function.c"] = self.mean_function.c
+        return d
+
+    # engine interface ------------------------------------------------------------------------
+    def program(self) -> Program:
+        mc = self.mean_function.c if isinstance(self.mean_function, ConstantMean) else None
+        return build_program(self.kernel, self.likelihood.variance, mc)
+
+    def to_spec(self) -> dict:
+        """Neutral JSON-able description (the format the test oracle consumes)."""
+        spec = {"kernel": self.kernel.to_spec(), "likelihood_variance": self.likelihood.variance.to_spec()}
+        if isinstance(self.mean_function, ConstantMean):
+            spec["mean"] = {"type": "constant", "c": self.mean_function.c.to_spec()}
+        else:
+            spec["mean"] = {"type": "zero"}
+        return spec
+
+    def log_posterior_density(self):
+        return self.log_posterior_density_value
+
+    def log_marginal_likelihood(self):
+        return self.log_marginal_likelihood_value
