@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the model-fitting hot path (BASELINE.json: "GP model fits/sec & LML+grad evals/sec, fp64, batched").
+
+Workload (config.workload): BASELINE.json configs[2] — iHMP-scale synthetic metabolome, n = 600 samples x 5
+covariates, 2000 Gaussian outcomes PER GPU, saturated horseshoe-penalised kernel (9 additive components, 17
+trainable parameters), L-BFGS-B with SciPy/GPflow options (maxiter = maxfun = 50000).  It is the configuration the
+north star quotes its target on and it fits one GPU (13.8 GB of workspace).  The other configs are parity-test cases.
+
+A "step" is one complete batched MAP fit of the rank's 2000 models (about 90 LML+gradient evaluations per model).
+  value  fits/s with X, Y resident in HBM (engine batch built outside the timed region)
+  e2e    fits/s through the public API (GPSearch.penalized_optimization on pandas/host inputs: standardisation,
+         kernel build, program encoding, H2D of X/Y/x0, fit, D2H of results, structure pruning)
+Weak scaling: every rank fits its own 2000 outcomes; there is no collective on the data path.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/gp_oracle.py: NumPy/SciPy objective +
+scipy L-BFGS-B — GPflow/TensorFlow are not installable here) on all host cores, one outcome per core.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_SUBJECTS, N_VISITS = 120, 5
+FP64_PEAK_TFLOPS = 35.5     # cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/r01_library_fp64_context.log);
+                            # MEASURED_PEAKS.json carries no fp64 entry.  Raw DMMA issue peak: 37.1 (r01_fp64_peak_microbench.log)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_workload(n_outcomes, seed):
+    from waveome_b200 import datasets
+    X, Y = datasets.ihmp_scale(n_subjects=N_SUBJECTS, n_visits=N_VISITS, n_outcomes=n_outcomes, seed=seed)
+    return X, Y
+
+
+def make_search(X, Y):
+    from waveome_b200.model_search import GPSearch
+    return GPSearch(X, Y, unit_col="participant", categorical_vars=["participant", "sex", "site"],
+                    Y_transform="standardize")
+
+
+def build_model(gps):
+    import waveome_b200 as wb
+    from waveome_b200.regularization import full_kernel_build
+    k = full_kernel_build(cat_vars=gps.cat_idx, num_vars=gps.cont_idx, unit_idx=gps.unit_idx, return_sum=True)
+    return wb.models.PenalizedGPR(k, mean_function=wb.ConstantMean(), penalization_factor=1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle restatement, one outcome per host core
+# ------------------------------------------------------------------------------------------------
+def _cpu_fit_one(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    spec, X, y = args
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(1)
+    except Exception:
+        ctx = None
+    import gp_oracle
+    t0 = time.perf_counter()
+    r = gp_oracle.fit(spec, X, y, maxiter=50000, maxfun=50000)
+    if ctx is not None:
+        ctx.restore_original_limits()
+    return r["nfev"], r["status"], time.perf_counter() - t0
+
+
+def cpu_reference_step(spec, Xn, Yn, cols, cores):
+    """Fit outcomes `cols` on `cores` processes; returns (fits, evals, seconds)."""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
+        out = list(ex.map(_cpu_fit_one, [(spec, Xn, Yn[:, c].copy()) for c in cols]))
+    dt = time.perf_counter() - t0
+    return len(cols), sum(o[0] for o in out), dt
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.stop_flag = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in o.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--outcomes", type=int, default=2000, help="outcomes (models) per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="outcomes in the CPU baseline sample (0 = one per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    n = N_SUBJECTS * N_VISITS
+    workload = (f"BASELINE configs[2] iHMP-scale synthetic metabolome: n={n}, D=5, {args.outcomes} Gaussian outcomes/GPU, "
+                "saturated kernel (9 components, P=17), horseshoe pf=1.0, L-BFGS-B maxiter=maxfun=50000")
+    config = {"workload": workload, "n": n, "D": 5, "outcomes_per_gpu": args.outcomes, "P": 17,
+              "parallelism": f"outcome-sharded x{world}, no collective", "l2_policy": "inputs >> L2 (13.8 GB workspace/GPU)"}
+
+    # -------------------------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        X, Y = make_workload(max(cores, args.cpu_sample or cores), seed=2024)
+        gps = make_search(X, Y)
+        spec = build_model(gps).to_spec()
+        Xn, Yn = gps.X.to_numpy(), gps.Y.to_numpy()
+        ncols = args.cpu_sample or cores
+        cols = list(range(ncols))
+        for _ in range(min(args.warmup, 1)):
+            cpu_reference_step(spec, Xn, Yn, cols[: max(1, ncols // 4)], cores)
+        fits = evals = 0
+        secs = 0.0
+        for _ in range(args.steps):
+            f, e, dt = cpu_reference_step(spec, Xn, Yn, cols, cores)
+            fits += f; evals += e; secs += dt
+        v = fits / secs
+        sample = f"{ncols} outcomes of the same workload per step, one per host core, BLAS threads pinned to 1"
+        line = {"impl": "reference", "metric": "gp_model_fits_per_sec", "value": v, "unit": "fits/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "lml_grad_evals_per_sec": evals / secs,
+                "cpu_baseline": {"value": v, "unit": "fits/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": v, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # -------------------------------------------------------------------------------- B200 arm
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from waveome_b200.engine import Batch
+    from waveome_b200.model_fitting import get_engine
+    X, Y = make_workload(args.outcomes, seed=2024 + rank)
+    gps = make_search(X, Y)
+    model = build_model(gps)
+    eng = get_engine(local_rank)
+    Xn = gps.X.to_numpy(dtype=np.float64)
+    Yn = np.ascontiguousarray(gps.Y.to_numpy(dtype=np.float64).T)
+    batch = Batch(eng, Xn, Yn, [model.program()])
+    x0 = batch.x0()
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
+    opts = dict(maxiter=50000, maxfun=50000)
+
+    for _ in range(args.warmup):
+        batch.fit(x0, **opts)
+    barrier()
+    c0 = batch.counters()
+    batch.profile(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    n_eval = 0
+    status_hist = {}
+    for _ in range(args.steps):
+        r = batch.fit(x0, **opts)
+        n_eval += int(r["n_eval"].sum()) + len(r["n_eval"])      # + the closing evaluation at the optimum
+        for s in r["status"]:
+            status_hist[int(s)] = status_hist.get(int(s), 0) + 1
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+    prof = batch.profile_read()
+    batch.profile(False)
+    c1 = batch.counters()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    tot = torch.tensor([args.steps * args.outcomes, n_eval, c1["launches"] - c0["launches"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    fits_total, evals_total, launches_total = [float(v) for v in tot.tolist()]
+    value = fits_total / (ms_max * 1e-3)
+
+    # ---------------- e2e through the public API: host pandas in, fitted model objects out
+    def e2e_step():
+        g = make_search(X, Y)
+        g.penalized_optimization(penalization_factor=1.0, gather=False)
+        return g
+    batch.close()
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = fits_total / float(t.item())
+    h2d = Xn.nbytes + Yn.nbytes + x0.nbytes
+    d2h = x0.nbytes + args.outcomes * (8 + 8 + 4 + 4 + 4)
+
+    # ---------------- roofline of the dominant kernel class (live CUDA-event times over the timed region)
+    peaks, peak_kind = load_peaks()
+    model_evals = c1["model_evals"] - c0["model_evals"]
+    dom = max(prof, key=lambda k: prof[k][0])
+    dom_ms, dom_launches = prof[dom]
+    step_ms = sum(v[0] for v in prof.values())
+    if dom in ("gram", "grad"):
+        alg = 8.0 * n * n * model_evals + 8.0 * n * 5 * model_evals          # bytes: K written / W read once + X
+        achieved = alg / (dom_ms * 1e-3) / 1e9
+        roof = {"kernel": f"wv_{dom}_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind + " copy bandwidth",
+                "note": "ALU-bound in practice: 6 fp64 exp per matrix element for this kernel tree (see DESIGN.md)"}
+    else:
+        share = {"chol_diag": 1.0 / 3, "chol_panel": 1.0 / 3, "trtri": 1.0 / 3, "kinv": 1.0 / 3}.get(dom, 0.0)
+        if dom in ("chol_diag", "chol_panel"):
+            dom_ms = prof["chol_diag"][0] + prof["chol_panel"][0]
+            dom = "chol_diag+chol_panel"
+        alg = share * float(n) ** 3 * model_evals
+        achieved = alg / (dom_ms * 1e-3) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                "peak_kind": "measured cuBLAS DGEMM fp64 on this pool (not in MEASURED_PEAKS.json)"}
+    roof["share_of_step"] = dom_ms / step_ms if step_ms else None
+    roof["launches"] = dom_launches
+    fact_ms = sum(prof[k][0] for k in ("chol_diag", "chol_panel", "trtri", "kinv"))
+    groups = {
+        "factorisation_tflops": float(n) ** 3 * model_evals / (fact_ms * 1e-3) / 1e12 if fact_ms else None,
+        "factorisation_frac_of_fp64_peak": float(n) ** 3 * model_evals / (fact_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS if fact_ms else None,
+        "class_ms": {k: round(v[0], 3) for k, v in prof.items()},
+    }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        ncols = args.cpu_sample or cores
+        spec = model.to_spec()
+        f, e, dt = cpu_reference_step(spec, Xn, gps.Y.to_numpy(dtype=np.float64), list(range(ncols)), cores)
+        cpu = {"value": f / dt, "unit": "fits/s", "cores": cores, "kind": "port",
+               "sample": f"first {ncols} outcomes of rank 0's workload, one per host core, BLAS threads pinned to 1 "
+                         f"({dt:.1f} s wall); oracle/gp_oracle.py + scipy L-BFGS-B",
+               "lml_grad_evals_per_sec": e / dt}
+
+    line = {"metric": "gp_model_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "lml_grad_evals_per_sec": evals_total / (ms_max * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "GPSearch.penalized_optimization (pandas in, fitted models out)"},
+            "gpu_launches": int(launches_total), "clocks": clocks, "roofline": roof, "roofline_groups": groups,
+            "cpu_baseline": cpu, "fit_status_hist": status_hist}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

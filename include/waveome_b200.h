@@ -83,6 +83,11 @@ typedef struct wv_lbfgs_opts {
   int32_t maxls;     /* SciPy default 20 */
   double ftol;       /* SciPy default 2.220446049250313e-09 (= factr * epsmch) */
   double gtol;       /* SciPy default 1e-5 (pgtol) */
+  int32_t chol_fail_policy; /* Cholesky failure at a line-search trial point: 0 = treat the trial as non-finite and let
+                               the search recover (default); 1 = abandon the fit there, as the TensorFlow exception does
+                               in the reference (waveome/model_classes.py:323-340).  A failure at the start point always
+                               abandons the fit. */
+  int32_t reserved;
 } wv_lbfgs_opts;
 
 int wv_engine_create(int device, wv_engine** out);
@@ -112,6 +117,12 @@ int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* opts, double
 
 /* counters since batch creation: kernels launched, batched evaluation rounds, model evaluations */
 void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t* rounds, int64_t* model_evals);
+
+/* Optional per-kernel-class device timing (CUDA events on the engine stream, resolved at the host syncs the fit
+ * loop already has).  Classes, in order: gram, chol_diag, chol_panel, trtri, extract, kinv, grad, finalize, lbfgs.
+ * wv_batch_profile_read fills ms[i] / launches[i] for i < n and returns the number of classes. */
+void wv_batch_profile_enable(wv_batch* b, int on);
+int wv_batch_profile_read(wv_batch* b, double* ms, int64_t* launches, int n);
 
 const char* wv_last_error(void);
 const char* wv_version(void);

@@ -431,8 +431,17 @@ STATUS_MAXITER = 4
 STATUS_LINESEARCH = 8
 
 
-def fit(model, X, y, maxiter=50000, maxfun=None, x0=None, maxcor=10, ftol=2.220446049250313e-09, gtol=1e-05, maxls=20):
-    """L-BFGS-B MAP fit.  Returns dict(x, f, lml, nit, nfev, status, message, model)."""
+def fit(model, X, y, maxiter=50000, maxfun=None, x0=None, maxcor=10, ftol=2.220446049250313e-09, gtol=1e-05, maxls=20,
+        on_chol_fail="nan"):
+    """L-BFGS-B MAP fit.  Returns dict(x, f, lml, nit, nfev, status, message, model).
+
+    on_chol_fail: what a Cholesky failure at a line-search trial point does.
+      "abort" - the reference's behaviour: TensorFlow raises, GPflow's minimize is abandoned with the parameters left
+                at the failing trial point (waveome/model_classes.py:323-340 then retries from there and fails again).
+      "nan"   - (default, and the engine's default) the trial is reported to L-BFGS-B as a non-finite value, the line
+                search backs out and the last finite iterate is kept.  Whether such a trial "fails" at all is a rounding
+                coin-flip (e.g. variance 1e10 + noise 1e-6), so this is the only policy that is reproducible across
+                LAPACK / Eigen / CUDA factorizations.  A failure at the start point always aborts."""
     import scipy.optimize as so
 
     model = copy.deepcopy(model)
@@ -440,10 +449,16 @@ def fit(model, X, y, maxiter=50000, maxfun=None, x0=None, maxcor=10, ftol=2.2204
         x0 = pack(model)
     if maxfun is None:
         maxfun = 15000
-    state = {"chol_fail": False}
+    state = {"n": 0}
 
     def fun(x):
-        f, g, _, _ = objective(model, X, y, x)
+        state["n"] += 1
+        try:
+            f, g, _, _ = objective(model, X, y, x)
+        except CholeskyFailure:
+            if on_chol_fail == "abort" or state["n"] == 1:
+                raise
+            f, g = float("nan"), np.full(len(x), float("nan"))
         return f, g
 
     try:
@@ -455,7 +470,11 @@ def fit(model, X, y, maxiter=50000, maxfun=None, x0=None, maxcor=10, ftol=2.2204
         return dict(x=None, f=math.inf, lml=-math.inf, nit=0, nfev=0, status=STATUS_CHOL_FAIL,
                     message="cholesky failed", model=None)
     unpack(model, res.x)
-    f, _, lml, lp = objective(model, X, y, res.x, want_grad=False)
+    try:
+        f, _, lml, lp = objective(model, X, y, res.x, want_grad=False)
+    except CholeskyFailure:
+        return dict(x=res.x, f=math.inf, lml=-math.inf, nit=int(res.nit), nfev=int(res.nfev), status=STATUS_CHOL_FAIL,
+                    message="cholesky failed at the returned point", model=model)
     status = STATUS_OK
     if not np.isfinite(res.fun):
         status |= STATUS_NONFINITE

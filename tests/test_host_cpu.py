@@ -1,0 +1,111 @@
+"""CPU-only checks of the boundary and the host logic: the C-ABI library loads and exports every symbol the header
+declares, program encoding, kernel naming / pruning arithmetic, data preparation, sharding."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import waveome_b200 as wb
+from waveome_b200 import datasets, program, regularization, utilities
+from waveome_b200.model_search import GPSearch, shard_bounds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from waveome_b200 import engine
+    hdr = open(os.path.join(ROOT, "include", "waveome_b200.h")).read()
+    declared = set(re.findall(r"\b(wv_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(engine.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(os.path.join(ROOT, "waveome_b200", "_lib", "libwaveome_b200.so"))
+    for s in declared:
+        assert hasattr(lib, s), s
+    lib.wv_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.wv_version()
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from waveome_b200.engine import Engine, EngineError
+    with pytest.raises(EngineError, match="no CPU fallback"):
+        Engine(0)
+
+
+def test_program_encoding_saturated_kernel():
+    k, names = regularization.full_kernel_build(cat_vars=[0, 3, 4], num_vars=[1, 2], unit_idx=0,
+                                                var_names=["participant", "age", "study_day", "sex", "site"],
+                                                return_sum=True)
+    assert names == ["categorical[participant]", "categorical[sex]", "categorical[site]",
+                     "squared_exponential[age]", "squared_exponential[study_day]",
+                     "categorical[sex]*squared_exponential[age]", "categorical[sex]*squared_exponential[study_day]",
+                     "categorical[site]*squared_exponential[age]", "categorical[site]*squared_exponential[study_day]"]
+    m = wb.models.PenalizedGPR(k, mean_function=wb.ConstantMean(), penalization_factor=2.0)
+    p = m.program()
+    assert (p.n_comp, p.n_leaves, p.n_x) == (9, 13, 17)
+    # frozen categorical variances inside products carry no prior and no packed index (regularization.py:131-132)
+    frozen = [s for s in range(p.n_slots) if p.slot_xindex[s] < 0]
+    assert len(frozen) == 4 and all(p.slot_prior[s] == 0 for s in frozen)
+    hs = [s for s in range(p.n_slots) if p.slot_prior[s] == program.PRIOR_CODE["horseshoe"]]
+    assert len(hs) == 9 and np.allclose(p.slot_pa[hs], 0.5)          # scale = 1 / penalization_factor
+    assert p.slot_transform[p.noise_slot] == program.TRANSFORM_CODE["softplus_shift"] and p.slot_shift[p.noise_slot] == 1e-6
+    assert len(m.trainable_parameters) == 17
+    x0 = p.x0()
+    p.assign(x0 + 0.5)
+    np.testing.assert_allclose(p.x0(), x0 + 0.5, rtol=1e-12)
+
+
+def test_product_of_sum_is_distributed():
+    a, b, c = wb.SquaredExponential(active_dims=[0]), wb.Lin(active_dims=[1]), wb.Categorical(active_dims=[2])
+    comps = program.expand_sum_of_products(wb.Product([wb.Sum([a, b]), c]))
+    assert [[l.name for l in comp] for comp in comps] == [["squared_exponential", "categorical"], ["lin", "categorical"]]
+    p = wb.GPR(wb.Product([wb.Sum([a, b]), c])).program()
+    assert p.leaf_s_var[1] == p.leaf_s_var[3]          # the shared categorical variance is one slot
+
+
+def test_names_dedup_and_pruning():
+    k = wb.Sum([wb.Categorical(active_dims=[0]), wb.Product([wb.Categorical(active_dims=[2]), wb.SquaredExponential(active_dims=[1])])])
+    assert utilities.kernel_name_string(k) == "categorical[0]+categorical[2]*squared_exponential[1]"
+    assert utilities.check_if_model_exists("squared_exponential[1]*categorical[2]+categorical[0]", [utilities.kernel_name_string(k)])
+    assert not utilities.check_if_model_exists("categorical[0]", [utilities.kernel_name_string(k)])
+    X = np.random.default_rng(0).normal(size=(30, 3))
+    m = wb.models.PenalizedGPR(k)
+    m.kernel.kernels[0].variance.assign(0.05)
+    m.cut_kernel_components(X)
+    assert m.kernel.name == "product"
+    m2 = wb.models.PenalizedGPR(wb.Sum([wb.SquaredExponential(active_dims=[1], lengthscales=100.0), wb.Lin(active_dims=[0])]))
+    m2.cut_kernel_components(X)                        # lengthscale >= 3 * range -> dropped (utilities.py:1150-1153)
+    assert m2.kernel.name == "lin"
+    m3 = wb.models.PenalizedGPR(wb.Sum([wb.Lin(active_dims=[0], variance=0.01), wb.Lin(active_dims=[1], variance=0.02)]))
+    m3.cut_kernel_components(X)
+    assert m3.kernel.name == "constant"
+    assert utilities.calc_bic(-12.5, 100, 6) == 37.0
+
+
+def test_gpsearch_data_preparation():
+    X, Y = datasets.iris()
+    gps = GPSearch(X, Y, categorical_vars=["species"])
+    assert gps.cat_idx == [2] and gps.cont_idx == [0, 1] and gps.unit_idx is None
+    np.testing.assert_allclose(gps.X["petal_length"].std(), 1.0)           # pandas std, ddof = 1
+    assert sorted(gps.X["species"].unique()) == [0.0, 1.0, 2.0]
+    Xo, Yo = datasets.overview_notebook()
+    # soft pins recorded in waveome_overview.ipynb: cell 4 head() and cell 11 Z[0] = [0., -1.44041, 0.]
+    np.testing.assert_allclose(Xo["time"].iloc[:2].to_numpy(), [1.175864, 1.843311], atol=5e-7)
+    np.testing.assert_allclose(Yo.iloc[0].to_numpy(), [0.889715, 0.381912, 1.314904], atol=5e-7)
+    g2 = GPSearch(Xo, Yo, unit_col="person_id", categorical_vars=["female"])
+    np.testing.assert_allclose(g2.X.iloc[0].to_numpy(), [0.0, -1.44041, 0.0], atol=5e-6)
+    with pytest.raises(TypeError):
+        GPSearch(X.to_numpy(), Y)
+
+
+def test_shard_bounds_cover_everything():
+    for n in (1, 7, 250, 2000):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1

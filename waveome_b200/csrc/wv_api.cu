@@ -11,7 +11,7 @@
 #include "wv_lbfgsb.h"
 
 int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
-                    double* d_g, double* d_lml, int* d_status, cudaStream_t st);
+                    double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf);
 
 static thread_local std::string g_err;
 static int wv_fail(const std::string& m) { g_err = m; return -1; }
@@ -38,6 +38,7 @@ struct wv_batch {
   int lb_m_alloc;
   int* h_count;   // pinned
   int64_t bytes, launches, rounds, model_evals;
+  WvProfiler prof;
 };
 
 template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
@@ -216,9 +217,25 @@ extern "C" void wv_batch_destroy(wv_batch* b) {
   if (!b) return;
   cudaSetDevice(b->eng->device);
   cudaStreamSynchronize(b->eng->stream);
+  b->prof.destroy();
   for (void* p : b->allocs) cudaFree(p);
   if (b->h_count) cudaFreeHost(b->h_count);
   delete b;
+}
+
+extern "C" void wv_batch_profile_enable(wv_batch* b, int on) {
+  if (!b) return;
+  b->prof.enabled = on != 0;
+  if (on) { for (int i = 0; i < WV_K_NCLASS; ++i) { b->prof.ms[i] = 0; b->prof.launches[i] = 0; } b->prof.n_ev = 0; }
+}
+
+extern "C" int wv_batch_profile_read(wv_batch* b, double* ms, int64_t* launches, int n) {
+  if (!b || !ms || !launches) return wv_fail("wv_batch_profile_read: null argument");
+  cudaSetDevice(b->eng->device);
+  cudaStreamSynchronize(b->eng->stream);
+  b->prof.resolve();
+  for (int i = 0; i < n && i < WV_K_NCLASS; ++i) { ms[i] = b->prof.ms[i]; launches[i] = b->prof.launches[i]; }
+  return WV_K_NCLASS;
 }
 
 extern "C" int64_t wv_batch_workspace_bytes(const wv_batch* b) { return b ? b->bytes : 0; }
@@ -242,7 +259,7 @@ extern "C" void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t*
 
 static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g, double* d_lml, int* d_status,
                        const int* d_active, int n_active) {
-  int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, b->eng->stream);
+  int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, b->eng->stream, &b->prof);
   if (l < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   b->launches += l; b->rounds += 1; b->model_evals += n_active;
   return 0;
@@ -303,11 +320,18 @@ __global__ void wv_lb_step_kernel(const int* __restrict__ active, int n_active, 
   WvLbState L;
   // the optimiser sees only the model's own trainable parameters (n_x <= Pstride)
   L.bind(sc + b, x + (size_t)b * Pstride, g + (size_t)b * Pstride, work + (size_t)b * wstride, nx_of_model[b], m);
-  if (status[b] & WV_STATUS_CHOL_FAIL) {   // TF raises InvalidArgumentError here and the fit is abandoned
-    task[b] = WV_LB_CHOLFAIL;
-    return;
+  double fb = f[b];
+  if (status[b] & WV_STATUS_CHOL_FAIL) {
+    // TensorFlow raises InvalidArgumentError here.  At the start point, or with policy 1, the fit is abandoned;
+    // otherwise the trial counts as a non-finite evaluation and the line search backs out of it.
+    if (opts.chol_fail_policy == 1 || sc[b].first) {
+      task[b] = WV_LB_CHOLFAIL;
+      return;
+    }
+    fb = nan("");
+    for (int k = 0; k < L.P; ++k) L.g[k] = fb;
   }
-  task[b] = wv_lb_step(L, opts, f[b]);
+  task[b] = wv_lb_step(L, opts, fb);
 }
 
 // ordered compaction of the models that still need an evaluation (single CTA, warp ballots)
@@ -373,7 +397,7 @@ extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o
   int *d_nx = b->d_nx, *d_iter = b->d_iter, *d_neval = b->d_neval, *d_st2 = b->d_st2;
   WvLbOpts opts;
   opts.m = m; opts.maxiter = o->maxiter; opts.maxfun = o->maxfun; opts.maxls = o->maxls;
-  opts.ftol = o->ftol; opts.pgtol = o->gtol;
+  opts.ftol = o->ftol; opts.pgtol = o->gtol; opts.chol_fail_policy = o->chol_fail_policy; opts.reserved = 0;
   const int tb = 64, gb = (B + tb - 1) / tb;
   WV_CUDA(cudaMemcpyAsync(b->d_x, x, (size_t)B * P * sizeof(double), cudaMemcpyHostToDevice, st));
   wv_nx_kernel<<<gb, tb, 0, st>>>(b->bd.programs, b->bd.prog_id, B, d_nx);
@@ -390,9 +414,11 @@ extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o
     wv_lb_step_kernel<<<(n_active + tb - 1) / tb, tb, 0, st>>>(cur, n_active, d_nx, P, m, opts, b->d_lbs, b->d_lbw,
                                                               wstride, b->d_x, b->d_g, b->d_f, b->d_status, b->d_task);
     wv_compact_kernel<<<1, 1024, 0, st>>>(b->d_task, B, nxt, b->d_count);
+    b->prof.mark(WV_K_LBFGS, st);
     b->launches += 2;
     WV_CUDA(cudaMemcpyAsync(b->h_count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
     WV_CUDA(cudaStreamSynchronize(st));
+    b->prof.resolve();
     n_active = b->h_count[0];
     int* tmp = cur; cur = nxt; nxt = tmp;
     if (++guard > guard_max) return wv_fail("wv_batch_fit_lbfgs: iteration guard tripped");

@@ -507,31 +507,42 @@ static cudaError_t wv_set_attrs() {
 
 // Returns the number of kernel launches enqueued (for bench.py's gpu_launches), or -1 on error.
 int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
-                    double* d_g, double* d_lml, int* d_status, cudaStream_t st) {
+                    double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf) {
   if (n_active <= 0) return 0;
   if (wv_set_attrs() != cudaSuccess) return -1;
   int launches = 0;
   const int nt = bd.nt;
   const int ntiles = nt * (nt + 1) / 2;
+  WvProfiler none;
+  if (!pf) pf = &none;
   cudaMemsetAsync(bd.chol_fail, 0, sizeof(int) * bd.B, st);
+  pf->mark(-1, st);
   wv_gram_kernel<<<dim3(ntiles, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(bd, d_active, d_x);
+  pf->mark(WV_K_GRAM, st);
   ++launches;
   for (int j = 0; j < nt; ++j) {
     wv_chol_diag_kernel<<<dim3(n_active), WV_GEMM_THREADS, sizeof(WvDiagSmem), st>>>(bd, d_active, j);
+    pf->mark(WV_K_CHOL_DIAG, st);
     ++launches;
     if (j + 1 < nt) {
       wv_panel_kernel<0><<<dim3(nt - j - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, j);
+      pf->mark(WV_K_CHOL_PANEL, st);
       ++launches;
     }
   }
   for (int i = 1; i < nt; ++i) {
     wv_panel_kernel<1><<<dim3(i, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, i);
+    pf->mark(WV_K_TRTRI, st);
     ++launches;
   }
   wv_extract_kernel<<<dim3(n_active), 256, 0, st>>>(bd, d_active);
+  pf->mark(WV_K_EXTRACT, st);
   wv_kinv_kernel<<<dim3(ntiles, n_active), WV_GEMM_THREADS, sizeof(WvGemmSmem), st>>>(bd, d_active);
+  pf->mark(WV_K_KINV, st);
   wv_grad_kernel<<<dim3(ntiles, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(bd, d_active, d_x);
+  pf->mark(WV_K_GRAD, st);
   wv_finalize_kernel<<<dim3(n_active), 64, 0, st>>>(bd, d_active, d_x, ntiles, d_f, d_g, d_lml, d_status);
+  pf->mark(WV_K_FINALIZE, st);
   launches += 4;
   if (cudaGetLastError() != cudaSuccess) return -1;
   return launches;

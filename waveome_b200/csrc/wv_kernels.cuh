@@ -44,6 +44,41 @@ struct WvBatchDev {
 };
 
 // ---------------------------------------------------------------------------------------------
+// optional per-kernel-class timing with CUDA events on the launching stream (bench.py's live roofline)
+// ---------------------------------------------------------------------------------------------
+enum WvKernelClass { WV_K_GRAM = 0, WV_K_CHOL_DIAG, WV_K_CHOL_PANEL, WV_K_TRTRI, WV_K_EXTRACT, WV_K_KINV, WV_K_GRAD,
+                     WV_K_FINALIZE, WV_K_LBFGS, WV_K_NCLASS };
+struct WvProfiler {
+  bool enabled = false;
+  cudaEvent_t ev[256];
+  int cls[256];
+  int n_ev = 0, n_alloc = 0;
+  double ms[WV_K_NCLASS] = {0};
+  long long launches[WV_K_NCLASS] = {0};
+  // mark the end of a kernel of class c (c < 0: start marker)
+  void mark(int c, cudaStream_t st) {
+    if (!enabled) return;
+    if (n_ev == 256) resolve();
+    if (n_ev >= n_alloc) { cudaEventCreate(&ev[n_alloc]); ++n_alloc; }
+    cudaEventRecord(ev[n_ev], st);
+    cls[n_ev++] = c;
+  }
+  void resolve() {   // requires the stream to be idle or blocks until the last event completes
+    if (n_ev == 0) return;
+    cudaEventSynchronize(ev[n_ev - 1]);
+    for (int i = 1; i < n_ev; ++i) {
+      if (cls[i] < 0) continue;
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[i - 1], ev[i]);
+      ms[cls[i]] += t;
+      launches[cls[i]] += 1;
+    }
+    n_ev = 0;
+  }
+  void destroy() { for (int i = 0; i < n_alloc; ++i) cudaEventDestroy(ev[i]); n_alloc = 0; n_ev = 0; }
+};
+
+// ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void wv_cp_async16(void* smem, const void* gmem, bool pred) {

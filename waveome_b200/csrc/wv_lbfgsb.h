@@ -37,6 +37,8 @@ struct WvLbOpts {
   int32_t maxls;
   double ftol;      // factr * epsmch
   double pgtol;
+  int32_t chol_fail_policy;   // 0: failed trial = non-finite value, 1: abandon the fit
+  int32_t reserved;
 };
 
 // scalar part of the per-model state

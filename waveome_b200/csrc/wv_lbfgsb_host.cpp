@@ -18,7 +18,7 @@ void* wvh_lb_create(int P, int m, int maxiter, int maxfun, int maxls, double fto
   HostLb* h = new HostLb();
   h->P = P; h->m = m;
   h->opts.m = m; h->opts.maxiter = maxiter; h->opts.maxfun = maxfun; h->opts.maxls = maxls;
-  h->opts.ftol = ftol; h->opts.pgtol = pgtol;
+  h->opts.ftol = ftol; h->opts.pgtol = pgtol; h->opts.chol_fail_policy = 0; h->opts.reserved = 0;
   h->x.assign(P, 0.0); h->g.assign(P, 0.0); h->work.assign(wv_lb_work_doubles(P, m), 0.0);
   memset(&h->sc, 0, sizeof(h->sc));
   h->L.bind(&h->sc, h->x.data(), h->g.data(), h->work.data(), P, m);

@@ -42,14 +42,15 @@ class _BatchDesc(C.Structure):
 
 class _LbfgsOpts(C.Structure):
     _fields_ = [("maxcor", C.c_int32), ("maxiter", C.c_int32), ("maxfun", C.c_int32), ("maxls", C.c_int32),
-                ("ftol", C.c_double), ("gtol", C.c_double)]
+                ("ftol", C.c_double), ("gtol", C.c_double), ("chol_fail_policy", C.c_int32), ("reserved", C.c_int32)]
 
 
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_batch_create", "wv_batch_destroy",
     "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
-    "wv_batch_counters", "wv_last_error", "wv_version",
+    "wv_batch_counters", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
+KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs"]
 
 _lib = None
 
@@ -78,6 +79,8 @@ def load_library():
     lib.wv_batch_fit_lbfgs.restype = C.c_int
     lib.wv_batch_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.wv_batch_counters.restype = None
+    lib.wv_batch_profile_enable.argtypes = [vp, C.c_int]; lib.wv_batch_profile_enable.restype = None
+    lib.wv_batch_profile_read.argtypes = [vp, _f64p, C.POINTER(C.c_int64), C.c_int]; lib.wv_batch_profile_read.restype = C.c_int
     lib.wv_last_error.argtypes = []; lib.wv_last_error.restype = C.c_char_p
     lib.wv_version.argtypes = []; lib.wv_version.restype = C.c_char_p
     _lib = lib
@@ -103,7 +106,8 @@ def _i32(a):
 
 #: SciPy L-BFGS-B defaults (scipy.optimize._lbfgsb_py._minimize_lbfgsb); waveome overrides maxiter/maxfun
 #: with 50000 at waveome/model_classes.py:310-315 and maxiter at waveome/model_fitting.py:280.
-DEFAULT_LBFGS = dict(maxcor=10, maxiter=15000, maxfun=15000, maxls=20, ftol=2.220446049250313e-09, gtol=1e-05)
+DEFAULT_LBFGS = dict(maxcor=10, maxiter=15000, maxfun=15000, maxls=20, ftol=2.220446049250313e-09, gtol=1e-05,
+                     on_chol_fail="nan")
 
 
 class Engine:
@@ -208,8 +212,10 @@ class Batch:
         x = self.x0() if x0 is None else np.array(x0, dtype=np.float64, order="C", copy=True)
         if x.shape != (self.B, self.P):
             raise ValueError(f"x0 must be [{self.B}, {self.P}]")
+        if o["on_chol_fail"] not in ("nan", "abort"):
+            raise ValueError("on_chol_fail must be 'nan' (failed trial = non-finite value) or 'abort'")
         co = _LbfgsOpts(int(o["maxcor"]), int(o["maxiter"]), int(o["maxfun"]), int(o["maxls"]), float(o["ftol"]),
-                        float(o["gtol"]))
+                        float(o["gtol"]), 1 if o["on_chol_fail"] == "abort" else 0, 0)
         f = np.empty(self.B); lml = np.empty(self.B)
         nit = np.empty(self.B, np.int32); nev = np.empty(self.B, np.int32); st = np.empty(self.B, np.int32)
         _check(self.lib.wv_batch_fit_lbfgs(self.handle, _f64(x), C.byref(co), _f64(f), _f64(lml), _i32(nit), _i32(nev),
@@ -220,6 +226,17 @@ class Batch:
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         self.lib.wv_batch_counters(self.handle, C.byref(a), C.byref(b), C.byref(c))
         return dict(launches=a.value, rounds=b.value, model_evals=c.value)
+
+    def profile(self, on: bool = True):
+        """Enable/disable CUDA-event timing per kernel class (resets the accumulators when enabling)."""
+        self.lib.wv_batch_profile_enable(self.handle, 1 if on else 0)
+
+    def profile_read(self):
+        """{class: (total_ms, launches)} since profile(True)."""
+        n = len(KERNEL_CLASSES)
+        ms = np.zeros(n); cnt = np.zeros(n, np.int64)
+        self.lib.wv_batch_profile_read(self.handle, _f64(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64)), n)
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_CLASSES)}
 
     @property
     def workspace_bytes(self) -> int:

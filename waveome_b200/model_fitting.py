@@ -1,0 +1,136 @@
+"""Batched model fitting on the engine — the replacement of the reference's per-model hot loop.
+
+* ``fit_models``       packs B models that share X into one ``engine.Batch`` and runs the device L-BFGS-B
+                       (replaces one Ray task + one ``gpflow.optimizers.Scipy().minimize`` per model:
+                       waveome/model_search.py:250-393, waveome/model_fitting.py:276-281)
+* ``kernel_test_reg``  drop-in for waveome/model_fitting.py:16-373 on the exact-GPR ("gaussian") path:
+                       best-of-restarts MAP fit of one kernel, returns ``(model, bic)``; failure -> ``(None, inf)``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import kernels as K
+from .models import GPR
+from .utilities import calc_bic, print_kernel_names
+
+_ENGINES: Dict[int, "object"] = {}
+
+
+def get_engine(device: Optional[int] = None):
+    """One engine per GPU per process (LOCAL_RANK picks the GPU under torchrun)."""
+    import os
+    from .engine import Engine
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _ENGINES:
+        _ENGINES[device] = Engine(device)
+    return _ENGINES[device]
+
+
+def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional[np.ndarray] = None,
+               engine=None, max_batch_bytes: float = 60e9, **lbfgs_opts) -> dict:
+    """MAP-fit ``models[b]`` to outcome ``Y[b]`` (Y is [B, n]); all models share X [n, D].
+
+    Models with identical kernel programs share one device program.  Fitted values are written back into the
+    models' Parameter objects; per-model ``fit_info`` / ``log_marginal_likelihood_value`` /
+    ``log_posterior_density_value`` are set.  Returns the raw arrays (x, f, lml, n_iter, n_eval, status)."""
+    from .engine import Batch
+    engine = engine or get_engine()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    B = len(models)
+    if Y.shape != (B, X.shape[0]):
+        raise ValueError("Y must be [len(models), n]")
+    progs = [m.program() for m in models]
+    uniq, prog_id, table = {}, np.empty(B, np.int32), []
+    for b, p in enumerate(progs):
+        sig = p.signature()
+        if sig not in uniq:
+            uniq[sig] = len(table)
+            table.append(p)
+        prog_id[b] = uniq[sig]
+    P = max(1, max(p.n_x for p in progs))
+    starts = np.zeros((B, P))
+    for b, p in enumerate(progs):
+        starts[b, : p.n_x] = p.x0()
+    if x0 is not None:
+        starts = np.array(x0, dtype=np.float64).reshape(B, P)
+    # bound the device workspace: two padded n x n matrices per model in flight
+    n = X.shape[0]
+    npad = ((n + 1 + 7) // 8 * 8 + 63) // 64 * 64
+    per_model = 2 * npad * npad * 8 + npad * 64 * 8
+    chunk = max(1, int(max_batch_bytes // per_model))
+    out = dict(x=np.empty((B, P)), f=np.empty(B), lml=np.empty(B), n_iter=np.empty(B, np.int32),
+               n_eval=np.empty(B, np.int32), status=np.empty(B, np.int32), launches=0, rounds=0)
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        batch = Batch(engine, X, Y[lo:hi], table, prog_id[lo:hi], P=P)
+        try:
+            r = batch.fit(starts[lo:hi], **lbfgs_opts)
+            c = batch.counters()
+        finally:
+            batch.close()
+        for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
+            out[key][lo:hi] = r[key]
+        out["launches"] += c["launches"]
+        out["rounds"] += c["rounds"]
+    for b, (m, p) in enumerate(zip(models, progs)):
+        p.assign(out["x"][b, : p.n_x])
+        m.log_marginal_likelihood_value = float(out["lml"][b])
+        m.log_posterior_density_value = float(-out["f"][b])
+        m.fit_info = dict(n_iter=int(out["n_iter"][b]), n_eval=int(out["n_eval"][b]), status=int(out["status"][b]))
+    return out
+
+
+def kernel_test_reg(X, Y, k, num_restarts=5, random_init=True, verbose=False, likelihood="gaussian", lasso=False,
+                    lam=0, use_priors=True, max_iter=50000, keep_data=False, freeze_variances=False,
+                    random_seed=None, engine=None, **unused):
+    """waveome/model_fitting.py:16-373 on the exact-GPR path.  The ``num_restarts`` restarts are one device
+    batch (same y, different starts) instead of a Python loop."""
+    if likelihood != "gaussian" or lasso:
+        raise NotImplementedError("kernel_test_reg on the B200 engine covers likelihood='gaussian', lasso=False "
+                                  "(objective A, SURVEY §0.3); VGP/SVPGPR paths are out of the hot path")
+    from .utilities import freeze_variance_parameters
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64).reshape(-1)
+    if random_seed is not None:
+        np.random.seed(random_seed)
+    models = []
+    for _ in range(num_restarts):
+        m = GPR(K.deepcopy(k))                      # Zero mean, noise variance 1.0 (reference :151-155)
+        if freeze_variances:
+            freeze_variance_parameters(m.kernel)
+        if lam > 0:
+            for name, p in m.parameter_dict().items():
+                if "kernel" in name and "variance" in name:
+                    p.prior = K.Laplace(0.0, 1.0 / lam)
+        if use_priors:
+            for name, p in m.parameter_dict().items():
+                if "kernel" in name and "variance" not in name and "W" not in name:
+                    p.prior = K.Uniform(0.0, 10.0)
+        if random_init:                              # reference :245-259: unconstrained ~ N(0, 1)
+            for p in m.kernel.trainable_parameters:
+                p.assign(p.transform_fn(np.random.normal(size=1)))
+            for p in m.likelihood.parameters:
+                if p.trainable:
+                    p.assign(p.transform_fn(np.random.normal(size=1)))
+        models.append(m)
+    res = fit_models(X, np.tile(Y, (num_restarts, 1)), models, engine=engine, maxiter=max_iter)
+    best_model, best_loglik = None, -np.inf
+    for b, m in enumerate(models):
+        st = int(res["status"][b])
+        if st & 1 or not np.isfinite(res["f"][b]):   # exception / not invertible -> restart skipped (:290-309)
+            continue
+        cur = -float(res["f"][b])
+        if cur > best_loglik:
+            best_loglik, best_model = cur, m
+    if best_model is None:
+        return None, -1 * best_loglik
+    bic = round(calc_bic(loglik=best_loglik, n=X.shape[0], k=len(best_model.trainable_parameters)), 2)
+    if verbose:
+        print(f"Model: {print_kernel_names(k)}, BIC: {bic}")
+    best_model.data = (X, Y.reshape(-1, 1)) if keep_data else None
+    return best_model, bic

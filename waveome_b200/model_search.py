@@ -1,0 +1,174 @@
+"""GPSearch — drop-in surface of waveome/model_search.py:47 for the model-fitting hot path.
+
+``__init__`` reproduces the reference's data preparation (:73-195: factorise categoricals, z-score the
+continuous X columns with pandas' ddof=1 std, optional Y transforms).  ``penalized_optimization``
+(:197-517) keeps its signature; instead of one Ray worker + TensorFlow graph + SciPy loop per outcome it
+packs all outcomes into engine batches (one per GPU when launched under torchrun) and runs the device
+L-BFGS-B on the exact-GPR objective (objective A).
+"""
+from __future__ import annotations
+
+import os
+import time
+import warnings
+from typing import Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+
+from . import kernels as K
+from .model_fitting import fit_models, get_engine
+from .models import ConstantMean, PenalizedGPR
+from .regularization import full_kernel_build
+
+
+def _rank_world():
+    """(rank, world) of the current torch.distributed job, (0, 1) otherwise."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def shard_bounds(n_items: int, rank: int, world: int):
+    """Static contiguous split of the model list over ranks: [lo, hi) of this rank."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GPSearch:
+    def __init__(self, X, Y, unit_col=None, standardize_X=True, Y_transform=None, categorical_vars=None,
+                 outcome_likelihood="gaussian"):
+        X = X.copy()
+        if not isinstance(X, pd.DataFrame):
+            raise TypeError("X is not a Pandas DataFrame")
+        if not isinstance(Y, pd.DataFrame):
+            raise TypeError("Y is not a Pandas DataFrame")
+        categorical_vars = list(categorical_vars or [])       # (the reference mutates a shared default list)
+        if unit_col is not None and unit_col not in categorical_vars:
+            categorical_vars += [unit_col]
+        self.categorical_dict = {}
+        for c in categorical_vars:
+            if X[c].dtype == object or str(X[c].dtype).startswith(("string", "str", "category")):
+                factor_out = pd.factorize(X[c])
+                self.categorical_dict[c] = factor_out
+                X[c] = factor_out[0].astype(float)
+        try:
+            X = X.astype(float)
+        except Exception:
+            raise TypeError("X columns must all be float type. Perhaps use pandas.factorize().")
+        try:
+            Y = Y.astype(float)
+        except Exception:
+            raise TypeError("Y columns must all be float type.")
+        assert X.isna().sum().sum() == 0, "NAs in X, waveome cannot currently handle missing values!"
+        assert Y.isna().sum().sum() == 0, "NAs in Y, waveome cannot currently handle missing values!"
+        self.X = X.copy()
+        self.Y = Y.copy()
+        self.feat_names = X.columns.tolist()
+        self.out_names = Y.columns.tolist()
+        self.cat_idx = [self.feat_names.index(x) for x in categorical_vars]
+        self.unit_idx = self.feat_names.index(unit_col) if unit_col is not None else None
+        self.likelihood = outcome_likelihood
+        self.cont_idx = np.where(~np.isin(np.arange(X.shape[1]), self.cat_idx))[0].tolist()
+        if standardize_X:
+            self.X_means = self.X.iloc[:, self.cont_idx].mean(axis=0)
+            self.X_stds = self.X.iloc[:, self.cont_idx].std(axis=0)
+            self.X_original = self.X.copy()
+            for c in self.cont_idx:
+                name = self.feat_names[c]
+                self.X[name] = (self.X[name] - self.X_means[name]) / self.X_stds[name]
+        if Y_transform == "standardize":
+            if self.likelihood != "gaussian":
+                warnings.warn("Standardizing Y without a gaussian likelihood is not advised!")
+            self.Y_means = self.Y.mean(axis=0)
+            self.Y_stds = self.Y.std(axis=0)
+            self.Y_original = self.Y.copy()
+            self.Y = (self.Y - self.Y_means) / self.Y_stds
+        elif Y_transform == "scale":
+            self.Y_stds = self.Y.std(axis=0)
+            self.Y_original = self.Y.copy()
+            self.Y = self.Y / self.Y_stds
+        self.models: Dict[str, PenalizedGPR] = {}
+        self.fit_report: Optional[dict] = None
+
+    # ------------------------------------------------------------------------------------------
+    def penalized_optimization(self, full_kernel=None, num_jobs=-1, verbose=False, mean_function=None,
+                               kernel_options=None, penalization_factor=1.0, num_factor_iter=5, num_restart=0,
+                               sparse_options=None, variational_options=None, optimization_options=None,
+                               random_seed=None, ray_dashboard=False, ray_logging=False, gather=True):
+        """Fit the saturated penalised kernel to every outcome (waveome/model_search.py:197-517).
+
+        ``num_jobs``, ``ray_*``, ``sparse_options`` and ``variational_options`` are accepted for signature
+        compatibility; the engine always fits the exact model on the GPU.  Under ``torch.distributed`` the
+        outcomes are sharded over ranks with no collective on the data path; with ``gather=True`` the fitted
+        models are exchanged afterwards so every rank holds ``self.models`` for all outcomes."""
+        if self.likelihood != "gaussian":
+            raise NotImplementedError("the B200 engine covers outcome_likelihood='gaussian' (objective A)")
+        if penalization_factor is None:
+            raise NotImplementedError("penalization_factor=None (iterated factor) needs predict_y: next row (§8f)")
+        self.model_selection_type = "penalized"
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        kernel_options = kernel_options or {"second_order_numeric": False, "categorical_numeric_interactions": True,
+                                            "unit_numeric_interactions": False, "kerns": [K.SquaredExponential()]}
+        optimization_options = dict(optimization_options or {"optimizer": "scipy"})
+        optimization_options.pop("optimizer", None)
+        num_opt_iter = int(optimization_options.pop("num_opt_iter", 50000))   # maxiter = maxfun (model_classes.py:310-315)
+        if full_kernel is None:
+            full_kernel, _ = full_kernel_build(cat_vars=self.cat_idx, num_vars=self.cont_idx, unit_idx=self.unit_idx,
+                                               var_names=self.feat_names, return_sum=True, **kernel_options)
+        mean_function = mean_function if mean_function is not None else ConstantMean()
+        rank, world = _rank_world()
+        lo, hi = shard_bounds(len(self.out_names), rank, world)
+        names = self.out_names[lo:hi]
+        t0 = time.time()
+        models: List[PenalizedGPR] = [
+            PenalizedGPR(K.deepcopy(full_kernel), mean_function=K.deepcopy(mean_function),
+                         penalization_factor=penalization_factor) for _ in names]
+        Xn = self.X.to_numpy(dtype=np.float64)
+        Yn = np.ascontiguousarray(self.Y[names].to_numpy(dtype=np.float64).T)
+        n_fits = max(1, int(num_restart)) if num_restart else 1
+        if verbose and rank == 0:
+            print(f"Building {len(self.out_names)} models on {world} GPU(s)...")
+        if num_restart and num_restart > 0:
+            # random_restart_optimize (model_classes.py:472-524): keep the restart with the best objective
+            best = None
+            for r in range(num_restart):
+                seed = r if random_seed is None else random_seed + r + 1
+                rs = np.random.RandomState(seed)
+                for m in models:
+                    for p in m.trainable_parameters:
+                        p.assign(p.transform_fn(rs.normal(loc=0.0, scale=1.0)))
+                res = fit_models(Xn, Yn, models, maxiter=num_opt_iter, maxfun=num_opt_iter)
+                if best is None:
+                    best = {k: np.array(v) for k, v in res.items() if isinstance(v, np.ndarray)}
+                else:
+                    better = -res["f"] > -best["f"]
+                    for k in best:
+                        best[k][better] = res[k][better]
+            res = best
+            for m, xb in zip(models, res["x"]):
+                m.program().assign(xb[: len(m.trainable_parameters)])
+        else:
+            res = fit_models(Xn, Yn, models, maxiter=num_opt_iter, maxfun=num_opt_iter)
+        for m in models:
+            m.cut_kernel_components(Xn)
+            m.update_kernel_name()
+        local = dict(zip(names, models))
+        report = dict(n_models=len(names), seconds=time.time() - t0, n_eval=int(np.sum(res["n_eval"])),
+                      status=np.asarray(res["status"]).copy(), n_fits_per_model=n_fits)
+        if world > 1 and gather:
+            import torch.distributed as dist
+            parts = [None] * world
+            dist.all_gather_object(parts, local)
+            local = {}
+            for p in parts:
+                local.update(p)
+        self.models = local
+        self.fit_report = report
+        return None

@@ -98,3 +98,46 @@ class GPR:
 
     def log_marginal_likelihood(self):
         return self.log_marginal_likelihood_value
+
+
+# ------------------------------------------------------------------------------------------------
+# penalised model: what PSVGP(penalized_options={"penalization_factor": pf}) is to the reference
+# ------------------------------------------------------------------------------------------------
+class PenalizedGPR(GPR):
+    """Exact-GPR counterpart of ``PenalizedGP`` (waveome/model_classes.py:777-1079): horseshoe prior with
+    scale 1/penalization_factor on every trainable kernel variance (:837-864), structure pruning by
+    ``cut_kernel_components`` (:1029-1079)."""
+
+    def __init__(self, kernel, mean_function=None, noise_variance=1.0, penalization_factor=1.0):
+        super().__init__(kernel, mean_function=mean_function, noise_variance=noise_variance)
+        self.name = "penalized_gpr"
+        self.feature_importances = None
+        self.set_penalization_factor(penalization_factor)
+        self.update_kernel_name()
+
+    def set_penalization_factor(self, penalization_factor, use_prior=True):
+        self.penalization_factor = float(penalization_factor)
+        if use_prior:
+            prior = K.Horseshoe(scale=1.0 / penalization_factor) if penalization_factor > 0 else None
+            for key, val in self.parameter_dict().items():
+                if "kernel" in key and "variance" in key:
+                    val.prior = prior
+
+    def update_kernel_name(self):
+        from .utilities import kernel_name_string
+        self.kernel_name = kernel_name_string(self.kernel, with_idx=True)
+
+    def cut_kernel_components(self, X, var_cutoff: float = 0.1):
+        from .utilities import find_variance_components, search_through_kernel_list_
+        var_parts = find_variance_components(self.kernel, sum_reduce=False)
+        var_flag = np.where(np.asarray(var_parts).reshape(-1) >= var_cutoff)[0]
+        if len(var_flag) > 1:
+            self.kernel = K.Sum([self.kernel.kernels[i] for i in var_flag])
+        elif len(var_flag) == 1:
+            if len(var_parts) > 1:
+                self.kernel = self.kernel.kernels[var_flag[0]]
+        else:
+            self.kernel = K.Constant()
+        if hasattr(self.kernel, "kernels"):
+            self.kernel = search_through_kernel_list_(self.kernel.kernels, list_type=self.kernel.name, X=np.asarray(X))
+        return None
