@@ -3,6 +3,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <set>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -39,6 +41,7 @@ struct wv_batch {
   int* h_count;   // pinned
   int64_t bytes, launches, rounds, model_evals;
   WvProfiler prof;
+  std::vector<int> perm;   // device row i holds caller row perm[i] (rows sorted by their categorical columns)
 };
 
 template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
@@ -186,10 +189,41 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
 #undef WV_TRY
   bd.Xt = dXt; bd.Y = dY; bd.programs = dprog; bd.prog_id = dpid;
   cudaStream_t st = e->stream;
+  // Row order on the device: sorted lexicographically by the categorical columns the programs use (fewest levels
+  // first).  The marginal likelihood is invariant under a simultaneous permutation of X rows and y entries; the sort
+  // turns the categorical masks into block patterns, so whole warps of the Gram / gradient kernels can skip the
+  // transcendental factors of categorical x numeric products where the mask is zero.
+  b->perm.resize(d->n);
+  for (int i = 0; i < d->n; ++i) b->perm[i] = i;
+  {
+    std::set<int> cat;
+    for (int p = 0; p < d->n_programs; ++p)
+      for (int l = 0; l < d->programs[p].n_leaves; ++l)
+        if (d->programs[p].leaf_type[l] == WV_LEAF_CAT) cat.insert(d->programs[p].leaf_dim[l]);
+    std::vector<std::pair<int, int>> order;   // (levels, dim)
+    for (int k : cat) {
+      std::set<long long> lv;
+      for (int i = 0; i < d->n; ++i) lv.insert((long long)rint(d->X[(size_t)i * d->D + k]));
+      order.push_back({(int)lv.size(), k});
+    }
+    std::sort(order.begin(), order.end());
+    const double* Xh = d->X;
+    const int Dh = d->D;
+    std::stable_sort(b->perm.begin(), b->perm.end(), [&](int a, int c) {
+      for (auto& o : order) {
+        double va = rint(Xh[(size_t)a * Dh + o.second]), vc = rint(Xh[(size_t)c * Dh + o.second]);
+        if (va != vc) return va < vc;
+      }
+      return false;
+    });
+  }
   // X -> column-major, zero padded
   std::vector<double> xt((size_t)d->D * np, 0.0);
   for (int i = 0; i < d->n; ++i)
-    for (int k = 0; k < d->D; ++k) xt[(size_t)k * np + i] = d->X[(size_t)i * d->D + k];
+    for (int k = 0; k < d->D; ++k) xt[(size_t)k * np + i] = d->X[(size_t)b->perm[i] * d->D + k];
+  std::vector<double> yp((size_t)B * d->n);
+  for (size_t m = 0; m < B; ++m)
+    for (int i = 0; i < d->n; ++i) yp[m * d->n + i] = d->Y[m * d->n + b->perm[i]];
   std::vector<int> ident(B);
   for (size_t i = 0; i < B; ++i) ident[i] = (int)i;
   cudaError_t ce = cudaSuccess;
@@ -201,7 +235,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   step(cudaMemsetAsync(bd.A, 0, B * np * np * sizeof(double), st));
   step(cudaMemsetAsync(bd.Mt, 0, B * np * np * sizeof(double), st));
   step(cudaMemsetAsync(dY, 0, B * np * sizeof(double), st));
-  step(cudaMemcpy2DAsync(dY, np * sizeof(double), d->Y, (size_t)d->n * sizeof(double), (size_t)d->n * sizeof(double), B,
+  step(cudaMemcpy2DAsync(dY, np * sizeof(double), yp.data(), (size_t)d->n * sizeof(double), (size_t)d->n * sizeof(double), B,
                          cudaMemcpyHostToDevice, st));
   step(cudaMallocHost((void**)&b->h_count, 4 * sizeof(int)));
   step(cudaStreamSynchronize(st));
@@ -244,7 +278,10 @@ extern "C" int wv_batch_set_y(wv_batch* b, const double* Y) {
   if (!b || !Y) return wv_fail("wv_batch_set_y: null argument");
   WV_CUDA(cudaSetDevice(b->eng->device));
   const WvBatchDev& bd = b->bd;
-  WV_CUDA(cudaMemcpy2DAsync((void*)bd.Y, (size_t)bd.npad * sizeof(double), Y, (size_t)bd.n * sizeof(double),
+  std::vector<double> yp((size_t)bd.B * bd.n);
+  for (size_t m = 0; m < (size_t)bd.B; ++m)
+    for (int i = 0; i < bd.n; ++i) yp[m * bd.n + i] = Y[m * bd.n + b->perm[i]];
+  WV_CUDA(cudaMemcpy2DAsync((void*)bd.Y, (size_t)bd.npad * sizeof(double), yp.data(), (size_t)bd.n * sizeof(double),
                             (size_t)bd.n * sizeof(double), bd.B, cudaMemcpyHostToDevice, b->eng->stream));
   WV_CUDA(cudaStreamSynchronize(b->eng->stream));
   return 0;

@@ -35,6 +35,17 @@ __device__ __forceinline__ void wv_elem_prologue(const WvBatchDev& bd, int b, in
   __syncthreads();
 }
 
+// thread -> micro-tile mapping: warp w owns the compact 16x32 region rows (w>>1)*16.., cols (w&1)*32..; lane l the
+// 4x4 micro-tile at (+ (l>>3)*4, + (l&7)*4).  Compact warp regions make "the categorical mask is zero for the whole
+// warp" common once the rows are sorted by their categorical columns (wv_batch_create does that).
+__device__ __forceinline__ void wv_elem_coords(int& r_off, int& c_off, bool& above_diag, bool diag_tile) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = (warp >> 1) * 16, wc = (warp & 1) * 32;
+  r_off = wr + (lane >> 3) * 4;
+  c_off = wc + (lane & 7) * 4;
+  above_diag = diag_tile && wc > wr + 15;     // every element of the warp's region has col > row
+}
+
 __global__ void __launch_bounds__(WV_ELEM_THREADS) wv_gram_kernel(WvBatchDev bd, const int* __restrict__ active,
                                                                   const double* __restrict__ xall) {
   WvElemSmem& sm = *reinterpret_cast<WvElemSmem*>(wv_smem_raw);
@@ -42,7 +53,10 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS) wv_gram_kernel(WvBatchDev bd,
   int ti, tj;
   wv_tile_from_linear(blockIdx.x, ti, tj);
   wv_elem_prologue(bd, b, ti, tj, xall, sm);
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  int r_off, c_off;
+  bool above;
+  wv_elem_coords(r_off, c_off, above, ti == tj);
+  if (above) return;                            // the strict upper part of a diagonal tile is never read
   const int n = bd.n;
   double acc[16];
 #pragma unroll
@@ -50,22 +64,20 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS) wv_gram_kernel(WvBatchDev bd,
   for (int c = 0; c < sm.pg.n_comp; ++c) {
     double prod[16];
     const int l0 = sm.pg.comp_start[c], l1 = sm.pg.comp_start[c + 1];
+    bool skip = false;
     for (int l = l0; l < l1; ++l) {
       const WvLeaf lf = sm.pg.leaves[l];
-      double xi[4], xj[4], val[16];
+      if (l > l0 && !wv_leaf_is_cheap(lf.type) && wv_warp_all_zero(prod)) { skip = true; break; }
+      double xi[4], xj[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lf.dim][ty * 4 + a]; xj[a] = sm.xc[lf.dim][tx * 4 + a]; }
-      wv_leaf_vals(lf, sm.theta, xi, xj, val);
-      if (l == l0) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) prod[e] = val[e];
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) prod[e] *= val[e];
-      }
+      for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lf.dim][r_off + a]; xj[a] = sm.xc[lf.dim][c_off + a]; }
+      if (l == l0) wv_leaf_mul<true>(lf, sm.theta, xi, xj, prod);
+      else wv_leaf_mul<false>(lf, sm.theta, xi, xj, prod);
     }
+    if (!skip) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) acc[e] += prod[e];
+      for (int e = 0; e < 16; ++e) acc[e] += prod[e];
+    }
   }
   const double s2 = sm.theta[sm.pg.noise_slot];
   const double cmean = sm.pg.mean_slot >= 0 ? sm.theta[sm.pg.mean_slot] : 0.0;
@@ -73,18 +85,18 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS) wv_gram_kernel(WvBatchDev bd,
   const double* yb = bd.Y + (size_t)b * bd.npad;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const int gi = ti * WV_NB + ty * 4 + a;
+    const int gi = ti * WV_NB + r_off + a;
     double out[4];
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) {
-      const int gj = tj * WV_NB + tx * 4 + bb;
+      const int gj = tj * WV_NB + c_off + bb;
       double v;
       if (gi < n && gj < n) v = acc[a * 4 + bb] + (gi == gj ? s2 : 0.0);
       else if (gi == n && gj < n) v = yb[gj] - cmean;     // RHS row d^T
       else v = (gi == gj) ? 1.0 : 0.0;                     // identity padding (incl. A[n][n] = 1)
       out[bb] = v;
     }
-    double2* dst = reinterpret_cast<double2*>(Ab + (size_t)gi * bd.npad + tj * WV_NB + tx * 4);
+    double2* dst = reinterpret_cast<double2*>(Ab + (size_t)gi * bd.npad + tj * WV_NB + c_off);
     dst[0] = make_double2(out[0], out[1]);
     dst[1] = make_double2(out[2], out[3]);
   }
@@ -343,71 +355,79 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS) wv_grad_kernel(WvBatchDev bd,
   int ti, tj;
   wv_tile_from_linear(blockIdx.x, ti, tj);
   wv_elem_prologue(bd, b, ti, tj, xall, sm);
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  int r_off, c_off;
+  bool above;
+  wv_elem_coords(r_off, c_off, above, ti == tj);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = bd.n, ld = bd.npad;
   for (int i = threadIdx.x; i < WV_MAX_SLOTS * 8; i += blockDim.x) (&sm.red[0][0])[i] = 0.0;
-  const double* Kb = bd.A + (size_t)b * ld * ld;
-  const double* al = bd.alpha + (size_t)b * ld;
-  double w[16];
-  double trw = 0.0;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int gi = ti * WV_NB + ty * 4 + a;
-    const double2* src = reinterpret_cast<const double2*>(Kb + (size_t)gi * ld + tj * WV_NB + tx * 4);
-    double2 k01 = src[0], k23 = src[1];
-    double kin[4] = {k01.x, k01.y, k23.x, k23.y};
-    const double ai = al[gi];
-#pragma unroll
-    for (int bb = 0; bb < 4; ++bb) {
-      const int gj = tj * WV_NB + tx * 4 + bb;
-      double wv = ai * al[gj] - kin[bb];
-      double wgt = (gi < n && gj < n) ? (gi > gj ? 2.0 : (gi == gj ? 1.0 : 0.0)) : 0.0;
-      w[a * 4 + bb] = wgt * wv;
-      if (gi == gj && gi < n) trw += wv;
-    }
-  }
   __syncthreads();
-  for (int c = 0; c < sm.pg.n_comp; ++c) {
-    const int l0 = sm.pg.comp_start[c], l1 = sm.pg.comp_start[c + 1];
-    for (int l = l0; l < l1; ++l) {
-      const WvLeaf lf = sm.pg.leaves[l];
-      const bool tv = lf.s_var >= 0 && sm.pg.slots[lf.s_var].xindex >= 0;
-      const bool tl = lf.s_ls >= 0 && sm.pg.slots[lf.s_ls].xindex >= 0;
-      const bool ta = lf.s_aux >= 0 && sm.pg.slots[lf.s_aux].xindex >= 0;
-      if (!(tv || tl || ta)) continue;
-      double wo[16];
+  if (!above) {
+    const double* Kb = bd.A + (size_t)b * ld * ld;
+    const double* al = bd.alpha + (size_t)b * ld;
+    double w[16];
+    double trw = 0.0;
+    double aj[4];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) wo[e] = w[e];
-      for (int l2 = l0; l2 < l1; ++l2) {
-        if (l2 == l) continue;
-        const WvLeaf lo = sm.pg.leaves[l2];
-        double xi[4], xj[4], val[16];
+    for (int bb = 0; bb < 4; ++bb) aj[bb] = al[tj * WV_NB + c_off + bb];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lo.dim][ty * 4 + a]; xj[a] = sm.xc[lo.dim][tx * 4 + a]; }
-        wv_leaf_vals(lo, sm.theta, xi, xj, val);
+    for (int a = 0; a < 4; ++a) {
+      const int gi = ti * WV_NB + r_off + a;
+      const double2* src = reinterpret_cast<const double2*>(Kb + (size_t)gi * ld + tj * WV_NB + c_off);
+      double2 k01 = src[0], k23 = src[1];
+      double kin[4] = {k01.x, k01.y, k23.x, k23.y};
+      const double ai = al[gi];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) wo[e] *= val[e];
-      }
-      double xi[4], xj[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lf.dim][ty * 4 + a]; xj[a] = sm.xc[lf.dim][tx * 4 + a]; }
-      double sv, sl, sa;
-      wv_leaf_grad_sums(lf, sm.theta, xi, xj, wo, sv, sl, sa);
-      for (int o = 16; o > 0; o >>= 1) {
-        sv += __shfl_xor_sync(0xffffffffu, sv, o);
-        sl += __shfl_xor_sync(0xffffffffu, sl, o);
-        sa += __shfl_xor_sync(0xffffffffu, sa, o);
-      }
-      if (lane == 0) {   // several leaves may share a slot: accumulate (warp-private column, no race)
-        if (tv) sm.red[lf.s_var][warp] += sv;
-        if (tl) sm.red[lf.s_ls][warp] += sl;
-        if (ta) sm.red[lf.s_aux][warp] += sa;
+      for (int bb = 0; bb < 4; ++bb) {
+        const int gj = tj * WV_NB + c_off + bb;
+        const double wv = ai * aj[bb] - kin[bb];
+        const bool in = gi < n && gj < n;
+        w[a * 4 + bb] = in ? (gi > gj ? 2.0 * wv : (gi == gj ? wv : 0.0)) : 0.0;
+        if (gi == gj && gi < n) trw += wv;
       }
     }
+    for (int c = 0; c < sm.pg.n_comp; ++c) {
+      const int l0 = sm.pg.comp_start[c], l1 = sm.pg.comp_start[c + 1];
+      for (int l = l0; l < l1; ++l) {
+        const WvLeaf lf = sm.pg.leaves[l];
+        const bool tv = lf.s_var >= 0 && sm.pg.slots[lf.s_var].xindex >= 0;
+        const bool tl = lf.s_ls >= 0 && sm.pg.slots[lf.s_ls].xindex >= 0;
+        const bool ta = lf.s_aux >= 0 && sm.pg.slots[lf.s_aux].xindex >= 0;
+        if (!(tv || tl || ta)) continue;
+        double wo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) wo[e] = w[e];
+        bool skip = false;
+        for (int l2 = l0; l2 < l1; ++l2) {
+          if (l2 == l) continue;
+          const WvLeaf lo = sm.pg.leaves[l2];
+          if (!wv_leaf_is_cheap(lo.type) && wv_warp_all_zero(wo)) { skip = true; break; }
+          double xi[4], xj[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lo.dim][r_off + a]; xj[a] = sm.xc[lo.dim][c_off + a]; }
+          wv_leaf_mul<false>(lo, sm.theta, xi, xj, wo);
+        }
+        if (skip || (!wv_leaf_is_cheap(lf.type) && wv_warp_all_zero(wo))) continue;   // every contribution is zero
+        double xi[4], xj[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lf.dim][r_off + a]; xj[a] = sm.xc[lf.dim][c_off + a]; }
+        double sv, sl, sa;
+        wv_leaf_grad_sums(lf, sm.theta, xi, xj, wo, sv, sl, sa);
+        for (int o = 16; o > 0; o >>= 1) {
+          sv += __shfl_xor_sync(0xffffffffu, sv, o);
+          sl += __shfl_xor_sync(0xffffffffu, sl, o);
+          sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        }
+        if (lane == 0) {   // several leaves may share a slot: accumulate (warp-private column, no race)
+          if (tv) sm.red[lf.s_var][warp] += sv;
+          if (tl) sm.red[lf.s_ls][warp] += sl;
+          if (ta) sm.red[lf.s_aux][warp] += sa;
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) trw += __shfl_xor_sync(0xffffffffu, trw, o);
+    if (lane == 0) sm.red[sm.pg.noise_slot][warp] += trw;
   }
-  for (int o = 16; o > 0; o >>= 1) trw += __shfl_xor_sync(0xffffffffu, trw, o);
-  if (lane == 0) sm.red[sm.pg.noise_slot][warp] += trw;
   __syncthreads();
   const int ntiles = gridDim.x;
   double* dst = bd.partial + ((size_t)b * ntiles + blockIdx.x) * bd.n_slots_max;

@@ -122,7 +122,11 @@ def build_program(kernel, likelihood_variance: K.Parameter, mean_c: Optional[K.P
         raise ValueError(f"model has {len(params)} parameters, engine limit is {MAX_SLOTS}")
 
     comp_start, ltype, ldim, lvar, lls, laux, ldeg = [0], [], [], [], [], [], []
+    cheap = ("categorical", "constant", "linear", "lin", "empty")
     for comp in comps:
+        # masks and other transcendental-free factors first: the device skips the expensive factors of a product
+        # wherever the partial product is zero for a whole warp (stable order otherwise)
+        comp = sorted(comp, key=lambda lf: 0 if lf.name in cheap else 1)
         for lf in comp:
             code = LEAF_CODE.get(lf.name)
             if code is None:
