@@ -64,7 +64,9 @@ def test_product_of_sum_is_distributed():
     comps = program.expand_sum_of_products(wb.Product([wb.Sum([a, b]), c]))
     assert [[l.name for l in comp] for comp in comps] == [["squared_exponential", "categorical"], ["lin", "categorical"]]
     p = wb.GPR(wb.Product([wb.Sum([a, b]), c])).program()
-    assert p.leaf_s_var[1] == p.leaf_s_var[3]          # the shared categorical variance is one slot
+    # the shared categorical variance is one slot (the encoder moves transcendental-free leaves to the front)
+    cat = [l for l in range(p.n_leaves) if p.leaf_type[l] == program.LEAF_CODE["categorical"]]
+    assert len(cat) == 2 and p.leaf_s_var[cat[0]] == p.leaf_s_var[cat[1]]
 
 
 def test_names_dedup_and_pruning():

@@ -105,102 +105,233 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS) wv_gram_kernel(WvBatchDev bd,
 // =============================================================================================
 // chol_diag(j): T = A[j,j] - sum_{k<j} L[j,k] L[j,k]^T ; L_jj = chol(T) ; Linv_jj = L_jj^{-1}
 // grid (n_active), 128 threads.  Row n (the RHS row) takes part as an ordinary row but is never a pivot.
+//
+// The 64x64 block is handled as 2x2 blocks of 32: each 32x32 Cholesky and triangular inverse runs in the registers
+// of ONE warp (lane r owns row r of L, lane j owns column j of L^{-1}; pivots and multipliers travel by shuffles,
+// everything fully unrolled so all register indices are static), the coupling products are 32^3 DMMA GEMMs from
+// shared memory:   L21 = T21 X11^T,  T22 -= L21 L21^T,  X21 = -X22 (L21 X11).
 // =============================================================================================
 struct WvDiagSmem {
   union {
     WvGemmSmem g;
     struct {
-      double T[WV_NB * WV_LDP];
-      double Li[WV_NB * WV_LDP];
+      double T[WV_NB * WV_LDT];   // T -> L (lower);  [0:32, 32:64] is scratch for X11^T
+      double X[WV_NB * WV_LDT];   // L^{-1} (lower);  [0:32, 32:64] is scratch for (L21 X11)^T
     } e;
   };
-  double diag[WV_NB];
+  double invd[WV_NB];
+  double logsum[2];
   int fail;
 };
 
-__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_chol_diag_kernel(WvBatchDev bd, const int* __restrict__ active,
+// 32x32 Cholesky in registers: lane r holds row r in a[0..31] (lower part meaningful).  `rhs` (warp-uniform, -1 if
+// none) is the local index of the augmented RHS row: unit diagonal, never a pivot.  The dependent chain per column is
+// shuffle -> rsqrt -> multiply -> shuffle -> fma; logs are taken afterwards, one pivot per lane, in parallel.
+// Returns sum of log(diag) over columns c < nreal; sets fail if a pivot is <= 0 (NaN pivots flow through, as in
+// Eigen's LLT).  myinv = 1 / L[lane][lane].
+__device__ __forceinline__ double wv_potrf32(double (&a)[32], double& myinv, int rhs, int nreal, bool& fail) {
+  const int lane = threadIdx.x & 31;
+  double mypiv = 1.0;
+  myinv = 1.0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    double d = __shfl_sync(0xffffffffu, a[c], c);
+    if (c == rhs) d = 1.0;
+    if (d <= 0.0) fail = true;
+    const double inv = rsqrt(d);
+    double l = a[c] * inv;                 // lane c: d * rsqrt(d) = sqrt(d)
+    if (lane == c) { mypiv = d; myinv = inv; }
+    if (lane < c) l = 0.0;
+    a[c] = l;
+#pragma unroll
+    for (int c2 = c + 1; c2 < 32; ++c2) {
+      const double v = __shfl_sync(0xffffffffu, l, c2);
+      a[c2] = fma(-l, v, a[c2]);
+    }
+  }
+  double lg = lane < nreal ? 0.5 * log(mypiv) : 0.0;
+  for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+  return lg;
+}
+
+// 32x32 lower-triangular inverse: L (row stride ldl) and 1/diag(L) are read from shared memory with warp-uniform
+// (broadcast) loads; lane j produces column j of X = L^{-1} in x[0..31] (x[r] = X[r][j], zero for r < j).
+// Four partial accumulators keep the dependent FMA chain at r/4.
+__device__ __forceinline__ void wv_trtri32(const double* __restrict__ Ls, int ldl, const double* __restrict__ invd,
+                                           double (&x)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    double s0 = (lane == r) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < r; ++k) {
+      const double lv = Ls[r * ldl + k];
+      if ((k & 3) == 0) s0 = fma(-lv, x[k], s0);
+      else if ((k & 3) == 1) s1 = fma(-lv, x[k], s1);
+      else if ((k & 3) == 2) s2 = fma(-lv, x[k], s2);
+      else s3 = fma(-lv, x[k], s3);
+    }
+    x[r] = ((s0 + s1) + (s2 + s3)) * invd[r];
+  }
+}
+
+// C[32x32] = sum_k A[m][k] B[n][k], k < 32, operands in shared memory (row strides lda, ldb); 4 warps, 16x16 each.
+__device__ __forceinline__ void wv_gemm32_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                             double (&acc)[2][2][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const double* as = A + ((warp >> 1) * 16 + fr) * lda + fk;
+  const double* bs = B + ((warp & 1) * 16 + fr) * ldb + fk;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < 32; kk += 4) {
+    double af[2], bf[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { af[i] = as[i * 8 * lda + kk]; bf[i] = bs[i * 8 * ldb + kk]; }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) wv_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+  }
+}
+// row/col of this thread's first accumulator element inside the 32x32 result (+ mi*8 rows, + ni*8 cols, +0/+1 col)
+__device__ __forceinline__ void wv_frag32_origin(int& r0, int& c0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  r0 = (warp >> 1) * 16 + (lane >> 2);
+  c0 = (warp & 1) * 16 + (lane & 3) * 2;
+}
+
+__global__ void __launch_bounds__(WV_GEMM_THREADS, 3) wv_chol_diag_kernel(WvBatchDev bd, const int* __restrict__ active,
                                                                        int j) {
   WvDiagSmem& sm = *reinterpret_cast<WvDiagSmem*>(wv_smem_raw);
   const int b = active[blockIdx.x];
   const int ld = bd.npad;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* Ab = bd.A + (size_t)b * ld * ld;
   const double* Lrow = Ab + (size_t)j * WV_NB * ld;
-  double acc[4][4][2];
-  wv_zero_acc(acc);
-  if (threadIdx.x == 0) sm.fail = 0;
-  if (j > 0) wv_gemm_nt_64(sm.g, Lrow, Lrow, ld, 0, j * WV_NB, acc);
-  else __syncthreads();
-  int r0, c0;
-  wv_frag_origin(r0, c0);
-  double* Tg = Ab + (size_t)j * WV_NB * ld + j * WV_NB;
-#pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-      int r = r0 + mi * 8, c = c0 + ni * 8;
-      double2 a = *reinterpret_cast<const double2*>(Tg + (size_t)r * ld + c);
-      sm.e.T[r * WV_LDP + c] = a.x - acc[mi][ni][0];
-      sm.e.T[r * WV_LDP + c + 1] = a.y - acc[mi][ni][1];
-    }
-  for (int i = threadIdx.x; i < WV_NB * WV_LDP; i += WV_GEMM_THREADS) sm.e.Li[i] = 0.0;
-  __syncthreads();
-
-  // ---- unblocked right-looking Cholesky in shared memory; thread pair (r, h) owns row r, columns == h mod 2
-  const int rhs_local = bd.n - j * WV_NB;   // local index of the RHS row if inside this block
-  const int r = threadIdx.x >> 1, h = threadIdx.x & 1;
-  double* T = sm.e.T;
-  for (int c = 0; c < WV_NB; ++c) {
-    const double d = T[c * WV_LDP + c];
-    if (c == rhs_local) {   // not a pivot: unit diagonal, nothing below depends on it
-      if (threadIdx.x == 0) sm.diag[c] = 1.0;
-      continue;
-    }
-    if (d <= 0.0) { if (threadIdx.x == 0) sm.fail = 1; }   // NaN pivots flow through, as in TF's Eigen LLT
-    const double sd = sqrt(d);
-    const double lrc = r > c ? T[r * WV_LDP + c] / sd : 0.0;
-    __syncwarp();
-    if (r > c && h == 0) T[r * WV_LDP + c] = lrc;
-    if (threadIdx.x == 0) sm.diag[c] = sd;
-    __syncthreads();
-    if (r > c) {
-      for (int cc = c + 1 + h; cc <= r; cc += 2) T[r * WV_LDP + cc] -= lrc * T[cc * WV_LDP + c];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x < WV_NB) T[threadIdx.x * WV_LDP + threadIdx.x] = sm.diag[threadIdx.x];
-  __syncthreads();
-
-  // ---- inverse of the 64x64 lower-triangular block: thread pair (jc, h) owns column jc
   {
-    const int jc = threadIdx.x >> 1;
-    double* Li = sm.e.Li;
-    if (h == 0) Li[jc * WV_LDP + jc] = 1.0 / T[jc * WV_LDP + jc];
+    double acc[4][4][2];
+    wv_zero_acc(acc);
+    if (threadIdx.x == 0) { sm.fail = 0; sm.logsum[0] = sm.logsum[1] = 0.0; }
+    if (j > 0) wv_gemm_nt_64(sm.g, Lrow, Lrow, ld, 0, j * WV_NB, acc);
+    else __syncthreads();
+    int r0, c0;
+    wv_frag_origin(r0, c0);
+    const double* Tg = Ab + (size_t)j * WV_NB * ld + j * WV_NB;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        int r = r0 + mi * 8, c = c0 + ni * 8;
+        double2 a = *reinterpret_cast<const double2*>(Tg + (size_t)r * ld + c);
+        *reinterpret_cast<double2*>(&sm.e.T[r * WV_LDT + c]) = make_double2(a.x - acc[mi][ni][0], a.y - acc[mi][ni][1]);
+      }
+  }
+  for (int i = threadIdx.x; i < WV_NB * WV_LDT; i += WV_GEMM_THREADS) sm.e.X[i] = 0.0;
+  __syncthreads();
+  double* T = sm.e.T;
+  double* X = sm.e.X;
+  const int rhs = bd.n - j * WV_NB;                       // local index of the RHS row (may be outside [0,64))
+  const int nreal = min(WV_NB, bd.n - j * WV_NB);         // pivots that belong to K (log-det terms)
+
+  // ---- block (1,1): warp 0
+  if (warp == 0) {
+    bool fail = false;
+    {
+      double a[32], myinv;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = T[lane * WV_LDT + c];
+      const double ls = wv_potrf32(a, myinv, rhs, nreal, fail);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) T[lane * WV_LDT + c] = a[c];      // L11 (zeros above the diagonal)
+      sm.invd[lane] = myinv;
+      if (lane == 0) { sm.logsum[0] = ls; if (fail) sm.fail = 1; }
+    }
     __syncwarp();
-    for (int rr = 1; rr < WV_NB; ++rr) {   // uniform trip count: the pair shuffle needs the full warp
-      double s = 0.0;
-      if (rr > jc)
-        for (int k = jc + h; k < rr; k += 2) s += T[rr * WV_LDP + k] * Li[k * WV_LDP + jc];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      if (rr > jc && h == 0) Li[rr * WV_LDP + jc] = -s / T[rr * WV_LDP + rr];
-      __syncwarp();
+    double x[32];
+    wv_trtri32(T, WV_LDT, sm.invd, x);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      X[c * WV_LDT + lane] = x[c];                  // X11[r=c][j=lane]
+      T[lane * WV_LDT + 32 + c] = x[c];             // scratch: X11^T[j=lane][r=c]
     }
   }
+  __syncthreads();
+  int r0, c0;
+  wv_frag32_origin(r0, c0);
+  double acc[2][2][2];
+  // ---- L21 = T21 X11^T   (in place over T21)
+  wv_gemm32_nt(T + 32 * WV_LDT, WV_LDT, X, WV_LDT, acc);
+  __syncthreads();
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni)
+      *reinterpret_cast<double2*>(&T[(32 + r0 + mi * 8) * WV_LDT + c0 + ni * 8]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+  __syncthreads();
+  // ---- T22 -= L21 L21^T
+  wv_gemm32_nt(T + 32 * WV_LDT, WV_LDT, T + 32 * WV_LDT, WV_LDT, acc);
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) {
+      double2* p = reinterpret_cast<double2*>(&T[(32 + r0 + mi * 8) * WV_LDT + 32 + c0 + ni * 8]);
+      double2 v = *p;
+      *p = make_double2(v.x - acc[mi][ni][0], v.y - acc[mi][ni][1]);
+    }
+  __syncthreads();
+  // ---- block (2,2): warp 0
+  if (warp == 0) {
+    bool fail = false;
+    {
+      double a[32], myinv;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = T[(32 + lane) * WV_LDT + 32 + c];
+      const double ls = wv_potrf32(a, myinv, rhs - 32, nreal - 32, fail);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) T[(32 + lane) * WV_LDT + 32 + c] = a[c];      // L22
+      sm.invd[32 + lane] = myinv;
+      if (lane == 0) { sm.logsum[1] = ls; if (fail) sm.fail = 1; }
+    }
+    __syncwarp();
+    double x[32];
+    wv_trtri32(T + 32 * WV_LDT + 32, WV_LDT, sm.invd + 32, x);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) X[(32 + c) * WV_LDT + 32 + lane] = x[c];      // X22[r=c][j=lane]
+  }
+  __syncthreads();
+  // ---- P^T = X11^T-rows x L21-rows:  Pt[n][m] = sum_k X11[k][n] L21[m][k]   -> scratch X[0:32, 32:64]
+  wv_gemm32_nt(T + 32, WV_LDT, T + 32 * WV_LDT, WV_LDT, acc);
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni)
+      *reinterpret_cast<double2*>(&X[(r0 + mi * 8) * WV_LDT + 32 + c0 + ni * 8]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+  __syncthreads();
+  // ---- X21 = -X22 P :  X21[m][n] = -sum_k X22[m][k] Pt[n][k]
+  wv_gemm32_nt(X + 32 * WV_LDT + 32, WV_LDT, X + 32, WV_LDT, acc);
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni)
+      *reinterpret_cast<double2*>(&X[(32 + r0 + mi * 8) * WV_LDT + c0 + ni * 8]) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
   __syncthreads();
 
   // ---- write L_jj (lower, zeros above), Linv_jj (row-major) and Linv_jj^T into Mt[j,j]
+  double* Tg = Ab + (size_t)j * WV_NB * ld + j * WV_NB;
   double* Mg = bd.Mt + (size_t)b * ld * ld + (size_t)j * WV_NB * ld + j * WV_NB;
   double* Dg = bd.Dinv + ((size_t)b * bd.nt + j) * WV_NB * WV_NB;
   for (int i = threadIdx.x; i < WV_NB * WV_NB; i += WV_GEMM_THREADS) {
     int rr = i >> 6, cc = i & 63;
-    Tg[(size_t)rr * ld + cc] = cc <= rr ? T[rr * WV_LDP + cc] : 0.0;
-    Dg[i] = sm.e.Li[rr * WV_LDP + cc];
-    Mg[(size_t)rr * ld + cc] = sm.e.Li[cc * WV_LDP + rr];
+    Tg[(size_t)rr * ld + cc] = cc <= rr ? T[rr * WV_LDT + cc] : 0.0;
+    Dg[i] = cc <= rr ? X[rr * WV_LDT + cc] : 0.0;
+    Mg[(size_t)rr * ld + cc] = rr <= cc ? X[cc * WV_LDT + rr] : 0.0;
   }
   if (threadIdx.x == 0) {
-    int nreal = min(WV_NB, bd.n - j * WV_NB);
-    double s = 0.0;
-    for (int c = 0; c < nreal; ++c) s += log(sm.diag[c]);
-    bd.logdet_part[(size_t)b * bd.nt + j] = s;
+    bd.logdet_part[(size_t)b * bd.nt + j] = sm.logsum[0] + sm.logsum[1];
     if (sm.fail) bd.chol_fail[b] = 1;
   }
 }
