@@ -94,6 +94,11 @@ int wv_engine_create(int device, wv_engine** out);
 void wv_engine_destroy(wv_engine* e);
 /* CUDA stream the engine launches on (cudaStream_t as void*), for event timing by the caller */
 void* wv_engine_stream(wv_engine* e);
+/* Batches with at least `nt` 64-row tiles ((n + 1 + 63) / 64) take the large-n schedule (right-looking panel Cholesky
+ * with look-ahead, recursive-doubling triangular inverse) instead of the batched left-looking one.  Default 16
+ * (n >= 960); the environment variable WV_BIG_NT overrides the default at engine creation.  Both schedules compute the
+ * same quantities; the switch only moves work between launch shapes. */
+int wv_engine_set_large_n_tiles(wv_engine* e, int nt);
 
 int wv_batch_create(wv_engine* e, const wv_batch_desc* desc, wv_batch** out);
 void wv_batch_destroy(wv_batch* b);
@@ -119,7 +124,8 @@ int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* opts, double
 void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t* rounds, int64_t* model_evals);
 
 /* Optional per-kernel-class device timing (CUDA events on the engine stream, resolved at the host syncs the fit
- * loop already has).  Classes, in order: gram, chol_diag, chol_panel, trtri, extract, kinv, grad, finalize, lbfgs.
+ * loop already has).  Classes, in order: gram, chol_diag, chol_panel, trtri, extract, kinv, grad, finalize, lbfgs,
+ * chol_syrk (trailing updates of the large-n path).
  * wv_batch_profile_read fills ms[i] / launches[i] for i < n and returns the number of classes. */
 void wv_batch_profile_enable(wv_batch* b, int on);
 int wv_batch_profile_read(wv_batch* b, double* ms, int64_t* launches, int n);

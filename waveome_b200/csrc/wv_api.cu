@@ -13,7 +13,7 @@
 #include "wv_lbfgsb.h"
 
 int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
-                    double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf);
+                    double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf, const WvAux* aux);
 
 static thread_local std::string g_err;
 static int wv_fail(const std::string& m) { g_err = m; return -1; }
@@ -26,6 +26,7 @@ static int wv_fail(const std::string& m) { g_err = m; return -1; }
 struct wv_engine {
   int device;
   cudaStream_t stream;
+  WvAux aux;   // side stream / events of the large-n look-ahead schedule
 };
 
 struct wv_batch {
@@ -70,7 +71,15 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
   WV_CUDA(cudaSetDevice(device));
   wv_engine* eng = new wv_engine();
   eng->device = device;
-  WV_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+  // the main stream carries the serial chain of the factorisation (diagonal blocks, panels): it gets the highest
+  // priority so that its few CTAs are placed ahead of the bulk trailing updates queued on the side stream
+  int prio_lo = 0, prio_hi = 0;
+  WV_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  WV_CUDA(cudaStreamCreateWithPriority(&eng->stream, cudaStreamNonBlocking, prio_hi));
+  WV_CUDA(cudaStreamCreateWithPriority(&eng->aux.side, cudaStreamNonBlocking, prio_lo));
+  WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_panel, cudaEventDisableTiming));
+  WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_bulk, cudaEventDisableTiming));
+  if (const char* v = getenv("WV_BIG_NT")) eng->aux.big_nt = atoi(v) > 1 ? atoi(v) : 2;
   *out = eng;
   return 0;
 }
@@ -79,10 +88,20 @@ extern "C" void wv_engine_destroy(wv_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamDestroy(e->stream);
+  if (e->aux.side) cudaStreamDestroy(e->aux.side);
+  if (e->aux.ev_panel) cudaEventDestroy(e->aux.ev_panel);
+  if (e->aux.ev_bulk) cudaEventDestroy(e->aux.ev_bulk);
   delete e;
 }
 
 extern "C" void* wv_engine_stream(wv_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+extern "C" int wv_engine_set_large_n_tiles(wv_engine* e, int nt) {
+  if (!e) return wv_fail("wv_engine_set_large_n_tiles: null engine");
+  if (nt < 2) return wv_fail("wv_engine_set_large_n_tiles: threshold must be >= 2 tiles");
+  e->aux.big_nt = nt;
+  return 0;
+}
 
 static int wv_build_program(const wv_program_desc& d, int D, WvProgram* p) {
   memset(p, 0, sizeof(WvProgram));
@@ -296,7 +315,8 @@ extern "C" void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t*
 
 static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g, double* d_lml, int* d_status,
                        const int* d_active, int n_active) {
-  int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, b->eng->stream, &b->prof);
+  int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, b->eng->stream, &b->prof,
+                          &b->eng->aux);
   if (l < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   b->launches += l; b->rounds += 1; b->model_evals += n_active;
   return 0;

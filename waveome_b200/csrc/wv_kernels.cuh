@@ -47,7 +47,15 @@ struct WvBatchDev {
 // optional per-kernel-class timing with CUDA events on the launching stream (bench.py's live roofline)
 // ---------------------------------------------------------------------------------------------
 enum WvKernelClass { WV_K_GRAM = 0, WV_K_CHOL_DIAG, WV_K_CHOL_PANEL, WV_K_TRTRI, WV_K_EXTRACT, WV_K_KINV, WV_K_GRAD,
-                     WV_K_FINALIZE, WV_K_LBFGS, WV_K_NCLASS };
+                     WV_K_FINALIZE, WV_K_LBFGS, WV_K_CHOL_SYRK, WV_K_NCLASS };
+
+// second stream + events of the large-n path (look-ahead: the next panel is factorised while the bulk of the trailing
+// update of the current one still runs), and the tile count from which that path is taken
+struct WvAux {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
+  int big_nt = 16;
+};
 struct WvProfiler {
   bool enabled = false;
   cudaEvent_t ev[256];
@@ -353,6 +361,11 @@ struct WvGemmSmem {
   double b[WV_STAGES][WV_NB * WV_LDS];
 };
 
+#define WV_LDN 68           // smem row stride of an NN B stage: [k][n], 16 k-rows x 64 columns (68 mod 16 == 4)
+
+// BNN = false: B operand rows are n, k contiguous (Bg[n * ld + k]);  BNN = true: B operand rows are k, n contiguous
+// (Bg[k * ld + n]) -- the stage is then kept [k][n] with stride WV_LDN and the DMMA B fragments read it transposed.
+template <bool BNN>
 __device__ __forceinline__ void wv_gemm_issue(WvGemmSmem& sm, int stage, const double* __restrict__ Ag,
                                               const double* __restrict__ Bg, int ld, int kc, int k1) {
   const int t = threadIdx.x;
@@ -364,20 +377,27 @@ __device__ __forceinline__ void wv_gemm_issue(WvGemmSmem& sm, int stage, const d
     bool ok = k < k1;
     int ks = ok ? k : kc;
     wv_cp_async16(&sm.a[stage][row * WV_LDS + ch * 2], Ag + (size_t)row * ld + ks, ok);
-    wv_cp_async16(&sm.b[stage][row * WV_LDS + ch * 2], Bg + (size_t)row * ld + ks, ok);
+    if (!BNN) {
+      wv_cp_async16(&sm.b[stage][row * WV_LDS + ch * 2], Bg + (size_t)row * ld + ks, ok);
+    } else {
+      int kr = q >> 5, cn = (q & 31) * 2;
+      bool okb = kc + kr < k1;
+      wv_cp_async16(&sm.b[stage][kr * WV_LDN + cn], Bg + (size_t)(okb ? kc + kr : kc) * ld + cn, okb);
+    }
   }
 }
 
-__device__ __forceinline__ void wv_gemm_nt_64(WvGemmSmem& sm, const double* __restrict__ Ag,
-                                              const double* __restrict__ Bg, int ld, int k0, int k1,
-                                              double (&acc)[4][4][2]) {
+template <bool BNN>
+__device__ __forceinline__ void wv_gemm_64(WvGemmSmem& sm, const double* __restrict__ Ag,
+                                           const double* __restrict__ Bg, int ld, int k0, int k1,
+                                           double (&acc)[4][4][2]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 1, wn = warp & 1;
   const int fr = lane >> 2, fk = lane & 3;
   const int nchunks = (k1 - k0 + WV_BK - 1) / WV_BK;
 #pragma unroll
   for (int s = 0; s < WV_STAGES - 1; ++s) {
-    if (s < nchunks) wv_gemm_issue(sm, s, Ag, Bg, ld, k0 + s * WV_BK, k1);
+    if (s < nchunks) wv_gemm_issue<BNN>(sm, s, Ag, Bg, ld, k0 + s * WV_BK, k1);
     wv_cp_commit();
   }
   for (int c = 0; c < nchunks; ++c) {
@@ -385,18 +405,19 @@ __device__ __forceinline__ void wv_gemm_nt_64(WvGemmSmem& sm, const double* __re
     __syncthreads();
     {
       int cn = c + WV_STAGES - 1;
-      if (cn < nchunks) wv_gemm_issue(sm, cn % WV_STAGES, Ag, Bg, ld, k0 + cn * WV_BK, k1);
+      if (cn < nchunks) wv_gemm_issue<BNN>(sm, cn % WV_STAGES, Ag, Bg, ld, k0 + cn * WV_BK, k1);
       wv_cp_commit();
     }
     const double* as = sm.a[c % WV_STAGES] + (wm * 32 + fr) * WV_LDS + fk;
-    const double* bs = sm.b[c % WV_STAGES] + (wn * 32 + fr) * WV_LDS + fk;
+    const double* bs = BNN ? sm.b[c % WV_STAGES] + fk * WV_LDN + wn * 32 + fr
+                           : sm.b[c % WV_STAGES] + (wn * 32 + fr) * WV_LDS + fk;
 #pragma unroll
     for (int kk = 0; kk < WV_BK; kk += 4) {
       double af[4], bf[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         af[i] = as[i * 8 * WV_LDS + kk];
-        bf[i] = bs[i * 8 * WV_LDS + kk];
+        bf[i] = BNN ? bs[kk * WV_LDN + i * 8] : bs[i * 8 * WV_LDS + kk];
       }
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
@@ -406,6 +427,11 @@ __device__ __forceinline__ void wv_gemm_nt_64(WvGemmSmem& sm, const double* __re
   }
   wv_cp_wait<0>();
   __syncthreads();
+}
+__device__ __forceinline__ void wv_gemm_nt_64(WvGemmSmem& sm, const double* __restrict__ Ag,
+                                              const double* __restrict__ Bg, int ld, int k0, int k1,
+                                              double (&acc)[4][4][2]) {
+  wv_gemm_64<false>(sm, Ag, Bg, ld, k0, k1, acc);
 }
 
 // second-stage product from shared memory operands (64x64x64): acc[m][n] = sum_k Ts[m][k] * Bs[n][k]

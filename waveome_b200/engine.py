@@ -46,11 +46,11 @@ class _LbfgsOpts(C.Structure):
 
 
 EXPORTED_SYMBOLS = [
-    "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_batch_create", "wv_batch_destroy",
+    "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
     "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
     "wv_batch_counters", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
-KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs"]
+KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk"]
 
 _lib = None
 
@@ -69,6 +69,7 @@ def load_library():
     lib.wv_engine_create.argtypes = [C.c_int, C.POINTER(vp)]; lib.wv_engine_create.restype = C.c_int
     lib.wv_engine_destroy.argtypes = [vp]; lib.wv_engine_destroy.restype = None
     lib.wv_engine_stream.argtypes = [vp]; lib.wv_engine_stream.restype = vp
+    lib.wv_engine_set_large_n_tiles.argtypes = [vp, C.c_int]; lib.wv_engine_set_large_n_tiles.restype = C.c_int
     lib.wv_batch_create.argtypes = [vp, C.POINTER(_BatchDesc), C.POINTER(vp)]; lib.wv_batch_create.restype = C.c_int
     lib.wv_batch_destroy.argtypes = [vp]; lib.wv_batch_destroy.restype = None
     lib.wv_batch_workspace_bytes.argtypes = [vp]; lib.wv_batch_workspace_bytes.restype = C.c_int64
@@ -113,12 +114,18 @@ DEFAULT_LBFGS = dict(maxcor=10, maxiter=15000, maxfun=15000, maxls=20, ftol=2.22
 class Engine:
     """One per GPU / host thread; owns the CUDA stream the batches launch on."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, large_n_tiles: Optional[int] = None):
         self.lib = load_library()
         h = C.c_void_p()
         _check(self.lib.wv_engine_create(int(device), C.byref(h)), "wv_engine_create")
         self.handle = h
         self.device = int(device)
+        if large_n_tiles is not None:
+            self.set_large_n_tiles(large_n_tiles)
+
+    def set_large_n_tiles(self, nt: int):
+        """Tile count ((n + 1 + 63) // 64) from which batches use the large-n schedule (default 16)."""
+        _check(self.lib.wv_engine_set_large_n_tiles(self.handle, int(nt)), "wv_engine_set_large_n_tiles")
 
     @property
     def stream(self) -> int:
