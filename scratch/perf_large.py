@@ -37,7 +37,7 @@ for it in range(3):
     print("eval %d: device %.2f ms; status %s; f[0]=%.9f lml[0]=%.9f" % (it, ms, s.tolist()[:4], f[0], lml[0]), flush=True)
 prof = bt.profile_read()
 print("per-class ms over 3 evals:", {k_: round(v[0], 2) for k_, v in prof.items()})
-chol_ms = (prof["chol_diag"][0] + prof["chol_panel"][0]) / 3
+chol_ms = (prof["chol_diag"][0] + prof["chol_panel"][0] + prof["chol_syrk"][0]) / 3
 print("n^3 flops/eval %.1f GF -> %.2f TFLOP/s; cholesky n^3/3: %.2f ms -> %.2f TFLOP/s" % (
     B * n**3 / 1e9, B * n**3 / (ms * 1e-3) / 1e12, chol_ms, B * n**3 / 3 / (chol_ms * 1e-3) / 1e12))
 if check:

@@ -80,6 +80,11 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
   WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_panel, cudaEventDisableTiming));
   WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_bulk, cudaEventDisableTiming));
   if (const char* v = getenv("WV_BIG_NT")) eng->aux.big_nt = atoi(v) > 1 ? atoi(v) : 2;
+  {
+    cudaDeviceProp prop;
+    WV_CUDA(cudaGetDeviceProperties(&prop, device));
+    eng->aux.resident_ctas = 3 * prop.multiProcessorCount;
+  }
   *out = eng;
   return 0;
 }
@@ -192,6 +197,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   WV_TRY(wv_alloc(b, &bd.quad, B));
   WV_TRY(wv_alloc(b, &bd.partial, B * ntiles * smax));
   WV_TRY(wv_alloc(b, &bd.chol_fail, B));
+  WV_TRY(wv_alloc(b, &bd.step_flag, B * bd.nt));
   WV_TRY(wv_alloc(b, &b->d_x, B * d->P));
   WV_TRY(wv_alloc(b, &b->d_g, B * d->P));
   WV_TRY(wv_alloc(b, &b->d_f, B));
@@ -253,6 +259,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   step(cudaMemcpyAsync(b->d_active, ident.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
   step(cudaMemsetAsync(bd.A, 0, B * np * np * sizeof(double), st));
   step(cudaMemsetAsync(bd.Mt, 0, B * np * np * sizeof(double), st));
+  step(cudaMemsetAsync(bd.step_flag, 0, B * bd.nt * sizeof(int), st));
   step(cudaMemsetAsync(dY, 0, B * np * sizeof(double), st));
   step(cudaMemcpy2DAsync(dY, np * sizeof(double), yp.data(), (size_t)d->n * sizeof(double), (size_t)d->n * sizeof(double), B,
                          cudaMemcpyHostToDevice, st));
@@ -315,6 +322,7 @@ extern "C" void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t*
 
 static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g, double* d_lml, int* d_status,
                        const int* d_active, int n_active) {
+  b->eng->aux.epoch += 1;
   int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, b->eng->stream, &b->prof,
                           &b->eng->aux);
   if (l < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));

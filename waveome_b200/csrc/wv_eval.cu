@@ -4,6 +4,14 @@
 // dynamic shared memory is carved by hand; the GEMM pipeline and the epilogue tiles alias each other.
 extern __shared__ __align__(16) unsigned char wv_smem_raw[];
 
+// phase clocks of the serial kernels for scratch/diag_bench.cu (compiled out of the library)
+#ifdef WV_DIAG_CLOCK
+__device__ long long wv_dbg_clk[64];
+#define WV_CLK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) wv_dbg_clk[i] = clock64(); } while (0)
+#else
+#define WV_CLK(i) do { } while (0)
+#endif
+
 // =============================================================================================
 // gram: lower tiles of K + sigma^2 I, RHS row, identity padding.
 // grid (n_lower_tiles, n_active), 256 threads, each thread a 4x4 micro-tile.
@@ -116,29 +124,93 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS) wv_gram_kernel(WvBatchDev bd,
 // =============================================================================================
 struct WvDiagSmem {
   union {
-    WvGemmSmem g;
+    WvGemmSmem g;                 // used as SIX single-operand stages by wv_syrk_self_64 (A and B are the same rows)
     struct {
-      double T[WV_NB * WV_LDT];   // T -> L (lower)
+      double T[WV_NB * WV_LDT];   // T -> L (lower, incl. diagonal); strict upper part: L^{-T} as it is assembled
       double X[WV_NB * WV_LDT];   // L^{-1} (lower); the upper off-diagonal blocks are scratch for (L_SF X_FF)^T
     } e;
   };
+  double piv[WV_NB];
   double invd[16];
-  double logsum;
+  double lcol[2][16];
+  double red[2];
   int fail;
 };
 
-// 16x16 Cholesky in registers: lane r < 16 holds row r in a[0..15] (lower part meaningful).  `rhs` (warp-uniform,
-// outside [0,16) if none) is the local index of the augmented RHS row: unit diagonal, never a pivot.  The dependent
-// chain per column is shuffle -> rsqrt -> multiply -> shuffle -> fma; logs are taken afterwards, one pivot per lane.
-// Returns sum of log(diag) over columns c < nreal; sets fail if a pivot is <= 0 (NaN pivots flow through, as in
-// Eigen's LLT).  myinv = 1 / L[lane][lane].
-__device__ __forceinline__ double wv_potrf16(double (&a)[16], double& myinv, int rhs, int nreal, bool& fail) {
+// Lower 8x8 tiles (i >= j) of the 64x64 product, spread over the four warps (10 / 9 / 9 / 8 tiles): the diagonal
+// update is symmetric, so the strictly upper tiles are never formed.  X(q, i, j): accumulator q of this warp is tile
+// (i, j).
+#define WV_SYM_W0(X) X(0,0,0) X(1,1,0) X(2,1,1) X(3,2,0) X(4,2,1) X(5,2,2) X(6,3,0) X(7,3,1) X(8,3,2) X(9,3,3)
+#define WV_SYM_W1(X) X(0,4,0) X(1,4,1) X(2,4,2) X(3,4,3) X(4,4,4) X(5,5,0) X(6,5,1) X(7,5,2) X(8,5,3)
+#define WV_SYM_W2(X) X(0,5,4) X(1,5,5) X(2,6,0) X(3,6,1) X(4,6,2) X(5,6,3) X(6,6,4) X(7,6,5) X(8,6,6)
+#define WV_SYM_W3(X) X(0,7,0) X(1,7,1) X(2,7,2) X(3,7,3) X(4,7,4) X(5,7,5) X(6,7,6) X(7,7,7)
+
+// acc = lower tiles of sum_{k in [k0,k1)} R[m][k] R[n][k] for one 64-row operand R (row stride ld): the diagonal-tile
+// update of the Cholesky.  Both DMMA operands come from ONE staged copy (six stages in the memory of three A/B
+// pairs): this kernel runs one CTA per model on the critical path and is bound by the FP64 tensor rate of a single
+// SM and by bytes in flight, not by bandwidth.
+#define WV_SELF_STAGES 6
+__device__ __forceinline__ void wv_self_issue(double* __restrict__ stage, const double* __restrict__ Rg, int ld, int kc,
+                                              int k1) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int q = threadIdx.x + WV_GEMM_THREADS * r;
+    const int row = q >> 3, ch = q & 7;
+    const int k = kc + ch * 2;
+    const bool ok = k < k1;
+    wv_cp_async16(&stage[row * WV_LDS + ch * 2], Rg + (size_t)row * ld + (ok ? k : kc), ok);
+  }
+}
+__device__ __forceinline__ void wv_syrk_self_64(WvGemmSmem& sm, const double* __restrict__ Rg, int ld, int k0, int k1,
+                                                double (&acc)[10][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  double* base = &sm.a[0][0];     // a[3][..] and b[3][..] are contiguous: six stages of 64 x WV_LDS doubles
+  const int nchunks = (k1 - k0 + WV_BK - 1) / WV_BK;
+#pragma unroll
+  for (int s = 0; s < WV_SELF_STAGES - 1; ++s) {
+    if (s < nchunks) wv_self_issue(base + s * (WV_NB * WV_LDS), Rg, ld, k0 + s * WV_BK, k1);
+    wv_cp_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    wv_cp_wait<WV_SELF_STAGES - 2>();
+    __syncthreads();
+    {
+      const int cn = c + WV_SELF_STAGES - 1;
+      if (cn < nchunks) wv_self_issue(base + (cn % WV_SELF_STAGES) * (WV_NB * WV_LDS), Rg, ld, k0 + cn * WV_BK, k1);
+      wv_cp_commit();
+    }
+    const double* st = base + (c % WV_SELF_STAGES) * (WV_NB * WV_LDS) + fr * WV_LDS + fk;
+#pragma unroll
+    for (int kk = 0; kk < WV_BK; kk += 4) {
+      double f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = st[i * 8 * WV_LDS + kk];
+#define WV_X(q, i, j) wv_dmma(acc[q][0], acc[q][1], f[i], f[j]);
+      if (warp == 0) { WV_SYM_W0(WV_X) }
+      else if (warp == 1) { WV_SYM_W1(WV_X) }
+      else if (warp == 2) { WV_SYM_W2(WV_X) }
+      else { WV_SYM_W3(WV_X) }
+#undef WV_X
+    }
+  }
+  wv_cp_wait<0>();
+  __syncthreads();
+}
+
+// 16x16 Cholesky in the registers of one warp: lane r < 16 holds row r of the block in a[0..15] (lower part
+// meaningful).  `rhs` (warp-uniform, outside [0,16) if none) is the local index of the augmented RHS row: unit
+// diagonal, never a pivot.  Per column the dependent chain is  pivot shuffle -> rsqrt -> multiply -> fma (next pivot,
+// formed by its own lane before anything else); the rank-1 update of the other columns reads the column through
+// shared memory (broadcast loads, double buffered) and stays off that chain.  Sets fail if a pivot is <= 0 (NaN pivots
+// flow through, as in Eigen's LLT).  mypiv / myinv: pivot of row `lane` and 1 / L[lane][lane].
+__device__ __forceinline__ void wv_potrf16(double (&a)[16], double (*lcol)[16], double& mypiv, double& myinv, int rhs,
+                                           bool& fail) {
   const int lane = threadIdx.x & 31;
-  double mypiv = 1.0;
-  myinv = 1.0;
+  mypiv = 1.0; myinv = 1.0;
+  double d = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
-    double d = __shfl_sync(0xffffffffu, a[c], c);
     if (c == rhs) d = 1.0;
     if (d <= 0.0) fail = true;
     const double inv = rsqrt(d);
@@ -146,15 +218,16 @@ __device__ __forceinline__ double wv_potrf16(double (&a)[16], double& myinv, int
     if (lane == c) { mypiv = d; myinv = inv; }
     if (lane < c) l = 0.0;
     a[c] = l;
+    if (c < 15) {
+      const double dn = fma(-l, l, a[c + 1]);          // lane c+1: its own diagonal entry = the next pivot
+      d = __shfl_sync(0xffffffffu, dn, c + 1);
+      if (lane < 16) lcol[c & 1][lane] = l;
+      __syncwarp();
 #pragma unroll
-    for (int c2 = c + 1; c2 < 16; ++c2) {
-      const double v = __shfl_sync(0xffffffffu, l, c2);
-      a[c2] = fma(-l, v, a[c2]);
+      for (int c2 = c + 1; c2 < 16; ++c2) a[c2] = fma(-l, lcol[c & 1][c2], a[c2]);
     }
+    WV_CLK(20 + c);
   }
-  double lg = lane < nreal ? 0.5 * log(mypiv) : 0.0;
-  for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
-  return lg;
 }
 
 // 16x16 lower-triangular inverse: L (row stride ldl) and 1/diag(L) are read from shared memory with warp-uniform
@@ -177,76 +250,94 @@ __device__ __forceinline__ void wv_trtri16(const double* __restrict__ Ls, int ld
   }
 }
 
-// One 8x8 DMMA output tile from shared-memory operands: (c0, c1) += sum_{k in [ka, kb)} A[fr][k] * B(k, fr), with
-// B(k, n) = Bp[n * ldb + k] (BT = false, "NT") or Bp[k * ldb + n] (BT = true).  ka, kb multiples of 4.  The thread
-// holds the elements (row fr, cols 2 fk, 2 fk + 1) of the tile.  Strides congruent to 4 mod 16 make all three access
-// patterns bank-conflict free.
-template <bool BT, bool NEGA>
-__device__ __forceinline__ void wv_tile8(const double* __restrict__ Ap, int lda, const double* __restrict__ Bp, int ldb,
-                                         int ka, int kb, double& c0, double& c1) {
-  const int lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3;
-  for (int k = ka; k < kb; k += 4) {
-    double a = Ap[fr * lda + k + fk];
-    const double b = BT ? Bp[(k + fk) * ldb + fr] : Bp[fr * ldb + k + fk];
-    if (NEGA) a = -a;
-    wv_dmma(c0, c1, a, b);
-  }
-}
-
 // X_SF = -X_SS (L_SF X_FF) for the diagonal sub-blocks F = [f0, f0+h), S = [f0+h, f0+2h) of the 64x64 block
-// (recursive doubling of the triangular inverse).  Two phases separated by the caller's barrier:
-//   phase 0: P = L_SF X_FF, stored transposed in the (otherwise unused) upper block X[F rows][S cols]
-//   phase 1: X_SF = -X_SS P
-// `w`/`nw`: index of this warp among the nw warps that share the block's h/8 x h/8 output tiles.
-__device__ __forceinline__ void wv_inv_couple(double* __restrict__ T, double* __restrict__ X, int f0, int h, int phase,
-                                              int w, int nw) {
+// (recursive doubling of the triangular inverse), h = 8 NBT.  Two phases (the caller synchronises between them):
+//   phase 0: P = L_SF X_FF, stored transposed in the (otherwise unused) upper block X[F rows][S cols];
+//            w = tile COLUMN (all its NBT tiles share the k range [8w, h): X_FF is lower triangular)
+//   phase 1: X_SF = -X_SS P, also stored transposed into the strict upper part of T (-> Mt);
+//            w = tile ROW (k range [0, 8w + 8): X_SS is lower triangular)
+// The NBT tiles of a call are independent accumulators, interleaved for latency.
+template <int NBT>
+__device__ __forceinline__ void wv_inv_couple(double* __restrict__ T, double* __restrict__ X, int f0, int phase, int w) {
   const int lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3;
-  const int s0 = f0 + h, nb = h >> 3;
-  for (int t = w; t < nb * nb; t += nw) {
-    const int mi = t / nb, ni = t % nb;
-    double c0 = 0.0, c1 = 0.0;
-    if (phase == 0) {
-      // P[m][n] = sum_{k >= n} L[s0+m][f0+k] X[f0+k][f0+n]      (X_FF lower triangular: k from the tile's first column)
-      wv_tile8<true, false>(T + (s0 + mi * 8) * WV_LDT + f0, WV_LDT, X + f0 * WV_LDT + f0 + ni * 8, WV_LDT, ni * 8, h, c0, c1);
-      X[(f0 + ni * 8 + 2 * fk) * WV_LDT + s0 + mi * 8 + fr] = c0;          // P^T
-      X[(f0 + ni * 8 + 2 * fk + 1) * WV_LDT + s0 + mi * 8 + fr] = c1;
-    } else {
-      // X_SF[m][n] = -sum_{k <= m} X[s0+m][s0+k] P[k][n],  P[k][n] = X[f0+n][s0+k]
-      wv_tile8<false, true>(X + (s0 + mi * 8) * WV_LDT + s0, WV_LDT, X + (f0 + ni * 8) * WV_LDT + s0, WV_LDT, 0, mi * 8 + 8, c0, c1);
-      *reinterpret_cast<double2*>(&X[(s0 + mi * 8 + fr) * WV_LDT + f0 + ni * 8 + 2 * fk]) = make_double2(c0, c1);
+  const int h = NBT * 8, s0 = f0 + h;
+  double c[NBT][2];
+#pragma unroll
+  for (int q = 0; q < NBT; ++q) c[q][0] = c[q][1] = 0.0;
+  if (phase == 0) {
+    const int ni = w;
+    for (int k = ni * 8; k < h; k += 4) {
+      const double bv = X[(f0 + k + fk) * WV_LDT + f0 + ni * 8 + fr];          // X_FF[k][n]
+#pragma unroll
+      for (int mi = 0; mi < NBT; ++mi) wv_dmma(c[mi][0], c[mi][1], T[(s0 + mi * 8 + fr) * WV_LDT + f0 + k + fk], bv);
+    }
+#pragma unroll
+    for (int mi = 0; mi < NBT; ++mi) {                                          // P^T
+      X[(f0 + ni * 8 + 2 * fk) * WV_LDT + s0 + mi * 8 + fr] = c[mi][0];
+      X[(f0 + ni * 8 + 2 * fk + 1) * WV_LDT + s0 + mi * 8 + fr] = c[mi][1];
+    }
+  } else {
+    const int mi = w;
+    for (int k = 0; k < mi * 8 + 8; k += 4) {
+      const double av = -X[(s0 + mi * 8 + fr) * WV_LDT + s0 + k + fk];          // -X_SS[m][k]
+#pragma unroll
+      for (int ni = 0; ni < NBT; ++ni) wv_dmma(c[ni][0], c[ni][1], av, X[(f0 + ni * 8 + fr) * WV_LDT + s0 + k + fk]);
+    }
+#pragma unroll
+    for (int ni = 0; ni < NBT; ++ni) {
+      *reinterpret_cast<double2*>(&X[(s0 + mi * 8 + fr) * WV_LDT + f0 + ni * 8 + 2 * fk]) = make_double2(c[ni][0], c[ni][1]);
+      T[(f0 + ni * 8 + 2 * fk) * WV_LDT + s0 + mi * 8 + fr] = c[ni][0];
+      T[(f0 + ni * 8 + 2 * fk + 1) * WV_LDT + s0 + mi * 8 + fr] = c[ni][1];
     }
   }
 }
 
-__global__ void __launch_bounds__(WV_GEMM_THREADS, 3) wv_chol_diag_kernel(WvBatchDev bd, const int* __restrict__ active,
-                                                                       int j, int k0) {
+// inverse of the 16x16 diagonal block at offset o by ONE warp: X_kk into X (lower), X_kk^T into the strict upper
+// part of T's diagonal block (-> Mt)
+__device__ __forceinline__ void wv_diag_block_inverse(double* __restrict__ T, double* __restrict__ X,
+                                                      const double* __restrict__ invd, int o) {
+  const int lane = threadIdx.x & 31;
+  double x[16];
+  wv_trtri16(T + o * WV_LDT + o, WV_LDT, invd, x);
+  if (lane < 16) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      X[(o + r) * WV_LDT + o + lane] = x[r];                          // X_kk[r][j = lane]
+      if (r > lane) T[(o + lane) * WV_LDT + o + r] = x[r];            // T[lane][r] = X[r][lane]
+    }
+  }
+}
+
+__device__ __forceinline__ void wv_diag_body(const WvBatchDev& bd, int b, int j, int k0, int epoch) {
   WvDiagSmem& sm = *reinterpret_cast<WvDiagSmem*>(wv_smem_raw);
-  const int b = active[blockIdx.x];
   const int ld = bd.npad;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   double* Ab = bd.A + (size_t)b * ld * ld;
   const double* Lrow = Ab + (size_t)j * WV_NB * ld;
+  double* Tg = Ab + (size_t)j * WV_NB * ld + j * WV_NB;
+  WV_CLK(0);
   {
-    double acc[4][4][2];
-    wv_zero_acc(acc);
-    if (threadIdx.x == 0) { sm.fail = 0; sm.logsum = 0.0; }
-    if (j * WV_NB > k0) wv_gemm_nt_64(sm.g, Lrow, Lrow, ld, k0, j * WV_NB, acc);
+    double acc[10][2];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) acc[q][0] = acc[q][1] = 0.0;
+    if (threadIdx.x == 0) sm.fail = 0;
+    if (j * WV_NB > k0) wv_syrk_self_64(sm.g, Lrow, ld, k0, j * WV_NB, acc);
     else __syncthreads();
-    int r0, c0;
-    wv_frag_origin(r0, c0);
-    const double* Tg = Ab + (size_t)j * WV_NB * ld + j * WV_NB;
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        int r = r0 + mi * 8, c = c0 + ni * 8;
-        double2 a = *reinterpret_cast<const double2*>(Tg + (size_t)r * ld + c);
-        *reinterpret_cast<double2*>(&sm.e.T[r * WV_LDT + c]) = make_double2(a.x - acc[mi][ni][0], a.y - acc[mi][ni][1]);
-      }
+#define WV_X(q, i, j)                                                                                         \
+    {                                                                                                         \
+      const double2 av = *reinterpret_cast<const double2*>(Tg + (size_t)((i) * 8 + fr) * ld + (j) * 8 + 2 * fk); \
+      *reinterpret_cast<double2*>(&sm.e.T[((i) * 8 + fr) * WV_LDT + (j) * 8 + 2 * fk]) =                      \
+          make_double2(av.x - acc[q][0], av.y - acc[q][1]);                                                   \
+    }
+    if (warp == 0) { WV_SYM_W0(WV_X) }
+    else if (warp == 1) { WV_SYM_W1(WV_X) }
+    else if (warp == 2) { WV_SYM_W2(WV_X) }
+    else { WV_SYM_W3(WV_X) }
+#undef WV_X
   }
-  for (int i = threadIdx.x; i < WV_NB * WV_LDT; i += WV_GEMM_THREADS) sm.e.X[i] = 0.0;
   __syncthreads();
+  WV_CLK(1);
   double* T = sm.e.T;
   double* X = sm.e.X;
   const int rhs = bd.n - j * WV_NB;                       // local index of the RHS row (may be outside [0,64))
@@ -254,83 +345,143 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS, 3) wv_chol_diag_kernel(WvBatc
 
   for (int kb = 0; kb < 4; ++kb) {
     const int o = kb * 16;
-    // ---- (a) 16x16 diagonal block: Cholesky + inverse, warp 0
+    // ---- (a) 16x16 diagonal block: Cholesky, warp 0 (the serial chain of the whole kernel)
     if (warp == 0) {
       bool fail = false;
-      double a[16], myinv;
+      double a[16], mypiv, myinv;
       const int row = lane & 15;
+      __syncwarp();                       // the block's last trailing update was written by other lanes of this warp
 #pragma unroll
-      for (int c = 0; c < 16; ++c) a[c] = T[(o + row) * WV_LDT + o + c];
-      const double ls = wv_potrf16(a, myinv, rhs - o, nreal - o, fail);
+      for (int c = 0; c < 16; c += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(&T[(o + row) * WV_LDT + o + c]);
+        a[c] = v.x; a[c + 1] = v.y;
+      }
+      WV_CLK(18);
+      wv_potrf16(a, sm.lcol, mypiv, myinv, rhs - o, fail);
+      WV_CLK(19);
       if (lane < 16) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) T[(o + lane) * WV_LDT + o + c] = a[c];      // L_kk (zeros above the diagonal)
+        for (int c = 0; c < 16; c += 2)
+          if (c <= lane)      // on/below the diagonal only: the strict upper part will receive X_kk^T
+            *reinterpret_cast<double2*>(&T[(o + lane) * WV_LDT + o + c]) =
+                make_double2(a[c], c + 1 <= lane ? a[c + 1] : T[(o + lane) * WV_LDT + o + c + 1]);
+        sm.piv[o + lane] = mypiv;
         sm.invd[lane] = myinv;
       }
-      if (lane == 0) { sm.logsum += ls; if (fail) sm.fail = 1; }
-      __syncwarp();
+      if (fail && lane == 0) sm.fail = 1;          // the pivots are warp-uniform, so is `fail`
+      WV_CLK(36);
+    }
+    __syncthreads();
+    WV_CLK(2 + kb * 3);
+    const int nrows = WV_NB - o - 16;
+    // ---- (b) rows below: solve x L_kk^T = t, one row per thread (warps 0..1), while warp 3 inverts the diagonal block
+    if ((int)threadIdx.x < nrows) {
+      double* trow = T + (o + 16 + threadIdx.x) * WV_LDT + o;
       double x[16];
-      wv_trtri16(T + o * WV_LDT + o, WV_LDT, sm.invd, x);
-      if (lane < 16) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) X[(o + r) * WV_LDT + o + lane] = x[r];      // X_kk[r][j = lane]
+      for (int c = 0; c < 16; c += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(trow + c);
+        x[c] = v.x; x[c + 1] = v.y;
       }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        double s0 = x[c], s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < c; ++k) {
+          const double lv = T[(o + c) * WV_LDT + o + k];
+          if (k & 1) s1 = fma(-lv, x[k], s1); else s0 = fma(-lv, x[k], s0);
+        }
+        x[c] = (s0 + s1) * sm.invd[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) *reinterpret_cast<double2*>(trow + c) = make_double2(x[c], x[c + 1]);
+    } else if (warp == 3) {
+      wv_diag_block_inverse(T, X, sm.invd, o);
     }
     __syncthreads();
+    WV_CLK(3 + kb * 3);
     if (kb == 3) break;
-    // ---- (b) L_ik = T_ik X_kk^T for the row blocks below: one warp owns whole 8-row blocks, so it may overwrite T_ik
-    const int nrb = (WV_NB - o - 16) >> 3;
-    for (int rb = warp; rb < nrb; rb += 4) {
-      const int m0 = o + 16 + rb * 8;
-      double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-      wv_tile8<false, false>(T + m0 * WV_LDT + o, WV_LDT, X + o * WV_LDT + o, WV_LDT, 0, 8, c[0][0], c[0][1]);
-      wv_tile8<false, false>(T + m0 * WV_LDT + o, WV_LDT, X + (o + 8) * WV_LDT + o, WV_LDT, 0, 16, c[1][0], c[1][1]);
-      __syncwarp();
-      *reinterpret_cast<double2*>(&T[(m0 + fr) * WV_LDT + o + 2 * fk]) = make_double2(c[0][0], c[0][1]);
-      *reinterpret_cast<double2*>(&T[(m0 + fr) * WV_LDT + o + 8 + 2 * fk]) = make_double2(c[1][0], c[1][1]);
+    // ---- (c) trailing update of the lower 8x8 tiles: T_ij -= L_ik L_jk^T.  Warp 0 takes the three tiles of the next
+    //      diagonal block and goes straight on to factorise it; warps 1..3 share the rest (<= 6 independent tiles
+    //      each); the barrier after the next (a) orders their writes before anybody reads them.
+    {
+      const int nrb = nrows >> 3;
+      const int ntl = nrb * (nrb + 1) / 2;
+      double2 cv[6];
+      int mo[6], no[6];
+      bool on[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const int t = warp == 0 ? q : 3 + (warp - 1) + 3 * q;
+        on[q] = warp == 0 ? q < 3 : t < ntl;
+        int ti = 0;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        mo[q] = o + 16 + ti * 8; no[q] = o + 16 + (t - ti * (ti + 1) / 2) * 8;
+        if (on[q]) cv[q] = *reinterpret_cast<const double2*>(&T[(mo[q] + fr) * WV_LDT + no[q] + 2 * fk]);
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k += 4) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+          if (on[q]) wv_dmma(cv[q].x, cv[q].y, -T[(mo[q] + fr) * WV_LDT + o + k + fk], T[(no[q] + fr) * WV_LDT + o + k + fk]);
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q)
+        if (on[q]) *reinterpret_cast<double2*>(&T[(mo[q] + fr) * WV_LDT + no[q] + 2 * fk]) = cv[q];
     }
-    __syncthreads();
-    // ---- (c) trailing update of the lower 8x8 tiles: T_ij -= L_ik L_jk^T
-    const int ntl = nrb * (nrb + 1) / 2;
-    for (int t = warp; t < ntl; t += 4) {
-      int ti = 0;
-      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-      const int tj = t - ti * (ti + 1) / 2;
-      const int m0 = o + 16 + ti * 8, n0 = o + 16 + tj * 8;
-      double2* cp = reinterpret_cast<double2*>(&T[(m0 + fr) * WV_LDT + n0 + 2 * fk]);
-      double2 cv = *cp;
-      wv_tile8<false, true>(T + m0 * WV_LDT + o, WV_LDT, T + n0 * WV_LDT + o, WV_LDT, 0, 16, cv.x, cv.y);
-      *cp = cv;
+    WV_CLK(4 + kb * 3);
+  }
+  // ---- assemble the 64x64 inverse.  Level 1 (16-blocks): warp 2 couples the pair (0,1), warp 3 the pair (2,3), each
+  //      alone (both phases, warp-level sync only); meanwhile warps 0..1 write L_jj, which is final, to global memory.
+  if (warp >= 2) {
+    const int f0 = (warp - 2) * 32;
+    wv_inv_couple<2>(T, X, f0, 0, 0);
+    wv_inv_couple<2>(T, X, f0, 0, 1);
+    __syncwarp();
+    wv_inv_couple<2>(T, X, f0, 1, 0);
+    wv_inv_couple<2>(T, X, f0, 1, 1);
+  } else {
+    for (int i = threadIdx.x; i < WV_NB * WV_NB / 2; i += 64) {
+      const int rr = i >> 5, cc = (i & 31) * 2;
+      const double2 tv = *reinterpret_cast<const double2*>(&T[rr * WV_LDT + cc]);
+      *reinterpret_cast<double2*>(Tg + (size_t)rr * ld + cc) = make_double2(cc <= rr ? tv.x : 0.0, cc + 1 <= rr ? tv.y : 0.0);
     }
-    __syncthreads();
   }
-  // ---- assemble the 64x64 inverse: level 1 (16-blocks: pairs (0,1) and (2,3)), level 2 (32-blocks)
+  __syncthreads();
+  //      Level 2 (32-blocks), all four warps.
   for (int phase = 0; phase < 2; ++phase) {
-    wv_inv_couple(T, X, (warp >> 1) * 32, 16, phase, warp & 1, 2);
+    wv_inv_couple<4>(T, X, 0, phase, warp);
     __syncthreads();
   }
-  for (int phase = 0; phase < 2; ++phase) {
-    wv_inv_couple(T, X, 0, 32, phase, warp, 4);
-    __syncthreads();
-  }
+  WV_CLK(12);
 
-  // ---- write L_jj (lower, zeros above), Linv_jj (row-major) and Linv_jj^T into Mt[j,j]
-  double* Tg = Ab + (size_t)j * WV_NB * ld + j * WV_NB;
+  // ---- write Linv_jj (row-major) and Linv_jj^T (-> Mt[j,j])
   double* Mg = bd.Mt + (size_t)b * ld * ld + (size_t)j * WV_NB * ld + j * WV_NB;
   double* Dg = bd.Dinv + ((size_t)b * bd.nt + j) * WV_NB * WV_NB;
   for (int i = threadIdx.x; i < WV_NB * WV_NB / 2; i += WV_GEMM_THREADS) {
     const int rr = i >> 5, cc = (i & 31) * 2;
     const double2 tv = *reinterpret_cast<const double2*>(&T[rr * WV_LDT + cc]);
     const double2 xv = *reinterpret_cast<const double2*>(&X[rr * WV_LDT + cc]);
-    *reinterpret_cast<double2*>(Tg + (size_t)rr * ld + cc) = make_double2(cc <= rr ? tv.x : 0.0, cc + 1 <= rr ? tv.y : 0.0);
+    const double xd = X[rr * WV_LDT + rr];
     *reinterpret_cast<double2*>(Dg + rr * WV_NB + cc) = make_double2(cc <= rr ? xv.x : 0.0, cc + 1 <= rr ? xv.y : 0.0);
-    const double m0 = rr <= cc ? X[cc * WV_LDT + rr] : 0.0, m1 = rr <= cc + 1 ? X[(cc + 1) * WV_LDT + rr] : 0.0;
-    *reinterpret_cast<double2*>(Mg + (size_t)rr * ld + cc) = make_double2(m0, m1);
+    *reinterpret_cast<double2*>(Mg + (size_t)rr * ld + cc) =
+        make_double2(cc > rr ? tv.x : (cc == rr ? xd : 0.0), cc + 1 > rr ? tv.y : (cc + 1 == rr ? xd : 0.0));
   }
+  // log-determinant terms, off the serial chain: one pivot per thread, fixed-order reduction
+  if (threadIdx.x < WV_NB) {
+    double lg = (int)threadIdx.x < nreal ? 0.5 * log(sm.piv[threadIdx.x]) : 0.0;
+    for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+    if (lane == 0) sm.red[warp] = lg;
+  }
+  __threadfence();                       // L_jj / Linv_jj / Mt_jj visible device-wide before the flag
+  __syncthreads();
   if (threadIdx.x == 0) {
-    bd.logdet_part[(size_t)b * bd.nt + j] = sm.logsum;
+    bd.logdet_part[(size_t)b * bd.nt + j] = sm.red[0] + sm.red[1];
     if (sm.fail) bd.chol_fail[b] = 1;
+    __threadfence();
+    *reinterpret_cast<volatile int*>(bd.step_flag + (size_t)b * bd.nt + j) = epoch;   // releases the panel CTAs
   }
+  WV_CLK(13);
 }
 
 // =============================================================================================
@@ -349,11 +500,11 @@ struct WvPanelSmem {
   };
 };
 
-template <int MODE>   // 0 = chol_panel, 1 = trtri
-__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_panel_kernel(WvBatchDev bd, const int* __restrict__ active,
-                                                                   int step, int kstart) {
+// body shared by the panel tiles of the fused Cholesky step (MODE 0, waits for the diagonal CTA's flag between the
+// two products) and the triangular-inverse step (MODE 1)
+template <int MODE>
+__device__ __forceinline__ void wv_panel_body(const WvBatchDev& bd, int b, int step, int tile, int kstart, int epoch) {
   WvPanelSmem& sm = *reinterpret_cast<WvPanelSmem*>(wv_smem_raw);
-  const int b = active[blockIdx.y];
   const int ld = bd.npad;
   double* Ab = bd.A + (size_t)b * ld * ld;
   double* Mb = bd.Mt + (size_t)b * ld * ld;
@@ -362,14 +513,14 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_panel_kernel(WvBatchDev bd
   const double* Cin;
   int k0, k1;
   if (MODE == 0) {
-    const int i = step + 1 + blockIdx.x, j = step;
+    const int i = step + 1 + tile, j = step;
     Ag = Ab + (size_t)i * WV_NB * ld;
     Bg = Ab + (size_t)j * WV_NB * ld;
     k0 = kstart; k1 = j * WV_NB;
     Out = Ab + (size_t)i * WV_NB * ld + j * WV_NB;
     Cin = Out;
   } else {
-    const int i = step, j = blockIdx.x;
+    const int i = step, j = tile;
     Ag = Mb + (size_t)j * WV_NB * ld;
     Bg = Ab + (size_t)i * WV_NB * ld;
     k0 = j * WV_NB; k1 = i * WV_NB;
@@ -396,11 +547,20 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_panel_kernel(WvBatchDev bd
       }
       *reinterpret_cast<double2*>(&sm.e.T[r * WV_LDT + c]) = v;
     }
-  // D = Linv of the step's diagonal block (row-major)
+  if (MODE == 0) {
+    // the inverse of the diagonal block is produced by CTA x = 0 of the same launch (dispatched before this one)
+    if (threadIdx.x == 0) {
+      const volatile int* f = reinterpret_cast<const volatile int*>(bd.step_flag + (size_t)b * bd.nt + step);
+      while (*f != epoch) __nanosleep(40);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  // D = Linv of the step's diagonal block (row-major); L2 loads: the block was written by another SM in this launch
   const double2* Dg = reinterpret_cast<const double2*>(bd.Dinv + ((size_t)b * bd.nt + step) * WV_NB * WV_NB);
   for (int i = threadIdx.x; i < WV_NB * WV_NB / 2; i += WV_GEMM_THREADS) {
     int rr = i >> 5, c2 = (i & 31) * 2;
-    *reinterpret_cast<double2*>(&sm.e.D[rr * WV_LDT + c2]) = Dg[i];
+    *reinterpret_cast<double2*>(&sm.e.D[rr * WV_LDT + c2]) = __ldcg(Dg + i);
   }
   __syncthreads();
   wv_zero_acc(acc);
@@ -412,6 +572,44 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_panel_kernel(WvBatchDev bd
       int r = r0 + mi * 8, c = c0 + ni * 8;
       *reinterpret_cast<double2*>(Out + (size_t)r * ld + c) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
     }
+}
+
+// One column step of the Cholesky factorisation in ONE launch: CTA x = 0 factorises the diagonal block (wv_diag_body),
+// CTAs x >= 1 are the panel tiles below it.  A panel tile first accumulates its update sum_k L[i,k] L[j,k]^T, which does
+// not depend on the diagonal block, and only then waits for the diagonal CTA's flag: the serial 64x64 factorisation
+// overlaps the tensor-pipe work instead of preceding it.  The wait cannot deadlock: CTAs are dispatched in linear
+// block order, so the diagonal CTA of a model (x = 0) is resident or finished whenever one of its panel CTAs runs.
+// grid (nt - j, n_active), 128 threads.
+// With many models in flight the overlap is not worth having waiting tiles hold SM slots: the host then launches the
+// diagonal CTAs (grid.x = 1, x0 = 0) and the panel tiles (x0 = 1) separately and the flag is already set.
+__global__ void __launch_bounds__(WV_GEMM_THREADS, 3) wv_chol_step_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                                       int j, int k0, int epoch, int x0) {
+  const int b = active[blockIdx.y];
+  const int x = blockIdx.x + x0;
+  if (x == 0) wv_diag_body(bd, b, j, k0, epoch);
+  else wv_panel_body<0>(bd, b, j, x - 1, k0, epoch);
+}
+
+// enqueue one Cholesky column step; fused into one launch iff all its CTAs can be resident at once
+static int wv_launch_chol_step(const WvBatchDev& bd, const int* d_active, int n_active, int j, int k0, cudaStream_t st,
+                               WvProfiler* pf, const WvAux& aux) {
+  const int nt = bd.nt;
+  const size_t smem = sizeof(WvPanelSmem) > sizeof(WvDiagSmem) ? sizeof(WvPanelSmem) : sizeof(WvDiagSmem);
+  if ((long)n_active * (nt - j) <= aux.resident_ctas || j + 1 == nt) {
+    wv_chol_step_kernel<<<dim3(nt - j, n_active), WV_GEMM_THREADS, smem, st>>>(bd, d_active, j, k0, aux.epoch, 0);
+    pf->mark(WV_K_CHOL_PANEL, st);
+    return 1;
+  }
+  wv_chol_step_kernel<<<dim3(1, n_active), WV_GEMM_THREADS, smem, st>>>(bd, d_active, j, k0, aux.epoch, 0);
+  pf->mark(WV_K_CHOL_DIAG, st);
+  wv_chol_step_kernel<<<dim3(nt - j - 1, n_active), WV_GEMM_THREADS, smem, st>>>(bd, d_active, j, k0, aux.epoch, 1);
+  pf->mark(WV_K_CHOL_PANEL, st);
+  return 2;
+}
+
+// trtri(i): tiles (j, i), j < i, of Mt = L^{-T}.  grid (i, n_active), 128 threads.
+__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_trtri_kernel(WvBatchDev bd, const int* __restrict__ active, int step) {
+  wv_panel_body<1>(bd, active[blockIdx.y], step, blockIdx.x, 0, 0);
 }
 
 // =============================================================================================
@@ -728,7 +926,7 @@ __global__ void __launch_bounds__(64 * WV_FIN_MAXG) wv_finalize_kernel(WvBatchDe
 // =============================================================================================
 // host-side launch sequence of one evaluation (enqueued on `stream`, no host sync)
 // =============================================================================================
-size_t wv_smem_gemm_bytes() { return sizeof(WvPanelSmem) > sizeof(WvDiagSmem) ? sizeof(WvPanelSmem) : sizeof(WvDiagSmem); }
+static size_t wv_smem_gemm_bytes() { return sizeof(WvPanelSmem) > sizeof(WvDiagSmem) ? sizeof(WvPanelSmem) : sizeof(WvDiagSmem); }
 
 static bool g_attr_done = false;
 static cudaError_t wv_set_attrs() {
@@ -739,9 +937,8 @@ static cudaError_t wv_set_attrs() {
   if (e != cudaSuccess) return e;
   WV_ATTR(wv_gram_kernel, sizeof(WvElemSmem));
   WV_ATTR(wv_grad_kernel, sizeof(WvElemSmem));
-  WV_ATTR(wv_chol_diag_kernel, sizeof(WvDiagSmem));
-  WV_ATTR(wv_panel_kernel<0>, sizeof(WvPanelSmem));
-  WV_ATTR(wv_panel_kernel<1>, sizeof(WvPanelSmem));
+  WV_ATTR(wv_chol_step_kernel, wv_smem_gemm_bytes());
+  WV_ATTR(wv_trtri_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_kinv_kernel, sizeof(WvGemmSmem));
   WV_ATTR(wv_syrk_kernel, sizeof(WvGemmSmem));
   WV_ATTR(wv_trtri_level_kernel<1>, sizeof(WvGemmSmem));
@@ -759,17 +956,7 @@ static int wv_enqueue_factor_big(const WvBatchDev& bd, const int* d_active, int 
   bool bulk_pending = false;
   for (int p0 = 0; p0 < nt; p0 += WV_PANEL_TILES) {
     const int p1 = p0 + WV_PANEL_TILES < nt ? p0 + WV_PANEL_TILES : nt;
-    for (int j = p0; j < p1; ++j) {
-      wv_chol_diag_kernel<<<dim3(n_active), WV_GEMM_THREADS, sizeof(WvDiagSmem), st>>>(bd, d_active, j, p0 * WV_NB);
-      pf->mark(WV_K_CHOL_DIAG, st);
-      ++launches;
-      if (j + 1 < nt) {
-        wv_panel_kernel<0><<<dim3(nt - j - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, j,
-                                                                                                   p0 * WV_NB);
-        pf->mark(WV_K_CHOL_PANEL, st);
-        ++launches;
-      }
-    }
+    for (int j = p0; j < p1; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, p0 * WV_NB, st, pf, aux);
     if (p1 >= nt) break;
     const int a_hi = p1 + WV_PANEL_TILES < nt ? p1 + WV_PANEL_TILES : nt;   // columns of the next panel
     cudaEventRecord(aux.ev_panel, st);
@@ -821,23 +1008,15 @@ int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, con
   wv_gram_kernel<<<dim3(ntiles, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(bd, d_active, d_x);
   pf->mark(WV_K_GRAM, st);
   ++launches;
-  if (aux && aux->side && nt >= aux->big_nt) {
+  if (!aux) return -1;
+  if (aux->side && nt >= aux->big_nt) {
     int l = wv_enqueue_factor_big(bd, d_active, n_active, st, pf, *aux);
     if (l < 0) return -1;
     launches += l;
   } else {
-    for (int j = 0; j < nt; ++j) {
-      wv_chol_diag_kernel<<<dim3(n_active), WV_GEMM_THREADS, sizeof(WvDiagSmem), st>>>(bd, d_active, j, 0);
-      pf->mark(WV_K_CHOL_DIAG, st);
-      ++launches;
-      if (j + 1 < nt) {
-        wv_panel_kernel<0><<<dim3(nt - j - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, j, 0);
-        pf->mark(WV_K_CHOL_PANEL, st);
-        ++launches;
-      }
-    }
+    for (int j = 0; j < nt; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, 0, st, pf, *aux);
     for (int i = 1; i < nt; ++i) {
-      wv_panel_kernel<1><<<dim3(i, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, i, 0);
+      wv_trtri_kernel<<<dim3(i, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, i);
       pf->mark(WV_K_TRTRI, st);
       ++launches;
     }

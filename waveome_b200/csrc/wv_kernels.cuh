@@ -41,6 +41,7 @@ struct WvBatchDev {
   double* quad;                     // [B]
   double* partial;                  // [B][n_tiles][n_slots_max]
   int* chol_fail;                   // [B]
+  int* step_flag;                   // [B][nt] epoch of the last finished diagonal block (fused Cholesky step)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -55,6 +56,8 @@ struct WvAux {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
   int big_nt = 16;
+  int resident_ctas = 444;   // 3 CTAs x 148 SMs: a Cholesky step is fused into one launch only if it fits
+  int epoch = 0;   // evaluation counter of the engine: the value the diagonal CTAs publish in step_flag
 };
 struct WvProfiler {
   bool enabled = false;
