@@ -475,14 +475,17 @@ def fit(model, X, y, maxiter=50000, maxfun=None, x0=None, maxcor=10, ftol=2.2204
     except CholeskyFailure:
         return dict(x=res.x, f=math.inf, lml=-math.inf, nit=int(res.nit), nfev=int(res.nfev), status=STATUS_CHOL_FAIL,
                     message="cholesky failed at the returned point", model=model)
+    # f is the objective AT THE RETURNED x (what log_posterior_density() reads after the optimiser returns,
+    # waveome/model_search.py:2311, and what wv_batch_fit_lbfgs reports): after an ABNORMAL line-search exit SciPy's
+    # res.fun still holds the last (possibly non-finite) trial value while res.x is the restored iterate.
     status = STATUS_OK
-    if not np.isfinite(res.fun):
+    if not np.isfinite(f):
         status |= STATUS_NONFINITE
     if res.status == 1:
         status |= STATUS_MAXITER
     if res.status == 2:
         status |= STATUS_LINESEARCH
-    return dict(x=res.x, f=float(res.fun), lml=lml, log_prior=lp, nit=int(res.nit), nfev=int(res.nfev),
+    return dict(x=res.x, f=float(f), lml=lml, log_prior=lp, nit=int(res.nit), nfev=int(res.nfev),
                 status=status, message=str(res.message), model=model)
 
 

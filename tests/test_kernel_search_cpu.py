@@ -1,0 +1,139 @@
+"""Host logic of the compositional kernel search (waveome/model_search.py:2239-3272) — candidate generation, naming,
+de-duplication, windows, pruning — checked against hand-derived expectations from the reference's rules, and one full
+search driven by the CPU oracle."""
+import numpy as np
+
+import helpers
+import waveome_b200 as wb
+from waveome_b200 import kernel_search as ks
+from oracle_fitter import oracle_fitter
+
+KL = lambda: [wb.SquaredExponential(), wb.Matern12(), wb.Lin(), wb.Periodic(wb.SquaredExponential())]
+
+
+def _request(cands):
+    return cands
+
+
+def test_first_level_candidates():
+    cands = _request(ks.loc_candidates(3, KL(), cat_vars=[0, 2], depth=1))
+    assert [c[0] for c in cands] == ["categorical[0]", "constant", "squared_exponential[1]", "matern12[1]", "lin[1]",
+                                     "periodic[1]", "categorical[2]"]
+    const = dict(cands)["constant"]
+    assert float(const.variance) == 1e-6 and not const.variance.trainable     # frozen "empty" candidate (:2385-2389)
+
+
+def test_sum_candidates_order_skip_and_dedup():
+    base = wb.SquaredExponential(active_dims=[1], lengthscales=0.3, variance=2.0)
+    cands = _request(ks.loc_candidates(3, KL(), base_kern=base, base_name="squared_exponential[1]", cat_vars=[0, 2],
+                                          depth=2, operation="sum", prev_models=["categorical[0]+squared_exponential[1]"]))
+    names = [c[0] for c in cands]
+    # categorical[0]+SE[1] already exists (any term order); names are joined in string order (:2415-2420)
+    assert names == ["squared_exponential[1]+squared_exponential[1]", "matern12[1]+squared_exponential[1]",
+                     "lin[1]+squared_exponential[1]", "periodic[1]+squared_exponential[1]",
+                     "categorical[2]+squared_exponential[1]"]
+    k = dict(cands)["lin[1]+squared_exponential[1]"]
+    assert [x.name for x in k.kernels] == ["lin", "squared_exponential"]
+    assert float(k.kernels[1].lengthscales) == 1.0 and float(k.kernels[1].variance) == 1.0    # base reset to 1 (:2405)
+    # a categorical feature already in the base is never added again (:2410)
+    cands = _request(ks.loc_candidates(3, KL(), base_kern=wb.Categorical(active_dims=[0]), base_name="categorical[0]",
+                                          cat_vars=[0, 2], depth=2, operation="sum", prev_models=[]))
+    assert all("categorical[0]+categorical[0]" != c[0] for c in cands)
+
+
+def test_product_candidates_freeze_new_factor():
+    base = wb.SquaredExponential(active_dims=[1])
+    cands = _request(ks.loc_candidates(3, KL(), base_kern=base, base_name="squared_exponential[1]", cat_vars=[0, 2],
+                                          depth=2, operation="product", prev_models=[]))
+    d = dict(cands)
+    assert "categorical[0]*squared_exponential[1]" in d and "periodic[1]*squared_exponential[1]" in d
+    k = d["categorical[0]*squared_exponential[1]"]
+    assert [x.name for x in k.kernels] == ["categorical", "squared_exponential"]
+    assert not k.kernels[0].variance.trainable and k.kernels[1].variance.trainable            # :2464-2468
+    kp = d["periodic[1]*squared_exponential[1]"]
+    assert not kp.kernels[0].base_kernel.variance.trainable
+    # products of products are not built (:2460)
+    cands = _request(ks.loc_candidates(3, KL(), base_kern=k, base_name="categorical[0]*squared_exponential[1]",
+                                          cat_vars=[0, 2], depth=3, operation="product", prev_models=[]))
+    assert cands == []
+
+
+def test_split_product_name_moves_but_kernel_stays():
+    base = wb.Sum([wb.Lin(active_dims=[1]), wb.SquaredExponential(active_dims=[1])])
+    new = wb.Categorical(active_dims=[0])
+    cands = ks.prod_kernel_candidates(base, "lin[1]+squared_exponential[1]", new, [])
+    names = [c[0] for c in cands]
+    # "categorical[0]" < "lin[1]": the product is named categorical[0]*lin[1] and its NAME is re-inserted before the
+    # first name that sorts after "categorical[0]" (:2607-2624); the kernel list keeps its positions
+    assert names == ["categorical[0]*lin[1]+squared_exponential[1]", "categorical[0]*squared_exponential[1]+lin[1]"]
+    k2 = cands[1][1]
+    assert [x.name for x in k2.kernels] == ["lin", "product"]
+    # a component that already holds the categorical of the new factor, or is a product, is skipped (:2591-2596)
+    base = wb.Sum([wb.Categorical(active_dims=[0]), wb.Product([wb.Categorical(active_dims=[2]), wb.Lin(active_dims=[1])])])
+    assert ks.prod_kernel_candidates(base, "categorical[0]+categorical[2]*lin[1]", new, []) == []
+
+
+def test_window_and_better_metric():
+    d = {"a": dict(bic=10.0, depth=1, try_next=True), "b": dict(bic=15.9, depth=1, try_next=True),
+         "c": dict(bic=16.01, depth=1, try_next=True), "a+b": dict(bic=9.5, depth=2, try_next=True)}
+    ks.keep_top_k(d, depth=1, metric_diff=6)
+    assert d["a"]["try_next"] and d["b"]["try_next"] and not d["c"]["try_next"]
+    assert ks.check_if_better_metric(d, 2) and not ks.check_if_better_metric(d, 3)
+
+
+def test_prune_requests():
+    m = ks.candidate_model(wb.Sum([wb.Categorical(active_dims=[0]),
+                                   wb.Product([wb.Categorical(active_dims=[2]), wb.SquaredExponential(active_dims=[1])])]))
+    res = {"categorical[0]+categorical[2]*squared_exponential[1]": dict(kernel=m.kernel, model=m, bic=5.0, depth=2,
+                                                                        parent="x", try_next=True),
+           "categorical[0]": dict(kernel=None, model=None, bic=9.0, depth=1, parent="None", try_next=True)}
+    gen = ks.prune_best_model2(res, depth=2)
+    req = next(gen)
+    # dropping categorical[0] leaves the product; the product's factors are tried next to the other component;
+    # "categorical[0]+categorical[2]" etc. are new, nothing collides with the existing "categorical[0]"
+    assert [r[0] for r in req] == ["categorical[2]*squared_exponential[1]", "categorical[0]+categorical[2]",
+                                   "categorical[0]+squared_exponential[1]"]
+    fitted = [(ks.candidate_model(k), b) for (n, k), b in zip(req, [4.0, 6.0, 4.5])]
+    try:
+        gen.send(fitted)
+    except StopIteration as e:
+        out = e.value
+    assert set(out) == set(res) | {"categorical[2]*squared_exponential[1]", "categorical[0]+squared_exponential[1]"}
+    assert out["categorical[0]+squared_exponential[1]"]["depth"] == 2
+
+
+def _toy():
+    rng = np.random.default_rng(5)
+    n = 60
+    subj = np.repeat(np.arange(12), 5).astype(float)
+    t = rng.normal(size=n)
+    grp = rng.integers(0, 2, size=n).astype(float)
+    X = np.stack([subj, t, grp], 1)
+    y = 1.5 * np.sin(2.0 * t) + rng.normal(size=12)[subj.astype(int)] + 0.1 * rng.normal(size=n)
+    return X, y
+
+
+def test_full_search_with_oracle_fits():
+    """y = smooth f(t) + subject offset + noise: the search must pick up both components; every rule of the depth loop
+    is visible in the result dictionary."""
+    X, y = _toy()
+    out = ks.full_kernel_search(X, y, [wb.SquaredExponential(), wb.Lin()], cat_vars=[0, 2], max_depth=3,
+                                fit=oracle_fitter(X), keep_only_best=False)
+    models = out["models"]
+    d1 = {k: v for k, v in models.items() if v["depth"] == 1}
+    assert set(d1) == {"categorical[0]", "constant", "squared_exponential[1]", "lin[1]", "categorical[2]"}
+    best2 = min((v["bic"], k) for k, v in models.items() if v["depth"] == 2)[1]
+    assert best2 == "categorical[0]+squared_exponential[1]"
+    best = out["best_model"]
+    assert "categorical[0]" in best and "squared_exponential[1]" in best
+    assert models[best]["bic"] == min(v["bic"] for v in models.values())
+    # window: first-level entries further than 6 from the level's best were not expanded (:2705-2707)
+    b1 = min(v["bic"] for v in d1.values())
+    for k, v in d1.items():
+        assert v["try_next"] == (v["bic"] - b1 <= 6)
+        if not v["try_next"]:
+            assert not any(p == k for p, _c in out["edges"])
+    # BIC = round(2 k - 2 log p, 2) with k = trainable Parameter objects (kernel + noise + mean)
+    m = models[best2]["model"]
+    assert len(m.trainable_parameters) == 5
+    assert models[best2]["bic"] == round(2 * 5 - 2 * m.log_posterior_density_value, 2)

@@ -9,5 +9,6 @@ from .kernels import (Categorical, Constant, Empty, Horseshoe, Laplace, Lin, Lin
                       Matern52, Parameter, Periodic, Poly, Polynomial, Product, SquaredExponential, Sum, Uniform,
                       deepcopy, set_trainable)
 from .models import GPR, ConstantMean, Gaussian, ZeroMean  # noqa: F401
+from .kernel_search import full_kernel_search, kernel_test  # noqa: F401
 
 __version__ = "0.1.0"

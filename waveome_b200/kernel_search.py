@@ -1,0 +1,483 @@
+"""Compositional kernel search (``GPSearch.run_search``) on the batch engine — BASELINE configs[1].
+
+Host-side restatement of the reference's greedy search (waveome/model_search.py):
+
+    kernel_test              :2239-2334   one candidate fit -> (model, "BIC" = round(2k - 2 log p, 2))
+    set_feature_kernels      :2337-2344
+    loc_kernel_search        :2347-2558   candidates of one base kernel: first level / sum / product / split product
+    prod_kernel_creation     :2561-2664   product of a new factor with each additive component of the base
+    check_if_better_metric   :2667-2681
+    keep_top_k               :2684-2710   BIC window (metric_diff) -> ``try_next`` flags
+    prune_best_model2        :2778-2885   leave-one-component-out refits of the level's best model
+    prune_prod_kernel        :2888-2984   ... and of the factors of its product components
+    full_kernel_search       :2987-3272   depth loop, early stopping, final arg-min by (bic, depth, name)
+
+The selection arithmetic (names, ordering by string comparison, de-duplication by canonicalised name, windows,
+what is frozen in a product) follows the reference decision by decision, including its quirks, because it determines
+*which fits exist* and which structure is selected.  What changes is the execution: every function here is a
+GENERATOR that yields the list of candidate kernels it needs fitted and receives ``(model, bic)`` pairs back, so a
+driver can run the searches of many outcomes in lock-step and hand the union of their requests to the engine as ONE
+batch ("outcomes x candidate kernel structures") instead of one process per outcome and one TensorFlow
+graph per candidate.  ``run_lockstep`` is that driver; the plain functions of the reference's names
+(``full_kernel_search`` ...) run a single search with one engine batch per request.
+
+Objective: the exact-GPR log marginal likelihood (objective A) maximised by the device L-BFGS-B; the
+reference's live path scores candidates with an Adam/NatGrad-fitted SVGP bound of the same quantity.
+"""
+from __future__ import annotations
+
+import re
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import kernels as K
+from .models import GPR, ConstantMean
+from .utilities import calc_bic, check_if_model_exists
+
+Candidate = Tuple[str, K.Kernel]                 # (name key, kernel to fit)
+Fitted = Tuple[Optional[GPR], float]             # (model or None if the fit failed, bic)
+
+
+# ------------------------------------------------------------------------------------------------
+# candidate construction
+# ------------------------------------------------------------------------------------------------
+def kernel_info(k: K.Kernel) -> str:
+    """``k.name + str(k.active_dims)`` (reference :2395, :2588); the frozen first-level constant is "constant"."""
+    return k.name if k.name == "constant" else k.name + "[" + str(int(k.active_dims[0])) + "]"
+
+
+def set_feature_kernels(f, kern_list, cat_vars):
+    """:2337-2344 — a categorical column gets the categorical kernel, any other column every kernel of the list."""
+    if f in cat_vars:
+        return [K.Categorical(active_dims=[f])]
+    k_list = list(kern_list)
+    for k_ in k_list:
+        k_.active_dims = [int(f)]
+    return k_list
+
+
+def _freeze_new_factor(k):
+    """:2464-2468 / :2513-2516 — the factor added by a product keeps variance 1 (Periodic: on its base kernel)."""
+    K.set_trainable(k.base_kernel.variance if k.name == "periodic" else k.variance, False)
+
+
+def _entry(kernel, model, bic, depth, parent):
+    return {"kernel": kernel, "model": model, "bic": bic, "depth": depth, "parent": parent, "try_next": True}
+
+
+def loc_candidates(n_features, kern_list, base_kern=None, base_name=None, cat_vars=(), depth=0, operation="sum",
+                   prev_models=None) -> List[Candidate]:
+    """Candidate kernels of one ``loc_kernel_search`` call (:2347-2558), in the reference's order."""
+    prev_models = list(prev_models) if prev_models is not None else []
+    cands: List[Candidate] = []
+    for f in range(n_features):
+        k_list = set_feature_kernels(f, [K.deepcopy(x) for x in kern_list], list(cat_vars))
+        if f == 0 and depth == 1:
+            empty_kernel = K.Constant(variance=1e-6)
+            K.set_trainable(empty_kernel.variance, False)
+            k_list = k_list + [empty_kernel]
+        for k in k_list:
+            k_info = kernel_info(k)
+            if base_kern is None:
+                cands.append((k_info, k))
+                continue
+            base_kern_ = K.deepcopy(base_kern)
+            for p in base_kern_.trainable_parameters:
+                p.assign(1.0)
+            if operation == "sum":
+                if "categorical[" + str(f) + "]" in base_name:
+                    continue
+                if base_name < k_info:
+                    k, k_info = K.Sum([base_kern_, k]), base_name + "+" + k_info
+                else:
+                    k, k_info = K.Sum([k, base_kern_]), k_info + "+" + base_name
+                if check_if_model_exists(k_info, prev_models):
+                    continue
+                cands.append((k_info, k))
+            elif operation == "product":
+                if "categorical[" + str(f) + "]" in base_name:
+                    continue
+                if "*" in base_name:               # two-way interactions only
+                    continue
+                _freeze_new_factor(k)
+                if base_name < k_info:
+                    k, k_info = K.Product([base_kern_, k]), base_name + "*" + k_info
+                else:
+                    k, k_info = K.Product([k, base_kern_]), k_info + "*" + base_name
+                if check_if_model_exists(k_info, prev_models):
+                    continue
+                cands.append((k_info, k))
+            elif operation == "split_product":
+                _freeze_new_factor(k)
+                cands += prod_kernel_candidates(base_kern_, base_name, k, prev_models)
+            else:
+                raise ValueError(f"unknown operation {operation!r}")
+    return cands
+
+
+def loc_kernel_search(n_features, kern_list, base_kern=None, base_name=None, cat_vars=(), depth=0, operation="sum",
+                      prev_models=None, cache=None):
+    """:2347-2558 as a generator: yields ONE request with every candidate of this call that is not in ``cache``
+    (name -> (kernel, (model, bic)) fitted ahead of time), returns the result dict (failed fits drop out, as the
+    reference's ``except Exception: None`` does)."""
+    cands = loc_candidates(n_features, kern_list, base_kern, base_name, cat_vars, depth, operation, prev_models)
+    parents = "None" if base_kern is None else base_name
+    cache = cache if cache is not None else {}
+    missing = [c for c in cands if c[0] not in cache]
+    if missing:
+        got = yield missing
+        for c, r in zip(missing, got):
+            cache[c[0]] = (c[1], r)
+    cands = [(name, cache[name][0]) for name, _k in cands]
+    fitted = [cache[name][1] for name, _k in cands]
+    out = {}
+    for (name, k), (m, bic) in zip(cands, fitted):
+        if m is not None:
+            out[name] = _entry(k, m, bic, depth, parents)
+    return out
+
+
+def prod_kernel_candidates(base_kernel, base_name, new_kernel, prev_models) -> List[Candidate]:
+    """:2561-2664 — ``new_kernel`` times each additive component of the base.  When the new factor sorts before the
+    component, the reference moves the component's NAME inside the '+'-joined key but leaves the kernel in place;
+    later stages index names and kernels in parallel, so that is kept as it is."""
+    out: List[Candidate] = []
+    for feat in range(len(base_kernel.kernels)):
+        temp_kernel = K.deepcopy(base_kernel)
+        temp_name = base_name.split("+")
+        k_info = kernel_info(new_kernel)
+        if "categorical[" + str(int(new_kernel.active_dims[0])) + "]" in temp_name[feat]:
+            continue
+        if "*" in temp_name[feat]:
+            continue
+        if temp_name[feat] < k_info:
+            temp_name[feat] = temp_name[feat] + "*" + k_info
+            temp_kernel.kernels[feat] = K.Product([temp_kernel.kernels[feat], new_kernel])
+        else:
+            temp_kernel.kernels[feat] = K.Product([new_kernel, temp_kernel.kernels[feat]])
+            later = [i for i, x in enumerate(temp_name) if k_info < x]
+            new_idx = later[0] if later else len(temp_name) - 1
+            cur_component_name = temp_name.pop(feat)
+            temp_name.insert(new_idx, k_info + "*" + cur_component_name)
+        name = "+".join(temp_name)
+        if check_if_model_exists(name, prev_models):
+            continue
+        out.append((name, temp_kernel))
+    return out
+
+
+def prod_kernel_creation(base_kernel, base_name, new_kernel, depth, prev_models=()):
+    """Generator form of :2561-2664 for callers that use it on its own."""
+    cands = prod_kernel_candidates(base_kernel, base_name, new_kernel, list(prev_models))
+    fitted = yield cands
+    return {name: _entry(k, m, bic, depth, base_name) for (name, k), (m, bic) in zip(cands, fitted) if m is not None}
+
+
+# ------------------------------------------------------------------------------------------------
+# selection
+# ------------------------------------------------------------------------------------------------
+def check_if_better_metric(model_dict, depth):
+    """:2667-2681"""
+    prev_vals = [x["bic"] for x in model_dict.values() if x["depth"] == depth - 1]
+    new_vals = [x["bic"] for x in model_dict.values() if x["depth"] == depth]
+    if len(prev_vals) > 0 and len(new_vals) > 0:
+        return min(new_vals) < min(prev_vals)
+    return False
+
+
+def keep_top_k(res_dict, depth, metric_diff=6, split=False):
+    """:2684-2710 — entries of this depth further than ``metric_diff`` from its best are not expanded."""
+    t = np.log(metric_diff) if split else metric_diff
+    best_bic = min(v["bic"] for v in res_dict.values() if v["depth"] == depth)
+    for v in res_dict.values():
+        if v["depth"] == depth and v["bic"] - best_bic > t:
+            v["try_next"] = False
+    return res_dict.copy()
+
+
+def _reset(k):
+    for p in k.trainable_parameters:
+        p.assign(1.0)
+    return k
+
+
+def _prune_prod_candidates(prod_kernel, prod_name, other_kernel=None, other_name="") -> List[Candidate]:
+    """Candidate list of :2888-2984 — each factor of a product component on its own (plus the other components)."""
+    other_kernel = K.deepcopy(other_kernel)
+    prod_kernel = K.deepcopy(prod_kernel)
+    kernel_parts = prod_name.split("*")
+    out: List[Candidate] = []
+    if prod_kernel.name != "product":
+        return out
+    for i in range(len(prod_kernel.kernels)):
+        if i >= len(kernel_parts):
+            break
+        new_piece = kernel_parts[i]
+        if other_name == "":
+            k_info, k = new_piece, prod_kernel.kernels[i]
+        else:
+            names = [other_name, new_piece]
+            order_set = sorted(range(2), key=lambda t: names[t])          # np.argsort of the two strings
+            k_info = "+".join(names[t] for t in order_set)
+            if not isinstance(other_kernel, list):
+                other_kernel = [other_kernel]
+            # the reference indexes ``np.array(other_kernel + [factor])`` with the length-2 permutation: with two or
+            # more other components only the first two entries survive (the factor itself is then not in the kernel)
+            pool = other_kernel + [prod_kernel.kernels[i]]
+            k = K.Sum([pool[t] for t in order_set])
+        out.append((k_info, _reset(K.deepcopy(k))))
+    return out
+
+
+def prune_prod_kernel(prod_kernel, prod_name, res_dict, best_bic, best_model_name, depth, other_kernel=None,
+                      other_name=""):
+    """:2888-2984 as a generator (one request with the factors that have not been fitted yet)."""
+    out_dict = res_dict.copy()
+    cands = [c for c in _prune_prod_candidates(prod_kernel, prod_name, other_kernel, other_name)
+             if not check_if_model_exists(c[0], list(res_dict.keys()))]
+    fitted = (yield cands) if cands else []
+    for (k_info, _k), (m, bic) in zip(cands, fitted):
+        if m is not None and bic < best_bic:
+            out_dict[k_info] = _entry(m.kernel, m, bic, depth, best_model_name)
+    return out_dict
+
+
+def prune_best_model2(res_dict, depth):
+    """:2778-2885 — leave-one-component-out refits of the best model of ``depth``; better ones join the dict.
+
+    All refits of one call are independent fits, so they are requested together; the bookkeeping is then replayed in
+    the reference's order (a product component's duplicate check sees what earlier components added)."""
+    best_bic, best_model_name, best_model = min(
+        ((i["bic"], k, i["model"]) for k, i in res_dict.items() if i["depth"] == depth), key=lambda t: (t[0], t[1]))
+    best_model = K.deepcopy(best_model)
+    kernel_names = re.split(r"\+", best_model_name)
+    if len(kernel_names) <= 1 and "*" not in kernel_names[0]:
+        return res_dict
+    model_kernels = list(getattr(best_model.kernel, "kernels", []))
+    plan = []           # (kind, candidates) per component, in order
+    for i in range(len(kernel_names)):
+        k_info = "+".join(x_ for i_, x_ in enumerate(kernel_names) if i_ != i)
+        kerns = [k_ for i_, k_ in enumerate(model_kernels) if i_ != i]
+        if "*" in kernel_names[i]:
+            if len(kernel_names) == 1:
+                prod_kernel, other_kernel, other_name = best_model.kernel, None, ""
+            elif i < len(model_kernels):
+                prod_kernel, other_kernel, other_name = model_kernels[i], kerns, k_info
+            else:
+                continue
+            plan.append(("prod", _prune_prod_candidates(prod_kernel, kernel_names[i], other_kernel, other_name)))
+            continue
+        if not kerns:
+            continue
+        k = K.Sum(kerns) if len(kerns) > 1 else kerns[0]
+        plan.append(("drop", [(k_info, _reset(K.deepcopy(k)))]))
+    known = list(res_dict.keys())
+    request = [c for _kind, cands in plan for c in cands if not check_if_model_exists(c[0], known)]
+    fitted = (yield request) if request else []
+    result = {id(c[1]): r for c, r in zip(request, fitted)}
+    out_dict = res_dict.copy()
+    for kind, cands in plan:
+        seen = list(res_dict.keys()) if kind == "drop" else list(out_dict.keys())
+        for k_info, k in cands:
+            if check_if_model_exists(k_info, seen) or id(k) not in result:
+                continue
+            m, bic = result[id(k)]
+            if m is not None and bic < best_bic:
+                out_dict[k_info] = _entry(m.kernel, m, bic, depth, best_model_name)
+    return out_dict
+
+
+def _best_of_depth(search_dict, d):
+    return min((i["bic"], i["depth"], k) for k, i in search_dict.items() if i["depth"] == d)[2]
+
+
+def full_kernel_search_gen(n_features, kern_list, cat_vars=(), max_depth=5, keep_all=False, metric_diff=6,
+                           early_stopping=True, prune=True, keep_only_best=True, softmax_select=False):
+    """:2987-3272 as a generator over fit requests; returns {"models", "edges", "best_model", "var_exp"}."""
+    if softmax_select:
+        raise NotImplementedError("softmax_select draws from np.random per outcome; not part of the batched search")
+    search_dict: Dict[str, dict] = {}
+    edge_list = []
+    for d in range(1, max_depth + 1):
+        if d == 1:
+            search_dict = yield from loc_kernel_search(n_features, kern_list, cat_vars=cat_vars, depth=d)
+        else:
+            bases = [k for k in search_dict.keys()
+                     if search_dict[k]["depth"] == d - 1 and search_dict[k]["try_next"] is not False and k != "constant"]
+            # The reference fits the expansions of one base kernel at a time and de-duplicates each against everything
+            # fitted so far.  Which candidates exist depends only on names unless a fit fails, so the whole level is
+            # generated ahead under the assumption that every fit succeeds and requested as ONE batch; the exact
+            # sequential bookkeeping below then finds its fits in the cache (and asks for more only after a failure).
+            cache, ahead, names_ahead = {}, [], list(search_dict.keys())
+            for k in bases:
+                cur_kern = search_dict[k]["kernel"]
+                for op in ("sum", "split_product" if cur_kern.name == "sum" else "product"):
+                    cs = loc_candidates(n_features, kern_list, cur_kern, k, cat_vars, d, op, names_ahead)
+                    ahead += cs
+                    names_ahead += [c[0] for c in cs]
+            if ahead:
+                got = yield ahead
+                for c, r in zip(ahead, got):
+                    cache.setdefault(c[0], (c[1], r))
+            temp_dict = search_dict.copy()
+            for k in bases:
+                cur_kern = search_dict[k]["kernel"]
+                new_res = yield from loc_kernel_search(n_features, kern_list, base_kern=cur_kern, base_name=k,
+                                                       cat_vars=cat_vars, depth=d, operation="sum",
+                                                       prev_models=temp_dict.keys(), cache=cache)
+                temp_dict.update(new_res)
+                edge_list += [(k, k_) for k_ in new_res.keys()]
+                op = "split_product" if cur_kern.name == "sum" else "product"
+                new_res = yield from loc_kernel_search(n_features, kern_list, base_kern=cur_kern, base_name=k,
+                                                       cat_vars=cat_vars, depth=d, operation=op,
+                                                       prev_models=temp_dict.keys(), cache=cache)
+                temp_dict.update(new_res)
+                edge_list += [(k, k_) for k_ in new_res.keys()]
+            search_dict = temp_dict
+        if not any(i["depth"] == d for i in search_dict.values()):
+            break          # (the reference raises on the empty min(); nothing left to expand)
+        best_model_name = _best_of_depth(search_dict, d)
+        if best_model_name == "constant":
+            break
+        if early_stopping and d > 1:
+            if not check_if_better_metric(search_dict, d):
+                if prune:
+                    search_dict = yield from prune_best_model2(search_dict, depth=d)
+                break
+        if d != max_depth and not keep_all:
+            search_dict = keep_top_k(search_dict, depth=d, metric_diff=metric_diff)
+        if prune:
+            search_dict = yield from prune_best_model2(search_dict, depth=d)
+    best_model_name = min((i["bic"], i["depth"], k) for k, i in search_dict.items())[2]
+    if keep_only_best:
+        search_dict = {best_model_name: search_dict[best_model_name]}
+    return {"models": search_dict, "edges": edge_list, "best_model": best_model_name, "var_exp": None}
+
+
+# ------------------------------------------------------------------------------------------------
+# execution: fitters and the lock-step driver
+# ------------------------------------------------------------------------------------------------
+def candidate_model(kernel, mean_function=None) -> GPR:
+    """The model ``kernel_test`` builds (:2269-2282): penalisation 0 (no prior), Gaussian noise 1.0, constant mean.
+    The model owns deep copies (BaseGP.__init__, waveome/model_classes.py:110-111)."""
+    return GPR(K.deepcopy(kernel), mean_function=K.deepcopy(mean_function) if mean_function is not None else ConstantMean())
+
+
+def candidate_bic(model: GPR, log_posterior_density: float) -> float:
+    """:2311-2321 — round(2 k - 2 log p, 2), k = number of trainable Parameter objects."""
+    return round(calc_bic(loglik=log_posterior_density, n=0, k=len(model.trainable_parameters)), 2)
+
+
+def engine_fitter(X: np.ndarray, engine=None, num_restart=1, random_seed=None, max_iter=50000) -> Callable:
+    """Returns ``fit(requests) -> results`` where requests is a list of (y [n], name, kernel): all of them become one
+    engine batch (restarts included: ``num_restart`` > 1 adds randomised starts as extra models of the batch,
+    waveome/model_classes.py:472-524, seeds ``random_seed + 1 + r`` or ``r``)."""
+    from .model_fitting import fit_models
+
+    def fit(requests):
+        if not requests:
+            return []
+        R = max(1, int(num_restart))
+        models, ys = [], []
+        for y, _name, kernel in requests:
+            for r in range(R):
+                m = candidate_model(kernel)
+                if R > 1:
+                    rs = np.random.RandomState(r if random_seed is None else random_seed + 1 + r)
+                    for p in m.trainable_parameters:
+                        p.assign(p.transform_fn(rs.normal(loc=0.0, scale=1.0)))
+                models.append(m)
+                ys.append(y)
+        res = fit_models(X, np.stack(ys), models, engine=engine, maxiter=max_iter, maxfun=max_iter)
+        out = []
+        for i in range(len(requests)):
+            best, best_lpd = None, -np.inf
+            for r in range(R):
+                b = i * R + r
+                ok = not (int(res["status"][b]) & 1) and np.isfinite(res["f"][b])
+                if ok and -float(res["f"][b]) > best_lpd:
+                    best, best_lpd = models[b], -float(res["f"][b])
+            out.append((None, np.inf) if best is None else (best, candidate_bic(best, best_lpd)))
+        return out
+
+    return fit
+
+
+def run_lockstep(searches: Dict[str, object], ys: Dict[str, np.ndarray], fit: Callable) -> Dict[str, dict]:
+    """Advance the search generators of many outcomes together: the requests they are waiting on are fitted as one
+    batch per round.  ``searches``: outcome -> generator; ``ys``: outcome -> y [n]."""
+    waiting, done = {}, {}
+    for o, g in searches.items():
+        try:
+            waiting[o] = next(g)
+        except StopIteration as e:
+            done[o] = e.value
+    rounds = 0
+    while waiting:
+        flat, owner = [], []
+        for o, cands in waiting.items():
+            for name, k in cands:
+                flat.append((ys[o], name, k))
+                owner.append(o)
+        results = fit(flat)
+        rounds += 1
+        pos = 0
+        nxt = {}
+        for o, cands in waiting.items():
+            r = results[pos: pos + len(cands)]
+            pos += len(cands)
+            try:
+                nxt[o] = searches[o].send(r)
+            except StopIteration as e:
+                done[o] = e.value
+        waiting = nxt
+    for v in done.values():
+        v["batches"] = rounds
+    return done
+
+
+def _drive_single(gen, y, fit):
+    return run_lockstep({"_": gen}, {"_": y}, fit)["_"]
+
+
+def kernel_test(X, Y, k, mean_function=None, num_restart=5, random_init=True, random_seed=None, verbose=False,
+                likelihood="gaussian", engine=None, keep_data=False, **unused):
+    """Drop-in for :2239-2334 on the Gaussian path: (fitted model, bic)."""
+    if likelihood != "gaussian":
+        raise NotImplementedError("kernel_test on the engine covers likelihood='gaussian'")
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(Y, dtype=np.float64).reshape(-1)
+    fit = engine_fitter(X, engine=engine, num_restart=num_restart if random_init else 1, random_seed=random_seed)
+    (m, bic), = fit([(y, "", k)])
+    if m is None:
+        raise RuntimeError("kernel_test: the fit failed (Cholesky failure or non-finite objective at the start point)")
+    if verbose:
+        from .utilities import print_kernel_names
+        print(f"Model: {print_kernel_names(k)}, BIC: {bic}")
+    m.data = (X, y.reshape(-1, 1)) if keep_data else None
+    return m, bic
+
+
+def full_kernel_search(X, Y, kern_list, cat_vars=(), max_depth=5, keep_all=False, metric_diff=6, early_stopping=True,
+                       prune=True, num_restart=5, lik="gaussian", verbose=False, debug=False, keep_only_best=True,
+                       softmax_select=False, random_seed=None, feature_name=None, engine=None, fit=None, **unused):
+    """Drop-in for :2987-3272 (one outcome).  ``fit`` overrides the engine fitter (the tests pass the CPU oracle)."""
+    if lik != "gaussian":
+        raise NotImplementedError("full_kernel_search on the engine covers lik='gaussian'")
+    if random_seed is not None:
+        np.random.seed(random_seed)
+    Xn = X.to_numpy() if hasattr(X, "to_numpy") else np.asarray(X)
+    Xn = np.asarray(Xn, dtype=np.float64).reshape(len(Xn), -1)
+    if hasattr(Y, "to_numpy"):
+        Yn = (Y if feature_name is None else Y[feature_name]).to_numpy()
+    else:
+        Yn = np.asarray(Y)
+    y = np.asarray(Yn, dtype=np.float64).reshape(-1)
+    ok = ~np.isnan(Xn).any(axis=1) & ~np.isnan(y)
+    Xn, y = Xn[ok], y[ok]
+    fit = fit or engine_fitter(Xn, engine=engine, num_restart=num_restart, random_seed=random_seed)
+    gen = full_kernel_search_gen(Xn.shape[1], kern_list, cat_vars=cat_vars, max_depth=max_depth, keep_all=keep_all,
+                                 metric_diff=metric_diff, early_stopping=early_stopping, prune=prune,
+                                 keep_only_best=keep_only_best, softmax_select=softmax_select)
+    return _drive_single(gen, y, fit)

@@ -172,3 +172,64 @@ class GPSearch:
         self.models = local
         self.fit_report = report
         return None
+
+    # ------------------------------------------------------------------------------------------
+    def run_search(self, kernels=None, max_depth=5, early_stopping=True, prune=True, keep_all=False, metric_diff=6,
+                   num_restart=1, random_seed=None, num_jobs=-1, verbose=False, debug=False, gather=True, fit=None):
+        """Greedy compositional kernel search per outcome (waveome/model_search.py:1069-1250 -> full_kernel_search
+        :2987-3272).  The searches of all outcomes (of this rank's shard) advance in lock-step; at every step the
+        candidate kernels they ask for are fitted as ONE engine batch (kernel_search.run_lockstep).
+        ``self.models[outcome]`` = best model, ``self.search_info[outcome]`` = {"models", "edges", "best_model"}.
+        ``num_jobs`` is accepted for signature compatibility.  ``fit`` replaces the engine fitter (tests)."""
+        from . import kernel_search as ks
+        if self.likelihood != "gaussian":
+            raise NotImplementedError("the B200 engine covers outcome_likelihood='gaussian' (objective A)")
+        self.model_selection_type = "stepwise"
+        self.verbose = verbose
+        if kernels is None:
+            kernels = [K.SquaredExponential(), K.Matern12(), K.Lin(), K.Periodic(K.SquaredExponential())]
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        rank, world = _rank_world()
+        lo, hi = shard_bounds(len(self.out_names), rank, world)
+        names = self.out_names[lo:hi]
+        t0 = time.time()
+        Xn = self.X.to_numpy(dtype=np.float64)
+        ys = {o: np.ascontiguousarray(self.Y[o].to_numpy(dtype=np.float64)) for o in names}
+        if verbose and rank == 0:
+            print(f"Building {len(self.out_names)} models on {world} GPU(s)...")
+        counters = dict(fits=0, batches=0)
+        inner = fit or ks.engine_fitter(Xn, num_restart=num_restart, random_seed=random_seed)
+
+        def counted(requests):
+            counters["fits"] += len(requests) * max(1, int(num_restart))
+            counters["batches"] += 1
+            return inner(requests)
+
+        gens = {o: ks.full_kernel_search_gen(Xn.shape[1], kernels, cat_vars=self.cat_idx, max_depth=max_depth,
+                                             keep_all=keep_all, metric_diff=metric_diff,
+                                             early_stopping=early_stopping, prune=prune) for o in names}
+        info = ks.run_lockstep(gens, ys, counted)
+        local_models, local_info = {}, {}
+        for o in names:
+            best = info[o]["models"][info[o]["best_model"]]["model"]
+            best.update_kernel_name() if hasattr(best, "update_kernel_name") else None
+            from .utilities import kernel_name_string
+            best.kernel_name = kernel_name_string(best.kernel, with_idx=True)
+            best.search_name = info[o]["best_model"]
+            local_models[o] = best
+            local_info[o] = info[o]
+        report = dict(n_models=len(names), seconds=time.time() - t0, n_fits=counters["fits"], batches=counters["batches"])
+        if world > 1 and gather:
+            import torch.distributed as dist
+            parts = [None] * world
+            dist.all_gather_object(parts, (local_models, {o: dict(best_model=v["best_model"], edges=v["edges"])
+                                                          for o, v in local_info.items()}))
+            local_models, local_info = {}, {}
+            for pm, pi in parts:
+                local_models.update(pm)
+                local_info.update(pi)
+        self.models = local_models
+        self.search_info = local_info
+        self.fit_report = report
+        return None
