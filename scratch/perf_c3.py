@@ -19,6 +19,7 @@ t0 = time.time()
 bt = Batch(eng, Xs.to_numpy(), Ys.to_numpy().T.copy(), [m.program()])
 print("batch create %.2fs workspace %.2f GB" % (time.time() - t0, bt.workspace_bytes / 1e9), flush=True)
 x = bt.x0()
+bt.profile(True)
 st = torch.cuda.ExternalStream(eng.stream)
 for it in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,6 +30,8 @@ for it in range(3):
         e1.record(st)
     torch.cuda.synchronize()
     print("eval %d: wall %.2f ms, device %.2f ms; status!=0: %d; f[0]=%.6f" % (it, (time.time() - t0) * 1e3, e0.elapsed_time(e1), int((s != 0).sum()), f[0]), flush=True)
+print("per-class ms/eval:", {k_: round(v[0] / 3, 2) for k_, v in bt.profile_read().items() if v[0] > 0})
+bt.profile(False)
 n = 600
 print("per-eval flops (n^3) GF: %.1f -> %.2f TFLOP/s" % (B * n**3 / 1e9, B * n**3 / (e0.elapsed_time(e1) * 1e-3) / 1e12))
 if do_fit:

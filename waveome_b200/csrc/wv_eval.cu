@@ -12,103 +12,7 @@ __device__ long long wv_dbg_clk[64];
 #define WV_CLK(i) do { } while (0)
 #endif
 
-// =============================================================================================
-// gram: lower tiles of K + sigma^2 I, RHS row, identity padding.
-// grid (n_lower_tiles, n_active), 256 threads, each thread a 4x4 micro-tile.
-// Algorithmic traffic: 8 n^2 bytes written (lower half + diagonal tiles actually written: ~4 n^2).
-// =============================================================================================
-struct WvElemSmem {
-  WvProgram pg;
-  double theta[WV_MAX_SLOTS];
-  double xr[WV_MAX_DIMS][WV_NB];
-  double xc[WV_MAX_DIMS][WV_NB];
-  double red[WV_MAX_SLOTS][8];   // per-warp partial sums (grad only)
-};
-
-__device__ __forceinline__ void wv_elem_prologue(const WvBatchDev& bd, int b, int ti, int tj, const double* xall,
-                                                 WvElemSmem& sm) {
-  const WvProgram* gp = bd.programs + bd.prog_id[b];
-  const int nwords = sizeof(WvProgram) / 4;
-  const int32_t* src = reinterpret_cast<const int32_t*>(gp);
-  int32_t* dst = reinterpret_cast<int32_t*>(&sm.pg);
-  for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
-  __syncthreads();
-  wv_load_theta(&sm.pg, xall + (size_t)b * bd.P, sm.theta);
-  for (int i = threadIdx.x; i < sm.pg.n_dims * WV_NB; i += blockDim.x) {
-    int d = i / WV_NB, r = i % WV_NB;
-    const double* col = bd.Xt + (size_t)sm.pg.dims[d] * bd.npad;
-    sm.xr[d][r] = col[ti * WV_NB + r];
-    sm.xc[d][r] = col[tj * WV_NB + r];
-  }
-  __syncthreads();
-}
-
-// thread -> micro-tile mapping: warp w owns the compact 16x32 region rows (w>>1)*16.., cols (w&1)*32..; lane l the
-// 4x4 micro-tile at (+ (l>>3)*4, + (l&7)*4).  Compact warp regions make "the categorical mask is zero for the whole
-// warp" common once the rows are sorted by their categorical columns (wv_batch_create does that).
-__device__ __forceinline__ void wv_elem_coords(int& r_off, int& c_off, bool& above_diag, bool diag_tile) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = (warp >> 1) * 16, wc = (warp & 1) * 32;
-  r_off = wr + (lane >> 3) * 4;
-  c_off = wc + (lane & 7) * 4;
-  above_diag = diag_tile && wc > wr + 15;     // every element of the warp's region has col > row
-}
-
-__global__ void __launch_bounds__(WV_ELEM_THREADS) wv_gram_kernel(WvBatchDev bd, const int* __restrict__ active,
-                                                                  const double* __restrict__ xall) {
-  WvElemSmem& sm = *reinterpret_cast<WvElemSmem*>(wv_smem_raw);
-  const int b = active[blockIdx.y];
-  int ti, tj;
-  wv_tile_from_linear(blockIdx.x, ti, tj);
-  wv_elem_prologue(bd, b, ti, tj, xall, sm);
-  int r_off, c_off;
-  bool above;
-  wv_elem_coords(r_off, c_off, above, ti == tj);
-  if (above) return;                            // the strict upper part of a diagonal tile is never read
-  const int n = bd.n;
-  double acc[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
-  for (int c = 0; c < sm.pg.n_comp; ++c) {
-    double prod[16];
-    const int l0 = sm.pg.comp_start[c], l1 = sm.pg.comp_start[c + 1];
-    bool skip = false;
-    for (int l = l0; l < l1; ++l) {
-      const WvLeaf lf = sm.pg.leaves[l];
-      if (l > l0 && !wv_leaf_is_cheap(lf.type) && wv_warp_all_zero(prod)) { skip = true; break; }
-      double xi[4], xj[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lf.dim][r_off + a]; xj[a] = sm.xc[lf.dim][c_off + a]; }
-      if (l == l0) wv_leaf_mul<true>(lf, sm.theta, xi, xj, prod);
-      else wv_leaf_mul<false>(lf, sm.theta, xi, xj, prod);
-    }
-    if (!skip) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) acc[e] += prod[e];
-    }
-  }
-  const double s2 = sm.theta[sm.pg.noise_slot];
-  const double cmean = sm.pg.mean_slot >= 0 ? sm.theta[sm.pg.mean_slot] : 0.0;
-  double* Ab = bd.A + (size_t)b * bd.npad * bd.npad;
-  const double* yb = bd.Y + (size_t)b * bd.npad;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int gi = ti * WV_NB + r_off + a;
-    double out[4];
-#pragma unroll
-    for (int bb = 0; bb < 4; ++bb) {
-      const int gj = tj * WV_NB + c_off + bb;
-      double v;
-      if (gi < n && gj < n) v = acc[a * 4 + bb] + (gi == gj ? s2 : 0.0);
-      else if (gi == n && gj < n) v = yb[gj] - cmean;     // RHS row d^T
-      else v = (gi == gj) ? 1.0 : 0.0;                     // identity padding (incl. A[n][n] = 1)
-      out[bb] = v;
-    }
-    double2* dst = reinterpret_cast<double2*>(Ab + (size_t)gi * bd.npad + tj * WV_NB + c_off);
-    dst[0] = make_double2(out[0], out[1]);
-    dst[1] = make_double2(out[2], out[3]);
-  }
-}
+#include "wv_elem.cuh"   // wv_gram_kernel, wv_grad_kernel
 
 // =============================================================================================
 // chol_diag(j): T = A[j,j] - sum_{k0<=k<j} L[j,k] L[j,k]^T ; L_jj = chol(T) ; Linv_jj = L_jj^{-1}
@@ -755,103 +659,6 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_trtri_level_kernel(WvBatch
 }
 
 // =============================================================================================
-// grad: partial[b][tile][slot] = sum over the tile of wgt_ij * W_ij * dK_ij/dtheta_slot,
-//   W = alpha alpha^T - K^{-1};  wgt = 2 below the diagonal, 1 on it, 0 above / outside [0,n).
-// dK/dtheta is regenerated from the kernel program; nothing of size n^2 is materialised.
-// grid (n_lower_tiles, n_active), 256 threads.  Algorithmic traffic: 8 n^2 bytes read.
-// =============================================================================================
-__global__ void __launch_bounds__(WV_ELEM_THREADS) wv_grad_kernel(WvBatchDev bd, const int* __restrict__ active,
-                                                                  const double* __restrict__ xall) {
-  WvElemSmem& sm = *reinterpret_cast<WvElemSmem*>(wv_smem_raw);
-  const int b = active[blockIdx.y];
-  int ti, tj;
-  wv_tile_from_linear(blockIdx.x, ti, tj);
-  wv_elem_prologue(bd, b, ti, tj, xall, sm);
-  int r_off, c_off;
-  bool above;
-  wv_elem_coords(r_off, c_off, above, ti == tj);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = bd.n, ld = bd.npad;
-  for (int i = threadIdx.x; i < WV_MAX_SLOTS * 8; i += blockDim.x) (&sm.red[0][0])[i] = 0.0;
-  __syncthreads();
-  if (!above) {
-    const double* Kb = bd.A + (size_t)b * ld * ld;
-    const double* al = bd.alpha + (size_t)b * ld;
-    double w[16];
-    double trw = 0.0;
-    double aj[4];
-#pragma unroll
-    for (int bb = 0; bb < 4; ++bb) aj[bb] = al[tj * WV_NB + c_off + bb];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int gi = ti * WV_NB + r_off + a;
-      const double2* src = reinterpret_cast<const double2*>(Kb + (size_t)gi * ld + tj * WV_NB + c_off);
-      double2 k01 = src[0], k23 = src[1];
-      double kin[4] = {k01.x, k01.y, k23.x, k23.y};
-      const double ai = al[gi];
-#pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
-        const int gj = tj * WV_NB + c_off + bb;
-        const double wv = ai * aj[bb] - kin[bb];
-        const bool in = gi < n && gj < n;
-        w[a * 4 + bb] = in ? (gi > gj ? 2.0 * wv : (gi == gj ? wv : 0.0)) : 0.0;
-        if (gi == gj && gi < n) trw += wv;
-      }
-    }
-    for (int c = 0; c < sm.pg.n_comp; ++c) {
-      const int l0 = sm.pg.comp_start[c], l1 = sm.pg.comp_start[c + 1];
-      for (int l = l0; l < l1; ++l) {
-        const WvLeaf lf = sm.pg.leaves[l];
-        const bool tv = lf.s_var >= 0 && sm.pg.slots[lf.s_var].xindex >= 0;
-        const bool tl = lf.s_ls >= 0 && sm.pg.slots[lf.s_ls].xindex >= 0;
-        const bool ta = lf.s_aux >= 0 && sm.pg.slots[lf.s_aux].xindex >= 0;
-        if (!(tv || tl || ta)) continue;
-        double wo[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) wo[e] = w[e];
-        bool skip = false;
-        for (int l2 = l0; l2 < l1; ++l2) {
-          if (l2 == l) continue;
-          const WvLeaf lo = sm.pg.leaves[l2];
-          if (!wv_leaf_is_cheap(lo.type) && wv_warp_all_zero(wo)) { skip = true; break; }
-          double xi[4], xj[4];
-#pragma unroll
-          for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lo.dim][r_off + a]; xj[a] = sm.xc[lo.dim][c_off + a]; }
-          wv_leaf_mul<false>(lo, sm.theta, xi, xj, wo);
-        }
-        if (skip || (!wv_leaf_is_cheap(lf.type) && wv_warp_all_zero(wo))) continue;   // every contribution is zero
-        double xi[4], xj[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { xi[a] = sm.xr[lf.dim][r_off + a]; xj[a] = sm.xc[lf.dim][c_off + a]; }
-        double sv, sl, sa;
-        wv_leaf_grad_sums(lf, sm.theta, xi, xj, wo, sv, sl, sa);
-        for (int o = 16; o > 0; o >>= 1) {
-          sv += __shfl_xor_sync(0xffffffffu, sv, o);
-          sl += __shfl_xor_sync(0xffffffffu, sl, o);
-          sa += __shfl_xor_sync(0xffffffffu, sa, o);
-        }
-        if (lane == 0) {   // several leaves may share a slot: accumulate (warp-private column, no race)
-          if (tv) sm.red[lf.s_var][warp] += sv;
-          if (tl) sm.red[lf.s_ls][warp] += sl;
-          if (ta) sm.red[lf.s_aux][warp] += sa;
-        }
-      }
-    }
-    for (int o = 16; o > 0; o >>= 1) trw += __shfl_xor_sync(0xffffffffu, trw, o);
-    if (lane == 0) sm.red[sm.pg.noise_slot][warp] += trw;
-  }
-  __syncthreads();
-  const int ntiles = gridDim.x;
-  double* dst = bd.partial + ((size_t)b * ntiles + blockIdx.x) * bd.n_slots_max;
-  for (int s = threadIdx.x; s < sm.pg.n_slots; s += blockDim.x) {
-    double t = 0.0;
-#pragma unroll
-    for (int wq = 0; wq < 8; ++wq) t += sm.red[s][wq];
-    dst[s] = t;
-  }
-}
-
-// =============================================================================================
 // finalize: f = -(LML + log prior), df/dx; status bits.  grid (n_active), 64 * G threads: thread (g, s) sums the
 // per-tile partials of slot s over tiles t = g mod G (fixed order), the G group sums are added in fixed order.
 // G = 1 up to 128 tiles; the large-n path (thousands of tiles per model) uses G = 16.
@@ -1005,7 +812,8 @@ int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, con
   if (!pf) pf = &none;
   cudaMemsetAsync(bd.chol_fail, 0, sizeof(int) * bd.B, st);
   pf->mark(-1, st);
-  wv_gram_kernel<<<dim3(ntiles, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(bd, d_active, d_x);
+  wv_gram_kernel<<<dim3((ntiles + WV_ELEM_TPC - 1) / WV_ELEM_TPC, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
+      bd, d_active, d_x, ntiles);
   pf->mark(WV_K_GRAM, st);
   ++launches;
   if (!aux) return -1;
@@ -1025,7 +833,8 @@ int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, con
   pf->mark(WV_K_EXTRACT, st);
   wv_kinv_kernel<<<dim3(ntiles, n_active), WV_GEMM_THREADS, sizeof(WvGemmSmem), st>>>(bd, d_active);
   pf->mark(WV_K_KINV, st);
-  wv_grad_kernel<<<dim3(ntiles, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(bd, d_active, d_x);
+  wv_grad_kernel<<<dim3((ntiles + WV_ELEM_TPC - 1) / WV_ELEM_TPC, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
+      bd, d_active, d_x, ntiles);
   pf->mark(WV_K_GRAD, st);
   wv_finalize_kernel<<<dim3(n_active), ntiles > 128 ? 64 * WV_FIN_MAXG : 64, 0, st>>>(bd, d_active, d_x, ntiles, d_f, d_g,
                                                                                   d_lml, d_status);

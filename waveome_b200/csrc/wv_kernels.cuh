@@ -125,32 +125,8 @@ __device__ __forceinline__ void wv_load_theta(const WvProgram* __restrict__ pg, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel-tree leaves on a 4x4 micro-tile  (waveome/kernels.py)
+// helpers of the kernel-tree leaves (the leaves themselves live in wv_elem.cuh)
 // ---------------------------------------------------------------------------------------------
-// Squared distance as gpflow.utilities.ops.square_distance on a = x / ell:  -2 a_i a_j + (a_i^2 + a_j^2).
-// The coordinates are scaled with one reciprocal per leaf (x * (1/ell)); mi = -2 a_i, si = a_i^2, sj = a_j^2 are
-// hoisted out of the pair loop so that a pair costs one DADD + one DFMA.  On the diagonal the result is within one
-// rounding of a^2 of zero, so exp(-r2/2) is exactly 1.
-struct WvScaled {
-  double mi[4], si[4], aj[4], sj[4];
-};
-__device__ __forceinline__ void wv_scale(const double (&xi)[4], const double (&xj)[4], double ell, WvScaled& s) {
-  const double inv = 1.0 / ell;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const double ai = xi[a] * inv, aj = xj[a] * inv;
-    s.mi[a] = -2.0 * ai; s.si[a] = ai * ai; s.aj[a] = aj; s.sj[a] = aj * aj;
-  }
-}
-__device__ __forceinline__ double wv_r2(const WvScaled& s, int a, int b) {
-  return fma(s.mi[a], s.aj[b], s.si[a] + s.sj[b]);
-}
-// Matern kernels take sqrt(max(r2, 1e-36)): the diagonal must be EXACTLY zero as in GPflow (a fused product leaves
-// ~1e-17, i.e. r ~ 3e-9 instead of 1e-18), so the product is rounded separately there.
-__device__ __forceinline__ double wv_r2_exact(const WvScaled& s, int a, int b) {
-  return __dadd_rn(__dmul_rn(s.mi[a], s.aj[b]), __dadd_rn(s.si[a], s.sj[b]));
-}
-
 __device__ __forceinline__ double wv_powi(double b, int d) {
   double r = 1.0;
   for (int i = 0; i < d; ++i) r *= b;
@@ -161,196 +137,6 @@ __device__ __forceinline__ double wv_powi(double b, int d) {
 // categorical mask can skip the expensive factors (the encoder orders the leaves of a component this way).
 __device__ __forceinline__ bool wv_leaf_is_cheap(int type) {
   return type == WV_LEAF_CAT || type == WV_LEAF_CONST || type == WV_LEAF_LINEAR || type == WV_LEAF_EMPTY;
-}
-
-// prod[e] = (FIRST ? 1 : prod[e]) * k(x_i[a], x_j[b]),  e = a*4+b
-template <bool FIRST>
-__device__ __forceinline__ void wv_leaf_mul(const WvLeaf& lf, const double* theta, const double (&xi)[4],
-                                            const double (&xj)[4], double (&prod)[16]) {
-  const double var = lf.s_var >= 0 ? theta[lf.s_var] : 1.0;
-#define WV_PUT(e, v) prod[e] = FIRST ? (v) : prod[e] * (v)
-  switch (lf.type) {
-    case WV_LEAF_SE: {
-      WvScaled s;
-      wv_scale(xi, xj, theta[lf.s_ls], s);
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) WV_PUT(a * 4 + b, var * exp(-0.5 * wv_r2(s, a, b)));
-    } break;
-    case WV_LEAF_M12:
-    case WV_LEAF_M32:
-    case WV_LEAF_M52: {
-      WvScaled s;
-      wv_scale(xi, xj, theta[lf.s_ls], s);
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          double r = sqrt(fmax(wv_r2_exact(s, a, b), 1e-36));
-          double e;
-          if (lf.type == WV_LEAF_M12) e = exp(-r);
-          else if (lf.type == WV_LEAF_M32) { double q = 1.7320508075688772 * r; e = (1.0 + q) * exp(-q); }
-          else { double q = 2.23606797749979 * r; e = (1.0 + q + 5.0 / 3.0 * r * r) * exp(-q); }
-          WV_PUT(a * 4 + b, var * e);
-        }
-    } break;
-    case WV_LEAF_PERIODIC: {
-      const double ell = theta[lf.s_ls], per = theta[lf.s_aux];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          double arg = 3.141592653589793 * (xi[a] - xj[b]) / per;
-          double ss = sin(arg) / ell;
-          WV_PUT(a * 4 + b, var * exp(-0.5 * (ss * ss)));
-        }
-    } break;
-    case WV_LEAF_LINEAR:
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) WV_PUT(a * 4 + b, var * (xi[a] * xj[b]));
-      break;
-    case WV_LEAF_CONST:
-#pragma unroll
-      for (int e = 0; e < 16; ++e) WV_PUT(e, var);
-      break;
-    case WV_LEAF_CAT: {
-      double ci[4], cj[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) { ci[a] = rint(xi[a]); cj[a] = rint(xj[a]); }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) WV_PUT(a * 4 + b, ci[a] == cj[b] ? var : 0.0);
-    } break;
-    case WV_LEAF_POLY: {
-      const double off = theta[lf.s_ls];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) WV_PUT(a * 4 + b, wv_powi(var * (xi[a] * xj[b]) + off, lf.degree));
-    } break;
-    default:
-#pragma unroll
-      for (int e = 0; e < 16; ++e) WV_PUT(e, 0.0);
-      break;
-  }
-#undef WV_PUT
-}
-
-// gradient sums of one leaf over the micro-tile: s_* = sum_e wo[e] * d k_e / d theta_*
-// (wo = W weight times the product of the other leaves of the component)
-__device__ __forceinline__ void wv_leaf_grad_sums(const WvLeaf& lf, const double* theta, const double (&xi)[4],
-                                                  const double (&xj)[4], const double (&wo)[16], double& s_var,
-                                                  double& s_ls, double& s_aux) {
-  s_var = 0.0; s_ls = 0.0; s_aux = 0.0;
-  const double var = lf.s_var >= 0 ? theta[lf.s_var] : 1.0;
-  switch (lf.type) {
-    case WV_LEAF_SE: {
-      const double ell = theta[lf.s_ls];
-      WvScaled s;
-      wv_scale(xi, xj, ell, s);
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const double r2 = wv_r2(s, a, b);
-          const double t = wo[a * 4 + b] * exp(-0.5 * r2);
-          s_var += t;
-          s_ls = fma(t, r2, s_ls);
-        }
-      s_ls *= var / ell;
-    } break;
-    case WV_LEAF_M12:
-    case WV_LEAF_M32:
-    case WV_LEAF_M52: {
-      const double ell = theta[lf.s_ls];
-      WvScaled s;
-      wv_scale(xi, xj, ell, s);
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const double w = wo[a * 4 + b];
-          const double r2 = wv_r2_exact(s, a, b);
-          const double r = sqrt(fmax(r2, 1e-36));
-          double e, de;  // de = dE/dr
-          if (lf.type == WV_LEAF_M12) { e = exp(-r); de = -e; }
-          else if (lf.type == WV_LEAF_M32) {
-            double q = 1.7320508075688772 * r, ex = exp(-q);
-            e = (1.0 + q) * ex; de = -3.0 * r * ex;
-          } else {
-            double q = 2.23606797749979 * r, ex = exp(-q);
-            e = (1.0 + q + 5.0 / 3.0 * r * r) * ex; de = -(5.0 / 3.0) * r * (1.0 + q) * ex;
-          }
-          s_var += w * e;
-          if (r2 > 1e-36) s_ls += w * de * (-r);
-        }
-      s_ls *= var / ell;
-    } break;
-    case WV_LEAF_PERIODIC: {
-      const double ell = theta[lf.s_ls], per = theta[lf.s_aux];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const double w = wo[a * 4 + b];
-          double arg = 3.141592653589793 * (xi[a] - xj[b]) / per;
-          double sn, cs;
-          sincos(arg, &sn, &cs);
-          double ss = sn / ell;
-          double r2 = ss * ss;
-          double t = w * exp(-0.5 * r2);
-          s_var += t;
-          s_ls = fma(t, r2, s_ls);
-          s_aux += t * (ss * cs) * arg;
-        }
-      s_ls *= var / ell;
-      s_aux *= var / (ell * per);
-    } break;
-    case WV_LEAF_LINEAR:
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) s_var += wo[a * 4 + b] * (xi[a] * xj[b]);
-      break;
-    case WV_LEAF_CONST:
-#pragma unroll
-      for (int e = 0; e < 16; ++e) s_var += wo[e];
-      break;
-    case WV_LEAF_CAT: {
-      double ci[4], cj[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) { ci[a] = rint(xi[a]); cj[a] = rint(xj[a]); }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) s_var += ci[a] == cj[b] ? wo[a * 4 + b] : 0.0;
-    } break;
-    case WV_LEAF_POLY: {
-      const double off = theta[lf.s_ls];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          double xx = xi[a] * xj[b];
-          double db = lf.degree * wv_powi(var * xx + off, lf.degree - 1);
-          s_var += wo[a * 4 + b] * db * xx;
-          s_ls += wo[a * 4 + b] * db;
-        }
-    } break;
-    default: break;
-  }
-}
-
-// warp-uniform test "every entry of v is zero in every lane" (NaN counts as non-zero)
-__device__ __forceinline__ bool wv_warp_all_zero(const double (&v)[16]) {
-  bool nz = false;
-#pragma unroll
-  for (int e = 0; e < 16; ++e) nz |= (v[e] != 0.0);
-  return !__any_sync(0xffffffffu, nz);
 }
 
 // ---------------------------------------------------------------------------------------------

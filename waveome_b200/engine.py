@@ -15,7 +15,8 @@ import numpy as np
 
 from .program import Program
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libwaveome_b200.so")
+_LIB_PATH = os.environ.get("WAVEOME_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
+                                                              "libwaveome_b200.so")
 
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)
