@@ -120,6 +120,14 @@ int wv_batch_eval_device(wv_batch* b, const double* d_x, double* d_f, double* d_
 int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* opts, double* f, double* lml,
                        int32_t* n_iter, int32_t* n_eval, int32_t* status);
 
+/* Post-fit quantities of the last evaluation (wv_batch_eval / wv_batch_eval_device / the final evaluation of
+ * wv_batch_fit_lbfgs): alpha = (K + sigma^2 I)^{-1} (y - c), HOST [B, n] in the caller's row order, and the posterior
+ * mean of every model at new inputs, mean[b][i] = c_b + sum_j k_b(xnew_i, x_j) alpha_b[j]  (gpflow GPR.predict_f mean,
+ * which waveome/utilities.py:614-707 calc_feature_importance_components and :710-974 consume).
+ * Xnew HOST [m, D] row-major, mean HOST [B, m].  At the training inputs the mean is y - sigma^2 alpha. */
+int wv_batch_get_alpha(wv_batch* b, double* alpha);
+int wv_batch_predict_mean(wv_batch* b, const double* Xnew, int32_t m, double* mean);
+
 /* counters since batch creation: kernels launched, batched evaluation rounds, model evaluations */
 void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t* rounds, int64_t* model_evals);
 

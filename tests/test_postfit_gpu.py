@@ -1,0 +1,99 @@
+"""Post-fit quantities on the engine vs the oracle's arithmetic: alpha, posterior means at training and new inputs,
+feature importances (waveome/utilities.py:614-707)."""
+import copy
+
+import numpy as np
+import pytest
+
+import gp_oracle as oracle
+import helpers
+import waveome_b200 as wb
+from waveome_b200 import postfit
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_alpha_mean(model, X, y, Xnew=None):
+    spec = copy.deepcopy(model.to_spec())
+    K, _ = oracle.kernel_K_and_grads(spec["kernel"], X, want_grads=False)
+    s2 = spec["likelihood_variance"]["value"]
+    c = spec["mean"]["c"]["value"] if spec["mean"]["type"] == "constant" else 0.0
+    alpha = np.linalg.solve(K + s2 * np.eye(len(y)), y - c)
+    if Xnew is None:
+        return alpha, c + K @ alpha
+    Kall, _ = oracle.kernel_K_and_grads(spec["kernel"], np.vstack([Xnew, X]), want_grads=False)
+    return alpha, c + Kall[: len(Xnew), len(Xnew):] @ alpha
+
+
+@pytest.mark.parametrize("n,m", [(50, 7), (150, 64), (333, 130)])
+def test_alpha_and_predict_mean(engine, n, m):
+    from waveome_b200.engine import Batch
+    X, y = helpers.make_data(n, seed=n)
+    rng = np.random.default_rng(n)
+    Xnew = X[rng.integers(0, n, size=m)].copy()
+    Xnew[:, 1:3] += 0.3 * rng.normal(size=(m, 2))
+    for kern in (helpers.all_leaf_kernel(), helpers.saturated_kernel()):
+        model = wb.GPR(kern, mean_function=wb.ConstantMean(0.2), noise_variance=0.3)
+        batch = Batch(engine, X, np.stack([y, -y]), [model.program()])
+        batch.eval(batch.x0())
+        a = batch.alpha()
+        mu = batch.predict_mean(Xnew)
+        batch.close()
+        ao, muo = _oracle_alpha_mean(model, X, y, Xnew)
+        np.testing.assert_allclose(a[0], ao, rtol=0, atol=1e-9 * np.max(np.abs(ao)))
+        np.testing.assert_allclose(mu[0], muo, rtol=0, atol=1e-9 * max(1.0, np.max(np.abs(muo))))
+        mu2, _ = model.predict_f(Xnew, data=(X, y))
+        np.testing.assert_array_equal(mu2[:, 0], mu[0])
+
+
+def test_feature_importances_match_reference_arithmetic(engine):
+    n = 120
+    X, y = helpers.make_data(n, seed=4)
+    k = wb.Sum([wb.Categorical(active_dims=[0], variance=0.4), wb.SquaredExponential(active_dims=[1], lengthscales=0.6),
+                wb.Product([wb.Categorical(active_dims=[3]), wb.SquaredExponential(active_dims=[1])])])
+    model = wb.GPR(k, mean_function=wb.ConstantMean(0.1), noise_variance=0.05)
+    single = wb.GPR(wb.SquaredExponential(active_dims=[1], lengthscales=0.5), mean_function=wb.ConstantMean(), noise_variance=0.1)
+    for rv in ("log_bf", "statistic", "de"):
+        got = postfit.feature_importances_batch(X, np.stack([y, y]), [model, single], return_value=rv)
+        # reference arithmetic with oracle means
+        exp = []
+        for mdl in (model, single):
+            _, mu_full = _oracle_alpha_mean(mdl, X, y)
+            null, mod, sat = postfit.calc_deviance_loglik(y, mu_full)
+            full_de = max(min(1, 1 - np.sum(mod - sat) / np.sum(null - sat)), 0) \
+                if np.sum(sat) >= np.sum(mod) >= np.sum(null) else 0
+            lst = []
+            if mdl.kernel.name == "sum":
+                for i in range(len(mdl.kernel.kernels)):
+                    mc = wb.deepcopy(mdl)
+                    mc.kernel.kernels.pop(i)
+                    _, mu_sub = _oracle_alpha_mean(mc, X, y)
+                    n2, sub, _ = postfit.calc_deviance_loglik(y, mu_sub)
+                    if rv == "statistic":
+                        lst.append(max(np.round(-2 * (np.sum(sub) - np.sum(mod)), 1), 0))
+                    elif rv == "log_bf":
+                        lst.append(np.round(np.sum(mod) - np.sum(sub), 1))
+                    else:
+                        lst.append(np.round(max(min(1, 1 - np.sum(sub - mod) / np.sum(n2 - mod)), 0), 3))
+            else:
+                lst.append({"statistic": np.round(-2 * (np.sum(null) - np.sum(mod)), 1),
+                            "log_bf": np.round(np.sum(mod) - np.sum(null), 1), "de": np.round(full_de, 3)}[rv])
+            lst.append(np.round(1 - full_de, 3))
+            exp.append(lst)
+        for g, e in zip(got, exp):
+            assert len(g) == len(e)
+            np.testing.assert_allclose(g, e, rtol=0, atol=0.11 if rv != "de" else 1.1e-3)   # one rounding step
+
+
+def test_penalized_optimization_sets_feature_importances():
+    from waveome_b200 import datasets
+    from waveome_b200.model_search import GPSearch
+    X, Y = datasets.overview_notebook(n_people=30, n_observations=5)
+    gps = GPSearch(X, Y, unit_col="person_id", categorical_vars=["female"])
+    gps.penalized_optimization(random_seed=1)
+    for o, m in gps.models.items():
+        ncomp = len(m.kernel.kernels) if m.kernel.name == "sum" else 1
+        assert len(m.feature_importances) == ncomp + 1
+        assert 0.0 <= m.feature_importances[-1] <= 1.0
+    # outcome1 = sin(time) + noise: almost nothing is left for the residual
+    assert gps.models["outcome1"].feature_importances[-1] < 0.1

@@ -24,10 +24,20 @@ def _worker(rank, world, port, q):
         return dict(x=np.zeros((B, 1)), f=np.arange(B, dtype=float), lml=np.zeros(B), n_iter=np.zeros(B, np.int32),
                     n_eval=np.ones(B, np.int32), status=np.zeros(B, np.int32))
     model_search.fit_models = fake_fit
+    model_search.feature_importances_batch = lambda X, Y, models, **kw: [[0.0, 1.0] for _ in models]
     X, Y = datasets.overview_synthetic(n_people=6, n_observations=4, n_outcomes=7)
     g = GPSearch(X, Y, unit_col="person_id", categorical_vars=["female"])
     g.penalized_optimization()
-    q.put((rank, sorted(g.models.keys()), g.fit_report["n_models"]))
+    n_pen = g.fit_report["n_models"]
+    pen_names = sorted(g.models.keys())
+    # run_search: the lock-step search of this rank's shard with a stub fitter, then the same exchange
+    from waveome_b200 import kernel_search as ks
+
+    def fake_search_fit(requests):
+        return [(ks.candidate_model(k), float(len(name))) for _y, name, k in requests]
+    g.run_search(max_depth=2, fit=fake_search_fit)
+    assert sorted(g.models.keys()) == pen_names and all(v["best_model"] for v in g.search_info.values())
+    q.put((rank, pen_names, n_pen))
     dist.destroy_process_group()
 
 

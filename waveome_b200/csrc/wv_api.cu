@@ -15,6 +15,9 @@
 int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
                     double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf, const WvAux* aux);
 
+int wv_enqueue_cross_mean(const WvBatchDev& bd, const double* d_x, const double* d_xnew_t, int m, int mpad, double* d_mean,
+                          cudaStream_t st);
+
 static thread_local std::string g_err;
 static int wv_fail(const std::string& m) { g_err = m; return -1; }
 #define WV_CUDA(x)                                                                                   \
@@ -41,6 +44,7 @@ struct wv_batch {
   int lb_m_alloc;
   int* h_count;   // pinned
   int64_t bytes, launches, rounds, model_evals;
+  const double* last_x;   // device pointer of the parameters of the last full evaluation (alpha belongs to them)
   WvProfiler prof;
   std::vector<int> perm;   // device row i holds caller row perm[i] (rows sorted by their categorical columns)
 };
@@ -163,6 +167,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   WV_CUDA(cudaSetDevice(e->device));
   wv_batch* b = new wv_batch();
   b->eng = e; b->bytes = 0; b->launches = b->rounds = b->model_evals = 0;
+  b->last_x = nullptr;
   b->d_lbs = nullptr; b->d_lbw = nullptr; b->lb_m_alloc = 0; b->h_count = nullptr;
   WvBatchDev& bd = b->bd;
   bd.n = d->n; bd.D = d->D; bd.B = d->B; bd.P = d->P;
@@ -342,6 +347,7 @@ extern "C" int wv_batch_eval_device(wv_batch* b, const double* d_x, double* d_f,
   const int B = b->bd.B;
   wv_iota_kernel<<<(B + 255) / 256, 256, 0, b->eng->stream>>>(b->d_active, B);
   b->launches += 1;
+  b->last_x = d_x;
   return wv_eval_all(b, d_x, d_f, d_grad, d_lml, d_status, b->d_active, B);
 }
 
@@ -492,6 +498,7 @@ extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o
   wv_iota_kernel<<<(B + 255) / 256, 256, 0, st>>>(b->d_active, B);
   b->launches += 1;
   if (wv_eval_all(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status, b->d_active, B) != 0) return -1;
+  b->last_x = b->d_x;
   wv_lb_report_kernel<<<gb, tb, 0, st>>>(B, b->d_lbs, b->d_task, b->d_status, d_iter, d_neval, d_st2);
   b->launches += 1;
   WV_CUDA(cudaMemcpyAsync(x, b->d_x, (size_t)B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -502,5 +509,47 @@ extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o
   WV_CUDA(cudaMemcpyAsync(status, d_st2, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   WV_CUDA(cudaStreamSynchronize(st));
   WV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// post-fit: alpha and posterior means (gpflow GPR.predict_f mean; waveome/utilities.py:614-707 consumes predict_y means)
+// ---------------------------------------------------------------------------------------------
+extern "C" int wv_batch_get_alpha(wv_batch* b, double* alpha) {
+  if (!b || !alpha) return wv_fail("wv_batch_get_alpha: null argument");
+  if (!b->last_x) return wv_fail("wv_batch_get_alpha: no evaluation has been run on this batch");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const WvBatchDev& bd = b->bd;
+  std::vector<double> tmp((size_t)bd.B * bd.npad);
+  WV_CUDA(cudaMemcpyAsync(tmp.data(), bd.alpha, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, b->eng->stream));
+  WV_CUDA(cudaStreamSynchronize(b->eng->stream));
+  for (size_t m = 0; m < (size_t)bd.B; ++m)
+    for (int i = 0; i < bd.n; ++i) alpha[m * bd.n + b->perm[i]] = tmp[m * bd.npad + i];
+  return 0;
+}
+
+extern "C" int wv_batch_predict_mean(wv_batch* b, const double* Xnew, int32_t m, double* mean) {
+  if (!b || !Xnew || !mean) return wv_fail("wv_batch_predict_mean: null argument");
+  if (m <= 0) return wv_fail("wv_batch_predict_mean: m must be positive");
+  if (!b->last_x) return wv_fail("wv_batch_predict_mean: no evaluation has been run on this batch");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const WvBatchDev& bd = b->bd;
+  const int mpad = (m + WV_NB - 1) / WV_NB * WV_NB;
+  std::vector<double> xt((size_t)bd.D * mpad, 0.0);
+  for (int i = 0; i < m; ++i)
+    for (int k = 0; k < bd.D; ++k) xt[(size_t)k * mpad + i] = Xnew[(size_t)i * bd.D + k];
+  double *d_xt = nullptr, *d_mean = nullptr;
+  cudaStream_t st = b->eng->stream;
+  WV_CUDA(cudaMalloc(&d_xt, xt.size() * sizeof(double)));
+  cudaError_t e = cudaMalloc(&d_mean, (size_t)bd.B * m * sizeof(double));
+  if (e != cudaSuccess) { cudaFree(d_xt); return wv_fail(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+  int rc = 0;
+  if (cudaMemcpyAsync(d_xt, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
+  if (rc == 0 && wv_enqueue_cross_mean(bd, b->last_x, d_xt, m, mpad, d_mean, st) < 0) rc = -1;
+  if (rc == 0 && cudaMemcpyAsync(mean, d_mean, (size_t)bd.B * m * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) rc = -1;
+  b->launches += 1;
+  cudaFree(d_xt); cudaFree(d_mean);
+  if (rc != 0) return wv_fail(std::string("wv_batch_predict_mean: ") + cudaGetErrorString(cudaGetLastError()));
   return 0;
 }

@@ -132,6 +132,26 @@ WV_HD double wv_exp2_fast(double u, const double* __restrict__ tab) {
   return r;
 }
 
+// Same for u <= 0 (the squared-exponential argument -(s d)^2): one clamp instead of the range checks.  Below -1021
+// the result is 2^-1021 ~ 4e-308 instead of 0 (absolute error irrelevant next to sigma^2 >= 1e-6); NaN propagates.
+#ifdef __CUDACC__
+__device__ __forceinline__ double wv_exp2_neg(double u, const double* __restrict__ tab) {
+  const double M = 1.5 * 70368744177664.0;
+  u = (u < -1021.0) ? -1021.0 : u;
+  const double tb = u + M;
+  const double f = u - (tb - M);
+  double p = fma(f, 1.3333558146428443e-03, 9.6181291076284772e-03);
+  p = fma(f, p, 5.5504108664821580e-02);
+  p = fma(f, p, 2.4022650695910071e-01);
+  p = fma(f, p, 6.9314718055994531e-01);
+  p = f * p;
+  const int ki = __double2loint(tb);
+  const double T = tab[ki & (WV_EXP2_TAB - 1)];
+  const double r = fma(T, p, T);
+  return __hiloint2double(__double2hiint(r) + ((ki >> 6) << 20), __double2loint(r));
+}
+#endif
+
 // tfd.Horseshoe(scale).log_prob(x) (TFP closed-form approximation) and d/dx.
 WV_HD void wv_horseshoe(double x, double s, double* logp, double* dlogp) {
   const double g = 0.5614594835668851, b = 1.0420764938351215, h_inf = 1.0801359952503342;

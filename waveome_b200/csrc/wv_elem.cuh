@@ -163,7 +163,7 @@ __device__ __forceinline__ void wv_leaf_mul_ne(const WvElemSmem& sm, int l, cons
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const double d = ai[a] - aj[b];
-          WV_PUT(a * 4 + b, var * wv_exp2_fast(-d * d, sm.tab));
+          WV_PUT(a * 4 + b, var * wv_exp2_neg(-d * d, sm.tab));
         }
     } break;
     case WV_LEAF_LINEAR:
@@ -282,7 +282,7 @@ __device__ __forceinline__ void wv_leaf_grad_sums_ne(const WvElemSmem& sm, int l
         for (int b = 0; b < 4; ++b) {
           const double d = ai[a] - aj[b];
           const double u = d * d;                                   // = r2 log2(e) / 2
-          const double t = wo[a * 4 + b] * wv_exp2_fast(-u, sm.tab);
+          const double t = wo[a * 4 + b] * wv_exp2_neg(-u, sm.tab);
           s_var += t;
           s_ls = fma(t, u, s_ls);
         }
@@ -487,5 +487,75 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAD_MINB) wv_grad_kernel(
       for (int wq = 0; wq < WV_ELEM_WARPS; ++wq) tt += sm.red[s][wq];
       dst[s] = tt;
     }
+  }
+}
+
+
+// =============================================================================================
+// cross mean: mean[b][i] = c_b + sum_j k_b(xnew_i, x_j) alpha_b[j]   (posterior mean of gpflow GPR.predict_f at new
+// inputs; alpha = (K + sigma^2 I)^{-1} (y - c) is left in bd.alpha by the last evaluation).
+// grid (ceil(m / 64), n_models), WV_ELEM_THREADS threads; one CTA owns 64 new points and walks the training tiles.
+// Xnew_t: [D][mpad] column-major, zero padded.  Fixed-order reductions (bit-reproducible).
+// =============================================================================================
+__global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_cross_mean_kernel(
+    WvBatchDev bd, const double* __restrict__ xall, const double* __restrict__ Xnew_t, int m, int mpad,
+    double* __restrict__ mean) {
+  WvElemSmem& sm = *reinterpret_cast<WvElemSmem*>(wv_smem_raw);
+  const int b = blockIdx.y, ti = blockIdx.x;
+  wv_elem_stage_model(bd, b, xall, sm);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* al = bd.alpha + (size_t)b * bd.npad;
+  int r_off, c_off;
+  bool above;
+  wv_elem_coords(r_off, c_off, above, false);
+  double rs[WV_ELEM_MR];
+#pragma unroll
+  for (int a = 0; a < WV_ELEM_MR; ++a) rs[a] = 0.0;
+  for (int tj = 0; tj < bd.nt; ++tj) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < sm.n_dims * WV_NB; i += blockDim.x) {
+      const int d = i / WV_NB, r = i % WV_NB;
+      sm.xr[d][r] = Xnew_t[(size_t)sm.dims[d] * mpad + ti * WV_NB + r];
+      sm.xc[d][r] = bd.Xt[(size_t)sm.dims[d] * bd.npad + tj * WV_NB + r];
+    }
+    __syncthreads();
+    double acc[WV_ELEM_NE];
+#pragma unroll
+    for (int e = 0; e < WV_ELEM_NE; ++e) acc[e] = 0.0;
+    for (int c = 0; c < sm.n_comp; ++c) {
+      double prod[WV_ELEM_NE];
+      const int l0 = sm.comp_start[c], l1 = sm.comp_start[c + 1];
+      for (int l = l0; l < l1; ++l) {
+        double xi[WV_ELEM_MR], xj[4];
+        wv_elem_load_x(sm, sm.leaves[l].dim, r_off, c_off, xi, xj);
+        if (l == l0) wv_leaf_mul_ne<true>(sm, l, xi, xj, prod);
+        else wv_leaf_mul_ne<false>(sm, l, xi, xj, prod);
+      }
+      if (l1 > l0) {
+#pragma unroll
+        for (int e = 0; e < WV_ELEM_NE; ++e) acc[e] += prod[e];
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const int gj = tj * WV_NB + c_off + bb;
+      const double aj = gj < bd.n ? al[gj] : 0.0;
+#pragma unroll
+      for (int a = 0; a < WV_ELEM_MR; ++a) rs[a] = fma(acc[a * 4 + bb], aj, rs[a]);
+    }
+  }
+  // the 8 lanes (lane & 7) of a row group, then the two warps that share the rows
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < WV_ELEM_MR; ++a) {
+    double v = rs[a];
+    for (int o = 1; o < 8; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((lane & 7) == 0) sm.red[r_off + a][warp & 1] = v;
+  }
+  __syncthreads();
+  const double cmean = sm.mean_slot >= 0 ? sm.theta[sm.mean_slot] : 0.0;
+  for (int r = threadIdx.x; r < WV_NB; r += blockDim.x) {
+    const int gi = ti * WV_NB + r;
+    if (gi < m) mean[(size_t)b * m + gi] = cmean + (sm.red[r][0] + sm.red[r][1]);
   }
 }

@@ -744,6 +744,7 @@ static cudaError_t wv_set_attrs() {
   if (e != cudaSuccess) return e;
   WV_ATTR(wv_gram_kernel, sizeof(WvElemSmem));
   WV_ATTR(wv_grad_kernel, sizeof(WvElemSmem));
+  WV_ATTR(wv_cross_mean_kernel, sizeof(WvElemSmem));
   WV_ATTR(wv_chol_step_kernel, wv_smem_gemm_bytes());
   WV_ATTR(wv_trtri_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_kinv_kernel, sizeof(WvGemmSmem));
@@ -842,4 +843,13 @@ int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, con
   launches += 4;
   if (cudaGetLastError() != cudaSuccess) return -1;
   return launches;
+}
+
+// posterior mean at new inputs for every model of the batch (uses bd.alpha of the last evaluation at d_x)
+int wv_enqueue_cross_mean(const WvBatchDev& bd, const double* d_x, const double* d_xnew_t, int m, int mpad, double* d_mean,
+                          cudaStream_t st) {
+  if (wv_set_attrs() != cudaSuccess) return -1;
+  wv_cross_mean_kernel<<<dim3(mpad / WV_NB, bd.B), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(bd, d_x, d_xnew_t, m, mpad,
+                                                                                             d_mean);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -49,7 +49,7 @@ class _LbfgsOpts(C.Structure):
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
     "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
-    "wv_batch_counters", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
+    "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_predict_mean", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
 KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk"]
 
@@ -81,6 +81,8 @@ def load_library():
     lib.wv_batch_fit_lbfgs.restype = C.c_int
     lib.wv_batch_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.wv_batch_counters.restype = None
+    lib.wv_batch_get_alpha.argtypes = [vp, _f64p]; lib.wv_batch_get_alpha.restype = C.c_int
+    lib.wv_batch_predict_mean.argtypes = [vp, _f64p, C.c_int32, _f64p]; lib.wv_batch_predict_mean.restype = C.c_int
     lib.wv_batch_profile_enable.argtypes = [vp, C.c_int]; lib.wv_batch_profile_enable.restype = None
     lib.wv_batch_profile_read.argtypes = [vp, _f64p, C.POINTER(C.c_int64), C.c_int]; lib.wv_batch_profile_read.restype = C.c_int
     lib.wv_last_error.argtypes = []; lib.wv_last_error.restype = C.c_char_p
@@ -229,6 +231,22 @@ class Batch:
         _check(self.lib.wv_batch_fit_lbfgs(self.handle, _f64(x), C.byref(co), _f64(f), _f64(lml), _i32(nit), _i32(nev),
                                            _i32(st)), "wv_batch_fit_lbfgs")
         return dict(x=x, f=f, lml=lml, n_iter=nit, n_eval=nev, status=st)
+
+    def alpha(self) -> np.ndarray:
+        """[B, n] alpha = (K + sigma^2 I)^{-1} (y - c) of the last evaluation, in the caller's row order."""
+        a = np.empty((self.B, self.n))
+        _check(self.lib.wv_batch_get_alpha(self.handle, _f64(a)), "wv_batch_get_alpha")
+        return a
+
+    def predict_mean(self, Xnew: np.ndarray) -> np.ndarray:
+        """[B, m] posterior means at new inputs [m, D] with the parameters of the last evaluation."""
+        Xnew = np.ascontiguousarray(Xnew, dtype=np.float64)
+        if Xnew.ndim != 2 or Xnew.shape[1] != self.D:
+            raise ValueError(f"Xnew must be [m, {self.D}]")
+        out = np.empty((self.B, Xnew.shape[0]))
+        _check(self.lib.wv_batch_predict_mean(self.handle, _f64(Xnew), int(Xnew.shape[0]), _f64(out)),
+               "wv_batch_predict_mean")
+        return out
 
     def counters(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

@@ -19,6 +19,7 @@ import pandas as pd
 from . import kernels as K
 from .model_fitting import fit_models, get_engine
 from .models import ConstantMean, PenalizedGPR
+from .postfit import feature_importances_batch
 from .regularization import full_kernel_build
 
 
@@ -159,6 +160,9 @@ class GPSearch:
         for m in models:
             m.cut_kernel_components(Xn)
             m.update_kernel_name()
+        # get_feature_importances of every model (model_search.py:383-387) as one more engine batch
+        for m, fi in zip(models, feature_importances_batch(Xn, Yn, models)):
+            m.feature_importances = fi
         local = dict(zip(names, models))
         report = dict(n_models=len(names), seconds=time.time() - t0, n_eval=int(np.sum(res["n_eval"])),
                       status=np.asarray(res["status"]).copy(), n_fits_per_model=n_fits)

@@ -96,6 +96,28 @@ class GPR:
     def log_posterior_density(self):
         return self.log_posterior_density_value
 
+    def predict_f(self, Xnew, data=None):
+        """Posterior mean at ``Xnew`` [m, D] -> ([m, 1], None).  ``data`` = (X, Y) as the reference's model methods
+        take it; defaults to the data the model was fitted on when it was kept.  (The predictive variance is not
+        produced by the engine yet; post-fit consumers on this path use the mean only)"""
+        from .postfit import predict_mean
+        data = data if data is not None else self.data
+        if data is None:
+            raise ValueError("predict_f needs data=(X, Y): the fitted model does not keep its training data")
+        mu = predict_mean(self, np.asarray(data[0]), np.asarray(data[1]).reshape(-1), Xnew)
+        return mu.reshape(-1, 1), None
+
+    def predict_y(self, Xnew, data=None):
+        return self.predict_f(Xnew, data=data)
+
+    def get_feature_importances(self, data=None, return_value="log_bf"):
+        """waveome/model_classes.py:546-573"""
+        from .postfit import feature_importances_batch
+        data = data if data is not None else self.data
+        X, y = np.asarray(data[0]), np.asarray(data[1]).reshape(1, -1)
+        self.feature_importances = feature_importances_batch(X, y, [self], return_value=return_value)[0]
+        return None
+
     def log_marginal_likelihood(self):
         return self.log_marginal_likelihood_value
 

@@ -1,0 +1,153 @@
+"""Post-fit quantities on the engine: posterior means and the per-component feature importances
+that ``penalized_optimization`` attaches to every model (waveome/model_search.py:383-387 ->
+waveome/model_classes.py:546-573 -> waveome/utilities.py:517-707).
+
+For the Gaussian likelihood only the posterior MEAN of ``predict_y`` enters the importances
+(``calc_deviance_explained`` evaluates ``gpflow.logdensities.gaussian(x, mu, var=np.var(y))``), and for the exact-GPR
+model it is  c + K alpha = y - sigma^2 alpha  at the training inputs, alpha = (K + sigma^2 I)^{-1}(y - c).  Every
+"model without component k" (the reference pops the component and predicts again with the same parameter values) is
+therefore ONE more factorisation: all variants of all models are evaluated as one engine batch."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import kernels as K
+from .models import GPR
+
+LOG2PI = 1.8378770664093453
+
+
+def gaussian_logdensity(x, mu, var):
+    """gpflow.logdensities.gaussian"""
+    return -0.5 * (LOG2PI + np.log(var) + np.square(mu - x) / var)
+
+
+def calc_deviance_loglik(y, model_mu, base_mu=None):
+    """The Gaussian branch of calc_deviance_explained(..., return_loglik=True) (utilities.py:544-552):
+    (base_ll, mod_ll, sat_ll) per observation."""
+    y = np.asarray(y, dtype=np.float64)
+    y_var = np.var(y)
+    sat_ll = gaussian_logdensity(y, y, y_var)
+    base_ll = gaussian_logdensity(y, np.mean(y) if base_mu is None else base_mu, y_var)
+    mod_ll = gaussian_logdensity(y, np.asarray(model_mu, dtype=np.float64), y_var)
+    return base_ll, mod_ll, sat_ll
+
+
+def _variants(model: GPR) -> List[GPR]:
+    """[full model] + [model without additive component k for every k] (parameter values kept, utilities.py:657-662)."""
+    out = [model]
+    k = model.kernel
+    if k.name == "sum":
+        for k_idx in range(len(k.kernels)):
+            mc = K.deepcopy(model)
+            mc.kernel.kernels.pop(k_idx)
+            out.append(mc)
+    return out
+
+
+def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], engine=None, max_batch_bytes: float = 60e9):
+    """Posterior mean of every model at the training inputs, [B, n], with the models' current parameter values
+    (one engine evaluation; mean = y - sigma^2 alpha)."""
+    from .engine import Batch
+    from .model_fitting import get_engine
+    engine = engine or get_engine()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    B = len(models)
+    progs = [m.program() for m in models]
+    uniq, prog_id, table = {}, np.empty(B, np.int32), []
+    for b, p in enumerate(progs):
+        sig = p.signature()
+        if sig not in uniq:
+            uniq[sig] = len(table)
+            table.append(p)
+        prog_id[b] = uniq[sig]
+    P = max(1, max(p.n_x for p in progs))
+    x = np.zeros((B, P))
+    for b, p in enumerate(progs):
+        x[b, : p.n_x] = p.x0()
+    n = X.shape[0]
+    npad = ((n + 1 + 7) // 8 * 8 + 63) // 64 * 64
+    chunk = max(1, int(max_batch_bytes // (2 * npad * npad * 8 + npad * 64 * 8)))
+    mean = np.empty((B, n))
+    status = np.empty(B, np.int32)
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        batch = Batch(engine, X, Y[lo:hi], table, prog_id[lo:hi], P=P)
+        try:
+            _f, _g, _lml, st = batch.eval(x[lo:hi])
+            alpha = batch.alpha()
+        finally:
+            batch.close()
+        s2 = np.array([float(m.likelihood.variance) for m in models[lo:hi]])
+        mean[lo:hi] = Y[lo:hi] - s2[:, None] * alpha
+        status[lo:hi] = st
+    return mean, status
+
+
+def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf", engine=None) -> List[list]:
+    """calc_feature_importance_components (utilities.py:614-707) for B models at once: one list per model with one
+    entry per additive component and a last entry for the residual (1 - deviance explained)."""
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    var_models, var_y, owner = [], [], []
+    for b, m in enumerate(models):
+        vs = _variants(m)
+        var_models += vs
+        var_y += [Y[b]] * len(vs)
+        owner += [b] * len(vs)
+    means, status = fitted_means(X, np.stack(var_y), var_models, engine=engine)
+    out, pos = [], 0
+    for b, m in enumerate(models):
+        nv = owner.count(b) if False else (1 + (len(m.kernel.kernels) if m.kernel.name == "sum" else 0))
+        mu = means[pos: pos + nv]
+        pos += nv
+        y = Y[b]
+        null_lls, mod_lls, sat_lls = calc_deviance_loglik(y, mu[0])
+        if np.sum(sat_lls) >= np.sum(mod_lls) and np.sum(mod_lls) >= np.sum(null_lls):
+            full_de = 1 - (-2 * np.sum(mod_lls - sat_lls) / (-2 * np.sum(null_lls - sat_lls)))
+            full_de = max(min(1, full_de), 0)
+        else:
+            full_de = 0
+        de_list = []
+        k = m.kernel
+        if k.name == "sum":
+            for k_idx in range(len(k.kernels)):
+                null_lls_k, sub_mod_lls, _ = calc_deviance_loglik(y, mu[1 + k_idx])
+                if return_value == "statistic":
+                    scaled = max(np.round(-2 * (np.sum(sub_mod_lls) - np.sum(mod_lls)), 1), 0)
+                elif return_value == "log_bf":
+                    scaled = np.round(np.sum(mod_lls) - np.sum(sub_mod_lls), 1)
+                else:
+                    scaled = 1 - (-2 * np.sum(sub_mod_lls - mod_lls) / (-2 * np.sum(null_lls_k - mod_lls)))
+                    scaled = np.round(max(min(1, scaled), 0), 3)
+                de_list.append(float(scaled))
+        elif k.name == "constant":
+            de_list.append(0.0)
+        else:
+            if return_value == "statistic":
+                de_list.append(float(np.round(-2 * (np.sum(null_lls) - np.sum(mod_lls)), 1)))
+            elif return_value == "log_bf":
+                de_list.append(float(np.round(np.sum(mod_lls) - np.sum(null_lls), 1)))
+            else:
+                de_list.append(float(np.round(full_de, 3)))
+        de_list.append(float(np.round(1 - full_de, 3)))
+        out.append(de_list)
+    return out
+
+
+def predict_mean(model: GPR, X, y, Xnew, engine=None) -> np.ndarray:
+    """gpflow GPR.predict_f(Xnew)[0] for one model: [m] posterior mean at new inputs."""
+    from .engine import Batch
+    from .model_fitting import get_engine
+    engine = engine or get_engine()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(1, -1)
+    p = model.program()
+    batch = Batch(engine, X, y, [p])
+    try:
+        batch.eval(batch.x0())
+        return batch.predict_mean(np.asarray(Xnew, dtype=np.float64))[0]
+    finally:
+        batch.close()
