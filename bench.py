@@ -269,8 +269,13 @@ def main():
         alg = 8.0 * n * n * model_evals + 8.0 * n * 5 * model_evals          # bytes: K written / W read once + X
         achieved = alg / (dom_ms * 1e-3) / 1e9
         roof = {"kernel": f"wv_{dom}_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind + " copy bandwidth",
-                "note": "ALU-bound in practice: 6 fp64 exp per matrix element for this kernel tree (see DESIGN.md)"}
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": {"gram": 804.3e6, "grad": 874.3e6}[dom], "peak_kind": peak_kind + " copy bandwidth",
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch with 500 models in flight "
+                                "(profiles/r01b_ncu_elem_summary.txt); algorithmic bytes of that launch: 1.45e9 "
+                                "(8 n^2 per model, the kernel touches the lower tiles only)",
+                "note": "FP64-issue bound, not HBM bound: up to 6 squared-exponential leaves per matrix element for this "
+                        "kernel tree, each a table-driven 2^u of 9 FP64 operations (see DESIGN.md section 4)"}
     else:
         share = {"chol_diag": 1.0 / 3, "chol_panel": 1.0 / 3, "trtri": 1.0 / 3, "kinv": 1.0 / 3}.get(dom, 0.0)
         if dom in ("chol_diag", "chol_panel"):

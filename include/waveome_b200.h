@@ -107,6 +107,11 @@ int64_t wv_batch_workspace_bytes(const wv_batch* b);
 /* replace the outcomes (HOST [B, n]) without rebuilding programs / workspaces */
 int wv_batch_set_y(wv_batch* b, const double* Y);
 
+/* Per-model mask over the additive components of its program (bit c = component c takes part in K; default all
+ * ones).  "The model without component k, same parameter values" is what the reference's feature importances
+ * evaluate (waveome/utilities.py:657-662 pops the component and predicts again): one program, B masks. HOST [B]. */
+int wv_batch_set_component_mask(wv_batch* b, const uint32_t* mask);
+
 /* One LML+gradient evaluation of every model.  HOST buffers:
  *   x [B, P] unconstrained parameters; f [B] = -(lml + log prior); grad [B, P] = df/dx; lml [B]; status [B]. */
 int wv_batch_eval(wv_batch* b, const double* x, double* f, double* grad, double* lml, int32_t* status);

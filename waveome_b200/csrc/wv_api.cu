@@ -203,6 +203,8 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   WV_TRY(wv_alloc(b, &bd.partial, B * ntiles * smax));
   WV_TRY(wv_alloc(b, &bd.chol_fail, B));
   WV_TRY(wv_alloc(b, &bd.step_flag, B * bd.nt));
+  unsigned* dmask;
+  WV_TRY(wv_alloc(b, &dmask, B));
   WV_TRY(wv_alloc(b, &b->d_x, B * d->P));
   WV_TRY(wv_alloc(b, &b->d_g, B * d->P));
   WV_TRY(wv_alloc(b, &b->d_f, B));
@@ -217,7 +219,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   WV_TRY(wv_alloc(b, &b->d_neval, B));
   WV_TRY(wv_alloc(b, &b->d_st2, B));
 #undef WV_TRY
-  bd.Xt = dXt; bd.Y = dY; bd.programs = dprog; bd.prog_id = dpid;
+  bd.Xt = dXt; bd.Y = dY; bd.programs = dprog; bd.prog_id = dpid; bd.comp_mask = dmask;
   cudaStream_t st = e->stream;
   // Row order on the device: sorted lexicographically by the categorical columns the programs use (fewest levels
   // first).  The marginal likelihood is invariant under a simultaneous permutation of X rows and y entries; the sort
@@ -265,6 +267,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   step(cudaMemsetAsync(bd.A, 0, B * np * np * sizeof(double), st));
   step(cudaMemsetAsync(bd.Mt, 0, B * np * np * sizeof(double), st));
   step(cudaMemsetAsync(bd.step_flag, 0, B * bd.nt * sizeof(int), st));
+  step(cudaMemsetAsync(dmask, 0xff, B * sizeof(unsigned), st));
   step(cudaMemsetAsync(dY, 0, B * np * sizeof(double), st));
   step(cudaMemcpy2DAsync(dY, np * sizeof(double), yp.data(), (size_t)d->n * sizeof(double), (size_t)d->n * sizeof(double), B,
                          cudaMemcpyHostToDevice, st));
@@ -314,6 +317,15 @@ extern "C" int wv_batch_set_y(wv_batch* b, const double* Y) {
     for (int i = 0; i < bd.n; ++i) yp[m * bd.n + i] = Y[m * bd.n + b->perm[i]];
   WV_CUDA(cudaMemcpy2DAsync((void*)bd.Y, (size_t)bd.npad * sizeof(double), yp.data(), (size_t)bd.n * sizeof(double),
                             (size_t)bd.n * sizeof(double), bd.B, cudaMemcpyHostToDevice, b->eng->stream));
+  WV_CUDA(cudaStreamSynchronize(b->eng->stream));
+  return 0;
+}
+
+extern "C" int wv_batch_set_component_mask(wv_batch* b, const uint32_t* mask) {
+  if (!b || !mask) return wv_fail("wv_batch_set_component_mask: null argument");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  WV_CUDA(cudaMemcpyAsync((void*)b->bd.comp_mask, mask, (size_t)b->bd.B * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                          b->eng->stream));
   WV_CUDA(cudaStreamSynchronize(b->eng->stream));
   return 0;
 }

@@ -33,7 +33,8 @@
 #define WV_ELEM_TPC 4                                       // tiles walked by one CTA
 
 struct WvElemSmem {
-  int n_comp, n_leaves, n_slots, noise_slot, mean_slot, n_dims, pad0, pad1;
+  int n_comp, n_leaves, n_slots, noise_slot, mean_slot, n_dims;
+  unsigned comp_mask, pad1;
   int comp_start[WV_MAX_COMP + 1];
   int dims[WV_MAX_DIMS];
   int slot_x[WV_MAX_SLOTS];                // packed index of the slot, -1 if frozen
@@ -54,6 +55,7 @@ __device__ __forceinline__ void wv_elem_stage_model(const WvBatchDev& bd, int b,
   if (threadIdx.x == 0) {
     sm.n_comp = nc; sm.n_leaves = nl; sm.n_slots = ns; sm.noise_slot = gp->noise_slot; sm.mean_slot = gp->mean_slot;
     sm.n_dims = gp->n_dims;
+    sm.comp_mask = bd.comp_mask[b];
   }
   for (int i = threadIdx.x; i <= nc; i += blockDim.x) sm.comp_start[i] = gp->comp_start[i];
   for (int i = threadIdx.x; i < WV_MAX_DIMS; i += blockDim.x) sm.dims[i] = gp->dims[i];
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_gram_kernel(
 #pragma unroll
     for (int e = 0; e < WV_ELEM_NE; ++e) acc[e] = 0.0;
     for (int c = 0; c < sm.n_comp; ++c) {
+      if (!((sm.comp_mask >> c) & 1u)) continue;
       double prod[WV_ELEM_NE];
       const int l0 = sm.comp_start[c], l1 = sm.comp_start[c + 1];
       bool skip = false;
@@ -440,6 +443,7 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAD_MINB) wv_grad_kernel(
         }
       }
       for (int c = 0; c < sm.n_comp; ++c) {
+        if (!((sm.comp_mask >> c) & 1u)) continue;
         const int l0 = sm.comp_start[c], l1 = sm.comp_start[c + 1];
         for (int l = l0; l < l1; ++l) {
           const WvLeaf lf = sm.leaves[l];
@@ -523,6 +527,7 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_cross_mean_k
 #pragma unroll
     for (int e = 0; e < WV_ELEM_NE; ++e) acc[e] = 0.0;
     for (int c = 0; c < sm.n_comp; ++c) {
+      if (!((sm.comp_mask >> c) & 1u)) continue;
       double prod[WV_ELEM_NE];
       const int l0 = sm.comp_start[c], l1 = sm.comp_start[c + 1];
       for (int l = l0; l < l1; ++l) {

@@ -41,6 +41,7 @@ struct WvBatchDev {
   double* quad;                     // [B]
   double* partial;                  // [B][n_tiles][n_slots_max]
   int* chol_fail;                   // [B]
+  const unsigned* comp_mask;        // [B] bit c = additive component c of the model's program takes part (default all)
   int* step_flag;                   // [B][nt] epoch of the last finished diagonal block (fused Cholesky step)
 };
 

@@ -48,7 +48,7 @@ class _LbfgsOpts(C.Structure):
 
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
-    "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
+    "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
     "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_predict_mean", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
 KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk"]
@@ -75,6 +75,7 @@ def load_library():
     lib.wv_batch_destroy.argtypes = [vp]; lib.wv_batch_destroy.restype = None
     lib.wv_batch_workspace_bytes.argtypes = [vp]; lib.wv_batch_workspace_bytes.restype = C.c_int64
     lib.wv_batch_set_y.argtypes = [vp, _f64p]; lib.wv_batch_set_y.restype = C.c_int
+    lib.wv_batch_set_component_mask.argtypes = [vp, C.POINTER(C.c_uint32)]; lib.wv_batch_set_component_mask.restype = C.c_int
     lib.wv_batch_eval.argtypes = [vp, _f64p, _f64p, _f64p, _f64p, _i32p]; lib.wv_batch_eval.restype = C.c_int
     lib.wv_batch_eval_device.argtypes = [vp, vp, vp, vp, vp, vp]; lib.wv_batch_eval_device.restype = C.c_int
     lib.wv_batch_fit_lbfgs.argtypes = [vp, _f64p, C.POINTER(_LbfgsOpts), _f64p, _f64p, _i32p, _i32p, _i32p]
@@ -194,6 +195,14 @@ class Batch:
         if Y.shape != (self.B, self.n):
             raise ValueError("Y must be [B, n]")
         _check(self.lib.wv_batch_set_y(self.handle, _f64(Y)), "wv_batch_set_y")
+
+    def set_component_mask(self, mask):
+        """[B] uint32: bit c enables additive component c of the model's program (default: all)."""
+        mask = np.ascontiguousarray(mask, dtype=np.uint32)
+        if mask.shape != (self.B,):
+            raise ValueError("mask must have one entry per model")
+        _check(self.lib.wv_batch_set_component_mask(self.handle, mask.ctypes.data_as(C.POINTER(C.c_uint32))),
+               "wv_batch_set_component_mask")
 
     def eval(self, x: np.ndarray):
         """One LML+gradient evaluation from HOST buffers.  Returns (f, grad, lml, status)."""

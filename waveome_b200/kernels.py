@@ -164,9 +164,42 @@ def set_trainable(obj, flag: bool):
             p.trainable = bool(flag)
 
 
+def _fast_copy(obj, memo):
+    oid = id(obj)
+    if oid in memo:
+        return memo[oid]
+    if obj is None or isinstance(obj, (bool, int, float, str, bytes, np.generic)):
+        return obj
+    if isinstance(obj, np.ndarray):
+        return obj                       # data arrays are read-only on this path: shared, not duplicated
+    if isinstance(obj, list):
+        new = []
+        memo[oid] = new
+        new.extend(_fast_copy(v, memo) for v in obj)
+        return new
+    if isinstance(obj, tuple):
+        return tuple(_fast_copy(v, memo) for v in obj)
+    if isinstance(obj, dict):
+        new = {}
+        memo[oid] = new
+        for k, v in obj.items():
+            new[k] = _fast_copy(v, memo)
+        return new
+    d = getattr(obj, "__dict__", None)
+    if d is not None and type(obj).__module__.startswith(__name__.rsplit(".", 1)[0]):
+        new = object.__new__(type(obj))
+        memo[oid] = new
+        nd = new.__dict__
+        for k, v in d.items():
+            nd[k] = _fast_copy(v, memo)
+        return new
+    return copy.deepcopy(obj, memo)
+
+
 def deepcopy(obj):
-    """gpflow.utilities.deepcopy."""
-    return copy.deepcopy(obj)
+    """gpflow.utilities.deepcopy for the objects of this package (kernel trees, parameters, priors, models): shared
+    sub-objects stay shared inside the copy; numpy data arrays are referenced, not duplicated."""
+    return _fast_copy(obj, {})
 
 
 # ----------------------------------------------------------------------------------------------

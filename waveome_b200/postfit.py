@@ -35,54 +35,74 @@ def calc_deviance_loglik(y, model_mu, base_mu=None):
     return base_ll, mod_ll, sat_ll
 
 
-def _variants(model: GPR) -> List[GPR]:
-    """[full model] + [model without additive component k for every k] (parameter values kept, utilities.py:657-662)."""
-    out = [model]
+def _component_masks(model: GPR) -> List[int]:
+    """Component masks of [full model] + [model without top-level additive component k for every k]: the reference
+    pops the component and predicts again with the same parameter values (utilities.py:657-662).  A top-level
+    component that is a product of sums expands into several program components; all of them are switched off."""
+    from .program import expand_sum_of_products
     k = model.kernel
+    full = 0xFFFFFFFF
+    out = [full]
     if k.name == "sum":
-        for k_idx in range(len(k.kernels)):
-            mc = K.deepcopy(model)
-            mc.kernel.kernels.pop(k_idx)
-            out.append(mc)
+        pos = 0
+        for child in k.kernels:
+            cnt = len(expand_sum_of_products(child))
+            bits = ((1 << cnt) - 1) << pos
+            out.append(full & ~bits)
+            pos += cnt
     return out
 
 
-def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], engine=None, max_batch_bytes: float = 60e9):
+def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], masks: Optional[Sequence[int]] = None, engine=None,
+                 max_batch_bytes: float = 60e9):
     """Posterior mean of every model at the training inputs, [B, n], with the models' current parameter values
-    (one engine evaluation; mean = y - sigma^2 alpha)."""
+    (one engine evaluation; mean = y - sigma^2 alpha).  ``masks``: optional component mask per model."""
     from .engine import Batch
     from .model_fitting import get_engine
     engine = engine or get_engine()
     X = np.ascontiguousarray(X, dtype=np.float64)
     Y = np.ascontiguousarray(Y, dtype=np.float64)
     B = len(models)
-    progs = [m.program() for m in models]
+    cache = {}
+    progs = []
+    for m in models:                       # the same model object may appear many times (once per mask)
+        if id(m) not in cache:
+            cache[id(m)] = m.program()
+        progs.append(cache[id(m)])
     uniq, prog_id, table = {}, np.empty(B, np.int32), []
+    sig_of = {}
     for b, p in enumerate(progs):
-        sig = p.signature()
+        if id(p) not in sig_of:
+            sig_of[id(p)] = p.signature()
+        sig = sig_of[id(p)]
         if sig not in uniq:
             uniq[sig] = len(table)
             table.append(p)
         prog_id[b] = uniq[sig]
     P = max(1, max(p.n_x for p in progs))
     x = np.zeros((B, P))
+    x0_of = {}
     for b, p in enumerate(progs):
-        x[b, : p.n_x] = p.x0()
+        if id(p) not in x0_of:
+            x0_of[id(p)] = p.x0()
+        x[b, : p.n_x] = x0_of[id(p)]
     n = X.shape[0]
     npad = ((n + 1 + 7) // 8 * 8 + 63) // 64 * 64
     chunk = max(1, int(max_batch_bytes // (2 * npad * npad * 8 + npad * 64 * 8)))
     mean = np.empty((B, n))
     status = np.empty(B, np.int32)
+    s2_all = np.array([float(m.likelihood.variance) for m in models])
     for lo in range(0, B, chunk):
         hi = min(B, lo + chunk)
         batch = Batch(engine, X, Y[lo:hi], table, prog_id[lo:hi], P=P)
         try:
+            if masks is not None:
+                batch.set_component_mask(np.asarray(masks[lo:hi], dtype=np.uint32))
             _f, _g, _lml, st = batch.eval(x[lo:hi])
             alpha = batch.alpha()
         finally:
             batch.close()
-        s2 = np.array([float(m.likelihood.variance) for m in models[lo:hi]])
-        mean[lo:hi] = Y[lo:hi] - s2[:, None] * alpha
+        mean[lo:hi] = Y[lo:hi] - s2_all[lo:hi, None] * alpha
         status[lo:hi] = st
     return mean, status
 
@@ -91,16 +111,16 @@ def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf"
     """calc_feature_importance_components (utilities.py:614-707) for B models at once: one list per model with one
     entry per additive component and a last entry for the residual (1 - deviance explained)."""
     Y = np.ascontiguousarray(Y, dtype=np.float64)
-    var_models, var_y, owner = [], [], []
+    var_models, var_masks, rows = [], [], []
     for b, m in enumerate(models):
-        vs = _variants(m)
-        var_models += vs
-        var_y += [Y[b]] * len(vs)
-        owner += [b] * len(vs)
-    means, status = fitted_means(X, np.stack(var_y), var_models, engine=engine)
+        ms = _component_masks(m)
+        var_models += [m] * len(ms)
+        var_masks += ms
+        rows += [b] * len(ms)
+    means, status = fitted_means(X, Y[rows], var_models, masks=var_masks, engine=engine)
     out, pos = [], 0
     for b, m in enumerate(models):
-        nv = owner.count(b) if False else (1 + (len(m.kernel.kernels) if m.kernel.name == "sum" else 0))
+        nv = 1 + (len(m.kernel.kernels) if m.kernel.name == "sum" else 0)
         mu = means[pos: pos + nv]
         pos += nv
         y = Y[b]
