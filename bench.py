@@ -194,12 +194,16 @@ def main():
 
     from waveome_b200.engine import Batch
     from waveome_b200.model_fitting import get_engine
-    X, Y = make_workload(args.outcomes, seed=2024 + rank)
+    # ONE global workload of outcomes x world columns (identical on every rank); rank r owns the contiguous shard
+    # [r * outcomes, (r + 1) * outcomes) -- exactly the split GPSearch.penalized_optimization makes under torchrun
+    X, Y = make_workload(args.outcomes * world, seed=2024)
     gps = make_search(X, Y)
     model = build_model(gps)
     eng = get_engine(local_rank)
+    from waveome_b200.model_search import shard_bounds
+    lo, hi = shard_bounds(args.outcomes * world, rank, world)
     Xn = gps.X.to_numpy(dtype=np.float64)
-    Yn = np.ascontiguousarray(gps.Y.to_numpy(dtype=np.float64).T)
+    Yn = np.ascontiguousarray(gps.Y.iloc[:, lo:hi].to_numpy(dtype=np.float64).T)
     batch = Batch(eng, Xn, Yn, [model.program()])
     x0 = batch.x0()
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
@@ -239,7 +243,8 @@ def main():
     fits_total, evals_total, launches_total = [float(v) for v in tot.tolist()]
     value = fits_total / (ms_max * 1e-3)
 
-    # ---------------- e2e through the public API: host pandas in, fitted model objects out
+    # ---------------- e2e through the public API: host pandas in (all outcomes of the job), fitted model objects out;
+    # under torchrun every rank builds the same GPSearch and fits its own shard (no gather: results stay per rank)
     def e2e_step():
         g = make_search(X, Y)
         g.penalized_optimization(penalization_factor=1.0, gather=False)
@@ -304,7 +309,7 @@ def main():
     if not args.no_cpu_baseline:
         ncols = args.cpu_sample or cores
         spec = model.to_spec()
-        f, e, dt = cpu_reference_step(spec, Xn, gps.Y.to_numpy(dtype=np.float64), list(range(ncols)), cores)
+        f, e, dt = cpu_reference_step(spec, Xn, gps.Y.to_numpy(dtype=np.float64)[:, lo:hi], list(range(ncols)), cores)
         cpu = {"value": f / dt, "unit": "fits/s", "cores": cores, "kind": "port",
                "sample": f"first {ncols} outcomes of rank 0's workload, one per host core, BLAS threads pinned to 1 "
                          f"({dt:.1f} s wall); oracle/gp_oracle.py + scipy L-BFGS-B",

@@ -24,6 +24,11 @@ def _worker(rank, world, port, q):
         return dict(x=np.zeros((B, 1)), f=np.arange(B, dtype=float), lml=np.zeros(B), n_iter=np.zeros(B, np.int32),
                     n_eval=np.ones(B, np.int32), status=np.zeros(B, np.int32))
     model_search.fit_models = fake_fit
+
+    def fake_replicated(X, Y, template, make_models=None, **kw):
+        models = make_models()
+        return fake_fit(X, Y, models), models
+    model_search.fit_replicated = fake_replicated
     model_search.feature_importances_batch = lambda X, Y, models, **kw: [[0.0, 1.0] for _ in models]
     X, Y = datasets.overview_synthetic(n_people=6, n_observations=4, n_outcomes=7)
     g = GPSearch(X, Y, unit_col="person_id", categorical_vars=["female"])

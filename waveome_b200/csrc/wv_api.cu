@@ -30,12 +30,22 @@ struct wv_engine {
   int device;
   cudaStream_t stream;
   WvAux aux;   // side stream / events of the large-n look-ahead schedule
+  // Large device buffers of destroyed batches, kept for the next batch of the engine: cudaMalloc / cudaFree of the
+  // multi-GB workspaces costs ~0.1 s each, which is visible next to a 4 s fit (fit -> post-fit batches, search levels).
+  std::vector<std::pair<size_t, void*>> cache;
 };
+static const size_t WV_CACHE_MIN_BYTES = (size_t)32 << 20;
+static const size_t WV_CACHE_MAX_ENTRIES = 6;
+
+static void wv_cache_flush(wv_engine* e) {
+  for (auto& c : e->cache) cudaFree(c.second);
+  e->cache.clear();
+}
 
 struct wv_batch {
   wv_engine* eng;
   WvBatchDev bd;
-  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> allocs;
   // device buffers
   double *d_x, *d_f, *d_g, *d_lml;
   int *d_status, *d_active, *d_active2, *d_count, *d_task, *d_nx, *d_iter, *d_neval, *d_st2;
@@ -53,9 +63,28 @@ template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
   void* q = nullptr;
   size_t bytes = count * sizeof(T);
   if (bytes == 0) bytes = sizeof(T);
-  cudaError_t e = cudaMalloc(&q, bytes);
-  if (e != cudaSuccess) return wv_fail(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
-  b->allocs.push_back(q);
+  if (bytes >= WV_CACHE_MIN_BYTES) {        // best fit from the engine's cache (at most 25 % larger than asked)
+    auto& cache = b->eng->cache;
+    int best = -1;
+    for (int i = 0; i < (int)cache.size(); ++i)
+      if (cache[i].first >= bytes && cache[i].first <= bytes + bytes / 4 && (best < 0 || cache[i].first < cache[best].first))
+        best = i;
+    if (best >= 0) {
+      q = cache[best].second;
+      bytes = cache[best].first;
+      cache.erase(cache.begin() + best);
+    }
+  }
+  if (!q) {
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess && !b->eng->cache.empty()) {     // give the cached buffers back and retry
+      cudaGetLastError();
+      wv_cache_flush(b->eng);
+      e = cudaMalloc(&q, bytes);
+    }
+    if (e != cudaSuccess) return wv_fail(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+  }
+  b->allocs.push_back({q, bytes});
   b->bytes += (int64_t)bytes;
   *p = reinterpret_cast<T*>(q);
   return 0;
@@ -96,6 +125,8 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
 extern "C" void wv_engine_destroy(wv_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  wv_cache_flush(e);
   cudaStreamDestroy(e->stream);
   if (e->aux.side) cudaStreamDestroy(e->aux.side);
   if (e->aux.ev_panel) cudaEventDestroy(e->aux.ev_panel);
@@ -286,7 +317,10 @@ extern "C" void wv_batch_destroy(wv_batch* b) {
   cudaSetDevice(b->eng->device);
   cudaStreamSynchronize(b->eng->stream);
   b->prof.destroy();
-  for (void* p : b->allocs) cudaFree(p);
+  for (auto& a : b->allocs) {
+    if (a.second >= WV_CACHE_MIN_BYTES && b->eng->cache.size() < WV_CACHE_MAX_ENTRIES) b->eng->cache.push_back({a.second, a.first});
+    else cudaFree(a.first);
+  }
   if (b->h_count) cudaFreeHost(b->h_count);
   delete b;
 }

@@ -85,6 +85,77 @@ def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional
     return out
 
 
+def packed_parameters(model: GPR):
+    """The model's trainable Parameter objects in the engine's packed order (program.x_params of ``model.program()``
+    without building the program): kernel leaves depth-first, likelihood variance, mean constant; shared objects once."""
+    from .program import iter_leaves
+    seen, out = set(), []
+    ps = [p for lf in iter_leaves(model.kernel) for p in lf.parameters] + list(model.likelihood.parameters) + \
+        list(model.mean_function.parameters)
+    for p in ps:
+        if id(p) not in seen:
+            seen.add(id(p))
+            if p.trainable:
+                out.append(p)
+    return out
+
+
+def fit_replicated(X: np.ndarray, Y: np.ndarray, template: GPR, make_models=None, engine=None,
+                   max_batch_bytes: float = 60e9, **lbfgs_opts):
+    """MAP-fit B copies of ONE model structure (same kernel tree, priors and start values) to the B outcomes Y[b]:
+    what GPSearch.penalized_optimization does (waveome/model_search.py:302-329 builds the same PSVGP for every
+    outcome).  The device fit runs on a worker thread (the C call releases the GIL) while ``make_models()`` -- the
+    per-outcome model objects the caller wants back -- is evaluated on the calling thread.  Returns (raw result dict,
+    models); the fitted values are written into the models' parameters."""
+    import threading
+    from .engine import Batch
+    engine = engine or get_engine()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    B = Y.shape[0]
+    prog = template.program()
+    P = max(1, prog.n_x)
+    n = X.shape[0]
+    npad = ((n + 1 + 7) // 8 * 8 + 63) // 64 * 64
+    chunk = max(1, int(max_batch_bytes // (2 * npad * npad * 8 + npad * 64 * 8)))
+    out = dict(x=np.empty((B, P)), f=np.empty(B), lml=np.empty(B), n_iter=np.empty(B, np.int32),
+               n_eval=np.empty(B, np.int32), status=np.empty(B, np.int32), launches=0, rounds=0)
+    err = []
+
+    def work():
+        try:
+            for lo in range(0, B, chunk):
+                hi = min(B, lo + chunk)
+                batch = Batch(engine, X, Y[lo:hi], [prog], P=P)
+                try:
+                    r = batch.fit(**lbfgs_opts)
+                    c = batch.counters()
+                finally:
+                    batch.close()
+                for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
+                    out[key][lo:hi] = r[key]
+                out["launches"] += c["launches"]
+                out["rounds"] += c["rounds"]
+        except BaseException as e:      # re-raised on the calling thread
+            err.append(e)
+
+    t = threading.Thread(target=work)
+    t.start()
+    try:
+        models = make_models() if make_models is not None else [K.deepcopy(template) for _ in range(B)]
+    finally:
+        t.join()
+    if err:
+        raise err[0]
+    for b, m in enumerate(models):
+        for p, u in zip(packed_parameters(m), out["x"][b]):
+            p.assign(p.transform_fn(u))
+        m.log_marginal_likelihood_value = float(out["lml"][b])
+        m.log_posterior_density_value = float(-out["f"][b])
+        m.fit_info = dict(n_iter=int(out["n_iter"][b]), n_eval=int(out["n_eval"][b]), status=int(out["status"][b]))
+    return out, models
+
+
 def kernel_test_reg(X, Y, k, num_restarts=5, random_init=True, verbose=False, likelihood="gaussian", lasso=False,
                     lam=0, use_priors=True, max_iter=50000, keep_data=False, freeze_variances=False,
                     random_seed=None, engine=None, **unused):

@@ -17,7 +17,7 @@ import numpy as np
 import pandas as pd
 
 from . import kernels as K
-from .model_fitting import fit_models, get_engine
+from .model_fitting import fit_models, fit_replicated, get_engine
 from .models import ConstantMean, PenalizedGPR
 from .postfit import feature_importances_batch
 from .regularization import full_kernel_build
@@ -128,15 +128,18 @@ class GPSearch:
         lo, hi = shard_bounds(len(self.out_names), rank, world)
         names = self.out_names[lo:hi]
         t0 = time.time()
-        models: List[PenalizedGPR] = [
-            PenalizedGPR(K.deepcopy(full_kernel), mean_function=K.deepcopy(mean_function),
-                         penalization_factor=penalization_factor) for _ in names]
+        template = PenalizedGPR(K.deepcopy(full_kernel), mean_function=K.deepcopy(mean_function),
+                                penalization_factor=penalization_factor)
+
+        def make_models() -> List[PenalizedGPR]:      # every outcome owns its copy (model_search.py:305-306)
+            return [K.deepcopy(template) for _ in names]
         Xn = self.X.to_numpy(dtype=np.float64)
         Yn = np.ascontiguousarray(self.Y[names].to_numpy(dtype=np.float64).T)
         n_fits = max(1, int(num_restart)) if num_restart else 1
         if verbose and rank == 0:
             print(f"Building {len(self.out_names)} models on {world} GPU(s)...")
         if num_restart and num_restart > 0:
+            models = make_models()
             # random_restart_optimize (model_classes.py:472-524): keep the restart with the best objective
             best = None
             for r in range(num_restart):
@@ -156,7 +159,9 @@ class GPSearch:
             for m, xb in zip(models, res["x"]):
                 m.program().assign(xb[: len(m.trainable_parameters)])
         else:
-            res = fit_models(Xn, Yn, models, maxiter=num_opt_iter, maxfun=num_opt_iter)
+            # one structure for every outcome: the device fit overlaps the construction of the model objects
+            res, models = fit_replicated(Xn, Yn, template, make_models=make_models, maxiter=num_opt_iter,
+                                         maxfun=num_opt_iter)
         for m in models:
             m.cut_kernel_components(Xn)
             m.update_kernel_name()
