@@ -38,7 +38,7 @@ enum { WVT_IDENTITY = 0, WVT_SOFTPLUS = 1, WVT_SOFTPLUS_SHIFT = 2, WVT_EXP = 3 }
 /* priors on the constrained value (tfd.Horseshoe / tfd.Laplace / tfd.Uniform) */
 enum { WVP_NONE = 0, WVP_HORSESHOE = 1, WVP_LAPLACE = 2, WVP_UNIFORM = 3 };
 /* per-model status bits */
-enum { WVS_OK = 0, WVS_CHOL_FAIL = 1, WVS_NONFINITE = 2, WVS_MAXITER = 4, WVS_LINESEARCH = 8 };
+enum { WVS_OK = 0, WVS_CHOL_FAIL = 1, WVS_NONFINITE = 2, WVS_MAXITER = 4, WVS_LINESEARCH = 8, WVS_INNER_CAP = 16 };
 
 /* One kernel program = sum over components of products of leaves, plus the parameter slot table.
  * Arrays are flat; a batch passes `n_programs` of these back to back. */
@@ -107,6 +107,17 @@ int64_t wv_batch_workspace_bytes(const wv_batch* b);
 /* replace the outcomes (HOST [B, n]) without rebuilding programs / workspaces */
 int wv_batch_set_y(wv_batch* b, const double* Y);
 
+/* Likelihood of every model of the batch: 0 Gaussian (default; exact GPR marginal likelihood), 1 Poisson with exp link
+ * (gpflow.likelihoods.Poisson), 2 negative binomial with log link and dispersion `param` = alpha
+ * (waveome/likelihoods.py:16-79).  For 1 and 2 the objective is the variational bound of gpflow.models.VGP / PSVGP
+ * with Z = X (waveome/model_fitting.py:158-185, waveome/model_classes.py:1082-1126) maximised over the variational
+ * distribution for the given hyper-parameters: f = -(max_q ELBO + log prior), `lml` reports max_q ELBO, Y holds the
+ * counts, the Gaussian noise slot of the programs is ignored.  Status bit 16: the inner iteration hit its sweep cap. */
+int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param);
+/* Posterior mean and variance of the latent f at the training inputs after the last evaluation of a non-Gaussian
+ * batch, HOST [B, n] each (predict_f at the training inputs). */
+int wv_batch_get_latent(wv_batch* b, double* fmean, double* fvar);
+
 /* Per-model mask over the additive components of its program (bit c = component c takes part in K; default all
  * ones).  "The model without component k, same parameter values" is what the reference's feature importances
  * evaluate (waveome/utilities.py:657-662 pops the component and predicts again): one program, B masks. HOST [B]. */
@@ -138,7 +149,7 @@ void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t* rounds, in
 
 /* Optional per-kernel-class device timing (CUDA events on the engine stream, resolved at the host syncs the fit
  * loop already has).  Classes, in order: gram, chol_diag, chol_panel, trtri, extract, kinv, grad, finalize, lbfgs,
- * chol_syrk (trailing updates of the large-n path).
+ * chol_syrk (trailing updates of the large-n path), sites (site sweeps of the variational path).
  * wv_batch_profile_read fills ms[i] / launches[i] for i < n and returns the number of classes. */
 void wv_batch_profile_enable(wv_batch* b, int on);
 int wv_batch_profile_read(wv_batch* b, double* ms, int64_t* launches, int n);

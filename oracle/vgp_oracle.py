@@ -1,0 +1,181 @@
+"""CPU oracle for the count-outcome path (BASELINE configs[4]: Poisson / negative-binomial outcomes via the
+variational GP).  TEST INFRASTRUCTURE ONLY — same rules as gp_oracle.py (nothing under ``waveome_b200/`` imports it).
+
+PARITY UNPINNED: the reference builds ``gpflow.models.VGP`` (waveome/model_fitting.py:158-185) or the SVGP-with-Z=X
+equivalent ``PSVGP`` (waveome/model_classes.py:1082-1126) with ``gpflow.likelihoods.Poisson`` or
+``waveome.likelihoods.NegativeBinomial`` (waveome/likelihoods.py:16-79); GPflow 2.9.1 is not vendored and cannot be
+installed here, and the reference has no tests.  Restated from the published algorithm:
+
+    K = k(X) + 1e-6 I,  L = chol(K),  f_mean = L q_mu + c,  f_var = rowsum((L q_sqrt)^2)
+    ELBO = sum_i E_{N(f_i; f_mean_i, f_var_i)}[log p(y_i | f_i)] - KL[N(q_mu, q_sqrt q_sqrt^T) || N(0, I)]
+    Poisson (exp link): E = y mu - exp(mu + v/2) - lgamma(y + 1)
+    NegativeBinomial:   20-point Gauss-Hermite of waveome/likelihoods.py:68-79 with m = exp(f)
+
+``vgp_elbo`` is that objective as a function of (theta, q_mu, q_sqrt) — what the reference hands to L-BFGS.
+``vgp_collapsed`` is the same objective maximised over (q_mu, q_sqrt) for fixed theta: for a factorising likelihood
+the optimal q is the posterior of a GP with Gaussian pseudo-observations ytilde_i of precision lam_i ("sites"),
+
+    S = (K^-1 + Lam)^-1,  m = c + K alpha,  alpha = (K + Lam^-1)^-1 (ytilde - c)
+    fixed point:  lam_i = -2 dE_i/dv_i,   alpha_i = dE_i/dm_i
+    F(theta) = log N(ytilde; c, K + Lam^-1) + sum_i [E_i + 1/2 log(2 pi / lam_i) + lam_i/2 ((ytilde_i - m_i)^2 + v_i)]
+    dF/dtheta = 1/2 tr((alpha alpha^T - (K + Lam^-1)^-1) dK/dtheta),  dF/dc = sum(alpha)      (envelope theorem)
+
+which is the form the engine evaluates (each fixed-point sweep is one heteroscedastic GPR factorisation).  The tests
+check F == max_q ELBO (stationarity of vgp_elbo at the q built from the sites, by torch autograd) and dF/dtheta against
+finite differences, before the engine is compared with F.
+"""
+from __future__ import annotations
+
+import copy
+import math
+
+import numpy as np
+
+import gp_oracle as go
+
+JITTER = 1e-6            # gpflow.config.default_jitter()
+GH_X, GH_W = np.polynomial.hermite.hermgauss(20)
+
+
+def lgamma(x):
+    from scipy.special import gammaln
+    return gammaln(x)
+
+
+# --------------------------------------------------------------------------------------------------
+# likelihoods: E_q[log p(y|f)] for f ~ N(m, v), and its derivatives wrt m and v
+# --------------------------------------------------------------------------------------------------
+def nb_logpmf(f, y, alpha):
+    """waveome/likelihoods.py:68-79 with m = exp(f) (log link), k = 1/alpha."""
+    k = 1.0 / alpha
+    m = np.exp(f)
+    return lgamma(k + y) - lgamma(y + 1) - lgamma(k) + y * np.log(m / (m + k)) - k * np.log1p(m * alpha)
+
+
+def var_exp(lik, y, m, v):
+    """(E, dE/dm, dE/dv) per observation."""
+    y = np.asarray(y, dtype=np.float64)
+    if lik["type"] == "poisson":
+        r = np.exp(m + 0.5 * v)
+        return y * m - r - lgamma(y + 1.0), y - r, -0.5 * r
+    if lik["type"] == "negative_binomial":
+        a = lik["alpha"]
+        sd = np.sqrt(2.0 * v)
+        f = m[:, None] + sd[:, None] * GH_X[None, :]
+        w = GH_W[None, :] / math.sqrt(math.pi)
+        lp = nb_logpmf(f, y[:, None], a)
+        # d log p / df = y - (y + 1/a) a e^f / (1 + a e^f);  d2 = -(y + 1/a) a e^f / (1 + a e^f)^2
+        ef = np.exp(f)
+        d1 = y[:, None] - (y[:, None] + 1.0 / a) * a * ef / (1.0 + a * ef)
+        d2 = -(y[:, None] + 1.0 / a) * a * ef / (1.0 + a * ef) ** 2
+        return np.sum(w * lp, 1), np.sum(w * d1, 1), 0.5 * np.sum(w * d2, 1)      # Bonnet / Price
+    raise ValueError(lik["type"])
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference objective: whitened VGP ELBO
+# --------------------------------------------------------------------------------------------------
+def _kernel_and_mean(model, X, x):
+    model = copy.deepcopy(model)
+    go.unpack(model, x)
+    K, _ = go.kernel_K_and_grads(model["kernel"], X, want_grads=False)
+    c = model["mean"]["c"]["value"] if model["mean"]["type"] == "constant" else 0.0
+    return model, K + JITTER * np.eye(len(X)), c
+
+
+def vgp_elbo(model, lik, X, y, x, q_mu, q_sqrt):
+    """gpflow.models.VGP.elbo (whitened) + log prior of the hyper-parameters (none on this path by default)."""
+    model, K, c = _kernel_and_mean(model, X, x)
+    L = np.linalg.cholesky(K)
+    fm = L @ q_mu + c
+    LS = L @ np.tril(q_sqrt)
+    fv = np.sum(LS * LS, 1)
+    E, _, _ = var_exp(lik, y, fm, fv)
+    n = len(y)
+    kl = 0.5 * (np.sum(q_mu ** 2) + np.sum(np.tril(q_sqrt) ** 2) - n - 2.0 * np.sum(np.log(np.abs(np.diag(q_sqrt)))))
+    return float(np.sum(E) - kl)
+
+
+# --------------------------------------------------------------------------------------------------
+# the collapsed form the engine evaluates
+# --------------------------------------------------------------------------------------------------
+def vgp_collapsed(model, lik, X, y, x, sites=None, tol=1e-12, maxit=500, rho=1.0, want_grad=True):
+    """F(theta) = max_q ELBO, its gradient wrt the packed unconstrained hyper-parameters, and the converged sites.
+
+    model: gp_oracle model dict WITHOUT a Gaussian likelihood variance being trainable (it is ignored);
+    x: packed unconstrained (kernel params..., mean).  sites = (lam, lam * ytilde) to warm-start."""
+    spec = copy.deepcopy(model)
+    go.unpack(spec, x)
+    n = len(y)
+    K, dKs = go.kernel_K_and_grads(spec["kernel"], X, want_grads=want_grad)
+    K = K + JITTER * np.eye(n)
+    c = spec["mean"]["c"]["value"] if spec["mean"]["type"] == "constant" else 0.0
+    y = np.asarray(y, dtype=np.float64)
+    if sites is None:
+        lam = np.ones(n)
+        eta = lam * (np.log(y + 1.0))          # precision-mean of the site: lam * ytilde
+    else:
+        lam, eta = [np.array(s, dtype=np.float64) for s in sites]
+    it = 0
+    for it in range(1, maxit + 1):
+        D = 1.0 / lam
+        yt = eta / lam
+        A = K + np.diag(D)
+        Ai = np.linalg.inv(A)
+        alpha = Ai @ (yt - c)
+        m = yt - D * alpha
+        v = D - D * D * np.diag(Ai)
+        E, g, h = var_exp(lik, y, m, v)
+        lam_t = np.maximum(-2.0 * h, 1e-300)
+        eta_t = g + lam_t * m
+        lam_n = (1.0 - rho) * lam + rho * lam_t
+        eta_n = (1.0 - rho) * eta + rho * eta_t
+        delta = max(np.max(np.abs(lam_n - lam) / (np.abs(lam) + 1e-300)), np.max(np.abs(eta_n - eta)) / (1.0 + np.max(np.abs(eta))))
+        lam, eta = lam_n, eta_n
+        if delta < tol:
+            break
+    D = 1.0 / lam
+    yt = eta / lam
+    A = K + np.diag(D)
+    Lc = np.linalg.cholesky(A)
+    z = np.linalg.solve(Lc, yt - c)
+    alpha = np.linalg.solve(Lc.T, z)
+    Ai = np.linalg.inv(A)
+    m = yt - D * alpha
+    v = D - D * D * np.diag(Ai)
+    E, g, h = var_exp(lik, y, m, v)
+    logZ = -0.5 * z @ z - np.sum(np.log(np.diag(Lc))) - 0.5 * n * go.LOG2PI
+    F = logZ + np.sum(E + 0.5 * np.log(2.0 * np.pi / lam) + 0.5 * lam * ((yt - m) ** 2 + v))
+    out = dict(F=float(F), sites=(lam, eta), m=m, v=v, iters=it, alpha=alpha)
+    if want_grad:
+        W = np.outer(alpha, alpha) - Ai
+        grads = []
+        # same packing as gp_oracle.pack: kernel params depth-first, (likelihood variance), mean
+        tp = go.trainable_params(spec)
+        dl = {}
+        for (p, dK) in dKs:
+            dl[id(p)] = dl.get(id(p), 0.0) + 0.5 * float(np.sum(W * dK))
+        for p, u in zip(tp, x):
+            if id(p) in dl:
+                dth = dl[id(p)]
+            elif spec["mean"]["type"] == "constant" and p is spec["mean"]["c"]:
+                dth = np.sum(alpha)
+            else:
+                dth = 0.0                      # the Gaussian noise variance does not exist on this path
+            grads.append(dth * go.transform_dtheta_du(p, u))
+        out["grad"] = np.array(grads)
+    return out
+
+
+def q_from_sites(model, X, y, x, sites):
+    """(q_mu, q_sqrt) of the whitened parameterisation for the Gaussian defined by the sites."""
+    spec, K, c = _kernel_and_mean(model, X, x)
+    lam, eta = sites
+    L = np.linalg.cholesky(K)
+    S = np.linalg.inv(np.linalg.inv(K) + np.diag(lam))
+    A = K + np.diag(1.0 / lam)
+    mf = c + K @ np.linalg.solve(A, eta / lam - c)
+    q_mu = np.linalg.solve(L, mf - c)
+    Sv = np.linalg.solve(L, np.linalg.solve(L, S).T)
+    Sv = 0.5 * (Sv + Sv.T)
+    return q_mu, np.linalg.cholesky(Sv)

@@ -1,0 +1,50 @@
+"""oracle/vgp_oracle.py pinned against itself: the collapsed site form equals the whitened gpflow-VGP ELBO
+ at the q defined by the sites, that q is a maximiser, and dF/dtheta matches finite differences."""
+import copy
+
+import numpy as np
+import pytest
+
+import gp_oracle as go
+import vgp_oracle as vo
+
+
+def _setup(seed=0, n=40):
+    rng = np.random.default_rng(seed)
+    subj = np.repeat(np.arange(8), n // 8).astype(float)
+    t = rng.normal(size=n)
+    X = np.stack([subj, t], 1)
+    f = 0.5 * rng.normal(size=8)[subj.astype(int)] + np.sin(2 * t) + 1.0
+    y = rng.poisson(np.exp(f)).astype(float)
+    kern = {"type": "sum", "kernels": [go.leaf("categorical", 0, variance=0.7),
+                                       go.leaf("squared_exponential", 1, variance=1.3, lengthscales=0.8)]}
+    model = go.gpr_model(kern, noise=1.0, mean="constant", c=0.3)
+    model["likelihood_variance"]["trainable"] = False
+    return model, X, y, go.pack(model), rng
+
+
+@pytest.mark.parametrize("lik", [{"type": "poisson"}, {"type": "negative_binomial", "alpha": 0.7}])
+def test_collapsed_equals_max_of_whitened_elbo(lik):
+    model, X, y, x, rng = _setup()
+    r = vo.vgp_collapsed(model, lik, X, y, x)
+    q_mu, q_sqrt = vo.q_from_sites(model, X, y, x, r["sites"])
+    e = vo.vgp_elbo(model, lik, X, y, x, q_mu, q_sqrt)
+    assert abs(e - r["F"]) <= 1e-10 * abs(e)
+    n = len(y)
+    for _ in range(8):                                   # any perturbation of q lowers the bound
+        dq, dS = 1e-3 * rng.normal(size=n), 1e-3 * np.tril(rng.normal(size=(n, n)))
+        assert vo.vgp_elbo(model, lik, X, y, x, q_mu + dq, q_sqrt + dS) < e
+    h, fd = 1e-5, []
+    for i in range(len(x)):
+        xp, xm = x.copy(), x.copy()
+        xp[i] += h; xm[i] -= h
+        fd.append((vo.vgp_collapsed(model, lik, X, y, xp, want_grad=False)["F"]
+                   - vo.vgp_collapsed(model, lik, X, y, xm, want_grad=False)["F"]) / (2 * h))
+    np.testing.assert_allclose(r["grad"], fd, rtol=1e-7)
+
+
+def test_damping_does_not_change_the_fixed_point():
+    model, X, y, x, _ = _setup(seed=3)
+    a = vo.vgp_collapsed(model, {"type": "poisson"}, X, y, x, rho=1.0, want_grad=False)
+    b = vo.vgp_collapsed(model, {"type": "poisson"}, X, y, x, rho=0.4, want_grad=False, maxit=2000)
+    assert abs(a["F"] - b["F"]) <= 1e-10 * abs(a["F"])

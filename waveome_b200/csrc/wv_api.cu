@@ -15,6 +15,14 @@
 int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
                     double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf, const WvAux* aux);
 
+int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, cudaStream_t st,
+                      WvProfiler* pf, const WvAux* aux);
+int wv_enqueue_grad_finalize(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
+                             double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf);
+int wv_enqueue_site_sweep(const WvBatchDev& bd, const WvVgpState& vs, const int* d_list, int n_list, const double* d_x,
+                          int* d_next, int* d_count, cudaStream_t st, WvProfiler* pf);
+int wv_enqueue_vgp_begin(const WvVgpState& vs, const int* d_list, int n_list, cudaStream_t st);
+int wv_enqueue_vgp_status(const WvVgpState& vs, const int* d_list, int n_list, int* d_status, cudaStream_t st);
 int wv_enqueue_cross_mean(const WvBatchDev& bd, const double* d_x, const double* d_xnew_t, int m, int mpad, double* d_mean,
                           cudaStream_t st);
 
@@ -54,6 +62,9 @@ struct wv_batch {
   int lb_m_alloc;
   int* h_count;   // pinned
   int64_t bytes, launches, rounds, model_evals;
+  WvVgpState vgp;         // site-iteration state (variational path), arrays allocated by wv_batch_set_likelihood
+  int *d_inner1, *d_inner2;
+  int64_t site_sweeps;
   const double* last_x;   // device pointer of the parameters of the last full evaluation (alpha belongs to them)
   WvProfiler prof;
   std::vector<int> perm;   // device row i holds caller row perm[i] (rows sorted by their categorical columns)
@@ -198,7 +209,8 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   WV_CUDA(cudaSetDevice(e->device));
   wv_batch* b = new wv_batch();
   b->eng = e; b->bytes = 0; b->launches = b->rounds = b->model_evals = 0;
-  b->last_x = nullptr;
+  b->last_x = nullptr; b->d_inner1 = b->d_inner2 = nullptr; b->site_sweeps = 0;
+  memset(&b->vgp, 0, sizeof(b->vgp));
   b->d_lbs = nullptr; b->d_lbw = nullptr; b->lb_m_alloc = 0; b->h_count = nullptr;
   WvBatchDev& bd = b->bd;
   bd.n = d->n; bd.D = d->D; bd.B = d->B; bd.P = d->P;
@@ -251,6 +263,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   WV_TRY(wv_alloc(b, &b->d_st2, B));
 #undef WV_TRY
   bd.Xt = dXt; bd.Y = dY; bd.programs = dprog; bd.prog_id = dpid; bd.comp_mask = dmask;
+  bd.lik = 0; bd.lik_param = 0.0; bd.jitter = 0.0; bd.site_lam = nullptr; bd.site_eta = nullptr; bd.vgp_extra = nullptr;
   cudaStream_t st = e->stream;
   // Row order on the device: sorted lexicographically by the categorical columns the programs use (fewest levels
   // first).  The marginal likelihood is invariant under a simultaneous permutation of X rows and y entries; the sort
@@ -341,6 +354,7 @@ extern "C" int wv_batch_profile_read(wv_batch* b, double* ms, int64_t* launches,
 }
 
 extern "C" int64_t wv_batch_workspace_bytes(const wv_batch* b) { return b ? b->bytes : 0; }
+extern "C" int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param);
 
 extern "C" int wv_batch_set_y(wv_batch* b, const double* Y) {
   if (!b || !Y) return wv_fail("wv_batch_set_y: null argument");
@@ -352,6 +366,72 @@ extern "C" int wv_batch_set_y(wv_batch* b, const double* Y) {
   WV_CUDA(cudaMemcpy2DAsync((void*)bd.Y, (size_t)bd.npad * sizeof(double), yp.data(), (size_t)bd.n * sizeof(double),
                             (size_t)bd.n * sizeof(double), bd.B, cudaMemcpyHostToDevice, b->eng->stream));
   WV_CUDA(cudaStreamSynchronize(b->eng->stream));
+  if (bd.lik != 0) return wv_batch_set_likelihood(b, bd.lik, bd.lik_param);     // new counts: restart the sites
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// likelihood of the batch: 0 gaussian (default), 1 poisson, 2 negative binomial (param = alpha)
+// ---------------------------------------------------------------------------------------------
+__global__ void wv_site_init_kernel(int B, int n, int npad, const double* __restrict__ Y, double* lam, double* eta,
+                                    double* lgam) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * npad) return;
+  const int r = (int)(i % npad);
+  const double y = r < n ? Y[i] : 0.0;
+  lam[i] = 1.0;
+  eta[i] = log(y + 1.0);          // pseudo-observation log(y + 1) with unit precision
+  lgam[i] = lgamma(y + 1.0);
+}
+
+extern "C" int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param) {
+  if (!b) return wv_fail("wv_batch_set_likelihood: null batch");
+  if (kind < 0 || kind > 2) return wv_fail("wv_batch_set_likelihood: kind must be 0 (gaussian), 1 (poisson) or 2 (negative binomial)");
+  if (kind == 2 && !(param > 0.0)) return wv_fail("wv_batch_set_likelihood: negative binomial alpha must be positive");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  WvBatchDev& bd = b->bd;
+  bd.lik = kind; bd.lik_param = param;
+  if (kind == 0) { bd.site_lam = bd.site_eta = bd.vgp_extra = nullptr; bd.jitter = 0.0; return 0; }
+  const size_t B = bd.B, np = bd.npad;
+  if (!b->vgp.lam_p) {
+    double* lg = nullptr;
+    if (wv_alloc(b, &bd.site_lam, B * np) || wv_alloc(b, &bd.site_eta, B * np) || wv_alloc(b, &bd.vgp_extra, B) ||
+        wv_alloc(b, &b->vgp.lam_p, B * np) || wv_alloc(b, &b->vgp.eta_p, B * np) || wv_alloc(b, &b->vgp.lam_t, B * np) ||
+        wv_alloc(b, &b->vgp.eta_t, B * np) || wv_alloc(b, &b->vgp.fmean, B * np) || wv_alloc(b, &b->vgp.fvar, B * np) ||
+        wv_alloc(b, &lg, B * np) || wv_alloc(b, &b->vgp.F_prev, B) || wv_alloc(b, &b->vgp.rho, B) ||
+        wv_alloc(b, &b->vgp.first, B) || wv_alloc(b, &b->vgp.inner_task, B) || wv_alloc(b, &b->vgp.sweeps, B) ||
+        wv_alloc(b, &b->vgp.good, B) ||
+        wv_alloc(b, &b->d_inner1, B) || wv_alloc(b, &b->d_inner2, B))
+      return -1;
+    b->vgp.lgam = lg;
+  }
+  bd.jitter = 1e-6;                 // gpflow.config.default_jitter()
+  b->vgp.tol = 1e-8;        // relative move of the sites; the bound is stationary there, so its error is ~tol^2
+  b->vgp.soft_tol = 1e-3;
+  b->vgp.max_sweeps = 80;
+  cudaStream_t st = b->eng->stream;
+  WV_CUDA(cudaMemsetAsync(bd.vgp_extra, 0, B * sizeof(double), st));
+  wv_site_init_kernel<<<(unsigned)((B * np + 255) / 256), 256, 0, st>>>((int)B, bd.n, (int)np, bd.Y, bd.site_lam, bd.site_eta,
+                                                                       (double*)b->vgp.lgam);
+  WV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// posterior mean and variance of f at the training inputs after the last evaluation (variational path), HOST [B, n]
+extern "C" int wv_batch_get_latent(wv_batch* b, double* fmean, double* fvar) {
+  if (!b || !fmean || !fvar) return wv_fail("wv_batch_get_latent: null argument");
+  if (b->bd.lik == 0) return wv_fail("wv_batch_get_latent: the batch has a Gaussian likelihood (use wv_batch_get_alpha)");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const WvBatchDev& bd = b->bd;
+  std::vector<double> t1((size_t)bd.B * bd.npad), t2((size_t)bd.B * bd.npad);
+  WV_CUDA(cudaMemcpyAsync(t1.data(), b->vgp.fmean, t1.size() * sizeof(double), cudaMemcpyDeviceToHost, b->eng->stream));
+  WV_CUDA(cudaMemcpyAsync(t2.data(), b->vgp.fvar, t2.size() * sizeof(double), cudaMemcpyDeviceToHost, b->eng->stream));
+  WV_CUDA(cudaStreamSynchronize(b->eng->stream));
+  for (size_t m = 0; m < (size_t)bd.B; ++m)
+    for (int i = 0; i < bd.n; ++i) {
+      fmean[m * bd.n + b->perm[i]] = t1[m * bd.npad + i];
+      fvar[m * bd.n + b->perm[i]] = t2[m * bd.npad + i];
+    }
   return 0;
 }
 
@@ -374,10 +454,40 @@ extern "C" void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t*
 static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g, double* d_lml, int* d_status,
                        const int* d_active, int n_active) {
   b->eng->aux.epoch += 1;
-  int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, b->eng->stream, &b->prof,
-                          &b->eng->aux);
-  if (l < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
-  b->launches += l; b->rounds += 1; b->model_evals += n_active;
+  cudaStream_t st = b->eng->stream;
+  if (b->bd.lik == 0) {
+    int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, &b->prof, &b->eng->aux);
+    if (l < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    b->launches += l; b->rounds += 1; b->model_evals += n_active;
+    return 0;
+  }
+  // variational path: site sweeps (one factorisation each) until every listed model has converged, then the gradient
+  if (n_active <= 0) return 0;
+  int l = wv_enqueue_vgp_begin(b->vgp, d_active, n_active, st);
+  const int* cur = d_active;
+  int n_in = n_active;
+  int* bufs[2] = {b->d_inner1, b->d_inner2};
+  int which = 0;
+  for (int sweep = 0; sweep < b->vgp.max_sweeps + 2 && n_in > 0; ++sweep) {
+    b->eng->aux.epoch += 1;
+    WV_CUDA(cudaMemsetAsync(b->bd.chol_fail, 0, sizeof(int) * b->bd.B, st));
+    int l1 = wv_enqueue_factor(b->bd, cur, n_in, d_x, st, &b->prof, &b->eng->aux);
+    int l2 = l1 < 0 ? -1 : wv_enqueue_site_sweep(b->bd, b->vgp, cur, n_in, d_x, bufs[which], b->d_count + 1, st, &b->prof);
+    if (l1 < 0 || l2 < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    l += l1 + l2;
+    WV_CUDA(cudaMemcpyAsync(b->h_count + 1, b->d_count + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    WV_CUDA(cudaStreamSynchronize(st));
+    b->prof.resolve();
+    b->site_sweeps += n_in;
+    n_in = b->h_count[1];
+    cur = bufs[which];
+    which ^= 1;
+  }
+  WvProfiler none;
+  int l3 = wv_enqueue_grad_finalize(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, &b->prof);
+  int l4 = l3 < 0 ? -1 : wv_enqueue_vgp_status(b->vgp, d_active, n_active, d_status, st);
+  if (l3 < 0 || l4 < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  b->launches += l + l3 + l4; b->rounds += 1; b->model_evals += n_active;
   return 0;
 }
 

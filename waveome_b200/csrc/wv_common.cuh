@@ -36,6 +36,7 @@ enum WvPrior : int32_t { WV_PRIOR_NONE = 0, WV_PRIOR_HORSESHOE = 1, WV_PRIOR_LAP
 #define WV_STATUS_NONFINITE 2
 #define WV_STATUS_MAXITER 4
 #define WV_STATUS_LINESEARCH 8
+#define WV_STATUS_INNER_CAP 16    // variational path: the site iteration hit its sweep cap
 
 struct WvLeaf {
   int32_t type;    // WvLeafType

@@ -345,6 +345,9 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_gram_kernel(
   const int n = bd.n;
   double* Ab = bd.A + (size_t)b * bd.npad * bd.npad;
   const double* yb = bd.Y + (size_t)b * bd.npad;
+  // variational path: the "observations" are the Gaussian sites (mean eta/lam, noise variance jitter + 1/lam)
+  const double* lam = bd.site_lam ? bd.site_lam + (size_t)b * bd.npad : nullptr;
+  const double* eta = bd.site_eta ? bd.site_eta + (size_t)b * bd.npad : nullptr;
   const int t1 = min(ntiles, (int)(blockIdx.x + 1) * WV_ELEM_TPC);
   for (int t = blockIdx.x * WV_ELEM_TPC; t < t1; ++t) {
     int ti, tj;
@@ -385,8 +388,8 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_gram_kernel(
       for (int bb = 0; bb < 4; ++bb) {
         const int gj = tj * WV_NB + c_off + bb;
         double v;
-        if (gi < n && gj < n) v = acc[a * 4 + bb] + (gi == gj ? s2 : 0.0);
-        else if (gi == n && gj < n) v = yb[gj] - cmean;     // RHS row d^T
+        if (gi < n && gj < n) v = acc[a * 4 + bb] + (gi == gj ? (lam ? bd.jitter + 1.0 / lam[gi] : s2) : 0.0);
+        else if (gi == n && gj < n) v = (lam ? eta[gj] / lam[gj] : yb[gj]) - cmean;     // RHS row d^T
         else v = (gi == gj) ? 1.0 : 0.0;                     // identity padding (incl. A[n][n] = 1)
         out[bb] = v;
       }

@@ -718,7 +718,8 @@ __global__ void __launch_bounds__(64 * WV_FIN_MAXG) wv_finalize_kernel(WvBatchDe
     for (int i = 0; i < pg->n_slots; ++i) lps += s_lp[i];
     double logdet = 0.0;
     for (int jb = 0; jb < bd.nt; ++jb) logdet += bd.logdet_part[(size_t)b * bd.nt + jb];
-    const double lml = -0.5 * bd.quad[b] - 0.5 * bd.n * 1.8378770664093453 - logdet;
+    double lml = -0.5 * bd.quad[b] - 0.5 * bd.n * 1.8378770664093453 - logdet;
+    if (bd.vgp_extra) lml += bd.vgp_extra[b];     // variational path: ELBO at the converged sites
     const double f = -(lml + lps);
     f_out[b] = f;
     lml_out[b] = lml;
@@ -801,23 +802,233 @@ static int wv_enqueue_factor_big(const WvBatchDev& bd, const int* d_active, int 
   return launches;
 }
 
-// Returns the number of kernel launches enqueued (for bench.py's gpu_launches), or -1 on error.
-int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
-                    double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf, const WvAux* aux) {
+// =============================================================================================
+// Variational path for count likelihoods (BASELINE configs[4]; reference: gpflow VGP / PSVGP with Z = X,
+// waveome/model_fitting.py:158-185, waveome/likelihoods.py:16-79).  For a factorising likelihood the optimal Gaussian q
+// of the VGP bound is the posterior of a GP with Gaussian pseudo-observations ("sites": precision lam_i, precision x
+// mean eta_i), so maximising the bound over q for fixed hyper-parameters is a fixed point of heteroscedastic GPR
+// solves -- each sweep is ONE run of the factorisation above with noise jitter + 1/lam_i and data eta_i/lam_i:
+//     m = ytilde - D alpha,   v = D - D^2 diag((K + D)^-1),   D = 1/lam
+//     targets:  lam_i <- -2 dE_i/dv_i,   eta_i <- dE_i/dm_i + lam_i m_i          (E_i = E_q log p(y_i | f_i))
+//     F = log N(ytilde; c, K + D) + sum_i [E_i + 1/2 log(2 pi / lam_i) + lam_i/2 ((ytilde_i - m_i)^2 + v_i)]
+// F is the exact ELBO of the q defined by the current sites (a lower bound at every sweep), which makes the step
+// safe: a damped move (1 - rho) sites + rho targets is accepted only if F did not decrease, otherwise rho is halved
+// and the move is retried from the last accepted sites.  At the fixed point dF/dtheta = 1/2 tr((alpha alpha^T -
+// (K + D)^-1) dK/dtheta) and dF/dc = sum(alpha) (envelope theorem): the Gaussian-path gradient kernel, unchanged.
+// grid (n_list), 256 threads.
+// =============================================================================================
+__device__ __forceinline__ void wv_var_exp(int lik, double alpha_nb, double y, double lgam, double m, double v, double& E,
+                                           double& g, double& h) {
+  if (lik == 1) {                       // Poisson, exp link: closed form (gpflow.likelihoods.Poisson)
+    const double r = exp(m + 0.5 * v);
+    E = y * m - r - lgam;
+    g = y - r;
+    h = -0.5 * r;
+    return;
+  }
+  // negative binomial, log link (waveome/likelihoods.py:68-79), 20-point Gauss-Hermite; derivatives by Bonnet / Price
+  const double gx[10] = {0.2453407083009012, 0.7374737285453944, 1.2340762153953231, 1.7385377121165861,
+                         2.2549740020892757, 2.7888060584281305, 3.3478545673832163, 3.9447640401156252,
+                         4.6036824495507442, 5.3874808900112328};
+  const double gw[10] = {4.622436696006101e-01, 2.866755053628341e-01, 1.090172060200233e-01, 2.481052088746361e-02,
+                         3.243773342237862e-03, 2.283386360163540e-04, 7.802556478532064e-06, 1.086069370769282e-07,
+                         4.399340992273181e-10, 2.229393645534151e-13};
+  const double k = 1.0 / alpha_nb, sd = sqrt(2.0 * v);
+  const double cst = lgamma(k + y) - lgam - lgamma(k);
+  double se = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int q = 0; q < 20; ++q) {
+    const double x = q < 10 ? -gx[9 - q] : gx[q - 10];
+    const double w = (q < 10 ? gw[9 - q] : gw[q - 10]) * 0.5641895835477563;      // / sqrt(pi)
+    const double f = m + sd * x;
+    const double ef = exp(f);
+    const double lp = cst + y * (f - log(ef + k)) - k * log1p(ef * alpha_nb);
+    const double t = alpha_nb * ef / (1.0 + alpha_nb * ef);
+    se += w * lp;
+    s1 += w * (y - (y + k) * t);
+    s2 += w * (-(y + k) * t / (1.0 + alpha_nb * ef));
+  }
+  E = se; g = s1; h = 0.5 * s2;
+}
+
+__global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVgpState vs, const int* __restrict__ list,
+                                                             const double* __restrict__ xall) {
+  __shared__ double red[8];
+  __shared__ double s_bcast[2];
+  __shared__ int s_dec;
+  const int b = list[blockIdx.x];
+  const int n = bd.n, ld = bd.npad;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const WvProgram* pg = bd.programs + bd.prog_id[b];
+  double cmean = 0.0;
+  if (pg->mean_slot >= 0) {
+    const WvSlot& sl = pg->slots[pg->mean_slot];
+    cmean = sl.xindex >= 0 ? wv_transform(sl.transform, xall[(size_t)b * bd.P + sl.xindex], sl.shift) : sl.fixed;
+  }
+  double* lam = bd.site_lam + (size_t)b * ld;
+  double* eta = bd.site_eta + (size_t)b * ld;
+  double* lam_p = vs.lam_p + (size_t)b * ld;
+  double* eta_p = vs.eta_p + (size_t)b * ld;
+  double* lam_t = vs.lam_t + (size_t)b * ld;
+  double* eta_t = vs.eta_t + (size_t)b * ld;
+  const double* al = bd.alpha + (size_t)b * ld;
+  const double* Ab = bd.A + (size_t)b * ld * ld;
+  const double* yb = bd.Y + (size_t)b * ld;
+  const double* lg = vs.lgam + (size_t)b * ld;
+  // ---- pass 1: posterior marginals, variational expectations, the bound, the targets of the next move
+  double part = 0.0, dmax = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double l = lam[i], e = eta[i];
+    const double D = 1.0 / l, yt = e * D;
+    const double m = yt - D * al[i];
+    const double v = D - D * D * Ab[(size_t)i * ld + i];
+    double E, g, h;
+    wv_var_exp(bd.lik, bd.lik_param, yb[i], lg[i], m, v, E, g, h);
+    part += E + 0.5 * log(6.283185307179586 / l) + 0.5 * l * ((yt - m) * (yt - m) + v);
+    const double lt = fmax(-2.0 * h, 1e-300);
+    const double et = g + lt * m;
+    vs.fmean[(size_t)b * ld + i] = m;
+    vs.fvar[(size_t)b * ld + i] = v;
+    // kept in registers would be cheaper, but a rejected sweep must not overwrite the accepted targets: stage in fmean
+    // / fvar's neighbours below only after the decision
+    const double d1 = fabs(lt - l) / (fabs(l) + 1e-300), d2 = fabs(et - e) / (1.0 + fabs(e));
+    dmax = fmax(dmax, fmax(d1, d2));
+    if (!(d1 == d1) || !(d2 == d2)) dmax = INFINITY;
+  }
+  // deterministic block reductions (sum, max)
+  for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xffffffffu, part, o); dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o)); }
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ssum = 0.0;
+    for (int w = 0; w < 8; ++w) ssum += red[w];
+    s_bcast[0] = ssum;
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = dmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mx = 0.0;
+    for (int w = 0; w < 8; ++w) mx = fmax(mx, red[w]);
+    double logdet = 0.0;
+    for (int jb = 0; jb < bd.nt; ++jb) logdet += bd.logdet_part[(size_t)b * bd.nt + jb];
+    const double extra = s_bcast[0];
+    const double F = -0.5 * bd.quad[b] - 0.5 * n * 1.8378770664093453 - logdet + extra;
+    const bool finite = (F - F == 0.0) && !bd.chol_fail[b];
+    const int first = vs.first[b];
+    // 0 converged, 1 accepted (move on), 2 rejected (retry with half the step), 3 give up, 4 sweep cap on an accepted state
+    int dec;
+    double rho = vs.rho[b];
+    int good = vs.good[b];
+    const int sweeps = vs.sweeps[b] + 1;
+    if (!finite || (!first && !(F >= vs.F_prev[b] - 1e-13 * (1.0 + fabs(vs.F_prev[b]))))) {
+      if (first || rho < 1e-6) dec = 3;
+      else { dec = 2; rho *= 0.5; good = 0; }
+    } else if (mx < vs.tol) {
+      dec = 0;
+    } else {
+      dec = 1;
+      vs.F_prev[b] = F;
+      if (!first && ++good >= 3) { rho = fmin(1.0, 1.5 * rho); good = 0; }     // grow the step only after a calm stretch
+    }
+    int flag = (dec == 1 || dec == 2) ? 1 : (dec == 0 ? 0 : -1);
+    if (sweeps >= vs.max_sweeps && dec == 1) { dec = 4; flag = mx < vs.soft_tol ? 0 : -1; }
+    if (sweeps >= vs.max_sweeps && dec == 2) { dec = 3; flag = -1; }
+    if (dec == 0 || dec == 4) bd.vgp_extra[b] = extra;
+    vs.rho[b] = rho;
+    vs.good[b] = good;
+    vs.first[b] = 0;
+    vs.sweeps[b] = sweeps;
+    vs.inner_task[b] = flag;
+    s_dec = dec;
+    s_bcast[1] = rho;
+  }
+  __syncthreads();
+  const int dec = s_dec;
+  const double rho = s_bcast[1];
+  // ---- pass 2: move the sites
+  if (dec == 1) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double l = lam[i], e = eta[i];
+      const double D = 1.0 / l, yt = e * D;
+      const double m = vs.fmean[(size_t)b * ld + i], v = vs.fvar[(size_t)b * ld + i];
+      double E, g, h;
+      wv_var_exp(bd.lik, bd.lik_param, yb[i], lg[i], m, v, E, g, h);
+      const double lt = fmax(-2.0 * h, 1e-300), et = g + lt * m;
+      lam_p[i] = l; eta_p[i] = e; lam_t[i] = lt; eta_t[i] = et;
+      lam[i] = (1.0 - rho) * l + rho * lt;
+      eta[i] = (1.0 - rho) * e + rho * et;
+      (void)yt;
+    }
+  } else if (dec == 2) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      lam[i] = (1.0 - rho) * lam_p[i] + rho * lam_t[i];
+      eta[i] = (1.0 - rho) * eta_p[i] + rho * eta_t[i];
+    }
+  } else if (dec == 3) {
+    // no acceptable move: fall back to the last accepted sites if there are any (the factorisation in memory then
+    // belongs to other sites; the caller flags the evaluation as non-finite)
+    if (!vs.first[b] && vs.sweeps[b] > 1)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) { lam[i] = lam_p[i]; eta[i] = eta_p[i]; }
+  }
+}
+
+// ordered compaction of list entries whose flag is 1 (single CTA)
+__global__ void wv_compact_list_kernel(const int* __restrict__ list, int n_list, const int* __restrict__ flag, int* out,
+                                       int* count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int start = 0; start < n_list; start += blockDim.x) {
+    const int i = start + threadIdx.x;
+    const int b = i < n_list ? list[i] : -1;
+    const bool act = b >= 0 && flag[b] == 1;
+    const unsigned bal = __ballot_sync(0xffffffffu, act);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (act) out[off + __popc(bal & ((1u << lane) - 1))] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < nw; ++w) t += warp_tot[w];
+      base += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base;
+}
+
+__global__ void wv_vgp_begin_kernel(WvVgpState vs, const int* __restrict__ list, int n_list) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_list) return;
+  const int b = list[i];
+  vs.first[b] = 1; vs.rho[b] = 1.0; vs.sweeps[b] = 0; vs.good[b] = 0; vs.inner_task[b] = 1;
+}
+
+// status bits of the site iteration, OR-ed into the evaluation status after finalize
+__global__ void wv_vgp_status_kernel(WvVgpState vs, const int* __restrict__ list, int n_list, int* __restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_list) return;
+  const int b = list[i];
+  if (vs.inner_task[b] == -1) status[b] |= (vs.sweeps[b] >= vs.max_sweeps ? WV_STATUS_INNER_CAP : WV_STATUS_NONFINITE);
+}
+
+// Gram + Cholesky + L^{-T} + alpha + K^{-1} of the listed models.  Returns launches or -1.
+int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, cudaStream_t st,
+                      WvProfiler* pf, const WvAux* aux) {
   if (n_active <= 0) return 0;
-  if (wv_set_attrs() != cudaSuccess) return -1;
+  if (wv_set_attrs() != cudaSuccess || !aux) return -1;
   int launches = 0;
   const int nt = bd.nt;
   const int ntiles = nt * (nt + 1) / 2;
-  WvProfiler none;
-  if (!pf) pf = &none;
-  cudaMemsetAsync(bd.chol_fail, 0, sizeof(int) * bd.B, st);
   pf->mark(-1, st);
   wv_gram_kernel<<<dim3((ntiles + WV_ELEM_TPC - 1) / WV_ELEM_TPC, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
       bd, d_active, d_x, ntiles);
   pf->mark(WV_K_GRAM, st);
   ++launches;
-  if (!aux) return -1;
   if (aux->side && nt >= aux->big_nt) {
     int l = wv_enqueue_factor_big(bd, d_active, n_active, st, pf, *aux);
     if (l < 0) return -1;
@@ -834,15 +1045,56 @@ int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, con
   pf->mark(WV_K_EXTRACT, st);
   wv_kinv_kernel<<<dim3(ntiles, n_active), WV_GEMM_THREADS, sizeof(WvGemmSmem), st>>>(bd, d_active);
   pf->mark(WV_K_KINV, st);
+  launches += 2;
+  return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+// gradient reduction + objective of the listed models (after wv_enqueue_factor)
+int wv_enqueue_grad_finalize(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
+                             double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf) {
+  if (n_active <= 0) return 0;
+  const int nt = bd.nt;
+  const int ntiles = nt * (nt + 1) / 2;
   wv_grad_kernel<<<dim3((ntiles + WV_ELEM_TPC - 1) / WV_ELEM_TPC, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
       bd, d_active, d_x, ntiles);
   pf->mark(WV_K_GRAD, st);
   wv_finalize_kernel<<<dim3(n_active), ntiles > 128 ? 64 * WV_FIN_MAXG : 64, 0, st>>>(bd, d_active, d_x, ntiles, d_f, d_g,
                                                                                   d_lml, d_status);
   pf->mark(WV_K_FINALIZE, st);
-  launches += 4;
-  if (cudaGetLastError() != cudaSuccess) return -1;
-  return launches;
+  return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
+// one sweep of the site iteration after wv_enqueue_factor, and the compaction of the models that go on
+int wv_enqueue_site_sweep(const WvBatchDev& bd, const WvVgpState& vs, const int* d_list, int n_list, const double* d_x,
+                          int* d_next, int* d_count, cudaStream_t st, WvProfiler* pf) {
+  wv_site_update_kernel<<<dim3(n_list), 256, 0, st>>>(bd, vs, d_list, d_x);
+  wv_compact_list_kernel<<<1, 1024, 0, st>>>(d_list, n_list, vs.inner_task, d_next, d_count);
+  pf->mark(WV_K_SITES, st);
+  return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
+int wv_enqueue_vgp_begin(const WvVgpState& vs, const int* d_list, int n_list, cudaStream_t st) {
+  wv_vgp_begin_kernel<<<(n_list + 255) / 256, 256, 0, st>>>(vs, d_list, n_list);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int wv_enqueue_vgp_status(const WvVgpState& vs, const int* d_list, int n_list, int* d_status, cudaStream_t st) {
+  wv_vgp_status_kernel<<<(n_list + 255) / 256, 256, 0, st>>>(vs, d_list, n_list, d_status);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// Returns the number of kernel launches enqueued (for bench.py's gpu_launches), or -1 on error.
+int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
+                    double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf, const WvAux* aux) {
+  if (n_active <= 0) return 0;
+  WvProfiler none;
+  if (!pf) pf = &none;
+  cudaMemsetAsync(bd.chol_fail, 0, sizeof(int) * bd.B, st);
+  const int l1 = wv_enqueue_factor(bd, d_active, n_active, d_x, st, pf, aux);
+  if (l1 < 0) return -1;
+  const int l2 = wv_enqueue_grad_finalize(bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, pf);
+  if (l2 < 0) return -1;
+  return l1 + l2;
 }
 
 // posterior mean at new inputs for every model of the batch (uses bd.alpha of the last evaluation at d_x)

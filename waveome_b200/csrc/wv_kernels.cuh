@@ -43,13 +43,31 @@ struct WvBatchDev {
   int* chol_fail;                   // [B]
   const unsigned* comp_mask;        // [B] bit c = additive component c of the model's program takes part (default all)
   int* step_flag;                   // [B][nt] epoch of the last finished diagonal block (fused Cholesky step)
+  // variational path for count likelihoods (nullptr / 0 on the Gaussian path), see wv_site_update_kernel:
+  int lik;                          // 0 gaussian, 1 poisson (exp link), 2 negative binomial (log link, fixed alpha)
+  double lik_param;                 // negative binomial: alpha
+  double jitter;                    // gpflow default_jitter() added to K on the variational path
+  double* site_lam;                 // [B][npad] precision of the Gaussian pseudo-observation of every row
+  double* site_eta;                 // [B][npad] precision x mean of the pseudo-observation
+  double* vgp_extra;                // [B] sum_i E_i + 1/2 log(2 pi / lam_i) + lam_i/2 ((ytilde_i - m_i)^2 + v_i)
+};
+
+// per-model state of the site iteration (device arrays owned by the batch)
+struct WvVgpState {
+  double *lam_p, *eta_p, *lam_t, *eta_t;   // [B][npad] previous accepted sites, their targets
+  double *F_prev, *rho;                    // [B]
+  double *fmean, *fvar;                    // [B][npad] posterior mean / variance of f at the training inputs
+  const double* lgam;                      // [B][npad] lgamma(y + 1)
+  int *first, *inner_task, *sweeps, *good; // [B]
+  double tol, soft_tol;                    // converged below tol; at the sweep cap accepted without a flag below soft_tol
+  int max_sweeps;
 };
 
 // ---------------------------------------------------------------------------------------------
 // optional per-kernel-class timing with CUDA events on the launching stream (bench.py's live roofline)
 // ---------------------------------------------------------------------------------------------
 enum WvKernelClass { WV_K_GRAM = 0, WV_K_CHOL_DIAG, WV_K_CHOL_PANEL, WV_K_TRTRI, WV_K_EXTRACT, WV_K_KINV, WV_K_GRAD,
-                     WV_K_FINALIZE, WV_K_LBFGS, WV_K_CHOL_SYRK, WV_K_NCLASS };
+                     WV_K_FINALIZE, WV_K_LBFGS, WV_K_CHOL_SYRK, WV_K_SITES, WV_K_NCLASS };
 
 // second stream + events of the large-n path (look-ahead: the next panel is factorised while the bulk of the trailing
 // update of the current one still runs), and the tile count from which that path is taken

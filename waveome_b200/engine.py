@@ -48,10 +48,10 @@ class _LbfgsOpts(C.Structure):
 
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
-    "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
+    "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_likelihood", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
     "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_predict_mean", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
-KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk"]
+KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk", "sites"]
 
 _lib = None
 
@@ -76,6 +76,8 @@ def load_library():
     lib.wv_batch_workspace_bytes.argtypes = [vp]; lib.wv_batch_workspace_bytes.restype = C.c_int64
     lib.wv_batch_set_y.argtypes = [vp, _f64p]; lib.wv_batch_set_y.restype = C.c_int
     lib.wv_batch_set_component_mask.argtypes = [vp, C.POINTER(C.c_uint32)]; lib.wv_batch_set_component_mask.restype = C.c_int
+    lib.wv_batch_set_likelihood.argtypes = [vp, C.c_int32, C.c_double]; lib.wv_batch_set_likelihood.restype = C.c_int
+    lib.wv_batch_get_latent.argtypes = [vp, _f64p, _f64p]; lib.wv_batch_get_latent.restype = C.c_int
     lib.wv_batch_eval.argtypes = [vp, _f64p, _f64p, _f64p, _f64p, _i32p]; lib.wv_batch_eval.restype = C.c_int
     lib.wv_batch_eval_device.argtypes = [vp, vp, vp, vp, vp, vp]; lib.wv_batch_eval_device.restype = C.c_int
     lib.wv_batch_fit_lbfgs.argtypes = [vp, _f64p, C.POINTER(_LbfgsOpts), _f64p, _f64p, _i32p, _i32p, _i32p]
@@ -203,6 +205,20 @@ class Batch:
             raise ValueError("mask must have one entry per model")
         _check(self.lib.wv_batch_set_component_mask(self.handle, mask.ctypes.data_as(C.POINTER(C.c_uint32))),
                "wv_batch_set_component_mask")
+
+    LIKELIHOODS = {"gaussian": 0, "poisson": 1, "negative_binomial": 2}
+
+    def set_likelihood(self, kind, param: float = 0.0):
+        """"gaussian" (default), "poisson", or "negative_binomial" (param = alpha): switches the objective to the
+        variational bound maximised over q (include/waveome_b200.h)."""
+        code = self.LIKELIHOODS[kind] if isinstance(kind, str) else int(kind)
+        _check(self.lib.wv_batch_set_likelihood(self.handle, code, float(param)), "wv_batch_set_likelihood")
+
+    def latent(self):
+        """(mean, var) of f at the training inputs after the last evaluation of a non-Gaussian batch, [B, n] each."""
+        m = np.empty((self.B, self.n)); v = np.empty((self.B, self.n))
+        _check(self.lib.wv_batch_get_latent(self.handle, _f64(m), _f64(v)), "wv_batch_get_latent")
+        return m, v
 
     def eval(self, x: np.ndarray):
         """One LML+gradient evaluation from HOST buffers.  Returns (f, grad, lml, status)."""
