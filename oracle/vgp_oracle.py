@@ -179,3 +179,24 @@ def q_from_sites(model, X, y, x, sites):
     Sv = np.linalg.solve(L, np.linalg.solve(L, S).T)
     Sv = 0.5 * (Sv + Sv.T)
     return q_mu, np.linalg.cholesky(Sv)
+
+
+def fit(model, lik, X, y, maxiter=50000, maxfun=50000, maxcor=10, ftol=2.220446049250313e-09, gtol=1e-05, maxls=20):
+    """What the reference does with this objective: L-BFGS-B (waveome/model_fitting.py:267-281) -- here on the collapsed
+    bound, i.e. over the hyper-parameters only, every evaluation at its optimal q.  Returns dict(x, F, nit, nfev)."""
+    import scipy.optimize as so
+    state = {"sites": None}
+
+    def fun(x):
+        try:
+            r = vgp_collapsed(model, lik, X, y, x, sites=state["sites"], rho=0.5, tol=1e-11, maxit=5000)
+        except np.linalg.LinAlgError:
+            return float("nan"), np.full(len(x), float("nan"))
+        if np.isfinite(r["F"]):
+            state["sites"] = r["sites"]
+        return -r["F"], -r["grad"]
+
+    res = so.minimize(fun, go.pack(model), jac=True, method="L-BFGS-B",
+                      options=dict(maxiter=maxiter, maxfun=maxfun, maxcor=maxcor, ftol=ftol, gtol=gtol, maxls=maxls))
+    r = vgp_collapsed(model, lik, X, y, res.x, sites=state["sites"], rho=0.5, tol=1e-11, maxit=5000, want_grad=False)
+    return dict(x=res.x, F=r["F"], nit=int(res.nit), nfev=int(res.nfev), message=str(res.message))

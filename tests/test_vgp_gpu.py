@@ -89,3 +89,40 @@ def test_sweep_cap_is_flagged_and_bound_stays_valid(engine):
     assert st[0] in (0, 16) and np.isfinite(f[0]) and np.all(np.isfinite(g))
     assert lml[0] <= r["F"] + 1e-8 and r["F"] - lml[0] < 1e-3 * abs(r["F"])
     batch.close()
+
+
+def test_fit_matches_oracle_lbfgs(engine):
+    """MAP fit of the hyper-parameters on the collapsed bound: device L-BFGS-B vs SciPy L-BFGS-B on the oracle."""
+    from waveome_b200.model_fitting import fit_models
+    from waveome_b200.models import make_likelihood
+    X, y = count_data(80, 16, seed=11)
+    rng = np.random.default_rng(5)
+    Y = np.stack([y, rng.poisson(np.exp(0.8 + np.sin(X[:, 1]))).astype(float)])
+    for lik, olik in (("poisson", {"type": "poisson"}), ("negative_binomial", {"type": "negative_binomial", "alpha": 1.0})):
+        models = []
+        for _ in range(2):
+            m = count_model()
+            m.likelihood = make_likelihood(lik)
+            models.append(m)
+        spec = copy.deepcopy(models[0].to_spec())
+        res = fit_models(X, Y, models, engine=engine)
+        for b in range(2):
+            ro = vo.fit(copy.deepcopy(spec), olik, X, Y[b])
+            assert res["status"][b] in (0, 8), res["status"]
+            assert abs(res["lml"][b] - ro["F"]) <= 1e-6 * abs(ro["F"]), (lik, b, res["lml"][b], ro["F"], res["n_iter"][b], ro["nit"])
+            np.testing.assert_allclose(res["x"][b][: len(ro["x"])], ro["x"], rtol=2e-3, atol=2e-3)
+
+
+def test_penalized_optimization_poisson_config5_shape():
+    """BASELINE configs[4] shape at a reduced outcome count: n = 500 (50 subjects x 10 times), Poisson outcomes, model
+    categorical[subject] + squared_exponential[time] (+ product) with horseshoe penalties."""
+    from waveome_b200 import datasets
+    from waveome_b200.model_search import GPSearch
+    X, Y = datasets.count_microbiome(n_outcomes=12)
+    gps = GPSearch(X, Y, unit_col="subject", outcome_likelihood="poisson")
+    gps.penalized_optimization()
+    assert len(gps.models) == 12
+    for o, m in gps.models.items():
+        assert m.likelihood.name == "poisson" and np.isfinite(m.log_posterior_density_value)
+        assert "categorical[0]" in m.kernel_name            # every taxon has a subject effect of sd 0.5
+    assert np.mean(["squared_exponential[1]" in m.kernel_name for m in gps.models.values()]) >= 0.5

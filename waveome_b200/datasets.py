@@ -109,3 +109,25 @@ def large_gpr(n_subjects=512, n_times=16, seed=11):
     y = f + rng.normal(scale=0.1 ** 0.5, size=n)
     X = pd.DataFrame({"subject": subj.astype(float), "t": t})
     return X, pd.DataFrame({"y": y})
+
+
+def count_microbiome(n_subjects=50, n_times=10, n_outcomes=1000, seed=7, family="poisson", alpha=1.0):
+    """Config 5: n = 500 (50 x 10) longitudinal samples, ``n_outcomes`` count outcomes y ~ Poisson(exp(f)) or
+    NB(mean exp(f), alpha), f = subject effect (sd 0.5) + smooth function of time + outcome-specific log abundance."""
+    rng = np.random.default_rng(seed)
+    n = n_subjects * n_times
+    subj = np.repeat(np.arange(n_subjects), n_times)
+    t = np.tile(np.linspace(0.0, 9.0, n_times), n_subjects) + rng.uniform(-0.3, 0.3, size=n)
+    X = pd.DataFrame({"subject": subj.astype(float), "time": t})
+    tz = (t - t.mean()) / t.std()
+    Y = np.empty((n, n_outcomes))
+    for j in range(n_outcomes):
+        amp, ph, base = rng.uniform(0.2, 1.0), rng.uniform(0, 2 * np.pi), rng.uniform(0.0, 3.0)
+        f = base + 0.5 * rng.normal(size=n_subjects)[subj] + amp * np.sin(1.5 * tz + ph)
+        mu = np.exp(f)
+        if family == "poisson":
+            Y[:, j] = rng.poisson(mu)
+        else:
+            k = 1.0 / alpha
+            Y[:, j] = rng.negative_binomial(k, k / (k + mu))
+    return X, pd.DataFrame(Y, columns=[f"taxon_{j}" for j in range(n_outcomes)])

@@ -358,10 +358,13 @@ def full_kernel_search_gen(n_features, kern_list, cat_vars=(), max_depth=5, keep
 # ------------------------------------------------------------------------------------------------
 # execution: fitters and the lock-step driver
 # ------------------------------------------------------------------------------------------------
-def candidate_model(kernel, mean_function=None) -> GPR:
-    """The model ``kernel_test`` builds (:2269-2282): penalisation 0 (no prior), Gaussian noise 1.0, constant mean.
-    The model owns deep copies (BaseGP.__init__, waveome/model_classes.py:110-111)."""
-    return GPR(K.deepcopy(kernel), mean_function=K.deepcopy(mean_function) if mean_function is not None else ConstantMean())
+def candidate_model(kernel, mean_function=None, likelihood="gaussian") -> GPR:
+    """The model ``kernel_test`` builds (:2269-2282): penalisation 0 (no prior), Gaussian noise 1.0 (or the count
+    likelihood of the search), constant mean.  The model owns deep copies (BaseGP.__init__,
+    waveome/model_classes.py:110-111)."""
+    from .models import make_likelihood
+    return GPR(K.deepcopy(kernel), mean_function=K.deepcopy(mean_function) if mean_function is not None else ConstantMean(),
+               likelihood=make_likelihood(likelihood))
 
 
 def candidate_bic(model: GPR, log_posterior_density: float) -> float:
@@ -369,7 +372,8 @@ def candidate_bic(model: GPR, log_posterior_density: float) -> float:
     return round(calc_bic(loglik=log_posterior_density, n=0, k=len(model.trainable_parameters)), 2)
 
 
-def engine_fitter(X: np.ndarray, engine=None, num_restart=1, random_seed=None, max_iter=50000) -> Callable:
+def engine_fitter(X: np.ndarray, engine=None, num_restart=1, random_seed=None, max_iter=50000,
+                  likelihood="gaussian") -> Callable:
     """Returns ``fit(requests) -> results`` where requests is a list of (y [n], name, kernel): all of them become one
     engine batch (restarts included: ``num_restart`` > 1 adds randomised starts as extra models of the batch,
     waveome/model_classes.py:472-524, seeds ``random_seed + 1 + r`` or ``r``)."""
@@ -382,7 +386,7 @@ def engine_fitter(X: np.ndarray, engine=None, num_restart=1, random_seed=None, m
         models, ys = [], []
         for y, _name, kernel in requests:
             for r in range(R):
-                m = candidate_model(kernel)
+                m = candidate_model(kernel, likelihood=likelihood)
                 if R > 1:
                     rs = np.random.RandomState(r if random_seed is None else random_seed + 1 + r)
                     for p in m.trainable_parameters:

@@ -30,6 +30,13 @@ def get_engine(device: Optional[int] = None):
     return _ENGINES[device]
 
 
+def likelihood_key(model) -> tuple:
+    """(engine likelihood name, parameter) of a model: ("gaussian", 0.0), ("poisson", 0.0), ("negative_binomial", alpha)."""
+    lik = model.likelihood
+    name = getattr(lik, "name", "gaussian")
+    return (name, float(getattr(lik, "engine_param", 0.0))) if name != "gaussian" else ("gaussian", 0.0)
+
+
 def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional[np.ndarray] = None,
                engine=None, max_batch_bytes: float = 60e9, **lbfgs_opts) -> dict:
     """MAP-fit ``models[b]`` to outcome ``Y[b]`` (Y is [B, n]); all models share X [n, D].
@@ -65,18 +72,26 @@ def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional
     chunk = max(1, int(max_batch_bytes // per_model))
     out = dict(x=np.empty((B, P)), f=np.empty(B), lml=np.empty(B), n_iter=np.empty(B, np.int32),
                n_eval=np.empty(B, np.int32), status=np.empty(B, np.int32), launches=0, rounds=0)
-    for lo in range(0, B, chunk):
-        hi = min(B, lo + chunk)
-        batch = Batch(engine, X, Y[lo:hi], table, prog_id[lo:hi], P=P)
-        try:
-            r = batch.fit(starts[lo:hi], **lbfgs_opts)
-            c = batch.counters()
-        finally:
-            batch.close()
-        for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
-            out[key][lo:hi] = r[key]
-        out["launches"] += c["launches"]
-        out["rounds"] += c["rounds"]
+    # one engine batch holds one likelihood: group the models by (likelihood, parameter), keep the caller's order
+    groups: Dict[tuple, list] = {}
+    for b, m in enumerate(models):
+        groups.setdefault(likelihood_key(m), []).append(b)
+    for (lik_name, lik_param), idx in groups.items():
+        idx = np.asarray(idx)
+        for lo in range(0, len(idx), chunk):
+            sel = idx[lo: lo + chunk]
+            batch = Batch(engine, X, Y[sel], table, prog_id[sel], P=P)
+            try:
+                if lik_name != "gaussian":
+                    batch.set_likelihood(lik_name, lik_param)
+                r = batch.fit(starts[sel], **lbfgs_opts)
+                c = batch.counters()
+            finally:
+                batch.close()
+            for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
+                out[key][sel] = r[key]
+            out["launches"] += c["launches"]
+            out["rounds"] += c["rounds"]
     for b, (m, p) in enumerate(zip(models, progs)):
         p.assign(out["x"][b, : p.n_x])
         m.log_marginal_likelihood_value = float(out["lml"][b])
@@ -114,6 +129,7 @@ def fit_replicated(X: np.ndarray, Y: np.ndarray, template: GPR, make_models=None
     Y = np.ascontiguousarray(Y, dtype=np.float64)
     B = Y.shape[0]
     prog = template.program()
+    lik_name, lik_param = likelihood_key(template)
     P = max(1, prog.n_x)
     n = X.shape[0]
     npad = ((n + 1 + 7) // 8 * 8 + 63) // 64 * 64
@@ -128,6 +144,8 @@ def fit_replicated(X: np.ndarray, Y: np.ndarray, template: GPR, make_models=None
                 hi = min(B, lo + chunk)
                 batch = Batch(engine, X, Y[lo:hi], [prog], P=P)
                 try:
+                    if lik_name != "gaussian":
+                        batch.set_likelihood(lik_name, lik_param)
                     r = batch.fit(**lbfgs_opts)
                     c = batch.counters()
                 finally:

@@ -18,7 +18,7 @@ import pandas as pd
 
 from . import kernels as K
 from .model_fitting import fit_models, fit_replicated, get_engine
-from .models import ConstantMean, PenalizedGPR
+from .models import ConstantMean, PenalizedGPR, make_likelihood
 from .postfit import feature_importances_batch
 from .regularization import full_kernel_build
 
@@ -108,8 +108,7 @@ class GPSearch:
         compatibility; the engine always fits the exact model on the GPU.  Under ``torch.distributed`` the
         outcomes are sharded over ranks with no collective on the data path; with ``gather=True`` the fitted
         models are exchanged afterwards so every rank holds ``self.models`` for all outcomes."""
-        if self.likelihood != "gaussian":
-            raise NotImplementedError("the B200 engine covers outcome_likelihood='gaussian' (objective A)")
+        make_likelihood(self.likelihood)              # raises for likelihoods the engine does not cover
         if penalization_factor is None:
             raise NotImplementedError("penalization_factor=None (iterated factor) needs predict_y: next row (§8f)")
         self.model_selection_type = "penalized"
@@ -129,7 +128,7 @@ class GPSearch:
         names = self.out_names[lo:hi]
         t0 = time.time()
         template = PenalizedGPR(K.deepcopy(full_kernel), mean_function=K.deepcopy(mean_function),
-                                penalization_factor=penalization_factor)
+                                penalization_factor=penalization_factor, likelihood=make_likelihood(self.likelihood))
 
         def make_models() -> List[PenalizedGPR]:      # every outcome owns its copy (model_search.py:305-306)
             return [K.deepcopy(template) for _ in names]
@@ -166,8 +165,9 @@ class GPSearch:
             m.cut_kernel_components(Xn)
             m.update_kernel_name()
         # get_feature_importances of every model (model_search.py:383-387) as one more engine batch
-        for m, fi in zip(models, feature_importances_batch(Xn, Yn, models)):
-            m.feature_importances = fi
+        if self.likelihood == "gaussian":
+            for m, fi in zip(models, feature_importances_batch(Xn, Yn, models)):
+                m.feature_importances = fi
         local = dict(zip(names, models))
         report = dict(n_models=len(names), seconds=time.time() - t0, n_eval=int(np.sum(res["n_eval"])),
                       status=np.asarray(res["status"]).copy(), n_fits_per_model=n_fits)
@@ -191,8 +191,7 @@ class GPSearch:
         ``self.models[outcome]`` = best model, ``self.search_info[outcome]`` = {"models", "edges", "best_model"}.
         ``num_jobs`` is accepted for signature compatibility.  ``fit`` replaces the engine fitter (tests)."""
         from . import kernel_search as ks
-        if self.likelihood != "gaussian":
-            raise NotImplementedError("the B200 engine covers outcome_likelihood='gaussian' (objective A)")
+        make_likelihood(self.likelihood)              # raises for likelihoods the engine does not cover
         self.model_selection_type = "stepwise"
         self.verbose = verbose
         if kernels is None:
@@ -208,7 +207,7 @@ class GPSearch:
         if verbose and rank == 0:
             print(f"Building {len(self.out_names)} models on {world} GPU(s)...")
         counters = dict(fits=0, batches=0)
-        inner = fit or ks.engine_fitter(Xn, num_restart=num_restart, random_seed=random_seed)
+        inner = fit or ks.engine_fitter(Xn, num_restart=num_restart, random_seed=random_seed, likelihood=self.likelihood)
 
         def counted(requests):
             counters["fits"] += len(requests) * max(1, int(num_restart))

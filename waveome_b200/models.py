@@ -27,6 +27,48 @@ class Gaussian:
         return [self.variance]
 
 
+class Poisson:
+    """gpflow.likelihoods.Poisson (exp inverse link, binsize 1): no parameters."""
+    name = "poisson"
+    parameters: list = []
+
+    def __init__(self):
+        self._dummy_noise = K.Parameter(1.0, transform=("softplus_shift", 1e-6), trainable=False)
+
+    @property
+    def engine_param(self):
+        return 0.0
+
+
+class NegativeBinomial:
+    """waveome/likelihoods.py:16-66: dispersion ``alpha`` with an Exp bijector, log link.  The engine evaluates the
+    bound for a FIXED alpha (the reference trains it; stated in DESIGN.md)."""
+    name = "negative_binomial"
+
+    def __init__(self, alpha=1.0):
+        self.alpha = K.Parameter(alpha, transform="exp", trainable=False)
+        self._dummy_noise = K.Parameter(1.0, transform=("softplus_shift", 1e-6), trainable=False)
+
+    @property
+    def parameters(self):
+        return [self.alpha]
+
+    @property
+    def engine_param(self):
+        return float(self.alpha)
+
+
+def make_likelihood(name, **kw):
+    """gp_likelihood_crosswalk (waveome/utilities.py:989-1009) for the likelihoods the engine covers."""
+    if name == "gaussian":
+        return Gaussian(**kw)
+    if name == "poisson":
+        return Poisson()
+    if name in ("negative_binomial", "negativebinomial"):
+        return NegativeBinomial(**kw)
+    raise NotImplementedError(f"likelihood {name!r} is not covered by the B200 engine (gaussian, poisson, negative_binomial)")
+
+
 class ConstantMean:
     """gpflow.mean_functions.Constant: trainable scalar ``c`` (identity bijector), default 0."""
     name = "constant"
@@ -46,7 +88,7 @@ class ZeroMean:
 
 
 class GPR:
-    def __init__(self, kernel: K.Kernel, mean_function=None, noise_variance: float = 1.0, likelihood: Optional[Gaussian] = None):
+    def __init__(self, kernel: K.Kernel, mean_function=None, noise_variance: float = 1.0, likelihood=None):
         self.kernel = kernel
         self.mean_function = mean_function if mean_function is not None else ZeroMean()
         self.likelihood = likelihood if likelihood is not None else Gaussian(noise_variance)
@@ -74,7 +116,10 @@ class GPR:
     def parameter_dict(self):
         """gpflow.utilities.parameter_dict(model)-style {path: Parameter}."""
         d = dict(self.kernel.named_parameters("kernel"))
-        d[".likelihood.variance"] = self.likelihood.variance
+        if isinstance(self.likelihood, Gaussian):
+            d[".likelihood.variance"] = self.likelihood.variance
+        elif isinstance(self.likelihood, NegativeBinomial):
+            d[".likelihood.alpha"] = self.likelihood.alpha
         if isinstance(self.mean_function, ConstantMean):
             d[".mean_function.c"] = self.mean_function.c
         return d
@@ -82,11 +127,18 @@ class GPR:
     # engine interface ------------------------------------------------------------------------
     def program(self) -> Program:
         mc = self.mean_function.c if isinstance(self.mean_function, ConstantMean) else None
-        return build_program(self.kernel, self.likelihood.variance, mc)
+        # count likelihoods: the program's noise slot is a frozen placeholder the engine ignores
+        noise = self.likelihood.variance if isinstance(self.likelihood, Gaussian) else self.likelihood._dummy_noise
+        return build_program(self.kernel, noise, mc)
 
     def to_spec(self) -> dict:
         """Neutral JSON-able description (the format the test oracle consumes)."""
-        spec = {"kernel": self.kernel.to_spec(), "likelihood_variance": self.likelihood.variance.to_spec()}
+        noise = self.likelihood.variance if isinstance(self.likelihood, Gaussian) else self.likelihood._dummy_noise
+        spec = {"kernel": self.kernel.to_spec(), "likelihood_variance": noise.to_spec()}
+        if not isinstance(self.likelihood, Gaussian):
+            spec["likelihood"] = {"type": self.likelihood.name}
+            if isinstance(self.likelihood, NegativeBinomial):
+                spec["likelihood"]["alpha"] = float(self.likelihood.alpha)
         if isinstance(self.mean_function, ConstantMean):
             spec["mean"] = {"type": "constant", "c": self.mean_function.c.to_spec()}
         else:
@@ -130,8 +182,8 @@ class PenalizedGPR(GPR):
     scale 1/penalization_factor on every trainable kernel variance (:837-864), structure pruning by
     ``cut_kernel_components`` (:1029-1079)."""
 
-    def __init__(self, kernel, mean_function=None, noise_variance=1.0, penalization_factor=1.0):
-        super().__init__(kernel, mean_function=mean_function, noise_variance=noise_variance)
+    def __init__(self, kernel, mean_function=None, noise_variance=1.0, penalization_factor=1.0, likelihood=None):
+        super().__init__(kernel, mean_function=mean_function, noise_variance=noise_variance, likelihood=likelihood)
         self.name = "penalized_gpr"
         self.feature_importances = None
         self.set_penalization_factor(penalization_factor)
