@@ -112,7 +112,9 @@ int wv_batch_set_y(wv_batch* b, const double* Y);
  * (waveome/likelihoods.py:16-79).  For 1 and 2 the objective is the variational bound of gpflow.models.VGP / PSVGP
  * with Z = X (waveome/model_fitting.py:158-185, waveome/model_classes.py:1082-1126) maximised over the variational
  * distribution for the given hyper-parameters: f = -(max_q ELBO + log prior), `lml` reports max_q ELBO, Y holds the
- * counts, the Gaussian noise slot of the programs is ignored.  Status bit 16: the inner iteration hit its sweep cap. */
+ * counts.  The programs' noise slot: ignored for Poisson; for the negative binomial a TRAINABLE noise slot (Exp
+ * bijector) is the dispersion alpha and gets d(bound)/d(alpha), a frozen one means alpha = `param`.
+ * Status bit 16: the inner iteration hit its sweep cap. */
 int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param);
 /* Posterior mean and variance of the latent f at the training inputs after the last evaluation of a non-Gaussian
  * batch, HOST [B, n] each (predict_f at the training inputs). */

@@ -52,6 +52,27 @@ def nb_logpmf(f, y, alpha):
     return lgamma(k + y) - lgamma(y + 1) - lgamma(k) + y * np.log(m / (m + k)) - k * np.log1p(m * alpha)
 
 
+def nb_dalpha(y, m, v, a):
+    """sum_i dE_i/d(alpha) for the negative binomial (20-point Gauss-Hermite of d log p / d alpha)."""
+    from scipy.special import digamma
+    y = np.asarray(y, dtype=np.float64)
+    k = 1.0 / a
+    f = m[:, None] + np.sqrt(2.0 * v)[:, None] * GH_X[None, :]
+    w = GH_W[None, :] / math.sqrt(math.pi)
+    ef = np.exp(f)
+    dk = (digamma(k + y) - digamma(k))[:, None] - y[:, None] / (ef + k) - np.log1p(ef * a) + ef / (k + ef)
+    return float(np.sum(w * dk) * (-k * k))
+
+
+def lik_of(model, lik):
+    """The likelihood dict with alpha taken from the model when it carries the dispersion in its (unused) Gaussian
+    noise slot: spec["likelihood_variance"] with an exp transform (how the product's NegativeBinomial is encoded)."""
+    lv = model["likelihood_variance"]
+    if lik["type"] == "negative_binomial" and lv.get("transform") == "exp":
+        return {"type": "negative_binomial", "alpha": lv["value"]}
+    return lik
+
+
 def var_exp(lik, y, m, v):
     """(E, dE/dm, dE/dv) per observation."""
     y = np.asarray(y, dtype=np.float64)
@@ -86,6 +107,7 @@ def _kernel_and_mean(model, X, x):
 def vgp_elbo(model, lik, X, y, x, q_mu, q_sqrt):
     """gpflow.models.VGP.elbo (whitened) + log prior of the hyper-parameters (none on this path by default)."""
     model, K, c = _kernel_and_mean(model, X, x)
+    lik = lik_of(model, lik)
     L = np.linalg.cholesky(K)
     fm = L @ q_mu + c
     LS = L @ np.tril(q_sqrt)
@@ -106,6 +128,7 @@ def vgp_collapsed(model, lik, X, y, x, sites=None, tol=1e-12, maxit=500, rho=1.0
     x: packed unconstrained (kernel params..., mean).  sites = (lam, lam * ytilde) to warm-start."""
     spec = copy.deepcopy(model)
     go.unpack(spec, x)
+    lik = lik_of(spec, lik)
     n = len(y)
     K, dKs = go.kernel_K_and_grads(spec["kernel"], X, want_grads=want_grad)
     K = K + JITTER * np.eye(n)
@@ -160,6 +183,8 @@ def vgp_collapsed(model, lik, X, y, x, sites=None, tol=1e-12, maxit=500, rho=1.0
                 dth = dl[id(p)]
             elif spec["mean"]["type"] == "constant" and p is spec["mean"]["c"]:
                 dth = np.sum(alpha)
+            elif p is spec["likelihood_variance"] and lik["type"] == "negative_binomial":
+                dth = nb_dalpha(y, m, v, lik["alpha"])          # the slot carries the NB dispersion
             else:
                 dth = 0.0                      # the Gaussian noise variance does not exist on this path
             grads.append(dth * go.transform_dtheta_du(p, u))

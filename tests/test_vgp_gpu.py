@@ -58,6 +58,27 @@ def test_collapsed_bound_and_gradient_match_oracle(engine, lik, param, n):
     batch.close()
 
 
+def test_trainable_dispersion_gradient(engine):
+    """waveome's NegativeBinomial trains alpha (Exp bijector, likelihoods.py:24-28): it rides in the program's noise slot
+    and receives d(bound)/d(alpha) = sum_i dE_i/d(alpha)."""
+    from waveome_b200.engine import Batch
+    from waveome_b200.models import NegativeBinomial
+    X, y = count_data(90, 15, seed=21)
+    model = count_model()
+    model.likelihood = NegativeBinomial(alpha=0.6)
+    p = model.program()
+    assert p.n_x == 5 and p.slot_xindex[p.noise_slot] >= 0
+    batch = Batch(engine, X, y[None, :], [p])
+    batch.set_likelihood("negative_binomial", 123.0)          # ignored: the slot is trainable
+    x = batch.x0() + 0.1
+    f, g, lml, st = batch.eval(x)
+    r = vo.vgp_collapsed(copy.deepcopy(model.to_spec()), {"type": "negative_binomial", "alpha": 123.0}, X, y, x[0],
+                         rho=0.5, tol=1e-12, maxit=2000)
+    assert st[0] == 0 and abs(lml[0] - r["F"]) <= 1e-8 * abs(r["F"])
+    np.testing.assert_allclose(g[0], -r["grad"], rtol=0, atol=1e-6 * np.max(np.abs(r["grad"])))
+    batch.close()
+
+
 def test_hard_regimes_converge(engine):
     """huge counts under a tight prior (the plain fixed point overflows on its first move) and low counts under a wide
     prior (it oscillates): the safeguarded iteration must still reach the oracle's optimum"""
@@ -126,3 +147,8 @@ def test_penalized_optimization_poisson_config5_shape():
         assert m.likelihood.name == "poisson" and np.isfinite(m.log_posterior_density_value)
         assert "categorical[0]" in m.kernel_name            # every taxon has a subject effect of sd 0.5
     assert np.mean(["squared_exponential[1]" in m.kernel_name for m in gps.models.values()]) >= 0.5
+    # feature importances with the Poisson deviance (utilities.py:553-558): one entry per component + residual
+    for m in gps.models.values():
+        ncomp = len(m.kernel.kernels) if m.kernel.name == "sum" else 1
+        assert len(m.feature_importances) == ncomp + 1 and 0.0 <= m.feature_importances[-1] <= 1.0
+        assert all(np.isfinite(v) for v in m.feature_importances)

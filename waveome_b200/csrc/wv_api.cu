@@ -263,7 +263,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   WV_TRY(wv_alloc(b, &b->d_st2, B));
 #undef WV_TRY
   bd.Xt = dXt; bd.Y = dY; bd.programs = dprog; bd.prog_id = dpid; bd.comp_mask = dmask;
-  bd.lik = 0; bd.lik_param = 0.0; bd.jitter = 0.0; bd.site_lam = nullptr; bd.site_eta = nullptr; bd.vgp_extra = nullptr;
+  bd.lik = 0; bd.lik_param = 0.0; bd.jitter = 0.0; bd.site_lam = nullptr; bd.site_eta = nullptr; bd.vgp_extra = nullptr; bd.vgp_dlik = nullptr;
   cudaStream_t st = e->stream;
   // Row order on the device: sorted lexicographically by the categorical columns the programs use (fewest levels
   // first).  The marginal likelihood is invariant under a simultaneous permutation of X rows and y entries; the sort
@@ -391,11 +391,11 @@ extern "C" int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param) 
   WV_CUDA(cudaSetDevice(b->eng->device));
   WvBatchDev& bd = b->bd;
   bd.lik = kind; bd.lik_param = param;
-  if (kind == 0) { bd.site_lam = bd.site_eta = bd.vgp_extra = nullptr; bd.jitter = 0.0; return 0; }
+  if (kind == 0) { bd.site_lam = bd.site_eta = bd.vgp_extra = bd.vgp_dlik = nullptr; bd.jitter = 0.0; return 0; }
   const size_t B = bd.B, np = bd.npad;
   if (!b->vgp.lam_p) {
     double* lg = nullptr;
-    if (wv_alloc(b, &bd.site_lam, B * np) || wv_alloc(b, &bd.site_eta, B * np) || wv_alloc(b, &bd.vgp_extra, B) ||
+    if (wv_alloc(b, &bd.site_lam, B * np) || wv_alloc(b, &bd.site_eta, B * np) || wv_alloc(b, &bd.vgp_extra, B) || wv_alloc(b, &bd.vgp_dlik, B) ||
         wv_alloc(b, &b->vgp.lam_p, B * np) || wv_alloc(b, &b->vgp.eta_p, B * np) || wv_alloc(b, &b->vgp.lam_t, B * np) ||
         wv_alloc(b, &b->vgp.eta_t, B * np) || wv_alloc(b, &b->vgp.fmean, B * np) || wv_alloc(b, &b->vgp.fvar, B * np) ||
         wv_alloc(b, &lg, B * np) || wv_alloc(b, &b->vgp.F_prev, B) || wv_alloc(b, &b->vgp.rho, B) ||
@@ -411,6 +411,7 @@ extern "C" int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param) 
   b->vgp.max_sweeps = 80;
   cudaStream_t st = b->eng->stream;
   WV_CUDA(cudaMemsetAsync(bd.vgp_extra, 0, B * sizeof(double), st));
+  WV_CUDA(cudaMemsetAsync(bd.vgp_dlik, 0, B * sizeof(double), st));
   wv_site_init_kernel<<<(unsigned)((B * np + 255) / 256), 256, 0, st>>>((int)B, bd.n, (int)np, bd.Y, bd.site_lam, bd.site_eta,
                                                                        (double*)b->vgp.lgam);
   WV_CUDA(cudaStreamSynchronize(st));

@@ -706,6 +706,7 @@ __global__ void __launch_bounds__(64 * WV_FIN_MAXG) wv_finalize_kernel(WvBatchDe
       for (int g = 0; g < G; ++g) dl += s_part[g][s];
       dl *= 0.5;
       if (s == pg->mean_slot) dl = s_sum_alpha;
+      if (bd.lik == 2 && s == pg->noise_slot) dl = bd.vgp_dlik[b];      // the noise slot is the NB dispersion there
       const double g = -(dl + dlp) * wv_transform_grad(sl.transform, u);
       g_out[(size_t)b * bd.P + sl.xindex] = g;
       if (!isfinite(g)) atomicOr(&s_bad, 1);
@@ -817,8 +818,18 @@ static int wv_enqueue_factor_big(const WvBatchDev& bd, const int* d_active, int 
 // (K + D)^-1) dK/dtheta) and dF/dc = sum(alpha) (envelope theorem): the Gaussian-path gradient kernel, unchanged.
 // grid (n_list), 256 threads.
 // =============================================================================================
+// digamma: recurrence up to x >= 10, then the asymptotic series (|error| < 1e-15 there)
+__device__ __forceinline__ double wv_digamma(double x) {
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  return r + log(x) - 0.5 / x -
+         f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f * (1.0 / 132.0)))));
+}
+
 __device__ __forceinline__ void wv_var_exp(int lik, double alpha_nb, double y, double lgam, double m, double v, double& E,
-                                           double& g, double& h) {
+                                           double& g, double& h, double& da) {
+  da = 0.0;
   if (lik == 1) {                       // Poisson, exp link: closed form (gpflow.likelihoods.Poisson)
     const double r = exp(m + 0.5 * v);
     E = y * m - r - lgam;
@@ -835,7 +846,8 @@ __device__ __forceinline__ void wv_var_exp(int lik, double alpha_nb, double y, d
                          4.399340992273181e-10, 2.229393645534151e-13};
   const double k = 1.0 / alpha_nb, sd = sqrt(2.0 * v);
   const double cst = lgamma(k + y) - lgam - lgamma(k);
-  double se = 0.0, s1 = 0.0, s2 = 0.0;
+  double se = 0.0, s1 = 0.0, s2 = 0.0, sk = 0.0;
+  const double dcst = wv_digamma(k + y) - wv_digamma(k);          // d cst / dk
   for (int q = 0; q < 20; ++q) {
     const double x = q < 10 ? -gx[9 - q] : gx[q - 10];
     const double w = (q < 10 ? gw[9 - q] : gw[q - 10]) * 0.5641895835477563;      // / sqrt(pi)
@@ -846,14 +858,18 @@ __device__ __forceinline__ void wv_var_exp(int lik, double alpha_nb, double y, d
     se += w * lp;
     s1 += w * (y - (y + k) * t);
     s2 += w * (-(y + k) * t / (1.0 + alpha_nb * ef));
+    // d log p / dk = psi(k+y) - psi(k) - y / (e^f + k) - log(1 + e^f / k) + e^f / (k + e^f)
+    sk += w * (dcst - y / (ef + k) - log1p(ef * alpha_nb) + ef / (k + ef));
   }
   E = se; g = s1; h = 0.5 * s2;
+  da = -k * k * sk;                     // dk / dalpha = -1 / alpha^2
 }
 
 __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVgpState vs, const int* __restrict__ list,
                                                              const double* __restrict__ xall) {
   __shared__ double red[8];
   __shared__ double s_bcast[2];
+  __shared__ double s_dal;
   __shared__ int s_dec;
   const int b = list[blockIdx.x];
   const int n = bd.n, ld = bd.npad;
@@ -863,6 +879,11 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
   if (pg->mean_slot >= 0) {
     const WvSlot& sl = pg->slots[pg->mean_slot];
     cmean = sl.xindex >= 0 ? wv_transform(sl.transform, xall[(size_t)b * bd.P + sl.xindex], sl.shift) : sl.fixed;
+  }
+  double lik_param = bd.lik_param;
+  if (bd.lik == 2) {        // a trainable noise slot is the dispersion alpha
+    const WvSlot& sl = pg->slots[pg->noise_slot];
+    if (sl.xindex >= 0) lik_param = wv_transform(sl.transform, xall[(size_t)b * bd.P + sl.xindex], sl.shift);
   }
   double* lam = bd.site_lam + (size_t)b * ld;
   double* eta = bd.site_eta + (size_t)b * ld;
@@ -875,14 +896,15 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
   const double* yb = bd.Y + (size_t)b * ld;
   const double* lg = vs.lgam + (size_t)b * ld;
   // ---- pass 1: posterior marginals, variational expectations, the bound, the targets of the next move
-  double part = 0.0, dmax = 0.0;
+  double part = 0.0, dmax = 0.0, dalpha = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double l = lam[i], e = eta[i];
     const double D = 1.0 / l, yt = e * D;
     const double m = yt - D * al[i];
     const double v = D - D * D * Ab[(size_t)i * ld + i];
-    double E, g, h;
-    wv_var_exp(bd.lik, bd.lik_param, yb[i], lg[i], m, v, E, g, h);
+    double E, g, h, da;
+    wv_var_exp(bd.lik, lik_param, yb[i], lg[i], m, v, E, g, h, da);
+    dalpha += da;
     part += E + 0.5 * log(6.283185307179586 / l) + 0.5 * l * ((yt - m) * (yt - m) + v);
     const double lt = fmax(-2.0 * h, 1e-300);
     const double et = g + lt * m;
@@ -895,13 +917,25 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
     if (!(d1 == d1) || !(d2 == d2)) dmax = INFINITY;
   }
   // deterministic block reductions (sum, max)
-  for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xffffffffu, part, o); dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o)); }
+  for (int o = 16; o > 0; o >>= 1) {
+    part += __shfl_xor_sync(0xffffffffu, part, o);
+    dalpha += __shfl_xor_sync(0xffffffffu, dalpha, o);
+    dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  }
   if (lane == 0) red[warp] = part;
   __syncthreads();
   if (threadIdx.x == 0) {
     double ssum = 0.0;
     for (int w = 0; w < 8; ++w) ssum += red[w];
     s_bcast[0] = ssum;
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = dalpha;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ssum = 0.0;
+    for (int w = 0; w < 8; ++w) ssum += red[w];
+    s_dal = ssum;
   }
   __syncthreads();
   if (lane == 0) red[warp] = dmax;
@@ -933,7 +967,7 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
     int flag = (dec == 1 || dec == 2) ? 1 : (dec == 0 ? 0 : -1);
     if (sweeps >= vs.max_sweeps && dec == 1) { dec = 4; flag = mx < vs.soft_tol ? 0 : -1; }
     if (sweeps >= vs.max_sweeps && dec == 2) { dec = 3; flag = -1; }
-    if (dec == 0 || dec == 4) bd.vgp_extra[b] = extra;
+    if (dec == 0 || dec == 4) { bd.vgp_extra[b] = extra; bd.vgp_dlik[b] = s_dal; }
     vs.rho[b] = rho;
     vs.good[b] = good;
     vs.first[b] = 0;
@@ -951,8 +985,8 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
       const double l = lam[i], e = eta[i];
       const double D = 1.0 / l, yt = e * D;
       const double m = vs.fmean[(size_t)b * ld + i], v = vs.fvar[(size_t)b * ld + i];
-      double E, g, h;
-      wv_var_exp(bd.lik, bd.lik_param, yb[i], lg[i], m, v, E, g, h);
+      double E, g, h, da;
+      wv_var_exp(bd.lik, lik_param, yb[i], lg[i], m, v, E, g, h, da);
       const double lt = fmax(-2.0 * h, 1e-300), et = g + lt * m;
       lam_p[i] = l; eta_p[i] = e; lam_t[i] = lt; eta_t[i] = et;
       lam[i] = (1.0 - rho) * l + rho * lt;

@@ -45,11 +45,13 @@ struct WvBatchDev {
   int* step_flag;                   // [B][nt] epoch of the last finished diagonal block (fused Cholesky step)
   // variational path for count likelihoods (nullptr / 0 on the Gaussian path), see wv_site_update_kernel:
   int lik;                          // 0 gaussian, 1 poisson (exp link), 2 negative binomial (log link, fixed alpha)
-  double lik_param;                 // negative binomial: alpha
+  double lik_param;                 // negative binomial: alpha when the programs' noise slot is frozen; a trainable
+                                    // noise slot (Exp bijector) IS alpha on this path (waveome/likelihoods.py:24-28)
   double jitter;                    // gpflow default_jitter() added to K on the variational path
   double* site_lam;                 // [B][npad] precision of the Gaussian pseudo-observation of every row
   double* site_eta;                 // [B][npad] precision x mean of the pseudo-observation
   double* vgp_extra;                // [B] sum_i E_i + 1/2 log(2 pi / lam_i) + lam_i/2 ((ytilde_i - m_i)^2 + v_i)
+  double* vgp_dlik;                 // [B] sum_i dE_i/d(alpha): gradient of the bound wrt the negative-binomial dispersion
 };
 
 // per-model state of the site iteration (device arrays owned by the batch)

@@ -165,9 +165,8 @@ class GPSearch:
             m.cut_kernel_components(Xn)
             m.update_kernel_name()
         # get_feature_importances of every model (model_search.py:383-387) as one more engine batch
-        if self.likelihood == "gaussian":
-            for m, fi in zip(models, feature_importances_batch(Xn, Yn, models)):
-                m.feature_importances = fi
+        for m, fi in zip(models, feature_importances_batch(Xn, Yn, models)):
+            m.feature_importances = fi
         local = dict(zip(names, models))
         report = dict(n_models=len(names), seconds=time.time() - t0, n_eval=int(np.sum(res["n_eval"])),
                       status=np.asarray(res["status"]).copy(), n_fits_per_model=n_fits)

@@ -41,13 +41,13 @@ class Poisson:
 
 
 class NegativeBinomial:
-    """waveome/likelihoods.py:16-66: dispersion ``alpha`` with an Exp bijector, log link.  The engine evaluates the
-    bound for a FIXED alpha (the reference trains it; stated in DESIGN.md)."""
+    """waveome/likelihoods.py:16-66: trainable dispersion ``alpha`` with an Exp bijector (:24-28), log link.  On the
+    engine alpha rides in the program's noise slot (there is no Gaussian noise on this path)."""
     name = "negative_binomial"
 
-    def __init__(self, alpha=1.0):
-        self.alpha = K.Parameter(alpha, transform="exp", trainable=False)
-        self._dummy_noise = K.Parameter(1.0, transform=("softplus_shift", 1e-6), trainable=False)
+    def __init__(self, alpha=1.0, trainable=True):
+        self.alpha = K.Parameter(alpha, transform="exp", trainable=trainable)
+        self._dummy_noise = self.alpha
 
     @property
     def parameters(self):

@@ -24,10 +24,25 @@ def gaussian_logdensity(x, mu, var):
     return -0.5 * (LOG2PI + np.log(var) + np.square(mu - x) / var)
 
 
-def calc_deviance_loglik(y, model_mu, base_mu=None):
-    """The Gaussian branch of calc_deviance_explained(..., return_loglik=True) (utilities.py:544-552):
-    (base_ll, mod_ll, sat_ll) per observation."""
+def nb_logpmf(m, Y, alpha):
+    """waveome/likelihoods.py:68-79"""
+    from scipy.special import gammaln
+    k = 1.0 / alpha
+    return gammaln(k + Y) - gammaln(Y + 1) - gammaln(k) + Y * np.log(m / (m + k)) - k * np.log1p(m * alpha)
+
+
+def calc_deviance_loglik(y, model_mu, base_mu=None, likelihood="gaussian", alpha=1.0):
+    """calc_deviance_explained(..., return_loglik=True) (utilities.py:517-583): (base_ll, mod_ll, sat_ll) per
+    observation for the Gaussian (:544-552), Poisson (:553-558) and negative-binomial (:559-581) branches."""
     y = np.asarray(y, dtype=np.float64)
+    model_mu = np.asarray(model_mu, dtype=np.float64)
+    if likelihood == "poisson":
+        from scipy.stats import poisson
+        return (poisson.logpmf(y, np.mean(y) if base_mu is None else base_mu), poisson.logpmf(y, model_mu),
+                poisson.logpmf(y, y))
+    if likelihood == "negative_binomial":
+        base = max(1e-6, np.mean(y)) if base_mu is None else base_mu
+        return nb_logpmf(base, y, alpha), nb_logpmf(model_mu, y, alpha), nb_logpmf(y + 1e-6, y, alpha)
     y_var = np.var(y)
     sat_ll = gaussian_logdensity(y, y, y_var)
     base_ll = gaussian_logdensity(y, np.mean(y) if base_mu is None else base_mu, y_var)
@@ -55,8 +70,9 @@ def _component_masks(model: GPR) -> List[int]:
 
 def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], masks: Optional[Sequence[int]] = None, engine=None,
                  max_batch_bytes: float = 60e9):
-    """Posterior mean of every model at the training inputs, [B, n], with the models' current parameter values
-    (one engine evaluation; mean = y - sigma^2 alpha).  ``masks``: optional component mask per model."""
+    """predict_y mean of every model at the training inputs, [B, n], with the models' current parameter values (one
+    engine evaluation).  Gaussian: y - sigma^2 alpha; count likelihoods: exp(m + v/2) at the converged sites.
+    ``masks``: optional component mask per model."""
     from .engine import Batch
     from .model_fitting import get_engine
     engine = engine or get_engine()
@@ -89,21 +105,33 @@ def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], masks: Opt
     n = X.shape[0]
     npad = ((n + 1 + 7) // 8 * 8 + 63) // 64 * 64
     chunk = max(1, int(max_batch_bytes // (2 * npad * npad * 8 + npad * 64 * 8)))
+    from .model_fitting import likelihood_key
     mean = np.empty((B, n))
     status = np.empty(B, np.int32)
-    s2_all = np.array([float(m.likelihood.variance) for m in models])
-    for lo in range(0, B, chunk):
-        hi = min(B, lo + chunk)
-        batch = Batch(engine, X, Y[lo:hi], table, prog_id[lo:hi], P=P)
-        try:
-            if masks is not None:
-                batch.set_component_mask(np.asarray(masks[lo:hi], dtype=np.uint32))
-            _f, _g, _lml, st = batch.eval(x[lo:hi])
-            alpha = batch.alpha()
-        finally:
-            batch.close()
-        mean[lo:hi] = Y[lo:hi] - s2_all[lo:hi, None] * alpha
-        status[lo:hi] = st
+    groups = {}
+    for b, m in enumerate(models):
+        groups.setdefault(likelihood_key(m), []).append(b)
+    masks = None if masks is None else np.asarray(masks, dtype=np.uint32)
+    for (lik_name, lik_param), idx in groups.items():
+        idx = np.asarray(idx)
+        for lo in range(0, len(idx), chunk):
+            sel = idx[lo: lo + chunk]
+            batch = Batch(engine, X, Y[sel], table, prog_id[sel], P=P)
+            try:
+                if lik_name != "gaussian":
+                    batch.set_likelihood(lik_name, lik_param)
+                if masks is not None:
+                    batch.set_component_mask(masks[sel])
+                _f, _g, _lml, st = batch.eval(x[sel])
+                if lik_name == "gaussian":
+                    s2 = np.array([float(models[b].likelihood.variance) for b in sel])
+                    mean[sel] = Y[sel] - s2[:, None] * batch.alpha()
+                else:       # E[y] under q(f) = N(m, v) with the log link (predict_y of the count likelihoods)
+                    fm, fv = batch.latent()
+                    mean[sel] = np.exp(fm + 0.5 * fv)
+            finally:
+                batch.close()
+            status[sel] = st
     return mean, status
 
 
@@ -124,7 +152,9 @@ def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf"
         mu = means[pos: pos + nv]
         pos += nv
         y = Y[b]
-        null_lls, mod_lls, sat_lls = calc_deviance_loglik(y, mu[0])
+        lk = dict(likelihood=getattr(m.likelihood, "name", "gaussian"),
+                  alpha=float(getattr(m.likelihood, "engine_param", 1.0)) or 1.0)
+        null_lls, mod_lls, sat_lls = calc_deviance_loglik(y, mu[0], **lk)
         if np.sum(sat_lls) >= np.sum(mod_lls) and np.sum(mod_lls) >= np.sum(null_lls):
             full_de = 1 - (-2 * np.sum(mod_lls - sat_lls) / (-2 * np.sum(null_lls - sat_lls)))
             full_de = max(min(1, full_de), 0)
@@ -134,7 +164,7 @@ def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf"
         k = m.kernel
         if k.name == "sum":
             for k_idx in range(len(k.kernels)):
-                null_lls_k, sub_mod_lls, _ = calc_deviance_loglik(y, mu[1 + k_idx])
+                null_lls_k, sub_mod_lls, _ = calc_deviance_loglik(y, mu[1 + k_idx], **lk)
                 if return_value == "statistic":
                     scaled = max(np.round(-2 * (np.sum(sub_mod_lls) - np.sum(mod_lls)), 1), 0)
                 elif return_value == "log_bf":
