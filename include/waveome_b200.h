@@ -144,6 +144,9 @@ int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* opts, double
  * which waveome/utilities.py:614-707 calc_feature_importance_components and :710-974 consume).
  * Xnew HOST [m, D] row-major, mean HOST [B, m].  At the training inputs the mean is y - sigma^2 alpha. */
 int wv_batch_get_alpha(wv_batch* b, double* alpha);
+/* diag((K + sigma^2 I)^-1) of the last evaluation, HOST [B, n]: the predictive variance at the training inputs is
+ * var f_i = sigma^2 - sigma^4 diag_i, var y_i = var f_i + sigma^2 (gpflow GPR.predict_f / predict_y, full_cov=False). */
+int wv_batch_get_kinv_diag(wv_batch* b, double* diag);
 int wv_batch_predict_mean(wv_batch* b, const double* Xnew, int32_t m, double* mean);
 
 /* counters since batch creation: kernels launched, batched evaluation rounds, model evaluations */

@@ -97,3 +97,28 @@ def test_penalized_optimization_sets_feature_importances():
         assert 0.0 <= m.feature_importances[-1] <= 1.0
     # outcome1 = sin(time) + noise: almost nothing is left for the residual
     assert gps.models["outcome1"].feature_importances[-1] < 0.1
+
+
+def test_train_predictive_variance_and_iterated_factor(engine):
+    """predict_y variances at the training inputs vs the oracle's linear algebra, and penalization_factor=None
+    (waveome/model_search.py:271-375): factors start at the formula value and only ever decrease."""
+    from scipy.stats import norm
+    from waveome_b200 import datasets
+    from waveome_b200.model_search import GPSearch
+    n = 90
+    X, y = helpers.make_data(n, seed=8)
+    model = wb.GPR(helpers.saturated_kernel(hs=0.0), mean_function=wb.ConstantMean(0.1), noise_variance=0.3)
+    var_y = postfit.train_predictive_variance(X, y[None, :], [model])[0]
+    spec = copy.deepcopy(model.to_spec())
+    K, _ = oracle.kernel_K_and_grads(spec["kernel"], X, want_grads=False)
+    s2 = 0.3
+    ref = np.diag(K - K @ np.linalg.solve(K + s2 * np.eye(n), K)) + s2
+    np.testing.assert_allclose(var_y, ref, rtol=1e-8, atol=1e-10)
+    Xd, Yd = datasets.overview_notebook(n_people=30, n_observations=5)
+    gps = GPSearch(Xd, Yd, unit_col="person_id", categorical_vars=["female"])
+    gps.penalized_optimization(penalization_factor=None, num_factor_iter=3)
+    p = 5                                                   # unit + female + SE[time] + unit... components of the saturated kernel
+    for o, m in gps.models.items():
+        start = 2 * 1.1 * np.std(gps.Y[o].to_numpy()) * np.sqrt(len(gps.X)) * norm().ppf(1 - 0.1 / (2 * 4))
+        assert m.penalization_factor <= start + 1e-9 and m.penalization_factor > 0
+        assert np.isfinite(m.log_posterior_density_value)

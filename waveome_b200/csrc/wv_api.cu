@@ -685,6 +685,36 @@ extern "C" int wv_batch_get_alpha(wv_batch* b, double* alpha) {
   return 0;
 }
 
+__global__ void wv_diag_gather_kernel(const double* __restrict__ A, int npad, size_t total, double* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t m = i / npad, r = i % npad;
+  out[i] = A[m * npad * npad + r * npad + r];
+}
+
+extern "C" int wv_batch_get_kinv_diag(wv_batch* b, double* diag) {
+  if (!b || !diag) return wv_fail("wv_batch_get_kinv_diag: null argument");
+  if (!b->last_x) return wv_fail("wv_batch_get_kinv_diag: no evaluation has been run on this batch");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const WvBatchDev& bd = b->bd;
+  const size_t total = (size_t)bd.B * bd.npad;
+  std::vector<double> tmp(total);
+  // the diagonal of A (= (K + noise)^-1 after the evaluation), gathered into the (free after extract) alpha-sized
+  // scratch of the gradient partial sums
+  double* d_tmp = bd.partial;       // [B][tiles][slots] >= B * npad doubles is not guaranteed: allocate when short
+  bool own = false;
+  const size_t have = (size_t)bd.B * (bd.nt * (bd.nt + 1) / 2) * bd.n_slots_max;
+  if (have < total) { WV_CUDA(cudaMalloc(&d_tmp, total * sizeof(double))); own = true; }
+  wv_diag_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, b->eng->stream>>>(bd.A, bd.npad, total, d_tmp);
+  cudaError_t e1 = cudaMemcpyAsync(tmp.data(), d_tmp, total * sizeof(double), cudaMemcpyDeviceToHost, b->eng->stream);
+  cudaError_t e2 = cudaStreamSynchronize(b->eng->stream);
+  if (own) cudaFree(d_tmp);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) return wv_fail("wv_batch_get_kinv_diag: copy failed");
+  for (size_t m = 0; m < (size_t)bd.B; ++m)
+    for (int i = 0; i < bd.n; ++i) diag[m * bd.n + b->perm[i]] = tmp[m * bd.npad + i];
+  return 0;
+}
+
 extern "C" int wv_batch_predict_mean(wv_batch* b, const double* Xnew, int32_t m, double* mean) {
   if (!b || !Xnew || !mean) return wv_fail("wv_batch_predict_mean: null argument");
   if (m <= 0) return wv_fail("wv_batch_predict_mean: m must be positive");

@@ -49,7 +49,7 @@ class _LbfgsOpts(C.Structure):
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
     "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_likelihood", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
-    "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_predict_mean", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
+    "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_get_kinv_diag", "wv_batch_predict_mean", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
 KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk", "sites"]
 
@@ -85,6 +85,7 @@ def load_library():
     lib.wv_batch_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.wv_batch_counters.restype = None
     lib.wv_batch_get_alpha.argtypes = [vp, _f64p]; lib.wv_batch_get_alpha.restype = C.c_int
+    lib.wv_batch_get_kinv_diag.argtypes = [vp, _f64p]; lib.wv_batch_get_kinv_diag.restype = C.c_int
     lib.wv_batch_predict_mean.argtypes = [vp, _f64p, C.c_int32, _f64p]; lib.wv_batch_predict_mean.restype = C.c_int
     lib.wv_batch_profile_enable.argtypes = [vp, C.c_int]; lib.wv_batch_profile_enable.restype = None
     lib.wv_batch_profile_read.argtypes = [vp, _f64p, C.POINTER(C.c_int64), C.c_int]; lib.wv_batch_profile_read.restype = C.c_int
@@ -262,6 +263,12 @@ class Batch:
         a = np.empty((self.B, self.n))
         _check(self.lib.wv_batch_get_alpha(self.handle, _f64(a)), "wv_batch_get_alpha")
         return a
+
+    def kinv_diag(self) -> np.ndarray:
+        """[B, n] diag((K + sigma^2 I)^-1) of the last evaluation, in the caller's row order."""
+        d = np.empty((self.B, self.n))
+        _check(self.lib.wv_batch_get_kinv_diag(self.handle, _f64(d)), "wv_batch_get_kinv_diag")
+        return d
 
     def predict_mean(self, Xnew: np.ndarray) -> np.ndarray:
         """[B, m] posterior means at new inputs [m, D] with the parameters of the last evaluation."""

@@ -19,7 +19,7 @@ import pandas as pd
 from . import kernels as K
 from .model_fitting import fit_models, fit_replicated, get_engine
 from .models import ConstantMean, PenalizedGPR, make_likelihood
-from .postfit import feature_importances_batch
+from .postfit import feature_importances_batch, train_predictive_variance
 from .regularization import full_kernel_build
 
 
@@ -109,8 +109,8 @@ class GPSearch:
         outcomes are sharded over ranks with no collective on the data path; with ``gather=True`` the fitted
         models are exchanged afterwards so every rank holds ``self.models`` for all outcomes."""
         make_likelihood(self.likelihood)              # raises for likelihoods the engine does not cover
-        if penalization_factor is None:
-            raise NotImplementedError("penalization_factor=None (iterated factor) needs predict_y: next row (§8f)")
+        if penalization_factor is None and self.likelihood != "gaussian":
+            raise NotImplementedError("penalization_factor=None iterates on predict_y variances: Gaussian outcomes only")
         self.model_selection_type = "penalized"
         if random_seed is not None:
             np.random.seed(random_seed)
@@ -128,7 +128,8 @@ class GPSearch:
         names = self.out_names[lo:hi]
         t0 = time.time()
         template = PenalizedGPR(K.deepcopy(full_kernel), mean_function=K.deepcopy(mean_function),
-                                penalization_factor=penalization_factor, likelihood=make_likelihood(self.likelihood))
+                                penalization_factor=1.0 if penalization_factor is None else penalization_factor,
+                                likelihood=make_likelihood(self.likelihood))
 
         def make_models() -> List[PenalizedGPR]:      # every outcome owns its copy (model_search.py:305-306)
             return [K.deepcopy(template) for _ in names]
@@ -137,7 +138,10 @@ class GPSearch:
         n_fits = max(1, int(num_restart)) if num_restart else 1
         if verbose and rank == 0:
             print(f"Building {len(self.out_names)} models on {world} GPU(s)...")
-        if num_restart and num_restart > 0:
+        if penalization_factor is None:
+            res, models = self._iterated_factor_fit(full_kernel, mean_function, names, Xn, Yn, num_factor_iter, num_opt_iter,
+                                                    verbose and rank == 0)
+        elif num_restart and num_restart > 0:
             models = make_models()
             # random_restart_optimize (model_classes.py:472-524): keep the restart with the best objective
             best = None
@@ -180,6 +184,48 @@ class GPSearch:
         self.models = local
         self.fit_report = report
         return None
+
+    # ------------------------------------------------------------------------------------------
+    def _iterated_factor_fit(self, full_kernel, mean_function, names, Xn, Yn, num_factor_iter, num_opt_iter, verbose):
+        """penalization_factor=None (waveome/model_search.py:271-375): start every outcome at
+        2 * 1.1 * sd(y) * sqrt(n) * Phi^-1(1 - 0.1 / (2 p)), p = number of additive components, then up to
+        ``num_factor_iter`` times re-estimate the residual sd from the predictive y-variance, recompute the factor and
+        continue the optimisation while it keeps decreasing.  All outcomes iterate together: one engine batch per step
+        for the models that are still moving."""
+        from scipy.stats import norm
+        from .utilities import find_variance_components
+        n = Xn.shape[0]
+        num_params = len(find_variance_components(full_kernel, sum_reduce=False))
+        z = norm().ppf(1 - (0.1 / (2 * num_params)))
+        models = []
+        for b in range(len(names)):
+            sigma_hat = 1 if num_factor_iter == 0 else float(np.std(Yn[b]))
+            models.append(PenalizedGPR(K.deepcopy(full_kernel), mean_function=K.deepcopy(mean_function),
+                                       penalization_factor=2 * 1.1 * sigma_hat * np.sqrt(n) * z))
+        res = fit_models(Xn, Yn, models, maxiter=num_opt_iter, maxfun=num_opt_iter)
+        active = list(range(len(models)))
+        for _ in range(int(num_factor_iter)):
+            if not active:
+                break
+            var_y = train_predictive_variance(Xn, Yn[active], [models[b] for b in active])
+            new_pf = 2 * 1.1 * np.sqrt(np.mean(var_y, axis=1)) * np.sqrt(n) * z
+            nxt = []
+            for b, pf in zip(active, new_pf):
+                cur = models[b].penalization_factor
+                if abs(pf - cur) <= 1e-3 or pf > cur:      # similar, or larger (the reference then stops with the current fit)
+                    continue
+                models[b].set_penalization_factor(float(pf))
+                nxt.append(b)
+            active = nxt
+            if verbose:
+                print(f"penalization factor iteration: {len(active)} outcomes continue")
+            if active:
+                r = fit_models(Xn, Yn[active], [models[b] for b in active], maxiter=num_opt_iter, maxfun=num_opt_iter)
+                for key in ("f", "lml", "n_iter", "n_eval", "status"):
+                    res[key][active] = r[key]
+                res["n_eval"] = res["n_eval"]
+        self.iterating_penalization_factor = True
+        return res, models
 
     # ------------------------------------------------------------------------------------------
     def run_search(self, kernels=None, max_depth=5, early_stopping=True, prune=True, keep_all=False, metric_diff=6,

@@ -135,6 +135,43 @@ def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], masks: Opt
     return mean, status
 
 
+def train_predictive_variance(X, Y, models: Sequence[GPR], engine=None, max_batch_bytes: float = 60e9) -> np.ndarray:
+    """``predict_y(X)[1]`` of gpflow GPR at the training inputs for B Gaussian models, [B, n]:
+    var f_i = sigma^2 - sigma^4 diag((K + sigma^2 I)^-1)_i, var y_i = var f_i + sigma^2."""
+    from .engine import Batch
+    from .model_fitting import get_engine
+    engine = engine or get_engine()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    B, n = len(models), X.shape[0]
+    progs = [m.program() for m in models]
+    uniq, prog_id, table = {}, np.empty(B, np.int32), []
+    for b, p in enumerate(progs):
+        sig = p.signature()
+        if sig not in uniq:
+            uniq[sig] = len(table)
+            table.append(p)
+        prog_id[b] = uniq[sig]
+    P = max(1, max(p.n_x for p in progs))
+    x = np.zeros((B, P))
+    for b, p in enumerate(progs):
+        x[b, : p.n_x] = p.x0()
+    npad = ((n + 1 + 7) // 8 * 8 + 63) // 64 * 64
+    chunk = max(1, int(max_batch_bytes // (2 * npad * npad * 8 + npad * 64 * 8)))
+    out = np.empty((B, n))
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        batch = Batch(engine, X, Y[lo:hi], table, prog_id[lo:hi], P=P)
+        try:
+            batch.eval(x[lo:hi])
+            d = batch.kinv_diag()
+        finally:
+            batch.close()
+        s2 = np.array([float(m.likelihood.variance) for m in models[lo:hi]])[:, None]
+        out[lo:hi] = (s2 - s2 * s2 * d) + s2
+    return out
+
+
 def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf", engine=None) -> List[list]:
     """calc_feature_importance_components (utilities.py:614-707) for B models at once: one list per model with one
     entry per additive component and a last entry for the residual (1 - deviance explained)."""
