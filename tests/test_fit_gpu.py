@@ -67,3 +67,29 @@ def test_fit_vs_oracle_structure(engine):
     assert names["outcome3"] == "categorical[0]+lin[1]"
     # noise variance soft pin (notebook cell 11, SVGP path: 0.010672; exact-GPR optimum per SURVEY App. C: 0.01075)
     assert abs(float(gps.models["outcome1"].likelihood.variance) - 0.0107) < 5e-4
+
+
+def test_readme_quickstart_iris_vs_oracle():
+    """BASELINE configs[0] — README quick-start: iris, X = petal_length, petal_width, species; Y = sepal_length,
+    sepal_width; GPSearch(...).penalized_optimization().  Every outcome: engine fit == oracle's SciPy L-BFGS-B fit of the
+    same saturated penalised model (objective, pruned structure)."""
+    from waveome_b200 import datasets
+    from waveome_b200.model_search import GPSearch
+    from waveome_b200.regularization import full_kernel_build
+    X, Y = datasets.iris()
+    gps = GPSearch(X, Y, categorical_vars=["species"])
+    gps.penalized_optimization()
+    Xn = gps.X.to_numpy(dtype=np.float64)
+    k, names = full_kernel_build(cat_vars=gps.cat_idx, num_vars=gps.cont_idx, unit_idx=None, var_names=gps.feat_names,
+                                 return_sum=True)
+    assert len(names) == 5                      # cat[species] + SE[pl] + SE[pw] + cat x SE[pl] + cat x SE[pw]
+    for o in gps.out_names:
+        m = wb.models.PenalizedGPR(wb.deepcopy(k), mean_function=wb.ConstantMean(), penalization_factor=1.0)
+        ro = oracle.fit(m.to_spec(), Xn, gps.Y[o].to_numpy(dtype=np.float64), maxiter=50000, maxfun=50000)
+        got = gps.models[o]
+        assert abs(-got.log_posterior_density_value - ro["f"]) <= 1e-6 * max(1.0, abs(ro["f"])), (o, got.log_posterior_density_value, ro["f"])
+        m.program().assign(ro["x"])
+        m.cut_kernel_components(Xn)
+        m.update_kernel_name()
+        assert got.kernel_name == m.kernel_name, (o, got.kernel_name, m.kernel_name)
+        assert len(got.feature_importances) >= 2
