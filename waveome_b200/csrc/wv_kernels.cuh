@@ -197,10 +197,13 @@ __device__ __forceinline__ void wv_gemm_issue(WvGemmSmem& sm, int stage, const d
   }
 }
 
+// `dead`: this warp's 32x32 part of the tile is padding (rows / columns beyond the model's n + 1): it keeps staging
+// operands and meeting the barriers but issues no DMMA, which frees the tensor pipe for the other warps of the SM
+// (the last tile row / column of a model holds (n + 1) mod 64 real rows -- 25 of 64 at n = 600).
 template <bool BNN>
 __device__ __forceinline__ void wv_gemm_64(WvGemmSmem& sm, const double* __restrict__ Ag,
                                            const double* __restrict__ Bg, int ld, int k0, int k1,
-                                           double (&acc)[4][4][2]) {
+                                           double (&acc)[4][4][2], bool dead = false) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 1, wn = warp & 1;
   const int fr = lane >> 2, fk = lane & 3;
@@ -218,6 +221,7 @@ __device__ __forceinline__ void wv_gemm_64(WvGemmSmem& sm, const double* __restr
       if (cn < nchunks) wv_gemm_issue<BNN>(sm, cn % WV_STAGES, Ag, Bg, ld, k0 + cn * WV_BK, k1);
       wv_cp_commit();
     }
+    if (dead) continue;
     const double* as = sm.a[c % WV_STAGES] + (wm * 32 + fr) * WV_LDS + fk;
     const double* bs = BNN ? sm.b[c % WV_STAGES] + fk * WV_LDN + wn * 32 + fr
                            : sm.b[c % WV_STAGES] + (wn * 32 + fr) * WV_LDS + fk;
@@ -240,13 +244,14 @@ __device__ __forceinline__ void wv_gemm_64(WvGemmSmem& sm, const double* __restr
 }
 __device__ __forceinline__ void wv_gemm_nt_64(WvGemmSmem& sm, const double* __restrict__ Ag,
                                               const double* __restrict__ Bg, int ld, int k0, int k1,
-                                              double (&acc)[4][4][2]) {
-  wv_gemm_64<false>(sm, Ag, Bg, ld, k0, k1, acc);
+                                              double (&acc)[4][4][2], bool dead = false) {
+  wv_gemm_64<false>(sm, Ag, Bg, ld, k0, k1, acc, dead);
 }
 
 // second-stage product from shared memory operands (64x64x64): acc[m][n] = sum_k Ts[m][k] * Bs[n][k]
 __device__ __forceinline__ void wv_gemm_nt_smem64(const double* __restrict__ Ts, const double* __restrict__ Bs,
-                                                  double (&acc)[4][4][2]) {
+                                                  double (&acc)[4][4][2], bool dead = false) {
+  if (dead) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 1, wn = warp & 1;
   const int fr = lane >> 2, fk = lane & 3;
