@@ -1,5 +1,6 @@
-"""wv_exp2_fast (csrc/wv_common.cuh, the 2^u of the squared-exponential leaves) compiled for the host and compared
-with long-double exp2l: relative error below 2 ulp over the range the Gram kernels use, exact special cases."""
+"""wv_exp2_neg / wv_exp2_fast (csrc/wv_common.cuh; wv_exp2_neg is the 2^u of the squared-exponential leaves) compiled for
+the host and compared with long-double exp2l: relative error below 2 ulp over the range the Gram kernels use, exact
+special cases."""
 import os
 import subprocess
 import sys
@@ -20,12 +21,14 @@ int main() {
     double u = (i & 1) ? U(g) : V(g);
     double r = wv_exp2_fast(u, tab);
     long double ref = exp2l((long double)u);
-    if (u <= -1021.0) { if (r != 0.0) return 2; continue; }
+    if (u <= 0.0 && u > -1021.0 && wv_exp2_neg(u, tab) != r) return 5;      // the device path shares the arithmetic
+    if (u <= -1021.0) { if (r != 0.0 || !(wv_exp2_neg(u, tab) < 1e-307)) return 2; continue; }
     double ulp = fabs((double)((r - ref) / ldexpl(1.0L, ilogbl(ref) - 52)));
     if (ulp > maxulp) maxulp = ulp;
   }
   printf("%%.4f\n", maxulp);
   if (wv_exp2_fast(0.0, tab) != 1.0 || wv_exp2_fast(-0.0, tab) != 1.0 || wv_exp2_fast(1.0, tab) != 2.0) return 3;
+  if (wv_exp2_neg(0.0, tab) != 1.0 || !std::isnan(wv_exp2_neg(NAN, tab))) return 6;
   if (wv_exp2_fast(-INFINITY, tab) != 0.0 || !std::isnan(wv_exp2_fast(NAN, tab)) || !std::isinf(wv_exp2_fast(2000.0, tab))) return 4;
   return 0;
 }

@@ -101,7 +101,8 @@ WV_HD double wv_transform_grad(int tr, double u) {
 // ---------------------------------------------------------------------------------------------
 #define WV_EXP2_TAB 64
 WV_HD void wv_exp2_table_entry(int j, double* out) { *out = exp2((double)j / WV_EXP2_TAB); }
-WV_HD double wv_exp2_fast(double u, const double* __restrict__ tab) {
+// 2^u for finite u in (-1022, 1024): no range handling (the callers below add it)
+WV_HD double wv_exp2_core(double u, const double* __restrict__ tab) {
   const double M = 1.5 * 70368744177664.0;                 // 1.5 * 2^46: adding it rounds u to a multiple of 1/64
   const double tb = u + M;
   const double f = u - (tb - M);                           // |f| <= 1/128
@@ -114,44 +115,33 @@ WV_HD double wv_exp2_fast(double u, const double* __restrict__ tab) {
 #ifdef __CUDA_ARCH__
   const int ki = __double2loint(tb);
   const double T = tab[ki & (WV_EXP2_TAB - 1)];
-  double r = fma(T, p, T);
-  const int e = ki >> 6;
-  r = __hiloint2double(__double2hiint(r) + (e << 20), __double2loint(r));
+  const double r = fma(T, p, T);
+  return __hiloint2double(__double2hiint(r) + ((ki >> 6) << 20), __double2loint(r));
 #else
   long long bits;
   memcpy(&bits, &tb, 8);
   const int ki = (int)(bits & 0xffffffffLL);
   const double T = tab[ki & (WV_EXP2_TAB - 1)];
   double r = fma(T, p, T);
-  const int e = ki >> 6;
   memcpy(&bits, &r, 8);
-  bits += (long long)e << 52;
+  bits += (long long)(ki >> 6) << 52;
   memcpy(&r, &bits, 8);
+  return r;
 #endif
+}
+// general argument: below 2^-1021 flushed to zero, above 2^1023 +inf, NaN propagates
+WV_HD double wv_exp2_fast(double u, const double* __restrict__ tab) {
+  double r = wv_exp2_core(u, tab);
   if (!(u > -1021.0)) r = (u != u) ? u : 0.0;
   if (u >= 1024.0) r = INFINITY;
   return r;
 }
-
-// Same for u <= 0 (the squared-exponential argument -(s d)^2): one clamp instead of the range checks.  Below -1021
-// the result is 2^-1021 ~ 4e-308 instead of 0 (absolute error irrelevant next to sigma^2 >= 1e-6); NaN propagates.
-#ifdef __CUDACC__
-__device__ __forceinline__ double wv_exp2_neg(double u, const double* __restrict__ tab) {
-  const double M = 1.5 * 70368744177664.0;
+// u <= 0 (the squared-exponential argument -(s d)^2): one clamp instead of the range checks.  Below -1021 the result is
+// 2^-1021 ~ 4e-308 instead of 0 (absolute error irrelevant next to sigma^2 >= 1e-6 on the diagonal); NaN propagates.
+WV_HD double wv_exp2_neg(double u, const double* __restrict__ tab) {
   u = (u < -1021.0) ? -1021.0 : u;
-  const double tb = u + M;
-  const double f = u - (tb - M);
-  double p = fma(f, 1.3333558146428443e-03, 9.6181291076284772e-03);
-  p = fma(f, p, 5.5504108664821580e-02);
-  p = fma(f, p, 2.4022650695910071e-01);
-  p = fma(f, p, 6.9314718055994531e-01);
-  p = f * p;
-  const int ki = __double2loint(tb);
-  const double T = tab[ki & (WV_EXP2_TAB - 1)];
-  const double r = fma(T, p, T);
-  return __hiloint2double(__double2hiint(r) + ((ki >> 6) << 20), __double2loint(r));
+  return wv_exp2_core(u, tab);
 }
-#endif
 
 // tfd.Horseshoe(scale).log_prob(x) (TFP closed-form approximation) and d/dx.
 WV_HD void wv_horseshoe(double x, double s, double* logp, double* dlogp) {

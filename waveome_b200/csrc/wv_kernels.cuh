@@ -136,15 +136,6 @@ __device__ __forceinline__ void wv_tile_from_linear(int t, int& ti, int& tj) {
   tj = t - i * (i + 1) / 2;
 }
 
-// theta (constrained values of every slot) of one model into shared memory
-__device__ __forceinline__ void wv_load_theta(const WvProgram* __restrict__ pg, const double* __restrict__ x,
-                                              double* theta_s) {
-  for (int s = threadIdx.x; s < pg->n_slots; s += blockDim.x) {
-    const WvSlot& sl = pg->slots[s];
-    theta_s[s] = sl.xindex >= 0 ? wv_transform(sl.transform, x[sl.xindex], sl.shift) : sl.fixed;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // helpers of the kernel-tree leaves (the leaves themselves live in wv_elem.cuh)
 // ---------------------------------------------------------------------------------------------
