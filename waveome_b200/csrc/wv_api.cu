@@ -124,6 +124,7 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
   WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_panel, cudaEventDisableTiming));
   WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_bulk, cudaEventDisableTiming));
   if (const char* v = getenv("WV_BIG_NT")) eng->aux.big_nt = atoi(v) > 1 ? atoi(v) : 2;
+  if (const char* v = getenv("WV_PANEL_TILES")) eng->aux.panel_tiles = atoi(v) > 0 ? atoi(v) : 4;
   {
     cudaDeviceProp prop;
     WV_CUDA(cudaGetDeviceProperties(&prop, device));

@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_kinv_kernel(WvBatchDev bd,
 // Large-n path (nt >= WvAux::big_nt, e.g. config 4: one n = 8192 model).  The left-looking batched scheme above has
 // one CTA per model on its critical path; for few, large models the factorisation is reorganised so that almost all
 // flops sit in wide launches of the same 64x64 DMMA tile GEMM:
-//   Cholesky   right-looking over panels of WV_PANEL_TILES tile columns: the panel is factorised with the kernels
+//   Cholesky   right-looking over panels of WvAux::panel_tiles tile columns: the panel is factorised with the kernels
 //              above (k0 = first panel column), then `wv_syrk_kernel` applies it to the trailing matrix.  The update
 //              is split into the columns of the NEXT panel (main stream) and the rest (side stream), so that the next
 //              panel factorisation overlaps the bulk of the update (look-ahead of one panel).
@@ -600,7 +600,6 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_kinv_kernel(WvBatchDev bd,
 //              (`wv_trtri_level_kernel<1>`: U = Mt_FF L_SF^T into the unused upper tiles of A;  <2>: Mt_FS = -U Mt_SS,
 //              the only product on the path whose B operand is not k-contiguous -> wv_gemm_64<true>).
 // =============================================================================================
-#define WV_PANEL_TILES 4
 
 // A[ti,tj] -= sum_{k in [k0,k1)} L[ti,k] L[tj,k]^T   for tj in [c_lo, c_hi), ti in [tj, nt).
 // c_hi == nt: triangular enumeration of the whole trailing block; otherwise a (nt - c_lo) x (c_hi - c_lo) rectangle
@@ -779,11 +778,12 @@ static int wv_enqueue_factor_big(const WvBatchDev& bd, const int* d_active, int 
   const int nt = bd.nt;
   int launches = 0;
   bool bulk_pending = false;
-  for (int p0 = 0; p0 < nt; p0 += WV_PANEL_TILES) {
-    const int p1 = p0 + WV_PANEL_TILES < nt ? p0 + WV_PANEL_TILES : nt;
+  const int PT = aux.panel_tiles;
+  for (int p0 = 0; p0 < nt; p0 += PT) {
+    const int p1 = p0 + PT < nt ? p0 + PT : nt;
     for (int j = p0; j < p1; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, p0 * WV_NB, st, pf, aux);
     if (p1 >= nt) break;
-    const int a_hi = p1 + WV_PANEL_TILES < nt ? p1 + WV_PANEL_TILES : nt;   // columns of the next panel
+    const int a_hi = p1 + PT < nt ? p1 + PT : nt;   // columns of the next panel
     cudaEventRecord(aux.ev_panel, st);
     // next panel's columns on the main stream (they also received the previous bulk update: wait for it)
     if (bulk_pending) cudaStreamWaitEvent(st, aux.ev_bulk, 0);

@@ -77,6 +77,7 @@ struct WvAux {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
   int big_nt = 16;
+  int panel_tiles = 4;       // tile columns per panel of the large-n right-looking Cholesky
   int resident_ctas = 444;   // 3 CTAs x 148 SMs: a Cholesky step is fused into one launch only if it fits
   int epoch = 0;   // evaluation counter of the engine: the value the diagonal CTAs publish in step_flag
 };
