@@ -148,6 +148,9 @@ int wv_batch_get_alpha(wv_batch* b, double* alpha);
  * var f_i = sigma^2 - sigma^4 diag_i, var y_i = var f_i + sigma^2 (gpflow GPR.predict_f / predict_y, full_cov=False). */
 int wv_batch_get_kinv_diag(wv_batch* b, double* diag);
 int wv_batch_predict_mean(wv_batch* b, const double* Xnew, int32_t m, double* mean);
+/* Same plus the predictive variance of f (gpflow GPR.predict_f, full_cov = False; predict_y adds sigma^2):
+ * var[b][i] = k_b(xnew_i, xnew_i) - k*_i^T (K_b + sigma^2 I)^-1 k*_i, HOST [B, m]; var may be NULL. */
+int wv_batch_predict_f(wv_batch* b, const double* Xnew, int32_t m, double* mean, double* var);
 
 /* counters since batch creation: kernels launched, batched evaluation rounds, model evaluations */
 void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t* rounds, int64_t* model_evals);

@@ -42,8 +42,18 @@ def test_alpha_and_predict_mean(engine, n, m):
         ao, muo = _oracle_alpha_mean(model, X, y, Xnew)
         np.testing.assert_allclose(a[0], ao, rtol=0, atol=1e-9 * np.max(np.abs(ao)))
         np.testing.assert_allclose(mu[0], muo, rtol=0, atol=1e-9 * max(1.0, np.max(np.abs(muo))))
-        mu2, _ = model.predict_f(Xnew, data=(X, y))
+        mu2, var2 = model.predict_f(Xnew, data=(X, y))
         np.testing.assert_array_equal(mu2[:, 0], mu[0])
+        # predictive variance: k** - k*^T (K + s2 I)^-1 k*
+        spec = copy.deepcopy(model.to_spec())
+        Kall, _ = oracle.kernel_K_and_grads(spec["kernel"], np.vstack([Xnew, X]), want_grads=False)
+        Kss, Ksx, Kxx = Kall[:m, :m], Kall[:m, m:], Kall[m:, m:]
+        vref = np.diag(Kss) - np.einsum("ij,ij->i", Ksx, np.linalg.solve(Kxx + 0.3 * np.eye(n), Ksx.T).T)
+        np.testing.assert_allclose(var2[:, 0], vref, rtol=0, atol=1e-9 * max(1.0, np.max(np.abs(vref))))
+        _, vy = model.predict_y(Xnew, data=(X, y))
+        np.testing.assert_allclose(vy[:, 0], vref + 0.3, rtol=0, atol=1e-9 * max(1.0, np.max(np.abs(vref))))
+        lp = model.predict_log_density((Xnew[:5], np.zeros(5)), data=(X, y))
+        assert lp.shape == (5,) and np.all(np.isfinite(lp))
 
 
 def test_feature_importances_match_reference_arithmetic(engine):

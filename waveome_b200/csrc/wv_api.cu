@@ -26,6 +26,9 @@ int wv_enqueue_vgp_status(const WvVgpState& vs, const int* d_list, int n_list, i
 int wv_enqueue_cross_mean(const WvBatchDev& bd, const double* d_x, const double* d_xnew_t, int m, int mpad, double* d_mean,
                           cudaStream_t st);
 
+int wv_enqueue_cross_var(const WvBatchDev& bd, const double* d_x, const double* d_xnew_t, int m, int mpad, double* d_part,
+                         double* d_prior, double* d_var, cudaStream_t st);
+
 static thread_local std::string g_err;
 static int wv_fail(const std::string& m) { g_err = m; return -1; }
 #define WV_CUDA(x)                                                                                   \
@@ -716,28 +719,46 @@ extern "C" int wv_batch_get_kinv_diag(wv_batch* b, double* diag) {
   return 0;
 }
 
+extern "C" int wv_batch_predict_f(wv_batch* b, const double* Xnew, int32_t m, double* mean, double* var);
+
 extern "C" int wv_batch_predict_mean(wv_batch* b, const double* Xnew, int32_t m, double* mean) {
-  if (!b || !Xnew || !mean) return wv_fail("wv_batch_predict_mean: null argument");
-  if (m <= 0) return wv_fail("wv_batch_predict_mean: m must be positive");
-  if (!b->last_x) return wv_fail("wv_batch_predict_mean: no evaluation has been run on this batch");
+  return wv_batch_predict_f(b, Xnew, m, mean, nullptr);
+}
+
+extern "C" int wv_batch_predict_f(wv_batch* b, const double* Xnew, int32_t m, double* mean, double* var) {
+  if (!b || !Xnew || !mean) return wv_fail("wv_batch_predict_f: null argument");
+  if (var && b->bd.lik != 0) return wv_fail("wv_batch_predict_f: variances at new inputs are built for the Gaussian likelihood only");
+  if (m <= 0) return wv_fail("wv_batch_predict_f: m must be positive");
+  if (!b->last_x) return wv_fail("wv_batch_predict_f: no evaluation has been run on this batch");
   WV_CUDA(cudaSetDevice(b->eng->device));
   const WvBatchDev& bd = b->bd;
   const int mpad = (m + WV_NB - 1) / WV_NB * WV_NB;
   std::vector<double> xt((size_t)bd.D * mpad, 0.0);
   for (int i = 0; i < m; ++i)
     for (int k = 0; k < bd.D; ++k) xt[(size_t)k * mpad + i] = Xnew[(size_t)i * bd.D + k];
-  double *d_xt = nullptr, *d_mean = nullptr;
+  double *d_xt = nullptr, *d_mean = nullptr, *d_part = nullptr;
   cudaStream_t st = b->eng->stream;
+  const size_t Bm = (size_t)bd.B * m;
+  const int ntiles = bd.nt * (bd.nt + 1) / 2;
   WV_CUDA(cudaMalloc(&d_xt, xt.size() * sizeof(double)));
-  cudaError_t e = cudaMalloc(&d_mean, (size_t)bd.B * m * sizeof(double));
-  if (e != cudaSuccess) { cudaFree(d_xt); return wv_fail(std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+  cudaError_t e = cudaMalloc(&d_mean, Bm * sizeof(double) * (var ? 3 : 1));      // mean | prior | var
+  if (e == cudaSuccess && var) e = cudaMalloc(&d_part, Bm * ntiles * sizeof(double));
+  if (e != cudaSuccess) {
+    cudaFree(d_xt); cudaFree(d_mean);
+    return wv_fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
   int rc = 0;
   if (cudaMemcpyAsync(d_xt, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
   if (rc == 0 && wv_enqueue_cross_mean(bd, b->last_x, d_xt, m, mpad, d_mean, st) < 0) rc = -1;
-  if (rc == 0 && cudaMemcpyAsync(mean, d_mean, (size_t)bd.B * m * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+  if (rc == 0 && cudaMemcpyAsync(mean, d_mean, Bm * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+  if (rc == 0 && var) {
+    if (wv_enqueue_cross_var(bd, b->last_x, d_xt, m, mpad, d_part, d_mean + Bm, d_mean + 2 * Bm, st) < 0) rc = -1;
+    if (rc == 0 && cudaMemcpyAsync(var, d_mean + 2 * Bm, Bm * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+    b->launches += 2;
+  }
   if (cudaStreamSynchronize(st) != cudaSuccess) rc = -1;
   b->launches += 1;
-  cudaFree(d_xt); cudaFree(d_mean);
-  if (rc != 0) return wv_fail(std::string("wv_batch_predict_mean: ") + cudaGetErrorString(cudaGetLastError()));
+  cudaFree(d_xt); cudaFree(d_mean); cudaFree(d_part);
+  if (rc != 0) return wv_fail(std::string("wv_batch_predict_f: ") + cudaGetErrorString(cudaGetLastError()));
   return 0;
 }

@@ -333,6 +333,33 @@ __device__ __forceinline__ void wv_elem_load_x(const WvElemSmem& sm, int dim, in
   for (int b = 0; b < 4; ++b) xj[b] = sm.xc[dim][c_off + b];
 }
 
+// acc[e] = sum over the enabled components of the product of their leaves on this thread's micro-tile, covariates
+// taken from sm.xr (rows) / sm.xc (columns).  Whole warps skip the transcendental factors of a product whose partial
+// product (a categorical mask) is zero for the warp.
+__device__ __forceinline__ void wv_elem_eval_kernel_tree(const WvElemSmem& sm, int r_off, int c_off,
+                                                         double (&acc)[WV_ELEM_NE]) {
+#pragma unroll
+  for (int e = 0; e < WV_ELEM_NE; ++e) acc[e] = 0.0;
+  for (int c = 0; c < sm.n_comp; ++c) {
+    if (!((sm.comp_mask >> c) & 1u)) continue;
+    double prod[WV_ELEM_NE];
+    const int l0 = sm.comp_start[c], l1 = sm.comp_start[c + 1];
+    bool skip = l1 <= l0;
+    for (int l = l0; l < l1; ++l) {
+      const int type = sm.leaves[l].type;
+      if (l > l0 && !wv_leaf_is_cheap(type) && wv_warp_all_zero_ne(prod)) { skip = true; break; }
+      double xi[WV_ELEM_MR], xj[4];
+      wv_elem_load_x(sm, sm.leaves[l].dim, r_off, c_off, xi, xj);
+      if (l == l0) wv_leaf_mul_ne<true>(sm, l, xi, xj, prod);
+      else wv_leaf_mul_ne<false>(sm, l, xi, xj, prod);
+    }
+    if (!skip) {
+#pragma unroll
+      for (int e = 0; e < WV_ELEM_NE; ++e) acc[e] += prod[e];
+    }
+  }
+}
+
 // =============================================================================================
 // gram.  grid (ceil(n_lower_tiles / WV_ELEM_TPC), n_active), WV_ELEM_THREADS threads.
 // Algorithmic traffic: 8 n^2 bytes written (lower tiles actually written: ~4 n^2).
@@ -358,26 +385,7 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_gram_kernel(
     wv_elem_coords(r_off, c_off, above, ti == tj);
     if (above) continue;                          // the strict upper part of a diagonal tile is never read
     double acc[WV_ELEM_NE];
-#pragma unroll
-    for (int e = 0; e < WV_ELEM_NE; ++e) acc[e] = 0.0;
-    for (int c = 0; c < sm.n_comp; ++c) {
-      if (!((sm.comp_mask >> c) & 1u)) continue;
-      double prod[WV_ELEM_NE];
-      const int l0 = sm.comp_start[c], l1 = sm.comp_start[c + 1];
-      bool skip = false;
-      for (int l = l0; l < l1; ++l) {
-        const int type = sm.leaves[l].type;
-        if (l > l0 && !wv_leaf_is_cheap(type) && wv_warp_all_zero_ne(prod)) { skip = true; break; }
-        double xi[WV_ELEM_MR], xj[4];
-        wv_elem_load_x(sm, sm.leaves[l].dim, r_off, c_off, xi, xj);
-        if (l == l0) wv_leaf_mul_ne<true>(sm, l, xi, xj, prod);
-        else wv_leaf_mul_ne<false>(sm, l, xi, xj, prod);
-      }
-      if (!skip) {
-#pragma unroll
-        for (int e = 0; e < WV_ELEM_NE; ++e) acc[e] += prod[e];
-      }
-    }
+    wv_elem_eval_kernel_tree(sm, r_off, c_off, acc);
     const double s2 = sm.theta[sm.noise_slot];
     const double cmean = sm.mean_slot >= 0 ? sm.theta[sm.mean_slot] : 0.0;
 #pragma unroll
@@ -527,23 +535,7 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_cross_mean_k
     }
     __syncthreads();
     double acc[WV_ELEM_NE];
-#pragma unroll
-    for (int e = 0; e < WV_ELEM_NE; ++e) acc[e] = 0.0;
-    for (int c = 0; c < sm.n_comp; ++c) {
-      if (!((sm.comp_mask >> c) & 1u)) continue;
-      double prod[WV_ELEM_NE];
-      const int l0 = sm.comp_start[c], l1 = sm.comp_start[c + 1];
-      for (int l = l0; l < l1; ++l) {
-        double xi[WV_ELEM_MR], xj[4];
-        wv_elem_load_x(sm, sm.leaves[l].dim, r_off, c_off, xi, xj);
-        if (l == l0) wv_leaf_mul_ne<true>(sm, l, xi, xj, prod);
-        else wv_leaf_mul_ne<false>(sm, l, xi, xj, prod);
-      }
-      if (l1 > l0) {
-#pragma unroll
-        for (int e = 0; e < WV_ELEM_NE; ++e) acc[e] += prod[e];
-      }
-    }
+    wv_elem_eval_kernel_tree(sm, r_off, c_off, acc);
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) {
       const int gj = tj * WV_NB + c_off + bb;
@@ -566,4 +558,98 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_cross_mean_k
     const int gi = ti * WV_NB + r;
     if (gi < m) mean[(size_t)b * m + gi] = cmean + (sm.red[r][0] + sm.red[r][1]);
   }
+}
+
+
+// =============================================================================================
+// cross variance: var f(xnew_i) = k(xnew_i, xnew_i) - k*_i^T W k*_i,  W = (K + sigma^2 I)^-1 (lower tiles of A after an
+// evaluation), k*_i = k(xnew_i, X)  (gpflow GPR.predict_f variance, full_cov = False).
+// grid (n_lower_tiles, ceil(m / 64), n_models), WV_ELEM_THREADS threads: CTA (t, ti, b) forms the two cross-Gram tiles
+// K*_j = k(xnew[ti], X[tj]) and K*_k = k(xnew[ti], X[tk]) of the W tile (tj >= tk) in shared memory and reduces
+//     part[b][t][i] = w sum_{j,k} K*_j[i][j] W[j][k] K*_k[i][k],   w = 2 off the diagonal, 1 on it;
+// the tile t = 0 CTA also writes the prior variance k(xnew_i, xnew_i).  wv_cross_var_reduce_kernel sums the parts
+// in fixed order.  A post-fit pass: recomputing the cross-Gram tiles per W tile keeps it a single simple kernel.
+// =============================================================================================
+struct WvCrossVarSmem {
+  WvElemSmem el;
+  double Kj[WV_NB * (WV_NB + 1)];
+  double Kk[WV_NB * (WV_NB + 1)];
+  double W[WV_NB * (WV_NB + 1)];
+};
+
+__global__ void __launch_bounds__(WV_ELEM_THREADS, 1) wv_cross_var_kernel(
+    WvBatchDev bd, const double* __restrict__ xall, const double* __restrict__ Xnew_t, int m, int mpad,
+    double* __restrict__ part, double* __restrict__ prior) {
+  WvCrossVarSmem& cs = *reinterpret_cast<WvCrossVarSmem*>(wv_smem_raw);
+  WvElemSmem& sm = cs.el;
+  const int b = blockIdx.z, ti = blockIdx.y, t = blockIdx.x;
+  const int ntiles = gridDim.x, LDK = WV_NB + 1;
+  int tj, tk;
+  wv_tile_from_linear(t, tj, tk);
+  wv_elem_stage_model(bd, b, xall, sm);
+  int r_off, c_off;
+  bool above;
+  wv_elem_coords(r_off, c_off, above, false);
+  // ---- the two cross-Gram tiles (columns beyond n are zero) and, for t = 0, the prior variances
+  for (int which = 0; which < (t == 0 ? 3 : 2); ++which) {
+    const int tc = which == 0 ? tj : tk;
+    __syncthreads();
+    for (int i = threadIdx.x; i < sm.n_dims * WV_NB; i += blockDim.x) {
+      const int d = i / WV_NB, r = i % WV_NB;
+      const double xr = Xnew_t[(size_t)sm.dims[d] * mpad + ti * WV_NB + r];
+      sm.xr[d][r] = xr;
+      sm.xc[d][r] = which == 2 ? xr : bd.Xt[(size_t)sm.dims[d] * bd.npad + tc * WV_NB + r];
+    }
+    __syncthreads();
+    double acc[WV_ELEM_NE];
+    wv_elem_eval_kernel_tree(sm, r_off, c_off, acc);
+    if (which == 2) {
+#pragma unroll
+      for (int a = 0; a < WV_ELEM_MR; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb)
+          if (r_off + a == c_off + bb && ti * WV_NB + r_off + a < m)
+            prior[(size_t)b * m + ti * WV_NB + r_off + a] = acc[a * 4 + bb];
+    } else {
+      double* dst = which == 0 ? cs.Kj : cs.Kk;
+#pragma unroll
+      for (int a = 0; a < WV_ELEM_MR; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb)
+          dst[(r_off + a) * LDK + c_off + bb] = (tc * WV_NB + c_off + bb < bd.n) ? acc[a * 4 + bb] : 0.0;
+    }
+  }
+  // ---- the W tile
+  const double* Wg = bd.A + (size_t)b * bd.npad * bd.npad + (size_t)tj * WV_NB * bd.npad + tk * WV_NB;
+  for (int i = threadIdx.x; i < WV_NB * WV_NB; i += blockDim.x) {
+    const int r = i >> 6, c = i & 63;
+    cs.W[r * LDK + c] = Wg[(size_t)r * bd.npad + c];
+  }
+  __syncthreads();
+  // ---- thread (i = tid / 4, q = tid % 4): T[i][k] = sum_j K*_j[i][j] W[j][k] for k in [16 q, 16 q + 16), then the dot
+  const int i = threadIdx.x >> 2, q = threadIdx.x & 3;
+  double tacc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) tacc[k] = 0.0;
+  for (int j = 0; j < WV_NB; ++j) {
+    const double a = cs.Kj[i * LDK + j];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tacc[k] = fma(a, cs.W[j * LDK + q * 16 + k], tacc[k]);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s = fma(tacc[k], cs.Kk[i * LDK + q * 16 + k], s);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if (q == 0 && ti * WV_NB + i < m) part[((size_t)b * ntiles + t) * m + ti * WV_NB + i] = (tj == tk ? 1.0 : 2.0) * s;
+}
+
+__global__ void wv_cross_var_reduce_kernel(int B, int ntiles, int m, const double* __restrict__ part,
+                                           const double* __restrict__ prior, double* __restrict__ var) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * m) return;
+  const size_t b = idx / m, i = idx % m;
+  double s = 0.0;
+  for (int t = 0; t < ntiles; ++t) s += part[(b * ntiles + t) * m + i];
+  var[idx] = prior[idx] - s;
 }

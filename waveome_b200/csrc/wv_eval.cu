@@ -761,6 +761,7 @@ static cudaError_t wv_set_attrs() {
   WV_ATTR(wv_gram_kernel, sizeof(WvElemSmem));
   WV_ATTR(wv_grad_kernel, sizeof(WvElemSmem));
   WV_ATTR(wv_cross_mean_kernel, sizeof(WvElemSmem));
+  WV_ATTR(wv_cross_var_kernel, sizeof(WvCrossVarSmem));
   WV_ATTR(wv_chol_step_kernel, wv_smem_gemm_bytes());
   WV_ATTR(wv_trtri_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_kinv_kernel, sizeof(WvGemmSmem));
@@ -1153,4 +1154,16 @@ int wv_enqueue_cross_mean(const WvBatchDev& bd, const double* d_x, const double*
   wv_cross_mean_kernel<<<dim3(mpad / WV_NB, bd.B), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(bd, d_x, d_xnew_t, m, mpad,
                                                                                              d_mean);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// predictive variance of f at new inputs for every model (uses K^-1 left in A by the last evaluation at d_x)
+int wv_enqueue_cross_var(const WvBatchDev& bd, const double* d_x, const double* d_xnew_t, int m, int mpad, double* d_part,
+                         double* d_prior, double* d_var, cudaStream_t st) {
+  if (wv_set_attrs() != cudaSuccess) return -1;
+  const int ntiles = bd.nt * (bd.nt + 1) / 2;
+  wv_cross_var_kernel<<<dim3(ntiles, mpad / WV_NB, bd.B), WV_ELEM_THREADS, sizeof(WvCrossVarSmem), st>>>(
+      bd, d_x, d_xnew_t, m, mpad, d_part, d_prior);
+  const size_t total = (size_t)bd.B * m;
+  wv_cross_var_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bd.B, ntiles, m, d_part, d_prior, d_var);
+  return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }

@@ -49,7 +49,7 @@ class _LbfgsOpts(C.Structure):
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
     "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_likelihood", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
-    "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_get_kinv_diag", "wv_batch_predict_mean", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
+    "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_get_kinv_diag", "wv_batch_predict_mean", "wv_batch_predict_f", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
 KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk", "sites"]
 
@@ -87,6 +87,7 @@ def load_library():
     lib.wv_batch_get_alpha.argtypes = [vp, _f64p]; lib.wv_batch_get_alpha.restype = C.c_int
     lib.wv_batch_get_kinv_diag.argtypes = [vp, _f64p]; lib.wv_batch_get_kinv_diag.restype = C.c_int
     lib.wv_batch_predict_mean.argtypes = [vp, _f64p, C.c_int32, _f64p]; lib.wv_batch_predict_mean.restype = C.c_int
+    lib.wv_batch_predict_f.argtypes = [vp, _f64p, C.c_int32, _f64p, _f64p]; lib.wv_batch_predict_f.restype = C.c_int
     lib.wv_batch_profile_enable.argtypes = [vp, C.c_int]; lib.wv_batch_profile_enable.restype = None
     lib.wv_batch_profile_read.argtypes = [vp, _f64p, C.POINTER(C.c_int64), C.c_int]; lib.wv_batch_profile_read.restype = C.c_int
     lib.wv_last_error.argtypes = []; lib.wv_last_error.restype = C.c_char_p
@@ -279,6 +280,16 @@ class Batch:
         _check(self.lib.wv_batch_predict_mean(self.handle, _f64(Xnew), int(Xnew.shape[0]), _f64(out)),
                "wv_batch_predict_mean")
         return out
+
+    def predict_f(self, Xnew: np.ndarray):
+        """([B, m] mean, [B, m] variance) of f at new inputs [m, D] with the parameters of the last evaluation."""
+        Xnew = np.ascontiguousarray(Xnew, dtype=np.float64)
+        if Xnew.ndim != 2 or Xnew.shape[1] != self.D:
+            raise ValueError(f"Xnew must be [m, {self.D}]")
+        mean = np.empty((self.B, Xnew.shape[0])); var = np.empty((self.B, Xnew.shape[0]))
+        _check(self.lib.wv_batch_predict_f(self.handle, _f64(Xnew), int(Xnew.shape[0]), _f64(mean), _f64(var)),
+               "wv_batch_predict_f")
+        return mean, var
 
     def counters(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

@@ -149,18 +149,30 @@ class GPR:
         return self.log_posterior_density_value
 
     def predict_f(self, Xnew, data=None):
-        """Posterior mean at ``Xnew`` [m, D] -> ([m, 1], None).  ``data`` = (X, Y) as the reference's model methods
-        take it; defaults to the data the model was fitted on when it was kept.  (The predictive variance is not
-        produced by the engine yet; post-fit consumers on this path use the mean only)"""
-        from .postfit import predict_mean
+        """gpflow GPModel.predict_f(Xnew) (full_cov=False): ([m, 1] mean, [m, 1] variance of f).  ``data`` = (X, Y) as
+        the reference's model methods take it; defaults to the data the model was fitted on when it was kept.  Count
+        likelihoods: the mean only (variance None)."""
+        from .postfit import predict_f, predict_mean
         data = data if data is not None else self.data
         if data is None:
             raise ValueError("predict_f needs data=(X, Y): the fitted model does not keep its training data")
-        mu = predict_mean(self, np.asarray(data[0]), np.asarray(data[1]).reshape(-1), Xnew)
-        return mu.reshape(-1, 1), None
+        X, y = np.asarray(data[0]), np.asarray(data[1]).reshape(-1)
+        if not isinstance(self.likelihood, Gaussian):
+            raise NotImplementedError("predict_f at new inputs is built for the Gaussian likelihood")
+        mu, var = predict_f(self, X, y, Xnew)
+        return mu.reshape(-1, 1), var.reshape(-1, 1)
 
     def predict_y(self, Xnew, data=None):
-        return self.predict_f(Xnew, data=data)
+        """gpflow GPModel.predict_y: the Gaussian likelihood adds its variance to predict_f's."""
+        mu, var = self.predict_f(Xnew, data=data)
+        return mu, var + float(self.likelihood.variance)
+
+    def predict_log_density(self, data_new, data=None):
+        """gpflow GPModel.predict_log_density((Xnew, Ynew)): log N(ynew | predict_y mean, variance), [m]."""
+        Xnew, Ynew = data_new
+        mu, var = self.predict_y(Xnew, data=data)
+        ynew = np.asarray(Ynew, dtype=np.float64).reshape(-1, 1)
+        return (-0.5 * (np.log(2 * np.pi) + np.log(var) + (ynew - mu) ** 2 / var)).reshape(-1)
 
     def get_feature_importances(self, data=None, return_value="log_bf"):
         """waveome/model_classes.py:546-573"""

@@ -224,6 +224,22 @@ def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf"
     return out
 
 
+def predict_f(model: GPR, X, y, Xnew, engine=None):
+    """gpflow GPR.predict_f(Xnew) (full_cov=False) for one Gaussian model: ([m] mean, [m] variance of f)."""
+    from .engine import Batch
+    from .model_fitting import get_engine
+    engine = engine or get_engine()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(1, -1)
+    batch = Batch(engine, X, y, [model.program()])
+    try:
+        batch.eval(batch.x0())
+        mean, var = batch.predict_f(np.asarray(Xnew, dtype=np.float64))
+        return mean[0], var[0]
+    finally:
+        batch.close()
+
+
 def predict_mean(model: GPR, X, y, Xnew, engine=None) -> np.ndarray:
     """gpflow GPR.predict_f(Xnew)[0] for one model: [m] posterior mean at new inputs."""
     from .engine import Batch
