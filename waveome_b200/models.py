@@ -209,6 +209,30 @@ class PenalizedGPR(GPR):
                 if "kernel" in key and "variance" in key:
                     val.prior = prior
 
+    def penalization_search(self, data=None, penalization_factor_list=(0.0, 1.0, 10.0, 100.0), k_fold=3, fit_best=True,
+                            random_seed=None, num_restart=5, selection_type="se", unit_col=None, **unused):
+        """waveome/model_classes.py:866-998 for this model: k-fold cross-validation over the factors, then (fit_best) the
+        model takes the best factor and the parameters of the refit on all rows.  Sets
+        ``self.penalization_search_results`` ([factors x folds, 3]: factor, fold, held-out mean log density)."""
+        from .penalization import penalization_search_batch
+        X, y = np.asarray(data[0], dtype=np.float64), np.asarray(data[1], dtype=np.float64).reshape(1, -1)
+        out = penalization_search_batch(X, y, self.kernel, mean_function=self.mean_function,
+                                        penalization_factor_list=penalization_factor_list, k_fold=k_fold,
+                                        unit_col=unit_col, fit_best=fit_best, random_seed=random_seed,
+                                        num_restart=num_restart, selection_type=selection_type)
+        res = out["results"][0]
+        self.penalization_search_results = np.array([[pf, k, res[fi, k]] for fi, pf in enumerate(out["factors"])
+                                                     for k in range(res.shape[1])])
+        if fit_best:
+            best = out["models"][0]
+            self.set_penalization_factor(float(out["best_factor"][0]) if np.isfinite(out["best_factor"][0]) else 0.0)
+            self.kernel, self.mean_function, self.likelihood = best.kernel, best.mean_function, best.likelihood
+            self.set_penalization_factor(self.penalization_factor)
+            self.log_marginal_likelihood_value = best.log_marginal_likelihood_value
+            self.log_posterior_density_value = best.log_posterior_density_value
+            self.fit_info = best.fit_info
+        return None
+
     def update_kernel_name(self):
         from .utilities import kernel_name_string
         self.kernel_name = kernel_name_string(self.kernel, with_idx=True)
