@@ -107,13 +107,15 @@ int64_t wv_batch_workspace_bytes(const wv_batch* b);
 /* replace the outcomes (HOST [B, n]) without rebuilding programs / workspaces */
 int wv_batch_set_y(wv_batch* b, const double* Y);
 
-/* Likelihood of every model of the batch: 0 Gaussian (default; exact GPR marginal likelihood), 1 Poisson with exp link
- * (gpflow.likelihoods.Poisson), 2 negative binomial with log link and dispersion `param` = alpha
- * (waveome/likelihoods.py:16-79).  For 1 and 2 the objective is the variational bound of gpflow.models.VGP / PSVGP
+/* Likelihood of every model of the batch (waveome/utilities.py:989-1009 gp_likelihood_crosswalk): 0 Gaussian (default;
+ * exact GPR marginal likelihood), 1 Poisson with exp link (gpflow.likelihoods.Poisson), 2 negative binomial with log
+ * link and dispersion `param` = alpha (waveome/likelihoods.py:16-79), 3 Bernoulli with gpflow's inv_probit link (y in
+ * {0, 1}), 4 Gamma with exp link and shape `param` (gpflow.likelihoods.Gamma).  For 1-4 the objective is the variational bound of gpflow.models.VGP / PSVGP
  * with Z = X (waveome/model_fitting.py:158-185, waveome/model_classes.py:1082-1126) maximised over the variational
  * distribution for the given hyper-parameters: f = -(max_q ELBO + log prior), `lml` reports max_q ELBO, Y holds the
- * counts.  The programs' noise slot: ignored for Poisson; for the negative binomial a TRAINABLE noise slot (Exp
- * bijector) is the dispersion alpha and gets d(bound)/d(alpha), a frozen one means alpha = `param`.
+ * observations.  The programs' noise slot: ignored for Poisson / Bernoulli; for the negative binomial and the Gamma a
+ * TRAINABLE noise slot is the likelihood parameter (alpha with an Exp bijector, shape with softplus) and gets
+ * d(bound)/d(parameter), a frozen one means parameter = `param`.
  * Status bit 16: the inner iteration hit its sweep cap. */
 int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param);
 /* Posterior mean and variance of the latent f at the training inputs after the last evaluation of a non-Gaussian

@@ -70,6 +70,8 @@ def lik_of(model, lik):
     lv = model["likelihood_variance"]
     if lik["type"] == "negative_binomial" and lv.get("transform") == "exp":
         return {"type": "negative_binomial", "alpha": lv["value"]}
+    if lik["type"] == "gamma" and lv.get("transform") == "softplus":
+        return {"type": "gamma", "shape": lv["value"]}
     return lik
 
 
@@ -79,6 +81,21 @@ def var_exp(lik, y, m, v):
     if lik["type"] == "poisson":
         r = np.exp(m + 0.5 * v)
         return y * m - r - lgamma(y + 1.0), y - r, -0.5 * r
+    if lik["type"] == "gamma":            # gpflow.likelihoods.Gamma, exp link, closed form
+        a = lik["shape"]
+        r = y * np.exp(-m + 0.5 * v)
+        return -a * m - lgamma(a) + (a - 1.0) * np.log(y) - r, -a + r, -0.5 * r
+    if lik["type"] == "bernoulli":        # gpflow.likelihoods.Bernoulli, inv_probit link, 20-point Gauss-Hermite
+        from scipy.special import erfc
+        f = m[:, None] + np.sqrt(2.0 * v)[:, None] * GH_X[None, :]
+        w = GH_W[None, :] / math.sqrt(math.pi)
+        p = 1e-3 + (1.0 - 2e-3) * 0.5 * erfc(-f / math.sqrt(2.0))
+        ph = (1.0 - 2e-3) * np.exp(-0.5 * f * f) / math.sqrt(2.0 * math.pi)
+        yy = y[:, None] > 0.5
+        pp = np.where(yy, p, 1.0 - p)
+        d1 = np.where(yy, ph, -ph) / pp
+        d2 = -f * d1 - d1 * d1
+        return np.sum(w * np.log(pp), 1), np.sum(w * d1, 1), 0.5 * np.sum(w * d2, 1)
     if lik["type"] == "negative_binomial":
         a = lik["alpha"]
         sd = np.sqrt(2.0 * v)
@@ -135,8 +152,13 @@ def vgp_collapsed(model, lik, X, y, x, sites=None, tol=1e-12, maxit=500, rho=1.0
     c = spec["mean"]["c"]["value"] if spec["mean"]["type"] == "constant" else 0.0
     y = np.asarray(y, dtype=np.float64)
     if sites is None:
-        lam = np.ones(n)
-        eta = lam * (np.log(y + 1.0))          # precision-mean of the site: lam * ytilde
+        lam = np.ones(n)                       # unit-precision pseudo-observations at a link-scale guess of f
+        if lik["type"] == "bernoulli":
+            eta = np.where(y > 0.5, 1.0, -1.0)
+        elif lik["type"] == "gamma":
+            eta = np.log(np.maximum(y, 1e-12))
+        else:
+            eta = np.log(y + 1.0)
     else:
         lam, eta = [np.array(s, dtype=np.float64) for s in sites]
     it = 0
@@ -185,6 +207,9 @@ def vgp_collapsed(model, lik, X, y, x, sites=None, tol=1e-12, maxit=500, rho=1.0
                 dth = np.sum(alpha)
             elif p is spec["likelihood_variance"] and lik["type"] == "negative_binomial":
                 dth = nb_dalpha(y, m, v, lik["alpha"])          # the slot carries the NB dispersion
+            elif p is spec["likelihood_variance"] and lik["type"] == "gamma":
+                from scipy.special import digamma
+                dth = float(np.sum(-m - digamma(lik["shape"]) + np.log(y)))
             else:
                 dth = 0.0                      # the Gaussian noise variance does not exist on this path
             grads.append(dth * go.transform_dtheta_du(p, u))

@@ -152,3 +152,61 @@ def test_penalized_optimization_poisson_config5_shape():
         ncomp = len(m.kernel.kernels) if m.kernel.name == "sum" else 1
         assert len(m.feature_importances) == ncomp + 1 and 0.0 <= m.feature_importances[-1] <= 1.0
         assert all(np.isfinite(v) for v in m.feature_importances)
+
+
+def other_data(n, n_subj, seed, lik):
+    rng = np.random.default_rng(seed)
+    subj = rng.integers(0, n_subj, size=n).astype(float)
+    t = rng.normal(size=n)
+    X = np.stack([subj, t], 1)
+    f = 0.6 * rng.normal(size=n_subj)[subj.astype(int)] + np.sin(2 * t)
+    if lik == "bernoulli":
+        return X, (rng.uniform(size=n) < 0.5 * (1 + np.tanh(f))).astype(float)
+    return X, rng.gamma(2.0, np.exp(f))
+
+
+@pytest.mark.parametrize("lik,param", [("bernoulli", 0.0), ("gamma", 1.7)])
+@pytest.mark.parametrize("n", [50, 200])
+def test_bernoulli_and_gamma_bounds_match_oracle(engine, lik, param, n):
+    """gp_likelihood_crosswalk's 'binomial'/'bernoulli' and 'gamma' entries (utilities.py:989-1009) on the same site
+    iteration: Bernoulli with gpflow's inv_probit link (Gauss-Hermite), Gamma with the exp link (closed form)."""
+    from waveome_b200.engine import Batch
+    X, y = other_data(n, max(4, n // 6), seed=n + 3, lik=lik)
+    X2, y2 = other_data(n, max(4, n // 6), seed=n + 4, lik=lik)
+    model = count_model(c=0.0)
+    Y = np.stack([y, y2])
+    batch = Batch(engine, X, Y, [model.program()])
+    batch.set_likelihood(lik, param)
+    rng = np.random.default_rng(n)
+    x = batch.x0() + 0.2 * rng.normal(size=(2, batch.P))
+    f, g, lml, st = batch.eval(x)
+    fm, fv = batch.latent()
+    olik = {"type": lik, "shape": param}
+    for b in range(2):
+        r = vo.vgp_collapsed(copy.deepcopy(model.to_spec()), olik, X, Y[b], x[b], rho=0.5, tol=1e-12, maxit=3000)
+        assert st[b] == 0
+        assert abs(lml[b] - r["F"]) <= 1e-8 * abs(r["F"]), (lml[b], r["F"])
+        np.testing.assert_allclose(g[b], -r["grad"], rtol=0, atol=1e-6 * np.max(np.abs(r["grad"])))
+        np.testing.assert_allclose(fm[b], r["m"], rtol=0, atol=1e-7 * (1 + np.max(np.abs(r["m"]))))
+        np.testing.assert_allclose(fv[b], r["v"], rtol=1e-6, atol=1e-9)
+    batch.close()
+
+
+def test_gamma_shape_is_trained_and_bernoulli_fits(engine):
+    """fit through the host API: Gamma's trainable shape rides in the noise slot (softplus); Bernoulli has none."""
+    from waveome_b200.model_fitting import fit_models
+    from waveome_b200.models import make_likelihood
+    from waveome_b200.postfit import fitted_means
+    for lik, olik in (("gamma", {"type": "gamma", "shape": 1.0}), ("bernoulli", {"type": "bernoulli"})):
+        X, y = other_data(90, 15, seed=31, lik=lik)
+        m = count_model(c=0.0)
+        m.likelihood = make_likelihood(lik)
+        spec = copy.deepcopy(m.to_spec())
+        res = fit_models(X, y[None, :], [m], engine=engine)
+        ro = vo.fit(copy.deepcopy(spec), olik, X, y)
+        assert res["status"][0] in (0, 8)
+        assert abs(res["lml"][0] - ro["F"]) <= 1e-5 * abs(ro["F"]), (lik, res["lml"][0], ro["F"])
+        mu, st = fitted_means(X, y[None, :], [m], engine=engine)
+        assert np.all(np.isfinite(mu)) and (lik != "bernoulli" or (mu.min() > 0 and mu.max() < 1))
+        if lik == "gamma":
+            assert abs(float(m.likelihood.shape) - 2.0) < 1.0 and float(m.likelihood.shape) != 1.0

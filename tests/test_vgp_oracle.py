@@ -48,3 +48,32 @@ def test_damping_does_not_change_the_fixed_point():
     a = vo.vgp_collapsed(model, {"type": "poisson"}, X, y, x, rho=1.0, want_grad=False)
     b = vo.vgp_collapsed(model, {"type": "poisson"}, X, y, x, rho=0.4, want_grad=False, maxit=2000)
     assert abs(a["F"] - b["F"]) <= 1e-10 * abs(a["F"])
+
+
+@pytest.mark.parametrize("kind", ["bernoulli", "gamma"])
+def test_bernoulli_and_gamma_collapsed_bounds(kind):
+    """the same three checks for gp_likelihood_crosswalk's Bernoulli (inv_probit) and Gamma (exp link, trainable shape
+    in the noise slot) entries"""
+    model, X, y, x, rng = _setup(seed=5)
+    if kind == "bernoulli":
+        lik, yy = {"type": "bernoulli"}, (y > np.median(y)).astype(float)
+    else:
+        lik, yy = {"type": "gamma", "shape": 2.0}, rng.gamma(2.0, np.exp(0.3 * np.sin(X[:, 1])))
+        model["likelihood_variance"] = {"value": 2.0, "trainable": True, "transform": "softplus", "prior": None}
+        x = go.pack(model)
+    kw = dict(rho=0.7, maxit=3000)
+    r = vo.vgp_collapsed(model, lik, X, yy, x, **kw)
+    q_mu, q_sqrt = vo.q_from_sites(model, X, yy, x, r["sites"])
+    e = vo.vgp_elbo(model, lik, X, yy, x, q_mu, q_sqrt)
+    assert abs(e - r["F"]) <= 1e-10 * abs(e)
+    n = len(yy)
+    for _ in range(8):
+        dq, dS = 1e-3 * rng.normal(size=n), 1e-3 * np.tril(rng.normal(size=(n, n)))
+        assert vo.vgp_elbo(model, lik, X, yy, x, q_mu + dq, q_sqrt + dS) < e
+    h, fd = 1e-5, []
+    for i in range(len(x)):
+        xp, xm = x.copy(), x.copy()
+        xp[i] += h; xm[i] -= h
+        fd.append((vo.vgp_collapsed(model, lik, X, yy, xp, want_grad=False, **kw)["F"]
+                   - vo.vgp_collapsed(model, lik, X, yy, xm, want_grad=False, **kw)["F"]) / (2 * h))
+    np.testing.assert_allclose(r["grad"], fd, rtol=1e-6, atol=1e-7)

@@ -377,21 +377,22 @@ extern "C" int wv_batch_set_y(wv_batch* b, const double* Y) {
 // ---------------------------------------------------------------------------------------------
 // likelihood of the batch: 0 gaussian (default), 1 poisson, 2 negative binomial (param = alpha)
 // ---------------------------------------------------------------------------------------------
-__global__ void wv_site_init_kernel(int B, int n, int npad, const double* __restrict__ Y, double* lam, double* eta,
-                                    double* lgam) {
+__global__ void wv_site_init_kernel(int B, int n, int npad, int kind, const double* __restrict__ Y, double* lam,
+                                    double* eta, double* lgam) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * npad) return;
   const int r = (int)(i % npad);
   const double y = r < n ? Y[i] : 0.0;
-  lam[i] = 1.0;
-  eta[i] = log(y + 1.0);          // pseudo-observation log(y + 1) with unit precision
+  lam[i] = 1.0;                   // unit-precision pseudo-observations at a link-scale guess of f
+  eta[i] = kind == 3 ? (y > 0.5 ? 1.0 : -1.0) : (kind == 4 ? log(fmax(y, 1e-12)) : log(y + 1.0));
   lgam[i] = lgamma(y + 1.0);
 }
 
 extern "C" int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param) {
   if (!b) return wv_fail("wv_batch_set_likelihood: null batch");
-  if (kind < 0 || kind > 2) return wv_fail("wv_batch_set_likelihood: kind must be 0 (gaussian), 1 (poisson) or 2 (negative binomial)");
-  if (kind == 2 && !(param > 0.0)) return wv_fail("wv_batch_set_likelihood: negative binomial alpha must be positive");
+  if (kind < 0 || kind > 4)
+    return wv_fail("wv_batch_set_likelihood: kind must be 0 (gaussian), 1 (poisson), 2 (negative binomial), 3 (bernoulli) or 4 (gamma)");
+  if ((kind == 2 || kind == 4) && !(param > 0.0)) return wv_fail("wv_batch_set_likelihood: the likelihood parameter must be positive");
   WV_CUDA(cudaSetDevice(b->eng->device));
   WvBatchDev& bd = b->bd;
   bd.lik = kind; bd.lik_param = param;
@@ -416,7 +417,7 @@ extern "C" int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param) 
   cudaStream_t st = b->eng->stream;
   WV_CUDA(cudaMemsetAsync(bd.vgp_extra, 0, B * sizeof(double), st));
   WV_CUDA(cudaMemsetAsync(bd.vgp_dlik, 0, B * sizeof(double), st));
-  wv_site_init_kernel<<<(unsigned)((B * np + 255) / 256), 256, 0, st>>>((int)B, bd.n, (int)np, bd.Y, bd.site_lam, bd.site_eta,
+  wv_site_init_kernel<<<(unsigned)((B * np + 255) / 256), 256, 0, st>>>((int)B, bd.n, (int)np, kind, bd.Y, bd.site_lam, bd.site_eta,
                                                                        (double*)b->vgp.lgam);
   WV_CUDA(cudaStreamSynchronize(st));
   return 0;

@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(64 * WV_FIN_MAXG) wv_finalize_kernel(WvBatchDe
       for (int g = 0; g < G; ++g) dl += s_part[g][s];
       dl *= 0.5;
       if (s == pg->mean_slot) dl = s_sum_alpha;
-      if (bd.lik == 2 && s == pg->noise_slot) dl = bd.vgp_dlik[b];      // the noise slot is the NB dispersion there
+      if ((bd.lik == 2 || bd.lik == 4) && s == pg->noise_slot) dl = bd.vgp_dlik[b];      // the slot is the likelihood parameter
       const double g = -(dl + dlp) * wv_transform_grad(sl.transform, u);
       g_out[(size_t)b * bd.P + sl.xindex] = g;
       if (!isfinite(g)) atomicOr(&s_bad, 1);
@@ -853,6 +853,15 @@ __device__ __forceinline__ void wv_var_exp(int lik, double alpha_nb, double y, d
     h = -0.5 * r;
     return;
   }
+  if (lik == 4) {                       // Gamma, exp link, shape a = alpha_nb: closed form (gpflow.likelihoods.Gamma)
+    const double a = alpha_nb;
+    const double r = y * exp(-m + 0.5 * v);
+    E = -a * m - lgamma(a) + (a - 1.0) * log(y) - r;
+    g = -a + r;
+    h = -0.5 * r;
+    da = -m - wv_digamma(a) + log(y);
+    return;
+  }
   // negative binomial, log link (waveome/likelihoods.py:68-79), 20-point Gauss-Hermite; derivatives by Bonnet / Price
   const double gx[10] = {0.2453407083009012, 0.7374737285453944, 1.2340762153953231, 1.7385377121165861,
                          2.2549740020892757, 2.7888060584281305, 3.3478545673832163, 3.9447640401156252,
@@ -860,7 +869,26 @@ __device__ __forceinline__ void wv_var_exp(int lik, double alpha_nb, double y, d
   const double gw[10] = {4.622436696006101e-01, 2.866755053628341e-01, 1.090172060200233e-01, 2.481052088746361e-02,
                          3.243773342237862e-03, 2.283386360163540e-04, 7.802556478532064e-06, 1.086069370769282e-07,
                          4.399340992273181e-10, 2.229393645534151e-13};
-  const double k = 1.0 / alpha_nb, sd = sqrt(2.0 * v);
+  const double sd = sqrt(2.0 * v);
+  if (lik == 3) {                       // Bernoulli, gpflow inv_probit link p = 1e-3 + (1 - 2e-3) Phi(f), y in {0, 1}
+    double se = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int q = 0; q < 20; ++q) {
+      const double x = q < 10 ? -gx[9 - q] : gx[q - 10];
+      const double w = (q < 10 ? gw[9 - q] : gw[q - 10]) * 0.5641895835477563;
+      const double f = m + sd * x;
+      const double ph = 0.3989422804014327 * exp(-0.5 * f * f) * (1.0 - 2e-3);      // dp/df
+      const double p = 1e-3 + (1.0 - 2e-3) * 0.5 * erfc(-f * 0.7071067811865476);
+      const double pp = y > 0.5 ? p : 1.0 - p;           // probability of the observed class
+      const double d1 = (y > 0.5 ? ph : -ph) / pp;       // d log pp / df
+      const double d2 = -f * d1 - d1 * d1;               // d2 log pp / df2  (dph/df = -f ph)
+      se += w * log(pp);
+      s1 += w * d1;
+      s2 += w * d2;
+    }
+    E = se; g = s1; h = 0.5 * s2;
+    return;
+  }
+  const double k = 1.0 / alpha_nb;
   const double cst = lgamma(k + y) - lgam - lgamma(k);
   double se = 0.0, s1 = 0.0, s2 = 0.0, sk = 0.0;
   const double dcst = wv_digamma(k + y) - wv_digamma(k);          // d cst / dk
@@ -897,7 +925,7 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
     cmean = sl.xindex >= 0 ? wv_transform(sl.transform, xall[(size_t)b * bd.P + sl.xindex], sl.shift) : sl.fixed;
   }
   double lik_param = bd.lik_param;
-  if (bd.lik == 2) {        // a trainable noise slot is the dispersion alpha
+  if (bd.lik == 2 || bd.lik == 4) {        // a trainable noise slot is the likelihood parameter (NB alpha, Gamma shape)
     const WvSlot& sl = pg->slots[pg->noise_slot];
     if (sl.xindex >= 0) lik_param = wv_transform(sl.transform, xall[(size_t)b * bd.P + sl.xindex], sl.shift);
   }

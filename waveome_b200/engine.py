@@ -208,7 +208,7 @@ class Batch:
         _check(self.lib.wv_batch_set_component_mask(self.handle, mask.ctypes.data_as(C.POINTER(C.c_uint32))),
                "wv_batch_set_component_mask")
 
-    LIKELIHOODS = {"gaussian": 0, "poisson": 1, "negative_binomial": 2}
+    LIKELIHOODS = {"gaussian": 0, "poisson": 1, "negative_binomial": 2, "bernoulli": 3, "gamma": 4}
 
     def set_likelihood(self, kind, param: float = 0.0):
         """"gaussian" (default), "poisson", or "negative_binomial" (param = alpha): switches the objective to the

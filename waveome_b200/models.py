@@ -58,6 +58,37 @@ class NegativeBinomial:
         return float(self.alpha)
 
 
+class Bernoulli:
+    """gpflow.likelihoods.Bernoulli (inv_probit link): no parameters, y in {0, 1}."""
+    name = "bernoulli"
+    parameters: list = []
+
+    def __init__(self):
+        self._dummy_noise = K.Parameter(1.0, transform=("softplus_shift", 1e-6), trainable=False)
+
+    @property
+    def engine_param(self):
+        return 0.0
+
+
+class Gamma:
+    """gpflow.likelihoods.Gamma (exp link): trainable ``shape`` with the positive() bijector; it rides in the program's
+    noise slot like the negative binomial's alpha."""
+    name = "gamma"
+
+    def __init__(self, shape=1.0, trainable=True):
+        self.shape = K.Parameter(shape, transform="softplus", trainable=trainable)
+        self._dummy_noise = self.shape
+
+    @property
+    def parameters(self):
+        return [self.shape]
+
+    @property
+    def engine_param(self):
+        return float(self.shape)
+
+
 def make_likelihood(name, **kw):
     """gp_likelihood_crosswalk (waveome/utilities.py:989-1009) for the likelihoods the engine covers."""
     if name == "gaussian":
@@ -66,7 +97,12 @@ def make_likelihood(name, **kw):
         return Poisson()
     if name in ("negative_binomial", "negativebinomial"):
         return NegativeBinomial(**kw)
-    raise NotImplementedError(f"likelihood {name!r} is not covered by the B200 engine (gaussian, poisson, negative_binomial)")
+    if name in ("bernoulli", "binomial"):
+        return Bernoulli()
+    if name == "gamma":
+        return Gamma(**kw)
+    raise NotImplementedError(f"likelihood {name!r} is not covered by the B200 engine "
+                              "(gaussian, poisson, negative_binomial, bernoulli, gamma)")
 
 
 class ConstantMean:
@@ -120,6 +156,8 @@ class GPR:
             d[".likelihood.variance"] = self.likelihood.variance
         elif isinstance(self.likelihood, NegativeBinomial):
             d[".likelihood.alpha"] = self.likelihood.alpha
+        elif isinstance(self.likelihood, Gamma):
+            d[".likelihood.shape"] = self.likelihood.shape
         if isinstance(self.mean_function, ConstantMean):
             d[".mean_function.c"] = self.mean_function.c
         return d
@@ -139,6 +177,8 @@ class GPR:
             spec["likelihood"] = {"type": self.likelihood.name}
             if isinstance(self.likelihood, NegativeBinomial):
                 spec["likelihood"]["alpha"] = float(self.likelihood.alpha)
+            if isinstance(self.likelihood, Gamma):
+                spec["likelihood"]["shape"] = float(self.likelihood.shape)
         if isinstance(self.mean_function, ConstantMean):
             spec["mean"] = {"type": "constant", "c": self.mean_function.c.to_spec()}
         else:

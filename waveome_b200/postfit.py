@@ -40,6 +40,13 @@ def calc_deviance_loglik(y, model_mu, base_mu=None, likelihood="gaussian", alpha
         from scipy.stats import poisson
         return (poisson.logpmf(y, np.mean(y) if base_mu is None else base_mu), poisson.logpmf(y, model_mu),
                 poisson.logpmf(y, y))
+    if likelihood == "bernoulli":       # gpflow.logdensities.bernoulli(x, p) = log(where(x == 1, p, 1 - p))
+        def bern(x, p):
+            with np.errstate(divide="ignore"):
+                return np.log(np.where(x == 1, p, 1.0 - p))
+        return bern(y, np.mean(y) if base_mu is None else base_mu), bern(y, model_mu), bern(y, y)
+    if likelihood not in ("gaussian", "negative_binomial"):
+        raise ValueError("Unknown likelihood to calculate deviance")
     if likelihood == "negative_binomial":
         base = max(1e-6, np.mean(y)) if base_mu is None else base_mu
         return nb_logpmf(base, y, alpha), nb_logpmf(model_mu, y, alpha), nb_logpmf(y + 1e-6, y, alpha)
@@ -126,9 +133,16 @@ def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], masks: Opt
                 if lik_name == "gaussian":
                     s2 = np.array([float(models[b].likelihood.variance) for b in sel])
                     mean[sel] = Y[sel] - s2[:, None] * batch.alpha()
-                else:       # E[y] under q(f) = N(m, v) with the log link (predict_y of the count likelihoods)
+                else:       # E[y] under q(f) = N(m, v) (predict_y of the non-Gaussian likelihoods)
                     fm, fv = batch.latent()
-                    mean[sel] = np.exp(fm + 0.5 * fv)
+                    if lik_name == "bernoulli":       # closed form of gpflow's Bernoulli with the inv_probit link
+                        from scipy.special import erfc
+                        mean[sel] = 1e-3 + (1.0 - 2e-3) * 0.5 * erfc(-fm / np.sqrt(2.0 * (1.0 + fv)))
+                    elif lik_name == "gamma":         # conditional mean shape * exp(f)
+                        shape = np.array([float(models[b].likelihood.shape) for b in sel])[:, None]
+                        mean[sel] = shape * np.exp(fm + 0.5 * fv)
+                    else:                             # log link of the count likelihoods
+                        mean[sel] = np.exp(fm + 0.5 * fv)
             finally:
                 batch.close()
             status[sel] = st
