@@ -4,8 +4,13 @@ TEST INFRASTRUCTURE ONLY.  Nothing under ``waveome_b200/`` may import this file;
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
 legs use it, and only as the checker / reported baseline.
 
-PARITY UNPINNED: the reference (omicsEye/waveome v0.1.3) ships no tests, golden vectors or
-fixtures for this path, and its arithmetic lives in third-party packages that are not vendored
+PARITY PINNED ON REFERENCE-RECORDED VALUES for the Gaussian objective (tests/reference_pins.py,
+tests/test_reference_pins_cpu.py): outputs of real GPflow runs committed in the reference's notebooks - log marginal
+likelihood -9.914289155637 reproduced to all 13 printed digits by this file's fit (SE; also Matern12, Periodic,
+Matern52 summaries, Categorical + Matern12 log density to 1e-10, Constant-mean SVGP ELBOs as bounds).
+PARITY UNPINNED for the priors (tfd.Horseshoe / Laplace / Uniform: no recorded value exists) - those follow the
+published algorithms only.  The reference (omicsEye/waveome v0.1.3) ships no tests or fixtures for this path, and
+its arithmetic lives in third-party packages that are not vendored
 in /root/reference and cannot be installed here (no network, Python 3.12 > requires-python):
 
     gpflow==2.9.1, tensorflow>=2.12,<2.16, tensorflow_probability>=0.20,<0.24, scipy>=1.11,<1.13
