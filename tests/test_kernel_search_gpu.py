@@ -69,3 +69,25 @@ def test_run_search_config2_shape_lockstep():
         else:
             assert names[o] == "constant", (o, names[o])                                        # pure noise
     assert gps.fit_report["batches"] <= 12              # one candidate batch + one pruning batch per depth
+
+
+def test_run_search_poisson_counts():
+    """The search with a count likelihood (model_fitting.py:158-185 builds a VGP per candidate; here every candidate is a
+    collapsed-bound fit): Poisson outcomes with a subject effect and a smooth time trend must select both, and an
+    outcome that only has the subject effect must not select time."""
+    X, Y = datasets.count_microbiome(n_subjects=20, n_times=6, n_outcomes=3, seed=3)
+    rng = np.random.default_rng(0)
+    subj = X["subject"].to_numpy().astype(int)
+    Y["flat"] = rng.poisson(np.exp(1.0 + 0.8 * rng.normal(size=20)[subj])).astype(float)
+    gps = GPSearch(X, Y, unit_col="subject", outcome_likelihood="poisson")
+    gps.run_search(kernels=[wb.SquaredExponential(), wb.Lin()], max_depth=2, random_seed=0)
+    for o in gps.out_names:
+        best = gps.search_info[o]["best_model"]
+        assert gps.models[o].likelihood.name == "poisson" and np.isfinite(gps.search_info[o]["models"][best]["bic"])
+        assert "categorical[0]" in best, (o, best)
+    assert "[1]" not in gps.search_info["flat"]["best_model"]
+    assert np.mean(["[1]" in gps.search_info[o]["best_model"] for o in gps.out_names[:3]]) >= 2 / 3
+    # kernel_test / full_kernel_search drop-ins take the likelihood as well
+    m, bic = ks.kernel_test(X.to_numpy(), Y["flat"].to_numpy(), wb.Categorical(active_dims=[0]), likelihood="poisson",
+                            num_restart=1)
+    assert m.likelihood.name == "poisson" and np.isfinite(bic)

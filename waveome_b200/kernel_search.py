@@ -447,12 +447,12 @@ def _drive_single(gen, y, fit):
 
 def kernel_test(X, Y, k, mean_function=None, num_restart=5, random_init=True, random_seed=None, verbose=False,
                 likelihood="gaussian", engine=None, keep_data=False, **unused):
-    """Drop-in for :2239-2334 on the Gaussian path: (fitted model, bic)."""
-    if likelihood != "gaussian":
-        raise NotImplementedError("kernel_test on the engine covers likelihood='gaussian'")
+    """Drop-in for :2239-2334: (fitted model, bic).  ``likelihood``: any name ``models.make_likelihood`` covers (it
+    raises NotImplementedError for the others)."""
     X = np.asarray(X, dtype=np.float64)
     y = np.asarray(Y, dtype=np.float64).reshape(-1)
-    fit = engine_fitter(X, engine=engine, num_restart=num_restart if random_init else 1, random_seed=random_seed)
+    fit = engine_fitter(X, engine=engine, num_restart=num_restart if random_init else 1, random_seed=random_seed,
+                        likelihood=likelihood)
     (m, bic), = fit([(y, "", k)])
     if m is None:
         raise RuntimeError("kernel_test: the fit failed (Cholesky failure or non-finite objective at the start point)")
@@ -467,8 +467,6 @@ def full_kernel_search(X, Y, kern_list, cat_vars=(), max_depth=5, keep_all=False
                        prune=True, num_restart=5, lik="gaussian", verbose=False, debug=False, keep_only_best=True,
                        softmax_select=False, random_seed=None, feature_name=None, engine=None, fit=None, **unused):
     """Drop-in for :2987-3272 (one outcome).  ``fit`` overrides the engine fitter (the tests pass the CPU oracle)."""
-    if lik != "gaussian":
-        raise NotImplementedError("full_kernel_search on the engine covers lik='gaussian'")
     if random_seed is not None:
         np.random.seed(random_seed)
     Xn = X.to_numpy() if hasattr(X, "to_numpy") else np.asarray(X)
@@ -480,7 +478,7 @@ def full_kernel_search(X, Y, kern_list, cat_vars=(), max_depth=5, keep_all=False
     y = np.asarray(Yn, dtype=np.float64).reshape(-1)
     ok = ~np.isnan(Xn).any(axis=1) & ~np.isnan(y)
     Xn, y = Xn[ok], y[ok]
-    fit = fit or engine_fitter(Xn, engine=engine, num_restart=num_restart, random_seed=random_seed)
+    fit = fit or engine_fitter(Xn, engine=engine, num_restart=num_restart, random_seed=random_seed, likelihood=lik)
     gen = full_kernel_search_gen(Xn.shape[1], kern_list, cat_vars=cat_vars, max_depth=max_depth, keep_all=keep_all,
                                  metric_diff=metric_diff, early_stopping=early_stopping, prune=prune,
                                  keep_only_best=keep_only_best, softmax_select=softmax_select)
