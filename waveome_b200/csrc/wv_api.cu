@@ -41,16 +41,31 @@ struct wv_engine {
   int device;
   cudaStream_t stream;
   WvAux aux;   // side stream / events of the large-n look-ahead schedule
-  // Large device buffers of destroyed batches, kept for the next batch of the engine: cudaMalloc / cudaFree of the
-  // multi-GB workspaces costs ~0.1 s each, which is visible next to a 4 s fit (fit -> post-fit batches, search levels).
+  // Device buffers of destroyed batches, kept for the next batch of the engine (oldest first): cudaMalloc / cudaFree
+  // of the multi-GB workspaces costs 0.1 - 2 s each and every cudaFree of a small one synchronises the device, which is
+  // visible next to a 4 s fit (fit -> post-fit batches, search levels).  Small buffers are binned to powers of two so
+  // that batches of different sizes share them.
   std::vector<std::pair<size_t, void*>> cache;
+  size_t cache_bytes = 0;
 };
-static const size_t WV_CACHE_MIN_BYTES = (size_t)32 << 20;
-static const size_t WV_CACHE_MAX_ENTRIES = 6;
+static const size_t WV_CACHE_SMALL_BYTES = (size_t)1 << 20;      // below: power-of-two bins
+static const size_t WV_CACHE_MAX_ENTRIES = 256;
+static const size_t WV_CACHE_MAX_BYTES = (size_t)110 << 30;      // of 180 GB; a failed cudaMalloc flushes the cache anyway
 
 static void wv_cache_flush(wv_engine* e) {
   for (auto& c : e->cache) cudaFree(c.second);
   e->cache.clear();
+  e->cache_bytes = 0;
+}
+
+static void wv_cache_put(wv_engine* e, void* p, size_t bytes) {
+  e->cache.push_back({bytes, p});
+  e->cache_bytes += bytes;
+  while (!e->cache.empty() && (e->cache.size() > WV_CACHE_MAX_ENTRIES || e->cache_bytes > WV_CACHE_MAX_BYTES)) {
+    cudaFree(e->cache.front().second);
+    e->cache_bytes -= e->cache.front().first;
+    e->cache.erase(e->cache.begin());
+  }
 }
 
 struct wv_batch {
@@ -77,7 +92,12 @@ template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
   void* q = nullptr;
   size_t bytes = count * sizeof(T);
   if (bytes == 0) bytes = sizeof(T);
-  if (bytes >= WV_CACHE_MIN_BYTES) {        // best fit from the engine's cache (at most 25 % larger than asked)
+  if (bytes < WV_CACHE_SMALL_BYTES) {
+    size_t bin = 512;
+    while (bin < bytes) bin <<= 1;
+    bytes = bin;
+  }
+  {        // best fit from the engine's cache (at most 25 % larger than asked)
     auto& cache = b->eng->cache;
     int best = -1;
     for (int i = 0; i < (int)cache.size(); ++i)
@@ -86,6 +106,7 @@ template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
     if (best >= 0) {
       q = cache[best].second;
       bytes = cache[best].first;
+      b->eng->cache_bytes -= bytes;
       cache.erase(cache.begin() + best);
     }
   }
@@ -334,10 +355,7 @@ extern "C" void wv_batch_destroy(wv_batch* b) {
   cudaSetDevice(b->eng->device);
   cudaStreamSynchronize(b->eng->stream);
   b->prof.destroy();
-  for (auto& a : b->allocs) {
-    if (a.second >= WV_CACHE_MIN_BYTES && b->eng->cache.size() < WV_CACHE_MAX_ENTRIES) b->eng->cache.push_back({a.second, a.first});
-    else cudaFree(a.first);
-  }
+  for (auto& a : b->allocs) wv_cache_put(b->eng, a.first, a.second);
   if (b->h_count) cudaFreeHost(b->h_count);
   delete b;
 }
