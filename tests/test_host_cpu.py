@@ -102,6 +102,14 @@ def test_gpsearch_data_preparation():
     np.testing.assert_allclose(g2.X.iloc[0].to_numpy(), [0.0, -1.44041, 0.0], atol=5e-6)
     with pytest.raises(TypeError):
         GPSearch(X.to_numpy(), Y)
+    # reverse_transform (model_search.py:1677-1715) undoes the standardisation; run_penalized_search is deprecated upstream
+    np.testing.assert_allclose(g2.reverse_transform(g2.X["time"].iloc[:2], feature_name="time", round_digits=6),
+                               [1.175864, 1.843311], atol=1e-6)
+    g3 = GPSearch(Xo, Yo, unit_col="person_id", categorical_vars=["female"], Y_transform="standardize")
+    np.testing.assert_allclose(g3.reverse_transform(g3.Y.iloc[0], input_type="Y", round_digits=6),
+                               [0.889715, 0.381912, 1.314904], atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        g2.run_penalized_search()
 
 
 def test_shard_bounds_cover_everything():

@@ -286,3 +286,25 @@ class GPSearch:
         self.search_info = local_info
         self.fit_report = report
         return None
+
+    # ------------------------------------------------------------------------------------------
+    def run_penalized_search(self, *args, **kwargs):
+        """model_search.py:933-958: deprecated upstream, raises there as well."""
+        raise NotImplementedError("run_penalized_search is deprecated, use penalized_optimization instead.")
+
+    def reverse_transform(self, array, feature_name=None, input_type="X", round_digits=1):
+        """Input values back on the original scale (model_search.py:1677-1715)."""
+        if input_type == "X":
+            assert hasattr(self, "X_stds"), "Standardize_X wasn't called in GPSearch()"
+            scale_vals = self.X_stds.values if feature_name is None else self.X_stds[feature_name]
+            shift_vals = self.X_means.values if feature_name is None else self.X_means[feature_name]
+        elif input_type == "Y":
+            assert hasattr(self, "Y_stds"), "Y_transform wasn't called in GPSearch()"
+            scale_vals = self.Y_stds.values if feature_name is None else self.Y_stds[feature_name]
+            if hasattr(self, "Y_means"):
+                shift_vals = self.Y_means.values if feature_name is None else self.Y_means[feature_name]
+            else:
+                shift_vals = np.zeros_like(scale_vals)
+        else:
+            raise ValueError("Unknown type requested for transform!")
+        return np.round(scale_vals * np.array(array) + shift_vals, decimals=round_digits)
