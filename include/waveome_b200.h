@@ -151,7 +151,9 @@ int wv_batch_get_alpha(wv_batch* b, double* alpha);
 int wv_batch_get_kinv_diag(wv_batch* b, double* diag);
 int wv_batch_predict_mean(wv_batch* b, const double* Xnew, int32_t m, double* mean);
 /* Same plus the predictive variance of f (gpflow GPR.predict_f, full_cov = False; predict_y adds sigma^2):
- * var[b][i] = k_b(xnew_i, xnew_i) - k*_i^T (K_b + sigma^2 I)^-1 k*_i, HOST [B, m]; var may be NULL. */
+ * var[b][i] = k_b(xnew_i, xnew_i) - k*_i^T (K_b + sigma^2 I)^-1 k*_i, HOST [B, m]; var may be NULL.  With a non-Gaussian
+ * likelihood (wv_batch_set_likelihood) both are the latent posterior under the converged sites, sigma^2 I replaced by
+ * jitter I + diag(1 / lam) (gpflow VGP.predict_f at the optimal q). */
 int wv_batch_predict_f(wv_batch* b, const double* Xnew, int32_t m, double* mean, double* var);
 
 /* counters since batch creation: kernels launched, batched evaluation rounds, model evaluations */

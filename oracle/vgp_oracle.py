@@ -234,6 +234,52 @@ def q_from_sites(model, X, y, x, sites):
     return q_mu, np.linalg.cholesky(Sv)
 
 
+def predict_f(model, X, y, x, sites, Xnew, whitened=False):
+    """gpflow VGP.predict_f(Xnew) (full_cov=False) at the q defined by the sites: (mean [m], variance [m]).
+    Default: the site form the engine uses, mean = c + K*^T (K + D)^-1 (ytilde - c), var = k** - K*^T (K + D)^-1 K*;
+    ``whitened=True``: gpflow's conditional with (q_mu, q_sqrt), mean = K*^T L^-T q_mu + c,
+    var = k** - |L^-1 K*|^2 + |q_sqrt^T L^-1 K*|^2 -- the two agree (tests/test_vgp_oracle.py)."""
+    spec = copy.deepcopy(model)
+    go.unpack(spec, x)
+    n = len(X)
+    Kall, _ = go.kernel_K_and_grads(spec["kernel"], np.vstack([X, Xnew]), want_grads=False)
+    K = Kall[:n, :n] + JITTER * np.eye(n)
+    Ks, kss = Kall[:n, n:], np.diag(Kall)[n:]
+    c = spec["mean"]["c"]["value"] if spec["mean"]["type"] == "constant" else 0.0
+    lam, eta = sites
+    if not whitened:
+        A = K + np.diag(1.0 / lam)
+        return c + Ks.T @ np.linalg.solve(A, eta / lam - c), kss - np.sum(Ks * np.linalg.solve(A, Ks), 0)
+    q_mu, q_sqrt = q_from_sites(model, X, y, x, sites)
+    L = np.linalg.cholesky(K)
+    B = np.linalg.solve(L, Ks)
+    return B.T @ q_mu + c, kss - np.sum(B * B, 0) + np.sum((q_sqrt.T @ B) ** 2, 0)
+
+
+def predict_y_moments(lik, fm, fv):
+    """likelihood.predict_mean_and_var(Fmu, Fvar): gpflow's 20-point Gauss-Hermite of the conditional moments (Poisson,
+    Gamma), its closed form for Bernoulli/inv_probit, and waveome's plug-in override for the negative binomial
+    (waveome/likelihoods.py:48-51: mean exp(Fmu), variance m + alpha m^2 at m = exp(Fmu))."""
+    from scipy.special import erfc
+    f = fm[:, None] + np.sqrt(2.0 * fv)[:, None] * GH_X[None, :]
+    w = GH_W[None, :] / math.sqrt(math.pi)
+    t = lik["type"]
+    if t == "negative_binomial":
+        m = np.exp(fm)
+        return m, m + lik["alpha"] * m * m
+    if t == "bernoulli":
+        p = 1e-3 + (1.0 - 2e-3) * 0.5 * erfc(-fm / np.sqrt(2.0 * (1.0 + fv)))
+        return p, p - p * p
+    if t == "poisson":
+        cm, cv = np.exp(f), np.exp(f)
+    elif t == "gamma":
+        cm, cv = lik["shape"] * np.exp(f), lik["shape"] * np.exp(2.0 * f)
+    else:
+        raise ValueError(t)
+    Ey = np.sum(w * cm, 1)
+    return Ey, np.sum(w * (cv + cm * cm), 1) - Ey * Ey
+
+
 def fit(model, lik, X, y, maxiter=50000, maxfun=50000, maxcor=10, ftol=2.220446049250313e-09, gtol=1e-05, maxls=20):
     """What the reference does with this objective: L-BFGS-B (waveome/model_fitting.py:267-281) -- here on the collapsed
     bound, i.e. over the hyper-parameters only, every evaluation at its optimal q.  Returns dict(x, F, nit, nfev)."""

@@ -210,3 +210,43 @@ def test_gamma_shape_is_trained_and_bernoulli_fits(engine):
         assert np.all(np.isfinite(mu)) and (lik != "bernoulli" or (mu.min() > 0 and mu.max() < 1))
         if lik == "gamma":
             assert abs(float(m.likelihood.shape) - 2.0) < 1.0 and float(m.likelihood.shape) != 1.0
+
+
+@pytest.mark.parametrize("lik", ["poisson", "negative_binomial", "bernoulli", "gamma"])
+def test_predictions_at_new_inputs_non_gaussian(engine, lik):
+    """predict_f / predict_y / predict_log_density of a fitted non-Gaussian model (gpflow VGP.predict_f + the
+    likelihood's predict_mean_and_var / predict_log_density) vs the oracle at the same hyper-parameters."""
+    from scipy.special import logsumexp
+    from waveome_b200.models import make_likelihood
+    from waveome_b200 import postfit
+    if lik in ("poisson", "negative_binomial"):
+        X, y = count_data(70, 12, seed=5)
+    else:
+        X, y = other_data(70, 12, seed=5, lik=lik)
+    m = count_model(c=0.1)
+    m.likelihood = make_likelihood(lik)
+    olik = {"type": lik, "alpha": 1.0, "shape": 1.0}
+    spec = copy.deepcopy(m.to_spec())
+    x = m.program().x0()
+    r = vo.vgp_collapsed(spec, olik, X, y, x, rho=0.5, tol=1e-12, maxit=4000, want_grad=False)
+    rng = np.random.default_rng(1)
+    Xnew = np.stack([rng.integers(0, 14, size=23).astype(float), rng.normal(size=23)], 1)
+    fm_o, fv_o = vo.predict_f(spec, X, y, x, r["sites"], Xnew)
+    fm, fv = m.predict_f(Xnew, data=(X, y))
+    np.testing.assert_allclose(fm[:, 0], fm_o, rtol=0, atol=1e-6 * (1 + np.max(np.abs(fm_o))))
+    np.testing.assert_allclose(fv[:, 0], fv_o, rtol=1e-5, atol=1e-8)
+    ym_o, yv_o = vo.predict_y_moments(vo.lik_of(spec, olik), fm_o, fv_o)
+    ym, yv = m.predict_y(Xnew, data=(X, y))
+    np.testing.assert_allclose(ym[:, 0], ym_o, rtol=1e-5)
+    np.testing.assert_allclose(yv[:, 0], yv_o, rtol=1e-5)
+    # predictive log density of plausible new observations: log-space quadrature of the oracle's log p(y | f)
+    ynew = np.round(ym_o) if lik in ("poisson", "negative_binomial") else ((ym_o > 0.5).astype(float) if lik == "bernoulli" else ym_o)
+    ld = m.predict_log_density((Xnew, ynew), data=(X, y))
+    if lik == "bernoulli":
+        want = np.log(np.where(ynew == 1, ym_o, 1 - ym_o))
+    else:
+        f = fm_o[:, None] + np.sqrt(2 * fv_o)[:, None] * vo.GH_X[None, :]
+        lp = np.stack([postfit._likelihood_log_prob(m.likelihood, f[:, k], ynew) for k in range(20)], 1)
+        want = logsumexp(lp + np.log(vo.GH_W / np.sqrt(np.pi))[None, :], axis=1)
+    np.testing.assert_allclose(ld, want, rtol=1e-5, atol=1e-7)
+    assert np.all(np.isfinite(ld))

@@ -77,3 +77,17 @@ def test_bernoulli_and_gamma_collapsed_bounds(kind):
         fd.append((vo.vgp_collapsed(model, lik, X, yy, xp, want_grad=False, **kw)["F"]
                    - vo.vgp_collapsed(model, lik, X, yy, xm, want_grad=False, **kw)["F"]) / (2 * h))
     np.testing.assert_allclose(r["grad"], fd, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("lik", [{"type": "poisson"}, {"type": "bernoulli"}])
+def test_site_form_prediction_equals_whitened_conditional(lik):
+    """predict_f at new inputs: the heteroscedastic-GPR form the engine evaluates == gpflow's whitened conditional"""
+    model, X, y, x, rng = _setup(seed=7)
+    yy = y if lik["type"] == "poisson" else (y > np.median(y)).astype(float)
+    r = vo.vgp_collapsed(model, lik, X, yy, x, rho=0.7, maxit=3000, want_grad=False)
+    Xnew = np.stack([rng.integers(0, 9, size=15).astype(float), rng.normal(size=15)], 1)      # incl. an unseen subject
+    m1, v1 = vo.predict_f(model, X, yy, x, r["sites"], Xnew)
+    m2, v2 = vo.predict_f(model, X, yy, x, r["sites"], Xnew, whitened=True)
+    np.testing.assert_allclose(m1, m2, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(v1, v2, rtol=0, atol=1e-9)
+    assert np.all(v1 > 0)

@@ -746,7 +746,6 @@ extern "C" int wv_batch_predict_mean(wv_batch* b, const double* Xnew, int32_t m,
 
 extern "C" int wv_batch_predict_f(wv_batch* b, const double* Xnew, int32_t m, double* mean, double* var) {
   if (!b || !Xnew || !mean) return wv_fail("wv_batch_predict_f: null argument");
-  if (var && b->bd.lik != 0) return wv_fail("wv_batch_predict_f: variances at new inputs are built for the Gaussian likelihood only");
   if (m <= 0) return wv_fail("wv_batch_predict_f: m must be positive");
   if (!b->last_x) return wv_fail("wv_batch_predict_f: no evaluation has been run on this batch");
   WV_CUDA(cudaSetDevice(b->eng->device));

@@ -190,29 +190,35 @@ class GPR:
 
     def predict_f(self, Xnew, data=None):
         """gpflow GPModel.predict_f(Xnew) (full_cov=False): ([m, 1] mean, [m, 1] variance of f).  ``data`` = (X, Y) as
-        the reference's model methods take it; defaults to the data the model was fitted on when it was kept.  Count
-        likelihoods: the mean only (variance None)."""
-        from .postfit import predict_f, predict_mean
+        the reference's model methods take it; defaults to the data the model was fitted on when it was kept.  The
+        non-Gaussian likelihoods give the latent posterior under the variational q (gpflow VGP.predict_f)."""
+        from .postfit import predict_f
         data = data if data is not None else self.data
         if data is None:
             raise ValueError("predict_f needs data=(X, Y): the fitted model does not keep its training data")
         X, y = np.asarray(data[0]), np.asarray(data[1]).reshape(-1)
-        if not isinstance(self.likelihood, Gaussian):
-            raise NotImplementedError("predict_f at new inputs is built for the Gaussian likelihood")
         mu, var = predict_f(self, X, y, Xnew)
         return mu.reshape(-1, 1), var.reshape(-1, 1)
 
     def predict_y(self, Xnew, data=None):
-        """gpflow GPModel.predict_y: the Gaussian likelihood adds its variance to predict_f's."""
+        """gpflow GPModel.predict_y = likelihood.predict_mean_and_var(predict_f): the Gaussian likelihood adds its
+        variance; the others integrate their conditional moments (postfit.likelihood_predict_mean_and_var)."""
         mu, var = self.predict_f(Xnew, data=data)
-        return mu, var + float(self.likelihood.variance)
+        if isinstance(self.likelihood, Gaussian):
+            return mu, var + float(self.likelihood.variance)
+        from .postfit import likelihood_predict_mean_and_var
+        return likelihood_predict_mean_and_var(self.likelihood, mu, var)
 
     def predict_log_density(self, data_new, data=None):
-        """gpflow GPModel.predict_log_density((Xnew, Ynew)): log N(ynew | predict_y mean, variance), [m]."""
+        """gpflow GPModel.predict_log_density((Xnew, Ynew)) = likelihood.predict_log_density(predict_f, Ynew), [m]."""
         Xnew, Ynew = data_new
-        mu, var = self.predict_y(Xnew, data=data)
         ynew = np.asarray(Ynew, dtype=np.float64).reshape(-1, 1)
-        return (-0.5 * (np.log(2 * np.pi) + np.log(var) + (ynew - mu) ** 2 / var)).reshape(-1)
+        if isinstance(self.likelihood, Gaussian):
+            mu, var = self.predict_y(Xnew, data=data)
+            return (-0.5 * (np.log(2 * np.pi) + np.log(var) + (ynew - mu) ** 2 / var)).reshape(-1)
+        from .postfit import likelihood_predict_log_density
+        mu, var = self.predict_f(Xnew, data=data)
+        return likelihood_predict_log_density(self.likelihood, mu, var, ynew).reshape(-1)
 
     def get_feature_importances(self, data=None, return_value="log_bf"):
         """waveome/model_classes.py:546-573"""

@@ -141,7 +141,9 @@ def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], masks: Opt
                     elif lik_name == "gamma":         # conditional mean shape * exp(f)
                         shape = np.array([float(models[b].likelihood.shape) for b in sel])[:, None]
                         mean[sel] = shape * np.exp(fm + 0.5 * fv)
-                    else:                             # log link of the count likelihoods
+                    elif lik_name == "negative_binomial":   # waveome's override plugs in Fmu (likelihoods.py:48-51)
+                        mean[sel] = np.exp(fm)
+                    else:                             # Poisson, exp link
                         mean[sel] = np.exp(fm + 0.5 * fv)
             finally:
                 batch.close()
@@ -239,14 +241,19 @@ def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf"
 
 
 def predict_f(model: GPR, X, y, Xnew, engine=None):
-    """gpflow GPR.predict_f(Xnew) (full_cov=False) for one Gaussian model: ([m] mean, [m] variance of f)."""
+    """gpflow GPModel.predict_f(Xnew) (full_cov=False) for one model: ([m] mean, [m] variance of f).  Non-Gaussian
+    likelihoods: the posterior of the latent GP under the converged Gaussian sites (the same cross-covariance kernels:
+    alpha and (K + D)^-1 of the last sweep are what the Gaussian path leaves behind)."""
     from .engine import Batch
-    from .model_fitting import get_engine
+    from .model_fitting import get_engine, likelihood_key
     engine = engine or get_engine()
     X = np.ascontiguousarray(X, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64).reshape(1, -1)
     batch = Batch(engine, X, y, [model.program()])
     try:
+        lik_name, lik_param = likelihood_key(model)
+        if lik_name != "gaussian":
+            batch.set_likelihood(lik_name, lik_param)
         batch.eval(batch.x0())
         mean, var = batch.predict_f(np.asarray(Xnew, dtype=np.float64))
         return mean[0], var[0]
@@ -268,3 +275,63 @@ def predict_mean(model: GPR, X, y, Xnew, engine=None) -> np.ndarray:
         return batch.predict_mean(np.asarray(Xnew, dtype=np.float64))[0]
     finally:
         batch.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# likelihood.predict_mean_and_var / predict_log_density of the non-Gaussian likelihoods (host side, [m] vectors)
+# ------------------------------------------------------------------------------------------------
+_GH_X, _GH_W = np.polynomial.hermite.hermgauss(20)         # gpflow's default quadrature
+
+
+def _likelihood_log_prob(lik, f, y):
+    """log p(y | f) of models.Poisson / NegativeBinomial / Bernoulli / Gamma, broadcast."""
+    from scipy.special import erfc, gammaln
+    name = lik.name
+    if name == "poisson":
+        return y * f - np.exp(f) - gammaln(y + 1.0)
+    if name == "negative_binomial":
+        return nb_logpmf(np.exp(f), y, float(lik.alpha))
+    if name == "bernoulli":
+        p = 1e-3 + (1.0 - 2e-3) * 0.5 * erfc(-f / np.sqrt(2.0))
+        return np.log(np.where(y == 1, p, 1.0 - p))
+    if name == "gamma":
+        a = float(lik.shape)
+        return -a * f - gammaln(a) + (a - 1.0) * np.log(y) - y * np.exp(-f)
+    raise NotImplementedError(name)
+
+
+def likelihood_predict_mean_and_var(lik, fm, fv):
+    """(E[y], Var[y]) under f ~ N(fm, fv): gpflow's 20-point Gauss-Hermite of the conditional moments (Poisson, Gamma),
+    its closed form for Bernoulli / inv_probit, waveome's plug-in override for the negative binomial
+    (waveome/likelihoods.py:41-51)."""
+    from scipy.special import erfc
+    fm, fv = np.asarray(fm, dtype=np.float64), np.asarray(fv, dtype=np.float64)
+    name = lik.name
+    if name == "negative_binomial":
+        m = np.exp(fm)
+        return m, m + float(lik.alpha) * m * m
+    if name == "bernoulli":
+        p = 1e-3 + (1.0 - 2e-3) * 0.5 * erfc(-fm / np.sqrt(2.0 * (1.0 + fv)))
+        return p, p - p * p
+    f = fm[..., None] + np.sqrt(2.0 * fv)[..., None] * _GH_X
+    w = _GH_W / np.sqrt(np.pi)
+    if name == "poisson":
+        cm, cv = np.exp(f), np.exp(f)
+    elif name == "gamma":
+        cm, cv = float(lik.shape) * np.exp(f), float(lik.shape) * np.exp(2.0 * f)
+    else:
+        raise NotImplementedError(name)
+    ey = np.sum(w * cm, -1)
+    return ey, np.sum(w * (cv + cm * cm), -1) - ey * ey
+
+
+def likelihood_predict_log_density(lik, fm, fv, y):
+    """log int p(y | f) N(f; fm, fv) df by the same quadrature in log space (gpflow ScalarLikelihood); Bernoulli: the
+    log density at the predictive mean (gpflow.likelihoods.Bernoulli._predict_log_density)."""
+    from scipy.special import logsumexp
+    fm, fv, y = (np.asarray(a, dtype=np.float64) for a in (fm, fv, y))
+    if lik.name == "bernoulli":
+        p, _ = likelihood_predict_mean_and_var(lik, fm, fv)
+        return np.log(np.where(y == 1, p, 1.0 - p))
+    f = fm[..., None] + np.sqrt(2.0 * fv)[..., None] * _GH_X
+    return logsumexp(_likelihood_log_prob(lik, f, y[..., None]) + np.log(_GH_W / np.sqrt(np.pi)), axis=-1)
