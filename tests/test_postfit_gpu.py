@@ -132,3 +132,38 @@ def test_train_predictive_variance_and_iterated_factor(engine):
         start = 2 * 1.1 * np.std(gps.Y[o].to_numpy()) * np.sqrt(len(gps.X)) * norm().ppf(1 - 0.1 / (2 * 4))
         assert m.penalization_factor <= start + 1e-9 and m.penalization_factor > 0
         assert np.isfinite(m.log_posterior_density_value)
+
+
+def test_component_predictions(engine):
+    """individual_kernel_predictions (waveome/utilities.py:710-974): per-component posterior mean and variance at new
+    inputs, joint (marginal=False) and as a stand-alone model (marginal=True, the reference's default)."""
+    from waveome_b200.utilities import individual_kernel_predictions
+    n, m = 140, 33
+    X, y = helpers.make_data(n, seed=8)
+    rng = np.random.default_rng(2)
+    Xnew = X[rng.integers(0, n, size=m)].copy()
+    Xnew[:, 1:3] += 0.2 * rng.normal(size=(m, 2))
+    kern = wb.Sum([wb.Categorical(active_dims=[0], variance=0.6),
+                   wb.SquaredExponential(active_dims=[1], variance=1.2, lengthscales=0.7),
+                   wb.Product([wb.Categorical(active_dims=[3]), wb.Matern32(active_dims=[2], lengthscales=1.3)])])
+    model = wb.GPR(kern, mean_function=wb.ConstantMean(0.15), noise_variance=0.25)
+    spec = copy.deepcopy(model.to_spec())
+    c, s2 = 0.15, 0.25
+    Kfull, _ = oracle.kernel_K_and_grads(spec["kernel"], X, want_grads=False)
+    for marginal in (False, True):
+        parts = postfit.component_predictions(model, X, y, Xnew, marginal=marginal)
+        assert len(parts) == 3
+        for k, sub in enumerate(spec["kernel"]["kernels"]):
+            Kall, _ = oracle.kernel_K_and_grads(sub, np.vstack([Xnew, X]), want_grads=False)
+            Kss, Ksx, Kxx = Kall[:m, :m], Kall[:m, m:], Kall[m:, m:]
+            A = (Kxx if marginal else Kfull) + s2 * np.eye(n)
+            mu_ref = c + Ksx @ np.linalg.solve(A, y - c)
+            var_ref = np.diag(Kss) - np.einsum("ij,ij->i", Ksx, np.linalg.solve(A, Ksx.T).T)
+            np.testing.assert_allclose(parts[k][0], mu_ref, rtol=0, atol=1e-9 * max(1.0, np.max(np.abs(mu_ref))))
+            np.testing.assert_allclose(parts[k][1], var_ref, rtol=0, atol=1e-9 * max(1.0, np.max(np.abs(var_ref))))
+    mu, var, samples, cov = individual_kernel_predictions(model, 1, data=(X, y), X=Xnew, marginal=False)
+    parts = postfit.component_predictions(model, X, y, Xnew, marginal=False)
+    assert mu.shape == (m, 1) and samples is None and cov is None
+    np.testing.assert_array_equal(mu[:, 0], parts[1][0])
+    with pytest.raises(ValueError):
+        individual_kernel_predictions(model, 5, data=(X, y), X=Xnew)

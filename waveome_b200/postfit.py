@@ -261,6 +261,45 @@ def predict_f(model: GPR, X, y, Xnew, engine=None):
         batch.close()
 
 
+def component_predictions(model: GPR, X, y, Xnew, marginal: bool = False, engine=None):
+    """Posterior of every top-level additive component at new inputs: list of ([m] mean, [m] variance), one entry per
+    component of ``model.kernel`` (one entry = the whole kernel when it is not a sum).
+
+    marginal=False — the component's share of the joint posterior (individual_kernel_predictions(..., marginal=False),
+    waveome/utilities.py:829-935): mean_k = c + K*_k^T (K + S)^-1 (y - c), var_k = k**_k - K*_k^T (K + S)^-1 K*_k with
+    K + S the FULL model's covariance (S = sigma^2 I, or the site covariance of a non-Gaussian model): one evaluation
+    with every component on, then one cross-covariance pass per component with only that component's mask.
+    marginal=True — the reference's default (:820-828): the model whose kernel IS the component, i.e. the mask is
+    applied to the factorisation as well."""
+    from .engine import Batch
+    from .model_fitting import get_engine, likelihood_key
+    engine = engine or get_engine()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(1, -1)
+    Xnew = np.asarray(Xnew, dtype=np.float64)
+    masks = _component_masks(model)
+    full = masks[0]
+    only = [full & ~m for m in masks[1:]] or [full]          # masks[1 + k] switches component k off
+    batch = Batch(engine, X, y, [model.program()])
+    out = []
+    try:
+        lik_name, lik_param = likelihood_key(model)
+        if lik_name != "gaussian":
+            batch.set_likelihood(lik_name, lik_param)
+        x = batch.x0()
+        if not marginal:
+            batch.eval(x)
+        for mk in only:
+            batch.set_component_mask(np.array([mk], dtype=np.uint32))
+            if marginal:
+                batch.eval(x)
+            mean, var = batch.predict_f(Xnew)
+            out.append((mean[0], var[0]))
+    finally:
+        batch.close()
+    return out
+
+
 def predict_mean(model: GPR, X, y, Xnew, engine=None) -> np.ndarray:
     """gpflow GPR.predict_f(Xnew)[0] for one model: [m] posterior mean at new inputs."""
     from .engine import Batch

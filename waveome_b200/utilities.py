@@ -97,3 +97,24 @@ def search_through_kernel_list_(kernel_list, list_type="sum", X=None):
     if len(out_list) == 1:
         return out_list[0]
     return K.Empty()
+
+
+def individual_kernel_predictions(model, kernel_idx, data=None, X=None, predict_type="func", marginal=True, **unused):
+    """Numerical part of waveome/utilities.py:710-974: (pred_mu [m, 1], pred_var [m], None, None) of additive component
+    ``kernel_idx`` at the inputs X.  The reference also returns posterior function samples and the full covariance for
+    its plots; those are not produced here.  ``predict_type="mean"`` maps through the likelihood's conditional moments at
+    pred_mu like the reference (:967-971)."""
+    from .postfit import component_predictions
+    data = data if data is not None else model.data
+    if data is None:
+        raise ValueError("individual_kernel_predictions needs data=(X, Y)")
+    Xtr, ytr = np.asarray(data[0]), np.asarray(data[1]).reshape(-1)
+    X = Xtr if X is None else np.asarray(X)
+    parts = component_predictions(model, Xtr, ytr, X, marginal=marginal)
+    if kernel_idx >= len(parts):
+        raise ValueError("Not enough kernel components for index requested!")
+    mu, var = parts[kernel_idx]
+    if predict_type == "mean" and getattr(model.likelihood, "name", "gaussian") != "gaussian":
+        from .postfit import likelihood_predict_mean_and_var
+        mu, var = likelihood_predict_mean_and_var(model.likelihood, mu, np.zeros_like(mu))
+    return mu.reshape(-1, 1), var, None, None
