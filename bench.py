@@ -141,6 +141,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner under torchrun,
+    # joblib workers) are sent to stderr; the line itself is written to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -176,7 +186,7 @@ def main():
                 "config": config, "lml_grad_evals_per_sec": evals / secs,
                 "cpu_baseline": {"value": v, "unit": "fits/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": v, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # -------------------------------------------------------------------------------- B200 arm
@@ -330,7 +340,7 @@ def main():
                     "api": "GPSearch.penalized_optimization (pandas in, fitted models out)"},
             "gpu_launches": int(launches_total), "clocks": clocks, "roofline": roof, "roofline_groups": groups,
             "cpu_baseline": cpu, "fit_status_hist": status_hist}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
