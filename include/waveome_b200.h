@@ -38,7 +38,9 @@ enum { WVT_IDENTITY = 0, WVT_SOFTPLUS = 1, WVT_SOFTPLUS_SHIFT = 2, WVT_EXP = 3 }
 /* priors on the constrained value (tfd.Horseshoe / tfd.Laplace / tfd.Uniform) */
 enum { WVP_NONE = 0, WVP_HORSESHOE = 1, WVP_LAPLACE = 2, WVP_UNIFORM = 3 };
 /* per-model status bits */
-enum { WVS_OK = 0, WVS_CHOL_FAIL = 1, WVS_NONFINITE = 2, WVS_MAXITER = 4, WVS_LINESEARCH = 8, WVS_INNER_CAP = 16 };
+enum { WVS_OK = 0, WVS_CHOL_FAIL = 1, WVS_NONFINITE = 2, WVS_MAXITER = 4, WVS_LINESEARCH = 8, WVS_INNER_CAP = 16,
+       WVS_SITE_BOUND = 32 /* ZINB: a site precision sits at its lower bound (1e-6): the value is a valid bound, the
+                              gradient omits the non-stationarity term of those sites */ };
 
 /* One kernel program = sum over components of products of leaves, plus the parameter slot table.
  * Arrays are flat; a batch passes `n_programs` of these back to back. */
@@ -62,6 +64,8 @@ typedef struct wv_program_desc {
   const double* slot_shift;      /* [n_slots] lower bound of WVT_SOFTPLUS_SHIFT */
   const double* slot_pa;         /* [n_slots] prior parameter a (scale | loc | low) */
   const double* slot_pb;         /* [n_slots] prior parameter b (  -   | scale | high) */
+  int32_t lik_slot2;             /* slot of a second likelihood parameter (zero-inflated negative binomial: km,
+                                    waveome/likelihoods.py:96-139), or -1 */
 } wv_program_desc;
 
 typedef struct wv_batch_desc {
@@ -110,7 +114,9 @@ int wv_batch_set_y(wv_batch* b, const double* Y);
 /* Likelihood of every model of the batch (waveome/utilities.py:989-1009 gp_likelihood_crosswalk): 0 Gaussian (default;
  * exact GPR marginal likelihood), 1 Poisson with exp link (gpflow.likelihoods.Poisson), 2 negative binomial with log
  * link and dispersion `param` = alpha (waveome/likelihoods.py:16-79), 3 Bernoulli with gpflow's inv_probit link (y in
- * {0, 1}), 4 Gamma with exp link and shape `param` (gpflow.likelihoods.Gamma).  For 1-4 the objective is the variational bound of gpflow.models.VGP / PSVGP
+ * {0, 1}), 4 Gamma with exp link and shape `param` (gpflow.likelihoods.Gamma), 5 zero-inflated negative binomial
+ * (waveome/likelihoods.py:96-139: alpha = `param`, km = the second parameter, see wv_batch_set_likelihood2; its zero
+ * branch is not log-concave, the bound is maximised over site precisions >= 1e-6).  For 1-5 the objective is the variational bound of gpflow.models.VGP / PSVGP
  * with Z = X (waveome/model_fitting.py:158-185, waveome/model_classes.py:1082-1126) maximised over the variational
  * distribution for the given hyper-parameters: f = -(max_q ELBO + log prior), `lml` reports max_q ELBO, Y holds the
  * observations.  The programs' noise slot: ignored for Poisson / Bernoulli; for the negative binomial and the Gamma a
@@ -118,6 +124,8 @@ int wv_batch_set_y(wv_batch* b, const double* Y);
  * d(bound)/d(parameter), a frozen one means parameter = `param`.
  * Status bit 16: the inner iteration hit its sweep cap. */
 int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param);
+/* Same with a second parameter (kind 5: km, used when the programs have no lik_slot2); wv_batch_set_likelihood passes 1. */
+int wv_batch_set_likelihood2(wv_batch* b, int32_t kind, double param, double param2);
 /* Posterior mean and variance of the latent f at the training inputs after the last evaluation of a non-Gaussian
  * batch, HOST [B, n] each (predict_f at the training inputs). */
 int wv_batch_get_latent(wv_batch* b, double* fmean, double* fvar);

@@ -341,6 +341,8 @@ def iter_kernel_params(node):
 def iter_model_params(model):
     yield from iter_kernel_params(model["kernel"])
     yield model["likelihood_variance"]
+    if "likelihood_aux" in model:          # second likelihood parameter (ZINB km), packed right after the first
+        yield model["likelihood_aux"]
     if model["mean"]["type"] == "constant":
         yield model["mean"]["c"]
 

@@ -67,6 +67,54 @@ def nb_dalpha(y, m, v, a):
     return float(np.sum(w * dk) * (-k * k))
 
 
+def zinb_terms(f, y, alpha, km):
+    """waveome/likelihoods.py:96-139 (ZeroInflatedNegativeBinomial, exp link): log p(y | f) and its derivatives wrt f
+    (first, second), alpha and km.  psi = km / (km + m) is the structural-zero probability, m = exp(f)."""
+    from scipy.special import digamma
+    m = np.exp(f)
+    Q = km + m
+    zero = (y == 0)
+    # y > 0: log(1 - psi) + NB(m, y, alpha) = f - log(km + m) + NB
+    k = 1.0 / alpha
+    lp_nz = f - np.log(Q) + nb_logpmf(f, y, alpha)
+    d1_nz = km / Q + y - (y + k) * alpha * m / (1.0 + alpha * m)
+    d2_nz = -km * m / Q ** 2 - (y + k) * alpha * m / (1.0 + alpha * m) ** 2
+    dk = digamma(k + y) - digamma(k) - y / (m + k) - np.log1p(m * alpha) + m / (k + m)
+    da_nz = dk * (-k * k)
+    dkm_nz = -1.0 / Q
+    # y = 0: log(psi + (1 - psi) (1 + alpha m)^(-1/alpha)) = log(km + u) - log(km + m), u = m (1 + alpha m)^(-1/alpha)
+    ls0 = -np.log1p(alpha * m) / alpha
+    u = m * np.exp(ls0)
+    P = km + u
+    r = (1.0 + (alpha - 1.0) * m) / (1.0 + alpha * m)            # d log u / df
+    u1 = u * r
+    u2 = u * (r * r - m / (1.0 + alpha * m) ** 2)
+    lp_z = np.log(P) - np.log(Q)
+    d1_z = u1 / P - m / Q
+    d2_z = u2 / P - (u1 / P) ** 2 - km * m / Q ** 2
+    da_z = u * (np.log1p(alpha * m) / alpha ** 2 - m / (alpha * (1.0 + alpha * m))) / P
+    dkm_z = 1.0 / P - 1.0 / Q
+    pick = lambda a, b: np.where(zero, a, b)
+    return pick(lp_z, lp_nz), pick(d1_z, d1_nz), pick(d2_z, d2_nz), pick(da_z, da_nz), pick(dkm_z, dkm_nz)
+
+
+def zinb_dparams(y, m, v, alpha, km):
+    """(sum_i dE_i/d alpha, sum_i dE_i/d km) by the same quadrature"""
+    y = np.asarray(y, dtype=np.float64)
+    f = m[:, None] + np.sqrt(2.0 * v)[:, None] * GH_X[None, :]
+    w = GH_W[None, :] / math.sqrt(math.pi)
+    _, _, _, da, dkm = zinb_terms(f, y[:, None], alpha, km)
+    return float(np.sum(w * da)), float(np.sum(w * dkm))
+
+
+# Smallest site precision: the ZINB zero branch is not log-concave in f, so the unconstrained optimum of q can have
+# negative site precisions, which the heteroscedastic-GPR form (K + 1/lam) cannot carry.  The collapsed bound is
+# therefore the maximum over the Gaussian family with site precisions >= LAM_MIN: still a lower bound of the evidence
+# (<= the unconstrained VGP optimum), and its theta-gradient is still the partial derivative at the optimal sites
+# (Danskin's theorem for the constrained maximum).  The log-concave likelihoods never reach the bound.
+LAM_MIN = {"zinb": 1e-6}
+
+
 def lik_of(model, lik):
     """The likelihood dict with alpha taken from the model when it carries the dispersion in its (unused) Gaussian
     noise slot: spec["likelihood_variance"] with an exp transform (how the product's NegativeBinomial is encoded)."""
@@ -75,6 +123,8 @@ def lik_of(model, lik):
         return {"type": "negative_binomial", "alpha": lv["value"]}
     if lik["type"] == "gamma" and lv.get("transform") == "softplus":
         return {"type": "gamma", "shape": lv["value"]}
+    if lik["type"] == "zinb" and "likelihood_aux" in model:
+        return {"type": "zinb", "alpha": lv["value"], "km": model["likelihood_aux"]["value"]}
     return lik
 
 
@@ -99,6 +149,11 @@ def var_exp(lik, y, m, v):
         d1 = np.where(yy, ph, -ph) / pp
         d2 = -f * d1 - d1 * d1
         return np.sum(w * np.log(pp), 1), np.sum(w * d1, 1), 0.5 * np.sum(w * d2, 1)
+    if lik["type"] == "zinb":
+        f = m[:, None] + np.sqrt(2.0 * v)[:, None] * GH_X[None, :]
+        w = GH_W[None, :] / math.sqrt(math.pi)
+        lp, d1, d2, _, _ = zinb_terms(f, y[:, None], lik["alpha"], lik["km"])
+        return np.sum(w * lp, 1), np.sum(w * d1, 1), 0.5 * np.sum(w * d2, 1)
     if lik["type"] == "negative_binomial":
         a = lik["alpha"]
         sd = np.sqrt(2.0 * v)
@@ -174,7 +229,7 @@ def vgp_collapsed(model, lik, X, y, x, sites=None, tol=1e-12, maxit=500, rho=1.0
         m = yt - D * alpha
         v = D - D * D * np.diag(Ai)
         E, g, h = var_exp(lik, y, m, v)
-        lam_t = np.maximum(-2.0 * h, 1e-300)
+        lam_t = np.maximum(-2.0 * h, LAM_MIN.get(lik["type"], 1e-300))
         eta_t = g + lam_t * m
         lam_n = (1.0 - rho) * lam + rho * lam_t
         eta_n = (1.0 - rho) * eta + rho * eta_t
@@ -210,6 +265,10 @@ def vgp_collapsed(model, lik, X, y, x, sites=None, tol=1e-12, maxit=500, rho=1.0
                 dth = np.sum(alpha)
             elif p is spec["likelihood_variance"] and lik["type"] == "negative_binomial":
                 dth = nb_dalpha(y, m, v, lik["alpha"])          # the slot carries the NB dispersion
+            elif p is spec["likelihood_variance"] and lik["type"] == "zinb":
+                dth = zinb_dparams(y, m, v, lik["alpha"], lik["km"])[0]
+            elif p is spec.get("likelihood_aux") and lik["type"] == "zinb":
+                dth = zinb_dparams(y, m, v, lik["alpha"], lik["km"])[1]
             elif p is spec["likelihood_variance"] and lik["type"] == "gamma":
                 from scipy.special import digamma
                 dth = float(np.sum(-m - digamma(lik["shape"]) + np.log(y)))

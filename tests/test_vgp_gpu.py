@@ -250,3 +250,107 @@ def test_predictions_at_new_inputs_non_gaussian(engine, lik):
         want = logsumexp(lp + np.log(vo.GH_W / np.sqrt(np.pi))[None, :], axis=1)
     np.testing.assert_allclose(ld, want, rtol=1e-5, atol=1e-7)
     assert np.all(np.isfinite(ld))
+
+
+def test_zinb_bound_gradient_and_fit(engine):
+    """Zero-inflated negative binomial (waveome/likelihoods.py:96-139; 'zeroinflated_negativebinomial' in
+    gp_likelihood_crosswalk): alpha in the noise slot, km in the second likelihood slot, both softplus."""
+    from test_vgp_oracle import zinb_sample
+    from waveome_b200.engine import Batch
+    from waveome_b200.model_fitting import fit_models
+    from waveome_b200.models import make_likelihood
+    rng = np.random.default_rng(12)
+    n = 120
+    subj = rng.integers(0, 15, size=n).astype(float)
+    t = rng.normal(size=n)
+    X = np.stack([subj, t], 1)
+    f = 0.5 * rng.normal(size=15)[subj.astype(int)] + 0.7 * np.sin(2 * t) + 1.2
+    Y = np.stack([zinb_sample(rng, f), zinb_sample(rng, f - 0.5, alpha=1.0, km=2.0)])
+    assert (Y == 0).sum() > 30
+    model = count_model(c=0.3)
+    model.likelihood = make_likelihood("zeroinflated_negativebinomial", alpha=0.7, km=1.5)
+    p = model.program()
+    assert p.n_x == 6 and p.lik_slot2 >= 0
+    batch = Batch(engine, X, Y, [p])
+    batch.set_likelihood("zinb", (9.0, 9.0))                 # ignored: both slots are trainable
+    x = batch.x0() + 0.15 * rng.normal(size=(2, batch.P))
+    fv_, g, lml, st = batch.eval(x)
+    fm, fvar = batch.latent()
+    spec = model.to_spec()
+    for b in range(2):
+        r = vo.vgp_collapsed(copy.deepcopy(spec), {"type": "zinb"}, X, Y[b], x[b], rho=0.5, tol=1e-12, maxit=5000)
+        assert st[b] == 0
+        assert abs(lml[b] - r["F"]) <= 1e-8 * abs(r["F"]), (lml[b], r["F"])
+        np.testing.assert_allclose(g[b], -r["grad"], rtol=0, atol=1e-6 * np.max(np.abs(r["grad"])))
+        np.testing.assert_allclose(fm[b], r["m"], rtol=0, atol=1e-6 * (1 + np.max(np.abs(r["m"]))))
+        np.testing.assert_allclose(fvar[b], r["v"], rtol=1e-5, atol=1e-8)
+    batch.close()
+    # fit through the host API and predictions with the fitted likelihood
+    m2 = count_model(c=0.0)
+    m2.likelihood = make_likelihood("zinb")
+    spec2 = copy.deepcopy(m2.to_spec())
+    res = fit_models(X, Y[:1], [m2], engine=engine)
+    ro = vo.fit(spec2, {"type": "zinb"}, X, Y[0])
+    assert res["status"][0] in (0, 8)
+    assert abs(res["lml"][0] - ro["F"]) <= 1e-5 * abs(ro["F"]), (res["lml"][0], ro["F"])
+    assert float(m2.likelihood.alpha) != 1.0 and float(m2.likelihood.km) != 1.0
+    ym, yv = m2.predict_y(X[:9], data=(X, Y[0]))
+    ld = m2.predict_log_density((X[:9], Y[0][:9]), data=(X, Y[0]))
+    assert np.all(ym > 0) and np.all(yv > 0) and np.all(np.isfinite(ld))
+
+
+def test_zinb_sites_at_the_precision_bound(engine):
+    """Zeros at a high latent mean under a tight prior: the ZINB zero branch is not log-concave there, the optimal site
+    precisions would be negative and sit at the bound 1e-6 instead.  The value must still be the oracle's (a valid
+    lower bound), the evaluation carries status bit 32, and the gradient -- which omits the non-stationarity term of
+    the bounded sites -- stays within a few percent of the oracle's finite differences."""
+    from test_vgp_oracle import zinb_sample
+    from waveome_b200.engine import Batch
+    from waveome_b200.models import make_likelihood
+    rng = np.random.default_rng(4)
+    n = 64
+    subj = np.repeat(np.arange(8), 8).astype(float)
+    t = rng.normal(size=n)
+    X = np.stack([subj, t], 1)
+    y = zinb_sample(rng, 0.3 * np.sin(2 * t) + 3.0, alpha=0.3, km=0.5)
+    y[::7] = 0.0
+    model = count_model(var=0.05, c=3.0)
+    model.likelihood = make_likelihood("zinb", alpha=0.3, km=0.5)
+    batch = Batch(engine, X, y[None, :], [model.program()])
+    batch.set_likelihood("zinb", (1.0, 1.0))          # placeholders: both parameters ride in trainable slots
+    x = batch.x0()
+    f, g, lml, st = batch.eval(x)
+    batch.close()
+    spec = model.to_spec()
+    kw = dict(rho=0.3, tol=1e-11, maxit=20000)
+    r = vo.vgp_collapsed(copy.deepcopy(spec), {"type": "zinb"}, X, y, x[0], **kw)
+    assert np.sum(r["sites"][0] <= 1.0001e-6) >= 5
+    assert st[0] == 32
+    assert abs(lml[0] - r["F"]) <= 1e-7 * abs(r["F"]), (lml[0], r["F"])
+    np.testing.assert_allclose(g[0], -r["grad"], rtol=0, atol=1e-5 * np.max(np.abs(r["grad"])))
+    h, fd = 1e-5, []
+    for i in range(len(x[0])):
+        xp, xm = x[0].copy(), x[0].copy()
+        xp[i] += h; xm[i] -= h
+        fd.append((vo.vgp_collapsed(copy.deepcopy(spec), {"type": "zinb"}, X, y, xp, want_grad=False, **kw)["F"]
+                   - vo.vgp_collapsed(copy.deepcopy(spec), {"type": "zinb"}, X, y, xm, want_grad=False, **kw)["F"]) / (2 * h))
+    assert np.max(np.abs(-g[0] - np.array(fd))) <= 0.05 * np.max(np.abs(fd))
+
+
+def test_penalized_optimization_zinb_outcomes():
+    """GPSearch with outcome_likelihood='zeroinflated_negativebinomial' (the crosswalk name): fits run on the engine;
+    the reference's deviance has no ZINB branch (utilities.py:544-581), so the importances are None."""
+    from test_vgp_oracle import zinb_sample
+    from waveome_b200 import datasets
+    from waveome_b200.model_search import GPSearch
+    X, Y = datasets.count_microbiome(n_subjects=15, n_times=6, n_outcomes=3, seed=5)
+    rng = np.random.default_rng(3)
+    for c in Y.columns:
+        Y[c] = zinb_sample(rng, np.log(Y[c].to_numpy() + 1.0) * 0.6 + 0.5, alpha=0.5, km=1.0)
+    gps = GPSearch(X, Y, unit_col="subject", outcome_likelihood="zeroinflated_negativebinomial")
+    gps.penalized_optimization()
+    assert len(gps.models) == 3
+    for m in gps.models.values():
+        assert m.likelihood.name == "zinb" and np.isfinite(m.log_posterior_density_value)
+        assert m.feature_importances is None
+        assert float(m.likelihood.alpha) > 0 and float(m.likelihood.km) > 0

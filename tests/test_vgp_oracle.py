@@ -91,3 +91,39 @@ def test_site_form_prediction_equals_whitened_conditional(lik):
     np.testing.assert_allclose(m1, m2, rtol=0, atol=1e-9)
     np.testing.assert_allclose(v1, v2, rtol=0, atol=1e-9)
     assert np.all(v1 > 0)
+
+
+def zinb_sample(rng, f, alpha=0.5, km=1.0):
+    """waveome/likelihoods.py:96-139 as a sampler: structural zero with probability km / (km + m), else NB(m, alpha)."""
+    m = np.exp(f)
+    k = 1.0 / alpha
+    keep = rng.uniform(size=len(m)) < m / (km + m)
+    return (keep * rng.negative_binomial(k, k / (k + m))).astype(float)
+
+
+def test_zinb_collapsed_bound():
+    """Zero-inflated negative binomial: the site form still equals the whitened ELBO at the q of the sites, and the
+    gradient (incl. d/d alpha and d/d km through the second likelihood slot) matches finite differences.  The zero
+    branch is not log-concave: max d2 log p / df2 > 0."""
+    model, X, _, _, rng = _setup(seed=9)
+    yz = zinb_sample(rng, 0.5 * np.sin(2 * X[:, 1]) + 1.0)
+    assert np.sum(yz == 0) >= 8
+    f = np.linspace(-3, 4, 29)
+    assert vo.zinb_terms(f, np.zeros_like(f), 0.3, 0.5)[2].max() > 0.05
+    model["likelihood_variance"] = {"value": 0.5, "trainable": True, "transform": "softplus", "prior": None}
+    model["likelihood_aux"] = {"value": 1.2, "trainable": True, "transform": "softplus", "prior": None}
+    x = go.pack(model)
+    assert len(x) == 6
+    lik = {"type": "zinb"}
+    kw = dict(rho=0.5, maxit=5000)
+    r = vo.vgp_collapsed(model, lik, X, yz, x, **kw)
+    q_mu, q_sqrt = vo.q_from_sites(model, X, yz, x, r["sites"])
+    e = vo.vgp_elbo(model, lik, X, yz, x, q_mu, q_sqrt)
+    assert abs(e - r["F"]) <= 1e-10 * abs(e)
+    h, fd = 1e-5, []
+    for i in range(len(x)):
+        xp, xm = x.copy(), x.copy()
+        xp[i] += h; xm[i] -= h
+        fd.append((vo.vgp_collapsed(model, lik, X, yz, xp, want_grad=False, **kw)["F"]
+                   - vo.vgp_collapsed(model, lik, X, yz, xm, want_grad=False, **kw)["F"]) / (2 * h))
+    np.testing.assert_allclose(r["grad"], fd, rtol=1e-6, atol=1e-7)

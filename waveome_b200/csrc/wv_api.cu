@@ -186,8 +186,9 @@ static int wv_build_program(const wv_program_desc& d, int D, WvProgram* p) {
   if (d.n_slots <= 0 || d.n_slots > WV_MAX_SLOTS) return wv_fail("program: too many parameter slots (max 64)");
   if (d.noise_slot < 0 || d.noise_slot >= d.n_slots) return wv_fail("program: bad noise_slot");
   if (d.mean_slot >= d.n_slots) return wv_fail("program: bad mean_slot");
+  if (d.lik_slot2 < -1 || d.lik_slot2 >= d.n_slots) return wv_fail("program: bad lik_slot2");
   p->n_comp = d.n_comp; p->n_leaves = d.n_leaves; p->n_slots = d.n_slots;
-  p->noise_slot = d.noise_slot; p->mean_slot = d.mean_slot;
+  p->noise_slot = d.noise_slot; p->mean_slot = d.mean_slot; p->lik_slot2 = d.lik_slot2;
   for (int c = 0; c <= d.n_comp; ++c) {
     p->comp_start[c] = d.comp_start[c];
     if (c > 0 && (d.comp_start[c] < d.comp_start[c - 1] || d.comp_start[c] > d.n_leaves))
@@ -288,7 +289,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   WV_TRY(wv_alloc(b, &b->d_st2, B));
 #undef WV_TRY
   bd.Xt = dXt; bd.Y = dY; bd.programs = dprog; bd.prog_id = dpid; bd.comp_mask = dmask;
-  bd.lik = 0; bd.lik_param = 0.0; bd.jitter = 0.0; bd.site_lam = nullptr; bd.site_eta = nullptr; bd.vgp_extra = nullptr; bd.vgp_dlik = nullptr;
+  bd.lik = 0; bd.lik_param = 0.0; bd.jitter = 0.0; bd.site_lam = nullptr; bd.site_eta = nullptr; bd.vgp_extra = nullptr; bd.vgp_dlik = nullptr; bd.vgp_dlik2 = nullptr; bd.lik_param2 = 1.0;
   cudaStream_t st = e->stream;
   // Row order on the device: sorted lexicographically by the categorical columns the programs use (fewest levels
   // first).  The marginal likelihood is invariant under a simultaneous permutation of X rows and y entries; the sort
@@ -388,7 +389,7 @@ extern "C" int wv_batch_set_y(wv_batch* b, const double* Y) {
   WV_CUDA(cudaMemcpy2DAsync((void*)bd.Y, (size_t)bd.npad * sizeof(double), yp.data(), (size_t)bd.n * sizeof(double),
                             (size_t)bd.n * sizeof(double), bd.B, cudaMemcpyHostToDevice, b->eng->stream));
   WV_CUDA(cudaStreamSynchronize(b->eng->stream));
-  if (bd.lik != 0) return wv_batch_set_likelihood(b, bd.lik, bd.lik_param);     // new counts: restart the sites
+  if (bd.lik != 0) return wv_batch_set_likelihood2(b, bd.lik, bd.lik_param, bd.lik_param2);     // new counts: restart the sites
   return 0;
 }
 
@@ -406,24 +407,32 @@ __global__ void wv_site_init_kernel(int B, int n, int npad, int kind, const doub
   lgam[i] = lgamma(y + 1.0);
 }
 
+extern "C" int wv_batch_set_likelihood2(wv_batch* b, int32_t kind, double param, double param2);
 extern "C" int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param) {
+  return wv_batch_set_likelihood2(b, kind, param, 1.0);
+}
+
+extern "C" int wv_batch_set_likelihood2(wv_batch* b, int32_t kind, double param, double param2) {
   if (!b) return wv_fail("wv_batch_set_likelihood: null batch");
-  if (kind < 0 || kind > 4)
-    return wv_fail("wv_batch_set_likelihood: kind must be 0 (gaussian), 1 (poisson), 2 (negative binomial), 3 (bernoulli) or 4 (gamma)");
-  if ((kind == 2 || kind == 4) && !(param > 0.0)) return wv_fail("wv_batch_set_likelihood: the likelihood parameter must be positive");
+  if (kind < 0 || kind > 5)
+    return wv_fail("wv_batch_set_likelihood: kind must be 0 (gaussian), 1 (poisson), 2 (negative binomial), 3 (bernoulli), "
+                   "4 (gamma) or 5 (zero-inflated negative binomial)");
+  if ((kind == 2 || kind == 4 || kind == 5) && !(param > 0.0))
+    return wv_fail("wv_batch_set_likelihood: the likelihood parameter must be positive");
+  if (kind == 5 && !(param2 > 0.0)) return wv_fail("wv_batch_set_likelihood: km must be positive");
   WV_CUDA(cudaSetDevice(b->eng->device));
   WvBatchDev& bd = b->bd;
-  bd.lik = kind; bd.lik_param = param;
-  if (kind == 0) { bd.site_lam = bd.site_eta = bd.vgp_extra = bd.vgp_dlik = nullptr; bd.jitter = 0.0; return 0; }
+  bd.lik = kind; bd.lik_param = param; bd.lik_param2 = param2;
+  if (kind == 0) { bd.site_lam = bd.site_eta = bd.vgp_extra = bd.vgp_dlik = bd.vgp_dlik2 = nullptr; bd.jitter = 0.0; return 0; }
   const size_t B = bd.B, np = bd.npad;
   if (!b->vgp.lam_p) {
     double* lg = nullptr;
-    if (wv_alloc(b, &bd.site_lam, B * np) || wv_alloc(b, &bd.site_eta, B * np) || wv_alloc(b, &bd.vgp_extra, B) || wv_alloc(b, &bd.vgp_dlik, B) ||
+    if (wv_alloc(b, &bd.site_lam, B * np) || wv_alloc(b, &bd.site_eta, B * np) || wv_alloc(b, &bd.vgp_extra, B) || wv_alloc(b, &bd.vgp_dlik, B) || wv_alloc(b, &bd.vgp_dlik2, B) ||
         wv_alloc(b, &b->vgp.lam_p, B * np) || wv_alloc(b, &b->vgp.eta_p, B * np) || wv_alloc(b, &b->vgp.lam_t, B * np) ||
         wv_alloc(b, &b->vgp.eta_t, B * np) || wv_alloc(b, &b->vgp.fmean, B * np) || wv_alloc(b, &b->vgp.fvar, B * np) ||
         wv_alloc(b, &lg, B * np) || wv_alloc(b, &b->vgp.F_prev, B) || wv_alloc(b, &b->vgp.rho, B) ||
         wv_alloc(b, &b->vgp.first, B) || wv_alloc(b, &b->vgp.inner_task, B) || wv_alloc(b, &b->vgp.sweeps, B) ||
-        wv_alloc(b, &b->vgp.good, B) ||
+        wv_alloc(b, &b->vgp.good, B) || wv_alloc(b, &b->vgp.at_bound, B) ||
         wv_alloc(b, &b->d_inner1, B) || wv_alloc(b, &b->d_inner2, B))
       return -1;
     b->vgp.lgam = lg;
@@ -435,6 +444,8 @@ extern "C" int wv_batch_set_likelihood(wv_batch* b, int32_t kind, double param) 
   cudaStream_t st = b->eng->stream;
   WV_CUDA(cudaMemsetAsync(bd.vgp_extra, 0, B * sizeof(double), st));
   WV_CUDA(cudaMemsetAsync(bd.vgp_dlik, 0, B * sizeof(double), st));
+  WV_CUDA(cudaMemsetAsync(bd.vgp_dlik2, 0, B * sizeof(double), st));
+  WV_CUDA(cudaMemsetAsync(b->vgp.at_bound, 0, B * sizeof(int), st));
   wv_site_init_kernel<<<(unsigned)((B * np + 255) / 256), 256, 0, st>>>((int)B, bd.n, (int)np, kind, bd.Y, bd.site_lam, bd.site_eta,
                                                                        (double*)b->vgp.lgam);
   WV_CUDA(cudaStreamSynchronize(st));

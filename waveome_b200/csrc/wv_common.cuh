@@ -37,6 +37,8 @@ enum WvPrior : int32_t { WV_PRIOR_NONE = 0, WV_PRIOR_HORSESHOE = 1, WV_PRIOR_LAP
 #define WV_STATUS_MAXITER 4
 #define WV_STATUS_LINESEARCH 8
 #define WV_STATUS_INNER_CAP 16    // variational path: the site iteration hit its sweep cap
+#define WV_STATUS_SITE_BOUND 32   // variational path (ZINB): a site precision sits at its lower bound; the value is a valid
+                                 // bound, the gradient omits those sites' non-stationarity term
 
 struct WvLeaf {
   int32_t type;    // WvLeafType
@@ -60,6 +62,7 @@ struct WvSlot {
 struct WvProgram {
   int32_t n_comp, n_leaves, n_slots, n_x;   // n_x = number of trainable (packed) parameters
   int32_t noise_slot, mean_slot;            // mean_slot = -1 for a zero mean function
+  int32_t lik_slot2;                        // second likelihood parameter (ZINB km), -1 if none
   int32_t n_dims, pad;                      // number of distinct covariate columns used
   int32_t comp_start[WV_MAX_COMP + 1];      // leaves of component c are [comp_start[c], comp_start[c+1])
   int32_t dims[WV_MAX_DIMS];                // distinct covariate columns; WvLeaf.dim indexes THIS table

@@ -720,7 +720,8 @@ __global__ void __launch_bounds__(64 * WV_FIN_MAXG) wv_finalize_kernel(WvBatchDe
       for (int g = 0; g < G; ++g) dl += s_part[g][s];
       dl *= 0.5;
       if (s == pg->mean_slot) dl = s_sum_alpha;
-      if ((bd.lik == 2 || bd.lik == 4) && s == pg->noise_slot) dl = bd.vgp_dlik[b];      // the slot is the likelihood parameter
+      if ((bd.lik == 2 || bd.lik == 4 || bd.lik == 5) && s == pg->noise_slot) dl = bd.vgp_dlik[b];   // the slot is the likelihood parameter
+      if (bd.lik == 5 && s == pg->lik_slot2) dl = bd.vgp_dlik2[b];
       const double g = -(dl + dlp) * wv_transform_grad(sl.transform, u);
       g_out[(size_t)b * bd.P + sl.xindex] = g;
       if (!isfinite(g)) atomicOr(&s_bad, 1);
@@ -843,9 +844,13 @@ __device__ __forceinline__ double wv_digamma(double x) {
          f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f * (1.0 / 132.0)))));
 }
 
-__device__ __forceinline__ void wv_var_exp(int lik, double alpha_nb, double y, double lgam, double m, double v, double& E,
-                                           double& g, double& h, double& da) {
-  da = 0.0;
+// smallest site precision: 1e-300 ("never") for the log-concave likelihoods; the ZINB zero branch is not log-concave, its
+// bound is maximised over the Gaussian family with site precisions >= 1e-6 (oracle/vgp_oracle.py LAM_MIN)
+__device__ __forceinline__ double wv_lam_min(int lik) { return lik == 5 ? 1e-6 : 1e-300; }
+
+__device__ __forceinline__ void wv_var_exp(int lik, double alpha_nb, double km, double y, double lgam, double m, double v,
+                                           double& E, double& g, double& h, double& da, double& da2) {
+  da = 0.0; da2 = 0.0;
   if (lik == 1) {                       // Poisson, exp link: closed form (gpflow.likelihoods.Poisson)
     const double r = exp(m + 0.5 * v);
     E = y * m - r - lgam;
@@ -889,14 +894,44 @@ __device__ __forceinline__ void wv_var_exp(int lik, double alpha_nb, double y, d
     return;
   }
   const double k = 1.0 / alpha_nb;
+  if (lik == 5 && y == 0.0) {
+    // ZINB (waveome/likelihoods.py:96-139), y = 0: log(psi + (1 - psi) NB(0)) = log(km + u) - log(km + e^f),
+    // u = e^f (1 + alpha e^f)^(-1/alpha), psi = km / (km + e^f)
+    double se = 0.0, s1 = 0.0, s2 = 0.0, sa = 0.0, sm = 0.0;
+    for (int q = 0; q < 20; ++q) {
+      const double x = q < 10 ? -gx[9 - q] : gx[q - 10];
+      const double w = (q < 10 ? gw[9 - q] : gw[q - 10]) * 0.5641895835477563;
+      const double f = m + sd * x;
+      const double ef = exp(f);
+      const double am = 1.0 + alpha_nb * ef, l1 = log1p(alpha_nb * ef);
+      const double u = ef * exp(-l1 * k);
+      const double P = km + u, Q = km + ef;
+      const double r = (1.0 + (alpha_nb - 1.0) * ef) / am;        // d log u / df
+      const double u1 = u * r, u2 = u * (r * r - ef / (am * am));
+      se += w * (log(P) - log(Q));
+      s1 += w * (u1 / P - ef / Q);
+      s2 += w * (u2 / P - (u1 / P) * (u1 / P) - km * ef / (Q * Q));
+      sa += w * (u * (l1 * k * k - ef * k / am) / P);
+      sm += w * (1.0 / P - 1.0 / Q);
+    }
+    E = se; g = s1; h = 0.5 * s2; da = sa; da2 = sm;
+    return;
+  }
   const double cst = lgamma(k + y) - lgam - lgamma(k);
-  double se = 0.0, s1 = 0.0, s2 = 0.0, sk = 0.0;
+  double se = 0.0, s1 = 0.0, s2 = 0.0, sk = 0.0, sm = 0.0;
   const double dcst = wv_digamma(k + y) - wv_digamma(k);          // d cst / dk
   for (int q = 0; q < 20; ++q) {
     const double x = q < 10 ? -gx[9 - q] : gx[q - 10];
     const double w = (q < 10 ? gw[9 - q] : gw[q - 10]) * 0.5641895835477563;      // / sqrt(pi)
     const double f = m + sd * x;
     const double ef = exp(f);
+    if (lik == 5) {        // ZINB, y > 0: log(1 - psi) + NB = f - log(km + e^f) + NB
+      const double Q = km + ef;
+      se += w * (f - log(Q));
+      s1 += w * (km / Q);
+      s2 += w * (-km * ef / (Q * Q));
+      sm += w * (-1.0 / Q);
+    }
     const double lp = cst + y * (f - log(ef + k)) - k * log1p(ef * alpha_nb);
     const double t = alpha_nb * ef / (1.0 + alpha_nb * ef);
     se += w * lp;
@@ -907,14 +942,15 @@ __device__ __forceinline__ void wv_var_exp(int lik, double alpha_nb, double y, d
   }
   E = se; g = s1; h = 0.5 * s2;
   da = -k * k * sk;                     // dk / dalpha = -1 / alpha^2
+  da2 = sm;
 }
 
 __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVgpState vs, const int* __restrict__ list,
                                                              const double* __restrict__ xall) {
   __shared__ double red[8];
   __shared__ double s_bcast[2];
-  __shared__ double s_dal;
-  __shared__ int s_dec;
+  __shared__ double s_dal, s_dal2;
+  __shared__ int s_dec, s_nbound;
   const int b = list[blockIdx.x];
   const int n = bd.n, ld = bd.npad;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -924,11 +960,16 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
     const WvSlot& sl = pg->slots[pg->mean_slot];
     cmean = sl.xindex >= 0 ? wv_transform(sl.transform, xall[(size_t)b * bd.P + sl.xindex], sl.shift) : sl.fixed;
   }
-  double lik_param = bd.lik_param;
-  if (bd.lik == 2 || bd.lik == 4) {        // a trainable noise slot is the likelihood parameter (NB alpha, Gamma shape)
+  double lik_param = bd.lik_param, lik_param2 = bd.lik_param2;
+  if (bd.lik == 2 || bd.lik == 4 || bd.lik == 5) {   // a trainable noise slot is the likelihood parameter (NB / ZINB alpha, Gamma shape)
     const WvSlot& sl = pg->slots[pg->noise_slot];
     if (sl.xindex >= 0) lik_param = wv_transform(sl.transform, xall[(size_t)b * bd.P + sl.xindex], sl.shift);
   }
+  if (bd.lik == 5 && pg->lik_slot2 >= 0) {           // ZINB km
+    const WvSlot& sl = pg->slots[pg->lik_slot2];
+    lik_param2 = sl.xindex >= 0 ? wv_transform(sl.transform, xall[(size_t)b * bd.P + sl.xindex], sl.shift) : sl.fixed;
+  }
+  const double lam_min = wv_lam_min(bd.lik);
   double* lam = bd.site_lam + (size_t)b * ld;
   double* eta = bd.site_eta + (size_t)b * ld;
   double* lam_p = vs.lam_p + (size_t)b * ld;
@@ -940,17 +981,22 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
   const double* yb = bd.Y + (size_t)b * ld;
   const double* lg = vs.lgam + (size_t)b * ld;
   // ---- pass 1: posterior marginals, variational expectations, the bound, the targets of the next move
-  double part = 0.0, dmax = 0.0, dalpha = 0.0;
+  double part = 0.0, dmax = 0.0, dalpha = 0.0, dalpha2 = 0.0;
+  int nbound = 0;
+  if (threadIdx.x == 0) s_nbound = 0;
+  __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double l = lam[i], e = eta[i];
     const double D = 1.0 / l, yt = e * D;
     const double m = yt - D * al[i];
     const double v = D - D * D * Ab[(size_t)i * ld + i];
-    double E, g, h, da;
-    wv_var_exp(bd.lik, lik_param, yb[i], lg[i], m, v, E, g, h, da);
+    double E, g, h, da, da2;
+    wv_var_exp(bd.lik, lik_param, lik_param2, yb[i], lg[i], m, v, E, g, h, da, da2);
     dalpha += da;
+    dalpha2 += da2;
     part += E + 0.5 * log(6.283185307179586 / l) + 0.5 * l * ((yt - m) * (yt - m) + v);
-    const double lt = fmax(-2.0 * h, 1e-300);
+    const double lt = fmax(-2.0 * h, lam_min);
+    if (bd.lik == 5 && -2.0 * h < lam_min) nbound = 1;
     const double et = g + lt * m;
     vs.fmean[(size_t)b * ld + i] = m;
     vs.fvar[(size_t)b * ld + i] = v;
@@ -960,10 +1006,12 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
     dmax = fmax(dmax, fmax(d1, d2));
     if (!(d1 == d1) || !(d2 == d2)) dmax = INFINITY;
   }
+  if (nbound) atomicOr(&s_nbound, 1);
   // deterministic block reductions (sum, max)
   for (int o = 16; o > 0; o >>= 1) {
     part += __shfl_xor_sync(0xffffffffu, part, o);
     dalpha += __shfl_xor_sync(0xffffffffu, dalpha, o);
+    dalpha2 += __shfl_xor_sync(0xffffffffu, dalpha2, o);
     dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
   }
   if (lane == 0) red[warp] = part;
@@ -980,6 +1028,14 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
     double ssum = 0.0;
     for (int w = 0; w < 8; ++w) ssum += red[w];
     s_dal = ssum;
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = dalpha2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ssum = 0.0;
+    for (int w = 0; w < 8; ++w) ssum += red[w];
+    s_dal2 = ssum;
   }
   __syncthreads();
   if (lane == 0) red[warp] = dmax;
@@ -1011,7 +1067,7 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
     int flag = (dec == 1 || dec == 2) ? 1 : (dec == 0 ? 0 : -1);
     if (sweeps >= vs.max_sweeps && dec == 1) { dec = 4; flag = mx < vs.soft_tol ? 0 : -1; }
     if (sweeps >= vs.max_sweeps && dec == 2) { dec = 3; flag = -1; }
-    if (dec == 0 || dec == 4) { bd.vgp_extra[b] = extra; bd.vgp_dlik[b] = s_dal; }
+    if (dec == 0 || dec == 4) { bd.vgp_extra[b] = extra; bd.vgp_dlik[b] = s_dal; bd.vgp_dlik2[b] = s_dal2; vs.at_bound[b] = s_nbound; }
     vs.rho[b] = rho;
     vs.good[b] = good;
     vs.first[b] = 0;
@@ -1029,9 +1085,9 @@ __global__ void __launch_bounds__(256) wv_site_update_kernel(WvBatchDev bd, WvVg
       const double l = lam[i], e = eta[i];
       const double D = 1.0 / l, yt = e * D;
       const double m = vs.fmean[(size_t)b * ld + i], v = vs.fvar[(size_t)b * ld + i];
-      double E, g, h, da;
-      wv_var_exp(bd.lik, lik_param, yb[i], lg[i], m, v, E, g, h, da);
-      const double lt = fmax(-2.0 * h, 1e-300), et = g + lt * m;
+      double E, g, h, da, da2;
+      wv_var_exp(bd.lik, lik_param, lik_param2, yb[i], lg[i], m, v, E, g, h, da, da2);
+      const double lt = fmax(-2.0 * h, lam_min), et = g + lt * m;
       lam_p[i] = l; eta_p[i] = e; lam_t[i] = lt; eta_t[i] = et;
       lam[i] = (1.0 - rho) * l + rho * lt;
       eta[i] = (1.0 - rho) * e + rho * et;
@@ -1092,6 +1148,7 @@ __global__ void wv_vgp_status_kernel(WvVgpState vs, const int* __restrict__ list
   if (i >= n_list) return;
   const int b = list[i];
   if (vs.inner_task[b] == -1) status[b] |= (vs.sweeps[b] >= vs.max_sweeps ? WV_STATUS_INNER_CAP : WV_STATUS_NONFINITE);
+  if (vs.at_bound[b]) status[b] |= WV_STATUS_SITE_BOUND;
 }
 
 // Gram + Cholesky + L^{-T} + alpha + K^{-1} of the listed models.  Returns launches or -1.

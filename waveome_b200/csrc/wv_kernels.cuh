@@ -51,6 +51,8 @@ struct WvBatchDev {
   double* site_lam;                 // [B][npad] precision of the Gaussian pseudo-observation of every row
   double* site_eta;                 // [B][npad] precision x mean of the pseudo-observation
   double* vgp_extra;                // [B] sum_i E_i + 1/2 log(2 pi / lam_i) + lam_i/2 ((ytilde_i - m_i)^2 + v_i)
+  double lik_param2;                // ZINB: km when the programs carry no (trainable) second likelihood slot
+  double* vgp_dlik2;                // [B] sum_i dE_i/d(km)
   double* vgp_dlik;                 // [B] sum_i dE_i/d(alpha): gradient of the bound wrt the negative-binomial dispersion
 };
 
@@ -61,6 +63,7 @@ struct WvVgpState {
   double *fmean, *fvar;                    // [B][npad] posterior mean / variance of f at the training inputs
   const double* lgam;                      // [B][npad] lgamma(y + 1)
   int *first, *inner_task, *sweeps, *good; // [B]
+  int* at_bound;                           // [B] sites at the lower precision bound in the last sweep
   double tol, soft_tol;                    // converged below tol; at the sweep cap accepted without a flag below soft_tol
   int max_sweeps;
 };

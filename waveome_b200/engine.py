@@ -30,6 +30,7 @@ class _ProgramDesc(C.Structure):
         ("leaf_s_ls", _i32p), ("leaf_s_aux", _i32p), ("leaf_degree", _i32p),
         ("slot_transform", _i32p), ("slot_xindex", _i32p), ("slot_prior", _i32p),
         ("slot_fixed", _f64p), ("slot_shift", _f64p), ("slot_pa", _f64p), ("slot_pb", _f64p),
+        ("lik_slot2", C.c_int32),
     ]
 
 
@@ -48,7 +49,7 @@ class _LbfgsOpts(C.Structure):
 
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
-    "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_likelihood", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
+    "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_likelihood", "wv_batch_set_likelihood2", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
     "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_get_kinv_diag", "wv_batch_predict_mean", "wv_batch_predict_f", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
 KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk", "sites"]
@@ -77,6 +78,7 @@ def load_library():
     lib.wv_batch_set_y.argtypes = [vp, _f64p]; lib.wv_batch_set_y.restype = C.c_int
     lib.wv_batch_set_component_mask.argtypes = [vp, C.POINTER(C.c_uint32)]; lib.wv_batch_set_component_mask.restype = C.c_int
     lib.wv_batch_set_likelihood.argtypes = [vp, C.c_int32, C.c_double]; lib.wv_batch_set_likelihood.restype = C.c_int
+    lib.wv_batch_set_likelihood2.argtypes = [vp, C.c_int32, C.c_double, C.c_double]; lib.wv_batch_set_likelihood2.restype = C.c_int
     lib.wv_batch_get_latent.argtypes = [vp, _f64p, _f64p]; lib.wv_batch_get_latent.restype = C.c_int
     lib.wv_batch_eval.argtypes = [vp, _f64p, _f64p, _f64p, _f64p, _i32p]; lib.wv_batch_eval.restype = C.c_int
     lib.wv_batch_eval_device.argtypes = [vp, vp, vp, vp, vp, vp]; lib.wv_batch_eval_device.restype = C.c_int
@@ -179,6 +181,7 @@ class Batch:
             d.leaf_degree = _i32(p.leaf_degree)
             d.slot_transform, d.slot_xindex, d.slot_prior = _i32(p.slot_transform), _i32(p.slot_xindex), _i32(p.slot_prior)
             d.slot_fixed, d.slot_shift, d.slot_pa, d.slot_pb = _f64(p.slot_fixed), _f64(p.slot_shift), _f64(p.slot_pa), _f64(p.slot_pb)
+            d.lik_slot2 = getattr(p, "lik_slot2", -1)
         bd = _BatchDesc(self.n, self.D, self.B, self.P, _f64(X), _f64(Y), len(self.programs), descs, _i32(pid))
         h = C.c_void_p()
         _check(self.lib.wv_batch_create(engine.handle, C.byref(bd), C.byref(h)), "wv_batch_create")
@@ -208,13 +211,16 @@ class Batch:
         _check(self.lib.wv_batch_set_component_mask(self.handle, mask.ctypes.data_as(C.POINTER(C.c_uint32))),
                "wv_batch_set_component_mask")
 
-    LIKELIHOODS = {"gaussian": 0, "poisson": 1, "negative_binomial": 2, "bernoulli": 3, "gamma": 4}
+    LIKELIHOODS = {"gaussian": 0, "poisson": 1, "negative_binomial": 2, "bernoulli": 3, "gamma": 4, "zinb": 5}
 
-    def set_likelihood(self, kind, param: float = 0.0):
-        """"gaussian" (default), "poisson", or "negative_binomial" (param = alpha): switches the objective to the
-        variational bound maximised over q (include/waveome_b200.h)."""
+    def set_likelihood(self, kind, param=0.0, param2: float = 1.0):
+        """"gaussian" (default), "poisson", "negative_binomial" (param = alpha), "bernoulli", "gamma" (param = shape) or
+        "zinb" (param = alpha, param2 = km; ``param`` may be the pair): switches the objective to the variational bound
+        maximised over q (include/waveome_b200.h)."""
         code = self.LIKELIHOODS[kind] if isinstance(kind, str) else int(kind)
-        _check(self.lib.wv_batch_set_likelihood(self.handle, code, float(param)), "wv_batch_set_likelihood")
+        if isinstance(param, (tuple, list)):
+            param, param2 = param
+        _check(self.lib.wv_batch_set_likelihood2(self.handle, code, float(param), float(param2)), "wv_batch_set_likelihood2")
 
     def latent(self):
         """(mean, var) of f at the training inputs after the last evaluation of a non-Gaussian batch, [B, n] each."""

@@ -31,10 +31,14 @@ def get_engine(device: Optional[int] = None):
 
 
 def likelihood_key(model) -> tuple:
-    """(engine likelihood name, parameter) of a model: ("gaussian", 0.0), ("poisson", 0.0), ("negative_binomial", alpha)."""
+    """(engine likelihood name, parameter) of a model: ("gaussian", 0.0), ("poisson", 0.0), ("negative_binomial", alpha),
+    ("gamma", shape), ("zinb", (alpha, km))."""
     lik = model.likelihood
     name = getattr(lik, "name", "gaussian")
-    return (name, float(getattr(lik, "engine_param", 0.0))) if name != "gaussian" else ("gaussian", 0.0)
+    if name == "gaussian":
+        return ("gaussian", 0.0)
+    p = getattr(lik, "engine_param", 0.0)
+    return (name, tuple(float(v) for v in p) if isinstance(p, tuple) else float(p))
 
 
 def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional[np.ndarray] = None,

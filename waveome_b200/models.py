@@ -89,6 +89,27 @@ class Gamma:
         return float(self.shape)
 
 
+class ZeroInflatedNegativeBinomial:
+    """waveome/likelihoods.py:96-139: NB with dispersion ``alpha`` and structural zeros with probability
+    psi = km / (km + exp(f)) (Michaelis-Menten constant ``km``), both positive() parameters.  alpha rides in the
+    program's noise slot, km in its second likelihood slot."""
+    name = "zinb"
+
+    def __init__(self, alpha=1.0, km=1.0, trainable=True):
+        self.alpha = K.Parameter(alpha, transform="softplus", trainable=trainable)
+        self.km = K.Parameter(km, transform="softplus", trainable=trainable)
+        self._dummy_noise = self.alpha
+        self._aux_param = self.km
+
+    @property
+    def parameters(self):
+        return [self.alpha, self.km]
+
+    @property
+    def engine_param(self):
+        return (float(self.alpha), float(self.km))
+
+
 def make_likelihood(name, **kw):
     """gp_likelihood_crosswalk (waveome/utilities.py:989-1009) for the likelihoods the engine covers."""
     if name == "gaussian":
@@ -101,8 +122,10 @@ def make_likelihood(name, **kw):
         return Bernoulli()
     if name == "gamma":
         return Gamma(**kw)
+    if name in ("zeroinflated_negativebinomial", "zero_inflated_negative_binomial", "zinb"):
+        return ZeroInflatedNegativeBinomial(**kw)
     raise NotImplementedError(f"likelihood {name!r} is not covered by the B200 engine "
-                              "(gaussian, poisson, negative_binomial, bernoulli, gamma)")
+                              "(gaussian, poisson, negative_binomial, bernoulli, gamma, zeroinflated_negativebinomial)")
 
 
 class ConstantMean:
@@ -158,6 +181,9 @@ class GPR:
             d[".likelihood.alpha"] = self.likelihood.alpha
         elif isinstance(self.likelihood, Gamma):
             d[".likelihood.shape"] = self.likelihood.shape
+        elif isinstance(self.likelihood, ZeroInflatedNegativeBinomial):
+            d[".likelihood.alpha"] = self.likelihood.alpha
+            d[".likelihood.km"] = self.likelihood.km
         if isinstance(self.mean_function, ConstantMean):
             d[".mean_function.c"] = self.mean_function.c
         return d
@@ -167,7 +193,7 @@ class GPR:
         mc = self.mean_function.c if isinstance(self.mean_function, ConstantMean) else None
         # count likelihoods: the program's noise slot is a frozen placeholder the engine ignores
         noise = self.likelihood.variance if isinstance(self.likelihood, Gaussian) else self.likelihood._dummy_noise
-        return build_program(self.kernel, noise, mc)
+        return build_program(self.kernel, noise, mc, likelihood_aux=getattr(self.likelihood, "_aux_param", None))
 
     def to_spec(self) -> dict:
         """Neutral JSON-able description (the format the test oracle consumes)."""
@@ -179,6 +205,8 @@ class GPR:
                 spec["likelihood"]["alpha"] = float(self.likelihood.alpha)
             if isinstance(self.likelihood, Gamma):
                 spec["likelihood"]["shape"] = float(self.likelihood.shape)
+            if isinstance(self.likelihood, ZeroInflatedNegativeBinomial):
+                spec["likelihood_aux"] = self.likelihood.km.to_spec()
         if isinstance(self.mean_function, ConstantMean):
             spec["mean"] = {"type": "constant", "c": self.mean_function.c.to_spec()}
         else:

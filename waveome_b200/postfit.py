@@ -143,6 +143,9 @@ def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], masks: Opt
                         mean[sel] = shape * np.exp(fm + 0.5 * fv)
                     elif lik_name == "negative_binomial":   # waveome's override plugs in Fmu (likelihoods.py:48-51)
                         mean[sel] = np.exp(fm)
+                    elif lik_name == "zinb":          # quadrature of the conditional mean m^2 / (km + m)
+                        mean[sel] = np.stack([likelihood_predict_mean_and_var(models[b].likelihood, fm[i], fv[i])[0]
+                                              for i, b in enumerate(sel)])
                     else:                             # Poisson, exp link
                         mean[sel] = np.exp(fm + 0.5 * fv)
             finally:
@@ -192,6 +195,14 @@ def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf"
     """calc_feature_importance_components (utilities.py:614-707) for B models at once: one list per model with one
     entry per additive component and a last entry for the residual (1 - deviance explained)."""
     Y = np.ascontiguousarray(Y, dtype=np.float64)
+    no_dev = [getattr(m.likelihood, "name", "gaussian") in ("gamma", "zinb") for m in models]
+    if any(no_dev):
+        # calc_deviance_explained has no branch for these likelihoods (utilities.py:544-581: "Unknown likelihood"):
+        # no importances rather than a failed fit
+        keep = [b for b in range(len(models)) if not no_dev[b]]
+        sub = feature_importances_batch(X, Y[keep], [models[b] for b in keep], return_value, engine) if keep else []
+        it = iter(sub)
+        return [None if no_dev[b] else next(it) for b in range(len(models))]
     var_models, var_masks, rows = [], [], []
     for b, m in enumerate(models):
         ms = _component_masks(m)
@@ -336,6 +347,12 @@ def _likelihood_log_prob(lik, f, y):
     if name == "gamma":
         a = float(lik.shape)
         return -a * f - gammaln(a) + (a - 1.0) * np.log(y) - y * np.exp(-f)
+    if name == "zinb":            # waveome/likelihoods.py:114-133
+        a, km = float(lik.alpha), float(lik.km)
+        m = np.exp(f)
+        log_p_zero = np.log(km + m * np.exp(-np.log1p(a * m) / a)) - np.log(km + m)
+        log_p_nonzero = f - np.log(km + m) + nb_logpmf(m, np.where(y == 0, 1.0, y), a)
+        return np.where(y == 0, log_p_zero, log_p_nonzero)
     raise NotImplementedError(name)
 
 
@@ -358,6 +375,12 @@ def likelihood_predict_mean_and_var(lik, fm, fv):
         cm, cv = np.exp(f), np.exp(f)
     elif name == "gamma":
         cm, cv = float(lik.shape) * np.exp(f), float(lik.shape) * np.exp(2.0 * f)
+    elif name == "zinb":          # waveome/likelihoods.py:135-143
+        a, km = float(lik.alpha), float(lik.km)
+        m = np.exp(f)
+        psi = 1.0 - m / (km + m)
+        cm = m * (1.0 - psi)
+        cv = m * (1.0 - psi) * (1.0 + m * (psi + a))
     else:
         raise NotImplementedError(name)
     ey = np.sum(w * cm, -1)

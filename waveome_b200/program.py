@@ -81,6 +81,7 @@ class Program:
     slot_pb: np.ndarray
     params: List[K.Parameter] = field(default_factory=list)   # slot -> Parameter object
     x_params: List[K.Parameter] = field(default_factory=list)  # packed index -> Parameter object
+    lik_slot2: int = -1            # slot of a second likelihood parameter (ZINB km), -1 if none
 
     def x0(self) -> np.ndarray:
         """Unconstrained start vector from the parameters' current values."""
@@ -96,10 +97,11 @@ class Program:
         return tuple(a.tobytes() for a in (
             self.comp_start, self.leaf_type, self.leaf_dim, self.leaf_s_var, self.leaf_s_ls, self.leaf_s_aux,
             self.leaf_degree, self.slot_transform, self.slot_xindex, self.slot_prior, self.slot_fixed,
-            self.slot_shift, self.slot_pa, self.slot_pb)) + (self.noise_slot, self.mean_slot)
+            self.slot_shift, self.slot_pa, self.slot_pb)) + (self.noise_slot, self.mean_slot, self.lik_slot2)
 
 
-def build_program(kernel, likelihood_variance: K.Parameter, mean_c: Optional[K.Parameter]) -> Program:
+def build_program(kernel, likelihood_variance: K.Parameter, mean_c: Optional[K.Parameter],
+                  likelihood_aux: Optional[K.Parameter] = None) -> Program:
     comps = expand_sum_of_products(kernel)
     if len(comps) > MAX_COMP:
         raise ValueError(f"kernel has {len(comps)} additive components, engine limit is {MAX_COMP}")
@@ -112,11 +114,13 @@ def build_program(kernel, likelihood_variance: K.Parameter, mean_c: Optional[K.P
             params.append(p)
         return slot_of[id(p)]
 
-    # register slots in packed order first: kernel depth-first, noise, mean
+    # register slots in packed order first: kernel depth-first, noise (or first likelihood parameter), second likelihood
+    # parameter, mean
     for lf in iter_leaves(kernel):
         for p in lf.parameters:
             slot(p)
     noise_slot = slot(likelihood_variance)
+    lik_slot2 = slot(likelihood_aux) if likelihood_aux is not None else -1
     mean_slot = slot(mean_c) if mean_c is not None else -1
     if len(params) > MAX_SLOTS:
         raise ValueError(f"model has {len(params)} parameters, engine limit is {MAX_SLOTS}")
@@ -173,4 +177,4 @@ def build_program(kernel, likelihood_variance: K.Parameter, mean_c: Optional[K.P
         mean_slot=mean_slot, comp_start=i32(comp_start), leaf_type=i32(ltype), leaf_dim=i32(ldim),
         leaf_s_var=i32(lvar), leaf_s_ls=i32(lls), leaf_s_aux=i32(laux), leaf_degree=i32(ldeg),
         slot_transform=tr, slot_xindex=xi, slot_prior=pr, slot_fixed=fx, slot_shift=sh, slot_pa=pa, slot_pb=pb,
-        params=params, x_params=x_params)
+        params=params, x_params=x_params, lik_slot2=lik_slot2)
