@@ -39,8 +39,8 @@ enum { WVT_IDENTITY = 0, WVT_SOFTPLUS = 1, WVT_SOFTPLUS_SHIFT = 2, WVT_EXP = 3 }
 enum { WVP_NONE = 0, WVP_HORSESHOE = 1, WVP_LAPLACE = 2, WVP_UNIFORM = 3 };
 /* per-model status bits */
 enum { WVS_OK = 0, WVS_CHOL_FAIL = 1, WVS_NONFINITE = 2, WVS_MAXITER = 4, WVS_LINESEARCH = 8, WVS_INNER_CAP = 16,
-       WVS_SITE_BOUND = 32 /* ZINB: a site precision sits at its lower bound (1e-6): the value is a valid bound, the
-                              gradient omits the non-stationarity term of those sites */ };
+       WVS_SITE_BOUND = 32 /* ZINB: a site precision sits at its lower bound (1e-6): the value is a valid lower bound,
+                              the envelope-theorem gradient is approximate */ };
 
 /* One kernel program = sum over components of products of leaves, plus the parameter slot table.
  * Arrays are flat; a batch passes `n_programs` of these back to back. */
@@ -116,7 +116,7 @@ int wv_batch_set_y(wv_batch* b, const double* Y);
  * link and dispersion `param` = alpha (waveome/likelihoods.py:16-79), 3 Bernoulli with gpflow's inv_probit link (y in
  * {0, 1}), 4 Gamma with exp link and shape `param` (gpflow.likelihoods.Gamma), 5 zero-inflated negative binomial
  * (waveome/likelihoods.py:96-139: alpha = `param`, km = the second parameter, see wv_batch_set_likelihood2; its zero
- * branch is not log-concave, the bound is maximised over site precisions >= 1e-6).  For 1-5 the objective is the variational bound of gpflow.models.VGP / PSVGP
+ * branch is not log-concave: site precisions are projected onto >= 1e-6, status bit WVS_SITE_BOUND when that binds).  For 1-5 the objective is the variational bound of gpflow.models.VGP / PSVGP
  * with Z = X (waveome/model_fitting.py:158-185, waveome/model_classes.py:1082-1126) maximised over the variational
  * distribution for the given hyper-parameters: f = -(max_q ELBO + log prior), `lml` reports max_q ELBO, Y holds the
  * observations.  The programs' noise slot: ignored for Poisson / Bernoulli; for the negative binomial and the Gamma a

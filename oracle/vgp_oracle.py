@@ -108,10 +108,10 @@ def zinb_dparams(y, m, v, alpha, km):
 
 
 # Smallest site precision: the ZINB zero branch is not log-concave in f, so the unconstrained optimum of q can have
-# negative site precisions, which the heteroscedastic-GPR form (K + 1/lam) cannot carry.  The collapsed bound is
-# therefore the maximum over the Gaussian family with site precisions >= LAM_MIN: still a lower bound of the evidence
-# (<= the unconstrained VGP optimum), and its theta-gradient is still the partial derivative at the optimal sites
-# (Danskin's theorem for the constrained maximum).  The log-concave likelihoods never reach the bound.
+# negative site precisions, which the heteroscedastic-GPR form (K + 1/lam) cannot carry.  The site iteration projects the
+# precisions onto >= LAM_MIN: the value is the ELBO of the resulting q (a valid lower bound of the evidence, equal to
+# the VGP optimum when no site sits at the bound); with sites at the bound q is not a stationary point of the ELBO and
+# the envelope-theorem gradient is approximate.  The log-concave likelihoods never reach the bound.
 LAM_MIN = {"zinb": 1e-6}
 
 
