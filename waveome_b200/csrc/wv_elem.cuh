@@ -623,7 +623,8 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, 1) wv_cross_var_kernel(
   const double* Wg = bd.A + (size_t)b * bd.npad * bd.npad + (size_t)tj * WV_NB * bd.npad + tk * WV_NB;
   for (int i = threadIdx.x; i < WV_NB * WV_NB; i += blockDim.x) {
     const int r = i >> 6, c = i & 63;
-    cs.W[r * LDK + c] = Wg[(size_t)r * bd.npad + c];
+    // diagonal tiles of K^-1 hold their lower 8x8 blocks only (wv_kinv_kernel): mirror
+    cs.W[r * LDK + c] = (tj == tk && (c >> 3) > (r >> 3)) ? Wg[(size_t)c * bd.npad + r] : Wg[(size_t)r * bd.npad + c];
   }
   __syncthreads();
   // ---- thread (i = tid / 4, q = tid % 4): T[i][k] = sum_j K*_j[i][j] W[j][k] for k in [16 q, 16 q + 16), then the dot

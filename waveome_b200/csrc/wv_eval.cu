@@ -566,6 +566,25 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_kinv_kernel(WvBatchDev bd,
   int ti, tj;
   wv_tile_from_linear(blockIdx.x, ti, tj);
   const double* Mb = bd.Mt + (size_t)b * ld * ld;
+  if (ti == tj) {
+    // diagonal tile: Mt_i Mt_i^T is symmetric -- one staged operand, only the lower 8x8 blocks are formed (36 of 64);
+    // the strict upper blocks of the tile keep stale values, every reader mirrors or masks them
+    double sacc[10][2];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) sacc[q][0] = sacc[q][1] = 0.0;
+    wv_syrk_self_64(sm, Mb + (size_t)ti * WV_NB * ld, ld, ti * WV_NB, bd.n8, sacc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    double* Out = bd.A + (size_t)b * ld * ld + (size_t)ti * WV_NB * ld + ti * WV_NB;
+#define WV_X(q, i, j) \
+    *reinterpret_cast<double2*>(Out + (size_t)((i) * 8 + fr) * ld + (j) * 8 + 2 * fk) = make_double2(sacc[q][0], sacc[q][1]);
+    if (warp == 0) { WV_SYM_W0(WV_X) }
+    else if (warp == 1) { WV_SYM_W1(WV_X) }
+    else if (warp == 2) { WV_SYM_W2(WV_X) }
+    else { WV_SYM_W3(WV_X) }
+#undef WV_X
+    return;
+  }
   double acc[4][4][2];
   wv_zero_acc(acc);
   // rows / columns beyond n of K^-1 are never read (the gradient pass masks them): padding warps of the last tile
