@@ -243,7 +243,8 @@ __device__ __forceinline__ void wv_gemm_nt_64(WvGemmSmem& sm, const double* __re
   wv_gemm_64<false>(sm, Ag, Bg, ld, k0, k1, acc, dead);
 }
 
-// second-stage product from shared memory operands (64x64x64): acc[m][n] = sum_k Ts[m][k] * Bs[n][k]
+// second-stage product from shared memory operands (64x64x64): acc[m][n] = sum_k Ts[m][k] * Bs[n][k], Bs LOWER
+// TRIANGULAR (Bs[n][k] = 0 for k > n)
 __device__ __forceinline__ void wv_gemm_nt_smem64(const double* __restrict__ Ts, const double* __restrict__ Bs,
                                                   double (&acc)[4][4][2], bool dead = false) {
   if (dead) return;
@@ -252,8 +253,11 @@ __device__ __forceinline__ void wv_gemm_nt_smem64(const double* __restrict__ Ts,
   const int fr = lane >> 2, fk = lane & 3;
   const double* as = Ts + (wm * 32 + fr) * WV_LDT + fk;
   const double* bs = Bs + (wn * 32 + fr) * WV_LDT + fk;
+  // Bs is lower triangular (the inverse of a Cholesky diagonal block): column block nb = wn * 4 + ni of the result
+  // only needs k < 8 (nb + 1) -- 56 % of the tile products, and the warps of the left half finish after k = 32
+  const int kend = (wn * 4 + 4) * 8;
 #pragma unroll 4
-  for (int kk = 0; kk < WV_NB; kk += 4) {
+  for (int kk = 0; kk < kend; kk += 4) {
     double af[4], bf[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -261,9 +265,11 @@ __device__ __forceinline__ void wv_gemm_nt_smem64(const double* __restrict__ Ts,
       bf[i] = bs[i * 8 * WV_LDT + kk];
     }
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+    for (int ni = 0; ni < 4; ++ni)
+      if (kk < (wn * 4 + ni + 1) * 8) {
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) wv_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        for (int mi = 0; mi < 4; ++mi) wv_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+      }
   }
 }
 
