@@ -324,7 +324,7 @@ def main():
         return 0
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
         ncols = args.cpu_sample or cores
         spec = model.to_spec()
         f, e, dt = cpu_reference_step(spec, Xn, gps.Y.to_numpy(dtype=np.float64)[:, lo:hi], list(range(ncols)), cores)
