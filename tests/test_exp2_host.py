@@ -22,6 +22,8 @@ int main() {
     double r = wv_exp2_fast(u, tab);
     long double ref = exp2l((long double)u);
     if (u <= 0.0 && u > -1021.0 && wv_exp2_neg(u, tab) != r) return 5;      // the device path shares the arithmetic
+    if (u > -1021.0 && wv_exp2_lo(u, tab) != r) return 7;                   // integer clamp: identical inside the range
+    if (u <= -1021.0 && !(wv_exp2_lo(u, tab) > 0.0 && wv_exp2_lo(u, tab) < 1e-307)) return 8;
     if (u <= -1021.0) { if (r != 0.0 || !(wv_exp2_neg(u, tab) < 1e-307)) return 2; continue; }
     double ulp = fabs((double)((r - ref) / ldexpl(1.0L, ilogbl(ref) - 52)));
     if (ulp > maxulp) maxulp = ulp;
@@ -29,6 +31,8 @@ int main() {
   printf("%%.4f\n", maxulp);
   if (wv_exp2_fast(0.0, tab) != 1.0 || wv_exp2_fast(-0.0, tab) != 1.0 || wv_exp2_fast(1.0, tab) != 2.0) return 3;
   if (wv_exp2_neg(0.0, tab) != 1.0 || !std::isnan(wv_exp2_neg(NAN, tab))) return 6;
+  if (wv_exp2_lo(0.0, tab) != 1.0 || wv_exp2_lo(-0.0, tab) != 1.0 || !std::isnan(wv_exp2_lo(NAN, tab))) return 9;
+  if (!(wv_exp2_lo(-INFINITY, tab) < 1e-307) || !(wv_exp2_lo(-1e300, tab) < 1e-307)) return 10;
   if (wv_exp2_fast(-INFINITY, tab) != 0.0 || !std::isnan(wv_exp2_fast(NAN, tab)) || !std::isinf(wv_exp2_fast(2000.0, tab))) return 4;
   return 0;
 }

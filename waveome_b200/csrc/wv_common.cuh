@@ -145,6 +145,23 @@ WV_HD double wv_exp2_neg(double u, const double* __restrict__ tab) {
   u = (u < -1021.0) ? -1021.0 : u;
   return wv_exp2_core(u, tab);
 }
+// u < 1024 (log2(variance) - (s d)^2 of a squared-exponential leaf): the clamp at -1021 as ONE unsigned integer minimum on
+// the high word instead of a double compare and two selects.  Below -1021 (and for -inf) the result is ~2^-1021 instead
+// of 0; a NaN with the sign bit clear -- what the FP64 units produce -- propagates.
+WV_HD double wv_exp2_lo(double u, const double* __restrict__ tab) {
+#ifdef __CUDA_ARCH__
+  const unsigned hi = min((unsigned)__double2hiint(u), 0xC08FE800u);          // 0xC08FE800 00000000 = -1021.0
+  return wv_exp2_core(__hiloint2double((int)hi, __double2loint(u)), tab);
+#else
+  unsigned long long bits;
+  memcpy(&bits, &u, 8);
+  unsigned hi = (unsigned)(bits >> 32);
+  if (hi > 0xC08FE800u) hi = 0xC08FE800u;
+  bits = ((unsigned long long)hi << 32) | (bits & 0xffffffffULL);
+  memcpy(&u, &bits, 8);
+  return wv_exp2_core(u, tab);
+#endif
+}
 
 // tfd.Horseshoe(scale).log_prob(x) (TFP closed-form approximation) and d/dx.
 WV_HD void wv_horseshoe(double x, double s, double* logp, double* dlogp) {

@@ -41,6 +41,7 @@ struct WvElemSmem {
   WvLeaf leaves[WV_MAX_LEAVES];
   double theta[WV_MAX_SLOTS];
   double lc[WV_MAX_LEAVES];                // per-leaf constant: SE sqrt(log2(e)/2) / lengthscale
+  double lv[WV_MAX_LEAVES];                // SE: log2(variance), folded into the exponent of the Gram value
   double tab[WV_EXP2_TAB];
   double xr[WV_MAX_DIMS][WV_NB];
   double xc[WV_MAX_DIMS][WV_NB];
@@ -77,6 +78,7 @@ __device__ __forceinline__ void wv_elem_stage_model(const WvBatchDev& bd, int b,
     const WvLeaf lf = sm.leaves[l];
     // exp(-r2/2) = 2^(-(s (x_i - x_j))^2),  s = sqrt(log2(e) / 2) / lengthscale
     sm.lc[l] = lf.type == WV_LEAF_SE ? 0.84932180028801907 / sm.theta[lf.s_ls] : 0.0;
+    sm.lv[l] = lf.type == WV_LEAF_SE ? log2(sm.theta[lf.s_var]) : 0.0;
   }
 }
 
@@ -154,7 +156,8 @@ __device__ __forceinline__ void wv_leaf_mul_ne(const WvElemSmem& sm, int l, cons
 #define WV_PUT(e, v) prod[e] = FIRST ? (v) : prod[e] * (v)
   switch (lf.type) {
     case WV_LEAF_SE: {
-      const double s = sm.lc[l];
+      // variance * exp(-r2 / 2) = 2^(log2(variance) - (s d)^2): the variance rides in the exponent
+      const double s = sm.lc[l], lv = sm.lv[l];
       double ai[WV_ELEM_MR], aj[4];
 #pragma unroll
       for (int a = 0; a < WV_ELEM_MR; ++a) ai[a] = xi[a] * s;
@@ -165,7 +168,7 @@ __device__ __forceinline__ void wv_leaf_mul_ne(const WvElemSmem& sm, int l, cons
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const double d = ai[a] - aj[b];
-          WV_PUT(a * 4 + b, var * wv_exp2_neg(-d * d, sm.tab));
+          WV_PUT(a * 4 + b, wv_exp2_lo(fma(-d, d, lv), sm.tab));
         }
     } break;
     case WV_LEAF_LINEAR:
@@ -284,7 +287,7 @@ __device__ __forceinline__ void wv_leaf_grad_sums_ne(const WvElemSmem& sm, int l
         for (int b = 0; b < 4; ++b) {
           const double d = ai[a] - aj[b];
           const double u = d * d;                                   // = r2 log2(e) / 2
-          const double t = wo[a * 4 + b] * wv_exp2_neg(-u, sm.tab);
+          const double t = wo[a * 4 + b] * wv_exp2_lo(-u, sm.tab);
           s_var += t;
           s_ls = fma(t, u, s_ls);
         }
