@@ -131,6 +131,9 @@ def lik_of(model, lik):
 def var_exp(lik, y, m, v):
     """(E, dE/dm, dE/dv) per observation."""
     y = np.asarray(y, dtype=np.float64)
+    if lik["type"] == "gaussian":         # gpflow.likelihoods.Gaussian: used to show objective (B) == objective (A)
+        s2 = lik["variance"]
+        return -0.5 * np.log(2.0 * np.pi * s2) - ((y - m) ** 2 + v) / (2.0 * s2), (y - m) / s2, np.full_like(m, -0.5 / s2)
     if lik["type"] == "poisson":
         r = np.exp(m + 0.5 * v)
         return y * m - r - lgamma(y + 1.0), y - r, -0.5 * r

@@ -127,3 +127,30 @@ def test_zinb_collapsed_bound():
         fd.append((vo.vgp_collapsed(model, lik, X, yz, xp, want_grad=False, **kw)["F"]
                    - vo.vgp_collapsed(model, lik, X, yz, xm, want_grad=False, **kw)["F"]) / (2 * h))
     np.testing.assert_allclose(r["grad"], fd, rtol=1e-6, atol=1e-7)
+
+
+def test_objective_b_collapses_to_objective_a_for_the_gaussian_likelihood():
+    """the reference's penalised path maximises the whitened SVGP ELBO with Z = X (objective B) over
+    (theta, q_mu, q_sqrt).  For the Gaussian likelihood its maximum over q is the exact log marginal likelihood
+    (objective A) with the noise variance increased by the 1e-6 jitter -- which is why the engine evaluates A."""
+    model, X, y, _, rng = _setup(seed=2)
+    y = np.log1p(y) + 0.1 * rng.normal(size=len(y))
+    s2 = 0.37
+    model["likelihood_variance"]["value"] = s2
+    x = go.pack(model)
+    lik = {"type": "gaussian", "variance": s2}
+    r = vo.vgp_collapsed(model, lik, X, y, x, want_grad=False)
+    assert r["iters"] <= 2                                   # the sites are exact after one sweep: lam = 1 / s2
+    np.testing.assert_allclose(r["sites"][0], 1.0 / s2, rtol=1e-12)
+    a_model = copy.deepcopy(model)
+    a_model["likelihood_variance"]["value"] = s2 + vo.JITTER
+    fa = go.objective(a_model, X, y, go.pack(a_model), want_grad=False)
+    lml = fa[2] if isinstance(fa, tuple) else -fa
+    assert abs(r["F"] - lml) <= 1e-10 * abs(lml), (r["F"], lml)
+    q_mu, q_sqrt = vo.q_from_sites(model, X, y, x, r["sites"])
+    e = vo.vgp_elbo(model, lik, X, y, x, q_mu, q_sqrt)
+    assert abs(e - lml) <= 1e-10 * abs(lml)
+    n = len(y)
+    for _ in range(5):
+        dq, dS = 1e-3 * rng.normal(size=n), 1e-3 * np.tril(rng.normal(size=(n, n)))
+        assert vo.vgp_elbo(model, lik, X, y, x, q_mu + dq, q_sqrt + dS) < e
