@@ -119,3 +119,24 @@ def test_shard_bounds_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_models_survive_pickle_and_deepcopy():
+    """fitted models travel between processes (Ray in the reference, all_gather_object here) and are
+    deep-copied by callers; every likelihood of the crosswalk must survive both with the same device program."""
+    import copy
+    import pickle
+    import waveome_b200 as wb
+    from waveome_b200 import kernels as K
+    from waveome_b200.models import PenalizedGPR, make_likelihood
+    k = wb.Sum([wb.Categorical(active_dims=[0]),
+                wb.Product([wb.Categorical(active_dims=[2]), wb.SquaredExponential(active_dims=[1])]),
+                wb.Periodic(wb.SquaredExponential(active_dims=[1]))])
+    for lik, n_x in (("gaussian", 9), ("poisson", 8), ("negative_binomial", 9), ("bernoulli", 8), ("gamma", 9),
+                     ("zeroinflated_negativebinomial", 10)):
+        m = PenalizedGPR(k, mean_function=wb.ConstantMean(0.1), likelihood=None if lik == "gaussian" else make_likelihood(lik))
+        assert m.program().n_x == n_x
+        for m2 in (pickle.loads(pickle.dumps(m)), copy.deepcopy(m)):
+            assert m2.kernel_name == m.kernel_name and m2.program().signature() == m.program().signature()
+            assert m2.kernel is not m.kernel and m2.likelihood is not m.likelihood
+        assert K.deepcopy(m.kernel).to_spec() == m.kernel.to_spec()
