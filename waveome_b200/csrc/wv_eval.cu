@@ -28,7 +28,7 @@ __device__ long long wv_dbg_clk[64];
 // =============================================================================================
 struct WvDiagSmem {
   union {
-    WvGemmSmem g;                 // used as SIX single-operand stages by wv_syrk_self_64 (A and B are the same rows)
+    WvGemmSmem g;                 // used as 2 * WV_STAGES single-operand stages by wv_syrk_self_64 (A and B are the same rows)
     struct {
       double T[WV_NB * WV_LDT];   // T -> L (lower, incl. diagonal); strict upper part: L^{-T} as it is assembled
       double X[WV_NB * WV_LDT];   // L^{-1} (lower); the upper off-diagonal blocks are scratch for (L_SF X_FF)^T
@@ -50,10 +50,10 @@ struct WvDiagSmem {
 #define WV_SYM_W3(X) X(0,7,0) X(1,7,1) X(2,7,2) X(3,7,3) X(4,7,4) X(5,7,5) X(6,7,6) X(7,7,7)
 
 // acc = lower tiles of sum_{k in [k0,k1)} R[m][k] R[n][k] for one 64-row operand R (row stride ld): the diagonal-tile
-// update of the Cholesky.  Both DMMA operands come from ONE staged copy (six stages in the memory of three A/B
+// update of the Cholesky.  Both DMMA operands come from ONE staged copy (2 * WV_STAGES stages in the memory of the A/B
 // pairs): this kernel runs one CTA per model on the critical path and is bound by the FP64 tensor rate of a single
 // SM and by bytes in flight, not by bandwidth.
-#define WV_SELF_STAGES 6
+#define WV_SELF_STAGES (2 * WV_STAGES)
 __device__ __forceinline__ void wv_self_issue(double* __restrict__ stage, const double* __restrict__ Rg, int ld, int kc,
                                               int k1) {
 #pragma unroll
@@ -69,7 +69,7 @@ __device__ __forceinline__ void wv_syrk_self_64(WvGemmSmem& sm, const double* __
                                                 double (&acc)[10][2]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fr = lane >> 2, fk = lane & 3;
-  double* base = &sm.a[0][0];     // a[3][..] and b[3][..] are contiguous: six stages of 64 x WV_LDS doubles
+  double* base = &sm.a[0][0];     // a[..] and b[..] are contiguous: 2 * WV_STAGES stages of 64 x WV_LDS doubles
   const int nchunks = (k1 - k0 + WV_BK - 1) / WV_BK;
 #pragma unroll
   for (int s = 0; s < WV_SELF_STAGES - 1; ++s) {

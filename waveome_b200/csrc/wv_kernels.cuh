@@ -22,7 +22,12 @@
 #define WV_LDS (WV_BK + 4)   // smem row stride (doubles) of a pipeline stage: (row*20 + k) mod 16 distinct -> conflict-free DMMA fragment loads
 #define WV_LDT 68            // smem row stride of a 64x64 DMMA operand tile (68 mod 16 == 4)
 #define WV_LDP 65            // smem row stride of a 64x64 scalar-access tile (potrf / trtri of a diagonal block)
-#define WV_STAGES 3
+// cp.async operand ring of the 64x64 tile GEMM.  Two stages (41 KB): five CTAs per SM for the kernels that only need the
+// ring (kinv, syrk, trtri levels) -- measured against three stages (61 KB, three CTAs): kinv 5.79 -> 5.37 ms per
+// 2000-model evaluation, n = 8192 Cholesky 8.97 -> 8.71 ms; occupancy beats pipeline depth here.
+#ifndef WV_STAGES
+#define WV_STAGES 2
+#endif
 #define WV_GEMM_THREADS 128
 #define WV_ELEM_THREADS 256
 
