@@ -399,7 +399,7 @@ struct WvPanelSmem {
     WvGemmSmem g;
     struct {
       double T[WV_NB * WV_LDT];
-      double D[WV_NB * WV_LDT];
+      double D[WV_DP_DOUBLES];      // packed triangular inverse block (wv_dp_load)
     } e;
   };
 };
@@ -468,12 +468,8 @@ __device__ __forceinline__ void wv_panel_body(const WvBatchDev& bd, int b, int s
     }
     __syncthreads();
   }
-  // D = Linv of the step's diagonal block (row-major); L2 loads: the block was written by another SM in this launch
-  const double2* Dg = reinterpret_cast<const double2*>(bd.Dinv + ((size_t)b * bd.nt + step) * WV_NB * WV_NB);
-  for (int i = threadIdx.x; i < WV_NB * WV_NB / 2; i += WV_GEMM_THREADS) {
-    int rr = i >> 5, c2 = (i & 31) * 2;
-    *reinterpret_cast<double2*>(&sm.e.D[rr * WV_LDT + c2]) = __ldcg(Dg + i);
-  }
+  // D = Linv of the step's diagonal block
+  wv_dp_load(sm.e.D, bd.Dinv + ((size_t)b * bd.nt + step) * WV_NB * WV_NB);
   __syncthreads();
   wv_zero_acc(acc);
   wv_gemm_nt_smem64(sm.e.T, sm.e.D, acc, dead);
@@ -503,6 +499,13 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS, 3) wv_chol_step_kernel(WvBatc
   else wv_panel_body<0>(bd, b, j, x - 1, k0, epoch);
 }
 
+// the panel tiles alone (many models in flight: the diagonal blocks were factorised by the launch before): without the
+// diagonal body the kernel needs ~100 registers and 55 KB, four CTAs per SM instead of three
+__global__ void __launch_bounds__(WV_GEMM_THREADS, 4) wv_chol_panel_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                                        int j, int k0, int epoch) {
+  wv_panel_body<0>(bd, active[blockIdx.y], j, blockIdx.x, k0, epoch);
+}
+
 // enqueue one Cholesky column step; fused into one launch iff all its CTAs can be resident at once
 static int wv_launch_chol_step(const WvBatchDev& bd, const int* d_active, int n_active, int j, int k0, cudaStream_t st,
                                WvProfiler* pf, const WvAux& aux) {
@@ -515,7 +518,7 @@ static int wv_launch_chol_step(const WvBatchDev& bd, const int* d_active, int n_
   }
   wv_chol_step_kernel<<<dim3(1, n_active), WV_GEMM_THREADS, smem, st>>>(bd, d_active, j, k0, aux.epoch, 0);
   pf->mark(WV_K_CHOL_DIAG, st);
-  wv_chol_step_kernel<<<dim3(nt - j - 1, n_active), WV_GEMM_THREADS, smem, st>>>(bd, d_active, j, k0, aux.epoch, 1);
+  wv_chol_panel_kernel<<<dim3(nt - j - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, j, k0, aux.epoch);
   pf->mark(WV_K_CHOL_PANEL, st);
   return 2;
 }
@@ -783,6 +786,7 @@ static cudaError_t wv_set_attrs() {
   WV_ATTR(wv_cross_mean_kernel, sizeof(WvElemSmem));
   WV_ATTR(wv_cross_var_kernel, sizeof(WvCrossVarSmem));
   WV_ATTR(wv_chol_step_kernel, wv_smem_gemm_bytes());
+  WV_ATTR(wv_chol_panel_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_trtri_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_kinv_kernel, sizeof(WvGemmSmem));
   WV_ATTR(wv_syrk_kernel, sizeof(WvGemmSmem));

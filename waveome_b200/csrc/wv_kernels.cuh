@@ -248,32 +248,51 @@ __device__ __forceinline__ void wv_gemm_nt_64(WvGemmSmem& sm, const double* __re
   wv_gemm_64<false>(sm, Ag, Bg, ld, k0, k1, acc, dead);
 }
 
-// second-stage product from shared memory operands (64x64x64): acc[m][n] = sum_k Ts[m][k] * Bs[n][k], Bs LOWER
-// TRIANGULAR (Bs[n][k] = 0 for k > n)
-__device__ __forceinline__ void wv_gemm_nt_smem64(const double* __restrict__ Ts, const double* __restrict__ Bs,
+// Packed lower-triangular 64x64 block (the inverse of a Cholesky diagonal block) in shared memory: the 8 rows of row
+// block nb keep their first 8 (nb + 1) columns with row stride 8 (nb + 1) + 4 (== 4 or 12 mod 16: the DMMA fragment
+// loads stay conflict free), 2560 doubles instead of 64 x 68 -- with it the panel / trtri CTAs need 55 KB and four fit
+// on an SM.
+#define WV_DP_DOUBLES 2560
+__device__ __forceinline__ int wv_dp_offset(int nb) { return 32 * nb * (nb + 2); }
+__device__ __forceinline__ int wv_dp_stride(int nb) { return 8 * (nb + 1) + 4; }
+
+// gmem row-major 64x64 (zeros above the diagonal) -> packed smem; L2 loads (in the fused Cholesky step the block was
+// written by another SM of the same launch)
+__device__ __forceinline__ void wv_dp_load(double* __restrict__ Dp, const double* __restrict__ Dg_) {
+  const double2* Dg = reinterpret_cast<const double2*>(Dg_);
+  for (int i = threadIdx.x; i < WV_NB * WV_NB / 2; i += WV_GEMM_THREADS) {
+    const int rr = i >> 5, c2 = (i & 31) * 2, nb = rr >> 3;
+    if (c2 < 8 * (nb + 1))
+      *reinterpret_cast<double2*>(&Dp[wv_dp_offset(nb) + (rr & 7) * wv_dp_stride(nb) + c2]) = __ldcg(Dg + i);
+  }
+}
+
+// second-stage product from shared memory operands (64x64x64): acc[m][n] = sum_k Ts[m][k] * B[n][k], B LOWER TRIANGULAR
+// and packed (wv_dp_load)
+__device__ __forceinline__ void wv_gemm_nt_smem64(const double* __restrict__ Ts, const double* __restrict__ Dp,
                                                   double (&acc)[4][4][2], bool dead = false) {
   if (dead) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 1, wn = warp & 1;
   const int fr = lane >> 2, fk = lane & 3;
   const double* as = Ts + (wm * 32 + fr) * WV_LDT + fk;
-  const double* bs = Bs + (wn * 32 + fr) * WV_LDT + fk;
-  // Bs is lower triangular (the inverse of a Cholesky diagonal block): column block nb = wn * 4 + ni of the result
-  // only needs k < 8 (nb + 1) -- 56 % of the tile products, and the warps of the left half finish after k = 32
+  const double* bs[4];
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni) bs[ni] = Dp + wv_dp_offset(wn * 4 + ni) + fr * wv_dp_stride(wn * 4 + ni) + fk;
+  // column block nb = wn * 4 + ni of the result only needs k < 8 (nb + 1) -- 56 % of the tile products, and the warps
+  // of the left half finish after k = 32
   const int kend = (wn * 4 + 4) * 8;
 #pragma unroll 4
   for (int kk = 0; kk < kend; kk += 4) {
-    double af[4], bf[4];
+    double af[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      af[i] = as[i * 8 * WV_LDT + kk];
-      bf[i] = bs[i * 8 * WV_LDT + kk];
-    }
+    for (int i = 0; i < 4; ++i) af[i] = as[i * 8 * WV_LDT + kk];
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni)
       if (kk < (wn * 4 + ni + 1) * 8) {
+        const double bf = bs[ni][kk];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) wv_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        for (int mi = 0; mi < 4; ++mi) wv_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf);
       }
   }
 }
