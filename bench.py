@@ -286,9 +286,9 @@ def main():
         achieved = alg / (dom_ms * 1e-3) / 1e9
         roof = {"kernel": f"wv_{dom}_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": {"gram": 3.396e9, "grad": 3.483e9}[dom], "peak_kind": peak_kind + " copy bandwidth",
+                "traffic": {"gram": 3.393e9, "grad": 3.483e9}[dom], "peak_kind": peak_kind + " copy bandwidth",
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch with 2000 models in flight "
-                                "(profiles/r01g_ncu_set_full_summary.txt); algorithmic bytes of that launch: 5.8e9 "
+                                "(profiles/r01i_ncu_set_full_summary.txt); algorithmic bytes of that launch: 5.8e9 "
                                 "(8 n^2 per model, the kernel touches the lower tiles only)",
                 "note": "FP64-issue bound, not HBM bound: up to 6 squared-exponential leaves per matrix element for this "
                         "kernel tree, each a table-driven 2^u of 9 FP64 operations (see DESIGN.md section 4)"}
@@ -300,13 +300,13 @@ def main():
         alg = share * float(n) ** 3 * model_evals
         achieved = alg / (dom_ms * 1e-3) / 1e12
         # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture with 2000 models in flight
-        # (profiles/r01g_ncu_set_full_summary.txt): trtri = its largest launch (step nt-1: 9 tiles per model, every Mt
+        # (profiles/r01i_ncu_set_full_summary.txt): trtri = its largest launch (step nt-1: 9 tiles per model, every Mt
         # and L tile read once from DRAM), kinv = its single launch, Cholesky = step 4 (diagonal + 5 panel tiles)
-        traffic = {"trtri": 3.921e9, "kinv": 6.275e9, "chol_diag+chol_panel": 2.698e9}.get(dom)
+        traffic = {"trtri": 3.943e9, "kinv": 6.301e9, "chol_diag+chol_panel": 2.671e9}.get(dom)
         roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
                 "traffic_note": "bytes of the class's largest launch at 2000 models (trtri step nt-1; kinv; Cholesky step 4), "
-                                "see profiles/r01g_ncu_set_full_summary.txt; achieved counts the algorithmic n^3/3 flops of the "
+                                "see profiles/r01i_ncu_set_full_summary.txt; achieved counts the algorithmic n^3/3 flops of the "
                                 "class, the kernels execute ~1.5x that (full diagonal tiles, inverse-block epilogues, padding)",
                 "peak_kind": "measured cuBLAS DGEMM fp64 on this pool (not in MEASURED_PEAKS.json)"}
     roof["share_of_step"] = dom_ms / step_ms if step_ms else None
@@ -316,6 +316,12 @@ def main():
         "factorisation_tflops": float(n) ** 3 * model_evals / (fact_ms * 1e-3) / 1e12 if fact_ms else None,
         "factorisation_frac_of_fp64_peak": float(n) ** 3 * model_evals / (fact_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS if fact_ms else None,
         "class_ms": {k: round(v[0], 3) for k, v in prof.items()},
+        # algorithmic n^3/3 flops of each factorisation class over its own time (Cholesky = diagonal + panel kernels)
+        "class_tflops": {
+            "cholesky": float(n) ** 3 / 3 * model_evals / ((prof["chol_diag"][0] + prof["chol_panel"][0]) * 1e-3) / 1e12
+            if prof["chol_diag"][0] + prof["chol_panel"][0] else None,
+            "trtri": float(n) ** 3 / 3 * model_evals / (prof["trtri"][0] * 1e-3) / 1e12 if prof["trtri"][0] else None,
+            "kinv": float(n) ** 3 / 3 * model_evals / (prof["kinv"][0] * 1e-3) / 1e12 if prof["kinv"][0] else None},
     }
 
     if rank != 0:
