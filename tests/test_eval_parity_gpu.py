@@ -144,6 +144,12 @@ def test_full_size_properties(engine):
     f3, g3, lml3, _ = b2.eval(x[perm])
     assert np.array_equal(f3, f[perm]) and np.array_equal(g3, g[perm])
     b2.close()
+    # ... nor on the schedule: alone, a model takes the fused one-launch Cholesky step; among 64 its early steps run as
+    # a diagonal launch + the panel-only kernel -- same arithmetic, bit-identical results
+    b1 = Batch(engine, Xn, Yn[17:18], [model.program()])
+    f1, g1, lml1, _ = b1.eval(x[17:18])
+    assert f1[0] == f[17] and np.array_equal(g1[0], g[17]) and lml1[0] == lml[17]
+    b1.close()
     # row-permutation invariance of the marginal likelihood (up to summation order)
     rp = rng.permutation(Xn.shape[0])
     b3 = Batch(engine, Xn[rp], Yn[:, rp], [model.program()])
