@@ -596,6 +596,55 @@ __global__ void wv_lb_step_kernel(const int* __restrict__ active, int n_active, 
   task[b] = wv_lb_step(L, opts, fb);
 }
 
+// The same step with the model's optimiser state staged in shared memory: one WARP per model copies workspace, iterate,
+// gradient and scalars in (coalesced), lane 0 runs the sequential state machine on them, the warp copies them back.
+// The thread-per-model kernel above walks ~9 KB of private state per model through dependent, uncoalesced global loads
+// (0.46 ms per round at 2000 models, 3 % of a fit); the arithmetic is identical, so are the results.
+__global__ void wv_lb_step_warp_kernel(const int* __restrict__ active, int n_active, const int* __restrict__ nx_of_model,
+                                       int Pstride, int m, WvLbOpts opts, WvLbScalars* sc, double* work, size_t wstride,
+                                       double* x, double* g, const double* __restrict__ f,
+                                       const int* __restrict__ status, int* task) {
+  extern __shared__ double wv_lb_sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int i = blockIdx.x * wpc + warp;
+  if (i >= n_active) return;
+  const int b = active[i];
+  const int nsc = (int)(sizeof(WvLbScalars) / sizeof(double));
+  double* sw = wv_lb_sm + (size_t)warp * (wstride + 2 * Pstride + nsc);
+  double* sx = sw + wstride;
+  double* sg = sx + Pstride;
+  double* ssc = sg + Pstride;
+  double* gw = work + (size_t)b * wstride;
+  double* gx = x + (size_t)b * Pstride;
+  double* gg = g + (size_t)b * Pstride;
+  double* gsc = reinterpret_cast<double*>(sc + b);
+  for (size_t k = lane; k < wstride; k += 32) sw[k] = gw[k];
+  for (int k = lane; k < Pstride; k += 32) { sx[k] = gx[k]; sg[k] = gg[k]; }
+  for (int k = lane; k < nsc; k += 32) ssc[k] = gsc[k];
+  __syncwarp();
+  if (lane == 0) {
+    WvLbScalars* ls = reinterpret_cast<WvLbScalars*>(ssc);
+    WvLbState L;
+    L.bind(ls, sx, sg, sw, nx_of_model[b], m);
+    double fb = f[b];
+    bool run = true;
+    if (status[b] & WV_STATUS_CHOL_FAIL) {
+      if (opts.chol_fail_policy == 1 || ls->first) {
+        task[b] = WV_LB_CHOLFAIL;
+        run = false;
+      } else {
+        fb = nan("");
+        for (int k = 0; k < L.P; ++k) L.g[k] = fb;
+      }
+    }
+    if (run) task[b] = wv_lb_step(L, opts, fb);
+  }
+  __syncwarp();
+  for (size_t k = lane; k < wstride; k += 32) gw[k] = sw[k];
+  for (int k = lane; k < Pstride; k += 32) { gx[k] = sx[k]; gg[k] = sg[k]; }
+  for (int k = lane; k < nsc; k += 32) gsc[k] = ssc[k];
+}
+
 // ordered compaction of the models that still need an evaluation (single CTA, warp ballots)
 __global__ void wv_compact_kernel(const int* __restrict__ task, int B, int* out, int* count) {
   __shared__ int warp_tot[32];
@@ -673,8 +722,17 @@ extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o
   const long guard_max = (long)o->maxfun + (long)o->maxiter + 1000;
   while (n_active > 0) {
     if (wv_eval_all(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status, cur, n_active) != 0) return -1;
-    wv_lb_step_kernel<<<(n_active + tb - 1) / tb, tb, 0, st>>>(cur, n_active, d_nx, P, m, opts, b->d_lbs, b->d_lbw,
-                                                              wstride, b->d_x, b->d_g, b->d_f, b->d_status, b->d_task);
+    {
+      static_assert(sizeof(WvLbScalars) % sizeof(double) == 0, "WvLbScalars is copied as doubles");
+      const size_t per = (wstride + 2 * (size_t)P + sizeof(WvLbScalars) / sizeof(double)) * sizeof(double);
+      const int wpc = (int)std::min<size_t>(4, (48 * 1024) / per);     // warps (= models) per CTA within 48 KB
+      if (wpc >= 1)
+        wv_lb_step_warp_kernel<<<(n_active + wpc - 1) / wpc, wpc * 32, wpc * per, st>>>(
+            cur, n_active, d_nx, P, m, opts, b->d_lbs, b->d_lbw, wstride, b->d_x, b->d_g, b->d_f, b->d_status, b->d_task);
+      else      // very long memories: the state does not fit, one thread per model on global memory
+        wv_lb_step_kernel<<<(n_active + tb - 1) / tb, tb, 0, st>>>(cur, n_active, d_nx, P, m, opts, b->d_lbs, b->d_lbw,
+                                                                  wstride, b->d_x, b->d_g, b->d_f, b->d_status, b->d_task);
+    }
     wv_compact_kernel<<<1, 1024, 0, st>>>(b->d_task, B, nxt, b->d_count);
     b->prof.mark(WV_K_LBFGS, st);
     b->launches += 2;
