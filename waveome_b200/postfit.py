@@ -218,9 +218,13 @@ def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf"
         y = Y[b]
         lk = dict(likelihood=getattr(m.likelihood, "name", "gaussian"),
                   alpha=float(getattr(m.likelihood, "engine_param", 1.0)) or 1.0)
-        null_lls, mod_lls, sat_lls = calc_deviance_loglik(y, mu[0], **lk)
-        if np.sum(sat_lls) >= np.sum(mod_lls) and np.sum(mod_lls) >= np.sum(null_lls):
-            full_de = 1 - (-2 * np.sum(mod_lls - sat_lls) / (-2 * np.sum(null_lls - sat_lls)))
+        # one vectorised call for the full model and every leave-one-component-out model (rows of mu)
+        null_lls, all_mod_lls, sat_lls = calc_deviance_loglik(y, mu, **lk)
+        null_sum, sat_sum = np.sum(null_lls), np.sum(sat_lls)
+        mod_sums = np.sum(np.atleast_2d(all_mod_lls), axis=-1)
+        mod_sum = mod_sums[0]
+        if sat_sum >= mod_sum and mod_sum >= null_sum:
+            full_de = 1 - (-2 * (mod_sum - sat_sum) / (-2 * (null_sum - sat_sum)))
             full_de = max(min(1, full_de), 0)
         else:
             full_de = 0
@@ -228,22 +232,22 @@ def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf"
         k = m.kernel
         if k.name == "sum":
             for k_idx in range(len(k.kernels)):
-                null_lls_k, sub_mod_lls, _ = calc_deviance_loglik(y, mu[1 + k_idx], **lk)
+                sub_sum = mod_sums[1 + k_idx]
                 if return_value == "statistic":
-                    scaled = max(np.round(-2 * (np.sum(sub_mod_lls) - np.sum(mod_lls)), 1), 0)
+                    scaled = max(np.round(-2 * (sub_sum - mod_sum), 1), 0)
                 elif return_value == "log_bf":
-                    scaled = np.round(np.sum(mod_lls) - np.sum(sub_mod_lls), 1)
+                    scaled = np.round(mod_sum - sub_sum, 1)
                 else:
-                    scaled = 1 - (-2 * np.sum(sub_mod_lls - mod_lls) / (-2 * np.sum(null_lls_k - mod_lls)))
+                    scaled = 1 - (-2 * (sub_sum - mod_sum) / (-2 * (null_sum - mod_sum)))
                     scaled = np.round(max(min(1, scaled), 0), 3)
                 de_list.append(float(scaled))
         elif k.name == "constant":
             de_list.append(0.0)
         else:
             if return_value == "statistic":
-                de_list.append(float(np.round(-2 * (np.sum(null_lls) - np.sum(mod_lls)), 1)))
+                de_list.append(float(np.round(-2 * (null_sum - mod_sum), 1)))
             elif return_value == "log_bf":
-                de_list.append(float(np.round(np.sum(mod_lls) - np.sum(null_lls), 1)))
+                de_list.append(float(np.round(mod_sum - null_sum, 1)))
             else:
                 de_list.append(float(np.round(full_de, 3)))
         de_list.append(float(np.round(1 - full_de, 3)))
