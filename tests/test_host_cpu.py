@@ -140,3 +140,22 @@ def test_models_survive_pickle_and_deepcopy():
             assert m2.kernel_name == m.kernel_name and m2.program().signature() == m.program().signature()
             assert m2.kernel is not m.kernel and m2.likelihood is not m.likelihood
         assert K.deepcopy(m.kernel).to_spec() == m.kernel.to_spec()
+
+
+def test_likelihood_key_ignores_trained_parameters():
+    """Fitted models with individual (trainable) dispersions must share one engine batch in the post-fit passes; a frozen
+    likelihood parameter is a batch-level value and does enter the key."""
+    from waveome_b200.model_fitting import likelihood_key
+    from waveome_b200.models import NegativeBinomial, ZeroInflatedNegativeBinomial, make_likelihood
+    import waveome_b200 as wb
+    k = wb.SquaredExponential(active_dims=[0])
+    a = wb.GPR(k, likelihood=NegativeBinomial(alpha=0.3))
+    b = wb.GPR(k, likelihood=NegativeBinomial(alpha=2.5))
+    assert likelihood_key(a) == likelihood_key(b) == ("negative_binomial", 1.0)
+    c = wb.GPR(k, likelihood=NegativeBinomial(alpha=2.5, trainable=False))
+    assert likelihood_key(c) == ("negative_binomial", 2.5)
+    z1 = wb.GPR(k, likelihood=ZeroInflatedNegativeBinomial(alpha=0.3, km=2.0))
+    z2 = wb.GPR(k, likelihood=ZeroInflatedNegativeBinomial(alpha=0.9, km=0.5))
+    assert likelihood_key(z1) == likelihood_key(z2)
+    assert likelihood_key(wb.GPR(k, likelihood=make_likelihood("poisson"))) == ("poisson", 0.0)
+    assert likelihood_key(wb.GPR(k)) == ("gaussian", 0.0)

@@ -49,7 +49,7 @@ struct wv_engine {
   size_t cache_bytes = 0;
 };
 static const size_t WV_CACHE_SMALL_BYTES = (size_t)1 << 20;      // below: power-of-two bins
-static const size_t WV_CACHE_MAX_ENTRIES = 256;
+static const size_t WV_CACHE_MAX_ENTRIES = 4096;    // small buffers are cheap to keep; evicting costs a device-wide sync
 static const size_t WV_CACHE_MAX_BYTES = (size_t)110 << 30;      // of 180 GB; a failed cudaMalloc flushes the cache anyway
 
 static void wv_cache_flush(wv_engine* e) {

@@ -32,12 +32,16 @@ def get_engine(device: Optional[int] = None):
 
 def likelihood_key(model) -> tuple:
     """(engine likelihood name, parameter) of a model: ("gaussian", 0.0), ("poisson", 0.0), ("negative_binomial", alpha),
-    ("gamma", shape), ("zinb", (alpha, km))."""
+    ("gamma", shape), ("zinb", (alpha, km)).  Models that share a key can share an engine batch.  A TRAINABLE likelihood
+    parameter rides in the model's program (noise slot / second likelihood slot) and the batch-level value is ignored,
+    so it does not enter the key: fitted models with individual dispersions still form one batch."""
     lik = model.likelihood
     name = getattr(lik, "name", "gaussian")
     if name == "gaussian":
         return ("gaussian", 0.0)
     p = getattr(lik, "engine_param", 0.0)
+    if all(q.trainable for q in getattr(lik, "parameters", [])):
+        return (name, (1.0, 1.0) if isinstance(p, tuple) else (1.0 if name in ("negative_binomial", "gamma") else 0.0))
     return (name, tuple(float(v) for v in p) if isinstance(p, tuple) else float(p))
 
 
