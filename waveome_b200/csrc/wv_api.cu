@@ -50,7 +50,7 @@ struct wv_engine {
 };
 static const size_t WV_CACHE_SMALL_BYTES = (size_t)1 << 20;      // below: power-of-two bins
 static const size_t WV_CACHE_MAX_ENTRIES = 4096;    // small buffers are cheap to keep; evicting costs a device-wide sync
-static const size_t WV_CACHE_MAX_BYTES = (size_t)110 << 30;      // of 180 GB; a failed cudaMalloc flushes the cache anyway
+static size_t WV_CACHE_MAX_BYTES = (size_t)110 << 30;      // of 180 GB (env WV_CACHE_MAX_GB); a failed cudaMalloc flushes the cache anyway
 
 static void wv_cache_flush(wv_engine* e) {
   for (auto& c : e->cache) cudaFree(c.second);
@@ -148,6 +148,7 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
   WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_panel, cudaEventDisableTiming));
   WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_bulk, cudaEventDisableTiming));
   if (const char* v = getenv("WV_BIG_NT")) eng->aux.big_nt = atoi(v) > 1 ? atoi(v) : 2;
+  if (const char* v = getenv("WV_CACHE_MAX_GB")) WV_CACHE_MAX_BYTES = (size_t)(atof(v) > 0 ? atof(v) : 0) << 30;
   if (const char* v = getenv("WV_PANEL_TILES")) eng->aux.panel_tiles = atoi(v) > 0 ? atoi(v) : 4;
   {
     cudaDeviceProp prop;
