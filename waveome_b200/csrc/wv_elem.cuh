@@ -6,7 +6,7 @@
 //          dK/dtheta is regenerated from the kernel program, nothing of size n^2 is materialised.
 //
 // Both interpret the flat kernel program (sum of products of leaves).  A CTA stages the program, the constrained
-// parameters, per-leaf constants and the 2^(j/64) table ONCE and then walks WV_ELEM_TPC tiles of the same model; a
+// parameters, per-leaf constants and the 2^(j/64) table ONCE and then walks `tpc` tiles of the same model; a
 // thread owns an MR x 4 micro-tile, a warp a compact (8 MR) x 32 region, so that after the host has sorted the rows by
 // their categorical columns a zero categorical mask usually covers whole warps and the transcendental factors of
 // categorical x numeric products are skipped.  The passes are bound by FP64 issue (one 2^u per squared-exponential
@@ -30,7 +30,13 @@
 #undef WV_ELEM_THREADS
 #define WV_ELEM_THREADS (WV_NB * WV_NB / WV_ELEM_NE)        // 256
 #define WV_ELEM_WARPS (WV_ELEM_THREADS / 32)
-#define WV_ELEM_TPC 4                                       // tiles walked by one CTA
+// Tiles walked by one CTA (it stages the model once): chosen per launch, 8 when the launch has work for many waves
+// (staging is ~4 % of the Gram pass at 4 tiles), down to 1 when few models are active and parallelism matters more.
+#define WV_ELEM_TPC_MAX 8
+__host__ inline int wv_elem_tpc(long total_tiles) {
+  long t = total_tiles / 2400;      // aim at >= ~8 CTAs per resident slot (148 SMs x 2)
+  return (int)(t < 1 ? 1 : (t > WV_ELEM_TPC_MAX ? WV_ELEM_TPC_MAX : t));
+}
 
 struct WvElemSmem {
   int n_comp, n_leaves, n_slots, noise_slot, mean_slot, n_dims;
@@ -364,11 +370,11 @@ __device__ __forceinline__ void wv_elem_eval_kernel_tree(const WvElemSmem& sm, i
 }
 
 // =============================================================================================
-// gram.  grid (ceil(n_lower_tiles / WV_ELEM_TPC), n_active), WV_ELEM_THREADS threads.
+// gram.  grid (ceil(n_lower_tiles / tpc), n_active), WV_ELEM_THREADS threads.
 // Algorithmic traffic: 8 n^2 bytes written (lower tiles actually written: ~4 n^2).
 // =============================================================================================
 __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_gram_kernel(WvBatchDev bd, const int* __restrict__ active,
-                                                                     const double* __restrict__ xall, int ntiles) {
+                                                                     const double* __restrict__ xall, int ntiles, int tpc) {
   WvElemSmem& sm = *reinterpret_cast<WvElemSmem*>(wv_smem_raw);
   const int b = active[blockIdx.y];
   wv_elem_stage_model(bd, b, xall, sm);
@@ -378,8 +384,8 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_gram_kernel(
   // variational path: the "observations" are the Gaussian sites (mean eta/lam, noise variance jitter + 1/lam)
   const double* lam = bd.site_lam ? bd.site_lam + (size_t)b * bd.npad : nullptr;
   const double* eta = bd.site_eta ? bd.site_eta + (size_t)b * bd.npad : nullptr;
-  const int t1 = min(ntiles, (int)(blockIdx.x + 1) * WV_ELEM_TPC);
-  for (int t = blockIdx.x * WV_ELEM_TPC; t < t1; ++t) {
+  const int t1 = min(ntiles, (int)(blockIdx.x + 1) * tpc);
+  for (int t = blockIdx.x * tpc; t < t1; ++t) {
     int ti, tj;
     wv_tile_from_linear(t, ti, tj);
     wv_elem_stage_tile(bd, ti, tj, sm);
@@ -412,11 +418,11 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAM_MINB) wv_gram_kernel(
 }
 
 // =============================================================================================
-// grad.  grid (ceil(n_lower_tiles / WV_ELEM_TPC), n_active), WV_ELEM_THREADS threads.
+// grad.  grid (ceil(n_lower_tiles / tpc), n_active), WV_ELEM_THREADS threads.
 //   wgt = 2 below the diagonal, 1 on it, 0 above / outside [0,n).  Algorithmic traffic: 8 n^2 bytes read.
 // =============================================================================================
 __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAD_MINB) wv_grad_kernel(WvBatchDev bd, const int* __restrict__ active,
-                                                                     const double* __restrict__ xall, int ntiles) {
+                                                                     const double* __restrict__ xall, int ntiles, int tpc) {
   WvElemSmem& sm = *reinterpret_cast<WvElemSmem*>(wv_smem_raw);
   const int b = active[blockIdx.y];
   wv_elem_stage_model(bd, b, xall, sm);
@@ -424,8 +430,8 @@ __global__ void __launch_bounds__(WV_ELEM_THREADS, WV_GRAD_MINB) wv_grad_kernel(
   const int n = bd.n, ld = bd.npad;
   const double* Kb = bd.A + (size_t)b * ld * ld;
   const double* al = bd.alpha + (size_t)b * ld;
-  const int t1 = min(ntiles, (int)(blockIdx.x + 1) * WV_ELEM_TPC);
-  for (int t = blockIdx.x * WV_ELEM_TPC; t < t1; ++t) {
+  const int t1 = min(ntiles, (int)(blockIdx.x + 1) * tpc);
+  for (int t = blockIdx.x * tpc; t < t1; ++t) {
     int ti, tj;
     wv_tile_from_linear(t, ti, tj);
     wv_elem_stage_tile(bd, ti, tj, sm);

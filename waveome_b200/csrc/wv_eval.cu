@@ -1183,8 +1183,9 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
   const int nt = bd.nt;
   const int ntiles = nt * (nt + 1) / 2;
   pf->mark(-1, st);
-  wv_gram_kernel<<<dim3((ntiles + WV_ELEM_TPC - 1) / WV_ELEM_TPC, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
-      bd, d_active, d_x, ntiles);
+  const int tpc = wv_elem_tpc((long)ntiles * n_active);
+  wv_gram_kernel<<<dim3((ntiles + tpc - 1) / tpc, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
+      bd, d_active, d_x, ntiles, tpc);
   pf->mark(WV_K_GRAM, st);
   ++launches;
   if (aux->side && nt >= aux->big_nt) {
@@ -1213,8 +1214,9 @@ int wv_enqueue_grad_finalize(const WvBatchDev& bd, const int* d_active, int n_ac
   if (n_active <= 0) return 0;
   const int nt = bd.nt;
   const int ntiles = nt * (nt + 1) / 2;
-  wv_grad_kernel<<<dim3((ntiles + WV_ELEM_TPC - 1) / WV_ELEM_TPC, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
-      bd, d_active, d_x, ntiles);
+  const int tpc = wv_elem_tpc((long)ntiles * n_active);
+  wv_grad_kernel<<<dim3((ntiles + tpc - 1) / tpc, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
+      bd, d_active, d_x, ntiles, tpc);
   pf->mark(WV_K_GRAD, st);
   wv_finalize_kernel<<<dim3(n_active), ntiles > 128 ? 64 * WV_FIN_MAXG : 64, 0, st>>>(bd, d_active, d_x, ntiles, d_f, d_g,
                                                                                   d_lml, d_status);
