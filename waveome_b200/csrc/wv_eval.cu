@@ -528,6 +528,19 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_trtri_kernel(WvBatchDev bd
   wv_panel_body<1>(bd, active[blockIdx.y], step, blockIdx.x, 0, 0);
 }
 
+// The whole triangular inverse in ONE launch: the tile rows of Mt = L^{-T} are independent (row j needs L and its own
+// earlier tiles only), so CTA (j, model) walks its row left to right, i = j + 1 .. nt - 1.  The tiles it has just written
+// come back from L2 instead of DRAM and the nt - 1 dependent launches (and their tails) become one.  Heavy rows first
+// (j = 0 has nt - 1 tiles).  grid (nt - 1, n_active), 128 threads.
+__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_trtri_rows_kernel(WvBatchDev bd, const int* __restrict__ active) {
+  const int b = active[blockIdx.y];
+  const int j = blockIdx.x;
+  for (int i = j + 1; i < bd.nt; ++i) {
+    wv_panel_body<1>(bd, b, i, j, 0, 0);
+    __syncthreads();          // the tile just stored is an operand of the next one (block-scope ordering)
+  }
+}
+
 // =============================================================================================
 // extract: alpha_j = -Mt[j][n], quad = |L[n][0:n]|^2 = |L^{-1} d|^2 ; then clear column n of Mt so that
 // kinv = Mt Mt^T excludes the augmented row.  grid (n_active), 256 threads.
@@ -788,6 +801,7 @@ static cudaError_t wv_set_attrs() {
   WV_ATTR(wv_chol_step_kernel, wv_smem_gemm_bytes());
   WV_ATTR(wv_chol_panel_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_trtri_kernel, sizeof(WvPanelSmem));
+  WV_ATTR(wv_trtri_rows_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_kinv_kernel, sizeof(WvGemmSmem));
   WV_ATTR(wv_syrk_kernel, sizeof(WvGemmSmem));
   WV_ATTR(wv_trtri_level_kernel<1>, sizeof(WvGemmSmem));
@@ -1194,10 +1208,16 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
     launches += l;
   } else {
     for (int j = 0; j < nt; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, 0, st, pf, *aux);
-    for (int i = 1; i < nt; ++i) {
-      wv_trtri_kernel<<<dim3(i, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, i);
+    if (aux->trtri_rows && nt > 1) {
+      wv_trtri_rows_kernel<<<dim3(nt - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active);
       pf->mark(WV_K_TRTRI, st);
       ++launches;
+    } else {
+      for (int i = 1; i < nt; ++i) {
+        wv_trtri_kernel<<<dim3(i, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, i);
+        pf->mark(WV_K_TRTRI, st);
+        ++launches;
+      }
     }
   }
   wv_extract_kernel<<<dim3(n_active), 256, 0, st>>>(bd, d_active);

@@ -87,6 +87,7 @@ struct WvAux {
   int big_nt = 16;
   int panel_tiles = 4;       // tile columns per panel of the large-n right-looking Cholesky
   int resident_ctas = 444;   // 3 CTAs x 148 SMs: a Cholesky step is fused into one launch only if it fits
+  int trtri_rows = 0;   // 1: the batched schedule's triangular inverse as one row-wise launch (wv_trtri_rows_kernel)
   int epoch = 0;   // evaluation counter of the engine: the value the diagonal CTAs publish in step_flag
 };
 struct WvProfiler {
