@@ -253,7 +253,15 @@ def vgp_collapsed(model, lik, X, y, x, sites=None, tol=1e-12, maxit=500, rho=1.0
     E, g, h = var_exp(lik, y, m, v)
     logZ = -0.5 * z @ z - np.sum(np.log(np.diag(Lc))) - 0.5 * n * go.LOG2PI
     F = logZ + np.sum(E + 0.5 * np.log(2.0 * np.pi / lam) + 0.5 * lam * ((yt - m) ** 2 + v))
-    out = dict(F=float(F), sites=(lam, eta), m=m, v=v, iters=it, alpha=alpha)
+    # hyper-parameter priors (gpflow log_prior_density; waveome/model_fitting.py:236-242 puts Uniform(0, 10) on the
+    # non-variance kernel parameters of the VGP branches): F stays the bound, f = -(F + log prior) is the MAP objective
+    log_prior, prior_grads = 0.0, []
+    for p in go.trainable_params(spec):
+        lp, dlp = go.prior_logp_and_grad(p.get("prior"), p["value"])
+        log_prior += lp
+        prior_grads.append(dlp)
+    out = dict(F=float(F), log_prior=float(log_prior), f=-(float(F) + float(log_prior)), sites=(lam, eta), m=m, v=v,
+               iters=it, alpha=alpha)
     if want_grad:
         W = np.outer(alpha, alpha) - Ai
         # Sites at the lower precision bound (ZINB only) are not stationary in their variance: at fixed sites
@@ -287,8 +295,8 @@ def vgp_collapsed(model, lik, X, y, x, sites=None, tol=1e-12, maxit=500, rho=1.0
                 dth = float(np.sum(-m - digamma(lik["shape"]) + np.log(y)))
             else:
                 dth = 0.0                      # the Gaussian noise variance does not exist on this path
-            grads.append(dth * go.transform_dtheta_du(p, u))
-        out["grad"] = np.array(grads)
+            grads.append((dth + prior_grads[len(grads)]) * go.transform_dtheta_du(p, u))
+        out["grad"] = np.array(grads)          # d(F + log prior) / du
     return out
 
 
@@ -354,7 +362,8 @@ def predict_y_moments(lik, fm, fv):
 
 def fit(model, lik, X, y, maxiter=50000, maxfun=50000, maxcor=10, ftol=2.220446049250313e-09, gtol=1e-05, maxls=20):
     """What the reference does with this objective: L-BFGS-B (waveome/model_fitting.py:267-281) -- here on the collapsed
-    bound, i.e. over the hyper-parameters only, every evaluation at its optimal q.  Returns dict(x, F, nit, nfev)."""
+    bound, i.e. over the hyper-parameters only, every evaluation at its optimal q.  Returns dict(x, F, f, log_prior, nit,
+    nfev): F the bound at x, f = -(F + log prior) the minimised MAP objective."""
     import scipy.optimize as so
     state = {"sites": None}
 
@@ -365,9 +374,10 @@ def fit(model, lik, X, y, maxiter=50000, maxfun=50000, maxcor=10, ftol=2.2204460
             return float("nan"), np.full(len(x), float("nan"))
         if np.isfinite(r["F"]):
             state["sites"] = r["sites"]
-        return -r["F"], -r["grad"]
+        return r["f"], -r["grad"]
 
     res = so.minimize(fun, go.pack(model), jac=True, method="L-BFGS-B",
                       options=dict(maxiter=maxiter, maxfun=maxfun, maxcor=maxcor, ftol=ftol, gtol=gtol, maxls=maxls))
     r = vgp_collapsed(model, lik, X, y, res.x, sites=state["sites"], rho=0.5, tol=1e-11, maxit=5000, want_grad=False)
-    return dict(x=res.x, F=r["F"], nit=int(res.nit), nfev=int(res.nfev), message=str(res.message))
+    return dict(x=res.x, F=r["F"], f=r["f"], log_prior=r["log_prior"], nit=int(res.nit), nfev=int(res.nfev),
+                message=str(res.message))

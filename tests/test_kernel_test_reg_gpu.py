@@ -1,0 +1,112 @@
+"""kernel_test_reg (waveome/model_fitting.py:16-373) on the engine: best-of-restarts MAP fit -> (model, bic), against the
+same protocol replayed on the CPU oracle (same np.random stream, SciPy L-BFGS-B on oracle/gp_oracle.py or
+oracle/vgp_oracle.py), for the exact-GPR branch (:150-155) and the VGP branches (:163-185)."""
+import copy
+
+import numpy as np
+import pytest
+
+import gp_oracle as go
+import helpers
+import vgp_oracle as vo
+import waveome_b200 as wb
+from waveome_b200 import kernels as K
+from waveome_b200.model_fitting import kernel_test_reg
+from waveome_b200.models import make_likelihood
+
+pytestmark = pytest.mark.gpu
+
+
+def replay_on_oracle(X, y, k, num_restarts, seed, likelihood="gaussian", olik=None, lam=0.0, use_priors=True):
+    """The reference's loop (:55-309) restated for the test: one oracle fit per restart, the np.random draws in the
+    reference's order (kernel trainables, then likelihood trainables: :245-259)."""
+    np.random.seed(seed)
+    best, best_ll, fits = None, -np.inf, []
+    for _ in range(num_restarts):
+        m = wb.GPR(K.deepcopy(k)) if likelihood == "gaussian" else wb.GPR(K.deepcopy(k), likelihood=make_likelihood(likelihood))
+        for name, p in m.parameter_dict().items():
+            if lam > 0 and "kernel" in name and "variance" in name:
+                p.prior = K.Laplace(0.0, 1.0 / lam)
+            if use_priors and "kernel" in name and "variance" not in name:
+                p.prior = K.Uniform(0.0, 10.0)
+        for p in m.kernel.trainable_parameters:
+            p.assign(p.transform_fn(np.random.normal(size=1)))
+        for p in m.likelihood.parameters:
+            if p.trainable:
+                p.assign(p.transform_fn(np.random.normal(size=1)))
+        spec = copy.deepcopy(m.to_spec())
+        if likelihood == "gaussian":
+            r = go.fit(spec, X, y, maxfun=50000)
+            ll = -r["f"]
+        else:
+            r = vo.fit(spec, dict(olik), X, y)      # a trainable Gamma shape is read from the spec's noise slot
+            ll = -r["f"]
+        fits.append(ll)
+        if np.isfinite(ll) and ll > best_ll:
+            best, best_ll = (m, r), ll
+    n_par = len(best[0].trainable_parameters) + (0 if likelihood == "gaussian" else 2)
+    return best, best_ll, round(2 * n_par - 2 * best_ll, 2), fits
+
+
+def small_kernel():
+    return wb.Sum([wb.Categorical(active_dims=[0]), wb.SquaredExponential(active_dims=[1]),
+                   wb.Product([wb.Categorical(active_dims=[3]), wb.Matern32(active_dims=[2])])])
+
+
+@pytest.mark.parametrize("lam", [0.0, 2.0])
+def test_gaussian_branch_matches_the_replayed_protocol(engine, lam):
+    X, y = helpers.make_data(120, seed=21)
+    k = small_kernel()
+    m, bic = kernel_test_reg(X, y.reshape(-1, 1), k, num_restarts=4, random_seed=11, lam=lam, engine=engine)
+    (mo, ro), ll, bic_o, fits = replay_on_oracle(X, y, k, 4, 11, lam=lam)
+    assert m is not None and m.data is None
+    # the caller's kernel is untouched (deep copies per restart, :52)
+    assert float(k.kernels[1].lengthscales) == 1.0
+    assert abs(m.log_posterior_density() - ll) <= 1e-5 * max(1.0, abs(ll)), (m.log_posterior_density(), ll, fits)
+    assert abs(bic - bic_o) <= 0.021, (bic, bic_o)
+    # BIC = round(2k - 2 log p, 2) with k = trainable Parameter objects (kernel 5 + noise; the mean is Zero)
+    assert len(m.trainable_parameters) == 6
+    assert bic == round(2 * 6 - 2 * m.log_posterior_density(), 2)
+    # lengthscales carry Uniform(0, 10) priors, variances Laplace(0, 1/lam) when lam > 0 (:198-242)
+    d = m.parameter_dict()
+    assert all(p.prior is not None for name, p in d.items() if "kernel" in name and "variance" not in name)
+    assert all((p.prior is not None) == (lam > 0) for name, p in d.items() if "kernel" in name and "variance" in name)
+
+
+def test_failure_convention_and_keep_data(engine):
+    X, y = helpers.make_data(60, seed=4)
+    k = wb.SquaredExponential(active_dims=[1])
+    bad = y.copy()
+    bad[3] = np.nan                                   # every restart is non-finite at its start point
+    m, bic = kernel_test_reg(X, bad, k, num_restarts=2, random_seed=1, engine=engine)
+    assert m is None and bic == np.inf                # (None, -1 * -inf), :333-334
+    m, bic = kernel_test_reg(X, y, k, num_restarts=1, random_init=False, keep_data=True, engine=engine)
+    assert m.data[0].shape == X.shape and m.data[1].shape == (60, 1) and np.isfinite(bic)
+    mu, var = m.predict_y(X[:5])
+    assert mu.shape == (5, 1) and np.all(var > 0)
+    with pytest.raises(NotImplementedError):
+        kernel_test_reg(X, y, k, lasso=True, engine=engine)
+    with pytest.raises(NotImplementedError):
+        kernel_test_reg(X, y, k, likelihood="exponential", engine=engine)
+
+
+@pytest.mark.parametrize("lik,olik", [("poisson", {"type": "poisson"}), ("bernoulli", {"type": "bernoulli"}),
+                                      ("gamma", {"type": "gamma", "shape": 1.0})])
+def test_vgp_branches_match_the_replayed_protocol(engine, lik, olik):
+    rng = np.random.default_rng(17)
+    n = 90
+    subj = rng.integers(0, 12, size=n).astype(float)
+    t = rng.normal(size=n)
+    X = np.stack([subj, t], 1)
+    f = 0.5 * rng.normal(size=12)[subj.astype(int)] + np.sin(2 * t)
+    y = {"poisson": lambda: rng.poisson(np.exp(f + 0.5)).astype(float),
+         "bernoulli": lambda: (rng.uniform(size=n) < 0.5 * (1 + np.tanh(f))).astype(float),
+         "gamma": lambda: rng.gamma(2.0, np.exp(f))}[lik]()
+    k = wb.Sum([wb.Categorical(active_dims=[0]), wb.SquaredExponential(active_dims=[1])])
+    m, bic = kernel_test_reg(X, y, k, num_restarts=3, random_seed=5, likelihood=lik, engine=engine)
+    (mo, ro), ll, bic_o, fits = replay_on_oracle(X, y, k, 3, 5, likelihood=lik, olik=olik)
+    assert m is not None and m.likelihood.name == lik
+    assert abs(m.log_posterior_density() - ll) <= 1e-5 * max(1.0, abs(ll)), (lik, m.log_posterior_density(), ll, fits)
+    assert abs(bic - bic_o) <= 0.021, (bic, bic_o)
+    n_par = 3 + (1 if lik == "gamma" else 0) + 2        # kernel + likelihood + (q_mu, q_sqrt) of the gpflow VGP
+    assert bic == round(2 * n_par - 2 * m.log_posterior_density(), 2)

@@ -3,8 +3,9 @@
 * ``fit_models``       packs B models that share X into one ``engine.Batch`` and runs the device L-BFGS-B
                        (replaces one Ray task + one ``gpflow.optimizers.Scipy().minimize`` per model:
                        waveome/model_search.py:250-393, waveome/model_fitting.py:276-281)
-* ``kernel_test_reg``  drop-in for waveome/model_fitting.py:16-373 on the exact-GPR ("gaussian") path:
-                       best-of-restarts MAP fit of one kernel, returns ``(model, bic)``; failure -> ``(None, inf)``.
+* ``kernel_test_reg``  drop-in for waveome/model_fitting.py:16-373 (exact GPR for "gaussian", the VGP branches for
+                       "poisson" / "gamma" / "bernoulli"): best-of-restarts MAP fit of one kernel, returns
+                       ``(model, bic)``; failure -> ``(None, inf)``.
 """
 from __future__ import annotations
 
@@ -13,7 +14,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import kernels as K
-from .models import GPR
+from .models import GPR, make_likelihood
 from .utilities import calc_bic, print_kernel_names
 
 _ENGINES: Dict[int, "object"] = {}
@@ -185,11 +186,15 @@ def fit_replicated(X: np.ndarray, Y: np.ndarray, template: GPR, make_models=None
 def kernel_test_reg(X, Y, k, num_restarts=5, random_init=True, verbose=False, likelihood="gaussian", lasso=False,
                     lam=0, use_priors=True, max_iter=50000, keep_data=False, freeze_variances=False,
                     random_seed=None, engine=None, **unused):
-    """waveome/model_fitting.py:16-373 on the exact-GPR path.  The ``num_restarts`` restarts are one device
-    batch (same y, different starts) instead of a Python loop."""
-    if likelihood != "gaussian" or lasso:
-        raise NotImplementedError("kernel_test_reg on the B200 engine covers likelihood='gaussian', lasso=False "
-                                  "(objective A, SURVEY §0.3); VGP/SVPGPR paths are out of the hot path")
+    """waveome/model_fitting.py:16-373 without the lasso (SVPGPR) branch.  ``likelihood="gaussian"`` is the exact GPR
+    (:150-155); "poisson" / "gamma" / "bernoulli" are the reference's ``gpflow.models.VGP`` branches (:163-185, zero
+    mean), fitted on the engine's collapsed bound max_q ELBO.  The ``num_restarts`` restarts are
+    one device batch (same y, different starts) instead of a Python loop."""
+    vgp_likelihoods = ("poisson", "gamma", "bernoulli")
+    if lasso or likelihood not in ("gaussian",) + vgp_likelihoods:
+        raise NotImplementedError("kernel_test_reg on the B200 engine covers likelihood='gaussian' (exact GPR) and "
+                                  "'poisson' / 'gamma' / 'bernoulli' (VGP) with lasso=False; the SVPGPR (lasso) and "
+                                  "'exponential' branches are not on the engine")
     from .utilities import freeze_variance_parameters
     X = np.asarray(X, dtype=np.float64)
     Y = np.asarray(Y, dtype=np.float64).reshape(-1)
@@ -197,7 +202,10 @@ def kernel_test_reg(X, Y, k, num_restarts=5, random_init=True, verbose=False, li
         np.random.seed(random_seed)
     models = []
     for _ in range(num_restarts):
-        m = GPR(K.deepcopy(k))                      # Zero mean, noise variance 1.0 (reference :151-155)
+        if likelihood == "gaussian":
+            m = GPR(K.deepcopy(k))                  # Zero mean, noise variance 1.0 (reference :151-155)
+        else:
+            m = GPR(K.deepcopy(k), likelihood=make_likelihood(likelihood))   # VGP, zero mean (:163-185)
         if freeze_variances:
             freeze_variance_parameters(m.kernel)
         if lam > 0:
@@ -226,7 +234,10 @@ def kernel_test_reg(X, Y, k, num_restarts=5, random_init=True, verbose=False, li
             best_loglik, best_model = cur, m
     if best_model is None:
         return None, -1 * best_loglik
-    bic = round(calc_bic(loglik=best_loglik, n=X.shape[0], k=len(best_model.trainable_parameters)), 2)
+    # :353-361: k = number of trainable Parameter objects; a gpflow VGP also carries q_mu and q_sqrt, which the
+    # collapsed bound has maximised out
+    n_par = len(best_model.trainable_parameters) + (2 if likelihood in vgp_likelihoods else 0)
+    bic = round(calc_bic(loglik=best_loglik, n=X.shape[0], k=n_par), 2)
     if verbose:
         print(f"Model: {print_kernel_names(k)}, BIC: {bic}")
     best_model.data = (X, Y.reshape(-1, 1)) if keep_data else None
