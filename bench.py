@@ -322,7 +322,13 @@ def main():
             if prof["chol_diag"][0] + prof["chol_panel"][0] else None,
             "trtri": float(n) ** 3 / 3 * model_evals / (prof["trtri"][0] * 1e-3) / 1e12 if prof["trtri"][0] else None,
             "kinv": float(n) ** 3 / 3 * model_evals / (prof["kinv"][0] * 1e-3) / 1e12 if prof["kinv"][0] else None},
+        # element-wise passes against HBM: algorithmic 8 n^2 (K written / W read once) + 8 n D bytes per model evaluation
+        # (the kernels touch the lower tiles only, i.e. move ~0.6x of it), over the class's own time
+        "class_hbm_gbs": {k: (8.0 * n * n + 8.0 * n * 5) * model_evals / (prof[k][0] * 1e-3) / 1e9 if prof[k][0] else None
+                          for k in ("gram", "grad")},
+        "hbm_peak_gbs": peaks["hbm_gbs"],
     }
+    groups["class_hbm_frac"] = {k: (v / peaks["hbm_gbs"] if v else None) for k, v in groups["class_hbm_gbs"].items()}
 
     if rank != 0:
         if world > 1:

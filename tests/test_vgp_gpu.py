@@ -154,6 +154,39 @@ def test_penalized_optimization_poisson_config5_shape():
         assert all(np.isfinite(v) for v in m.feature_importances)
 
 
+def test_predictive_variance_and_iterated_factor_for_counts(engine):
+    """penalization_factor=None (waveome/model_search.py:271-375) with a count likelihood: the factor iteration reads
+    sqrt(mean(predict_y(X)[1])); predict_y's variance = the likelihood's predict_mean_and_var of the latent posterior,
+    checked against the oracle's q(f) + 20-point Gauss-Hermite moments."""
+    from scipy.stats import norm
+    from waveome_b200 import datasets, postfit
+    from waveome_b200.model_search import GPSearch
+    from waveome_b200.models import make_likelihood
+    X, y = count_data(70, 10, seed=23)
+    for lik, olik in (("poisson", {"type": "poisson"}), ("negative_binomial", {"type": "negative_binomial", "alpha": 1.0})):
+        m = count_model()
+        m.likelihood = make_likelihood(lik)
+        spec = copy.deepcopy(m.to_spec())
+        var_y = postfit.train_predictive_variance(X, y[None, :], [m], engine=engine)[0]
+        r = vo.vgp_collapsed(copy.deepcopy(spec), olik, X, y, go.pack(spec), tol=1e-13, maxit=2000, want_grad=False)
+        ref = vo.predict_y_moments(vo.lik_of(spec, olik), r["m"], r["v"])[1]
+        np.testing.assert_allclose(var_y, ref, rtol=1e-6, atol=1e-9)
+    Xd, Yd = datasets.count_microbiome(n_outcomes=4, n_subjects=12, n_times=6)
+    gps = GPSearch(Xd, Yd, unit_col="subject", outcome_likelihood="poisson")
+    gps.penalized_optimization(penalization_factor=None, num_factor_iter=2)
+    assert gps.iterating_penalization_factor is True
+    from waveome_b200.regularization import full_kernel_build
+    from waveome_b200.utilities import find_variance_components
+    fk, _ = full_kernel_build(cat_vars=gps.cat_idx, num_vars=gps.cont_idx, unit_idx=gps.unit_idx, var_names=gps.feat_names,
+                              return_sum=True, second_order_numeric=False, categorical_numeric_interactions=True,
+                              unit_numeric_interactions=False, kerns=[wb.SquaredExponential()])
+    p = len(find_variance_components(fk, sum_reduce=False))
+    for o, m in gps.models.items():
+        start = 2 * 1.1 * np.std(gps.Y[o].to_numpy()) * np.sqrt(len(gps.X)) * norm().ppf(1 - 0.1 / (2 * p))
+        assert m.likelihood.name == "poisson" and 0 < m.penalization_factor <= start + 1e-9
+        assert np.isfinite(m.log_posterior_density_value)
+
+
 def other_data(n, n_subj, seed, lik):
     rng = np.random.default_rng(seed)
     subj = rng.integers(0, n_subj, size=n).astype(float)

@@ -109,8 +109,6 @@ class GPSearch:
         outcomes are sharded over ranks with no collective on the data path; with ``gather=True`` the fitted
         models are exchanged afterwards so every rank holds ``self.models`` for all outcomes."""
         make_likelihood(self.likelihood)              # raises for likelihoods the engine does not cover
-        if penalization_factor is None and self.likelihood != "gaussian":
-            raise NotImplementedError("penalization_factor=None iterates on predict_y variances: Gaussian outcomes only")
         self.model_selection_type = "penalized"
         if random_seed is not None:
             np.random.seed(random_seed)
@@ -201,7 +199,8 @@ class GPSearch:
         for b in range(len(names)):
             sigma_hat = 1 if num_factor_iter == 0 else float(np.std(Yn[b]))
             models.append(PenalizedGPR(K.deepcopy(full_kernel), mean_function=K.deepcopy(mean_function),
-                                       penalization_factor=2 * 1.1 * sigma_hat * np.sqrt(n) * z))
+                                       penalization_factor=2 * 1.1 * sigma_hat * np.sqrt(n) * z,
+                                       likelihood=make_likelihood(self.likelihood)))
         res = fit_models(Xn, Yn, models, maxiter=num_opt_iter, maxfun=num_opt_iter)
         active = list(range(len(models)))
         for _ in range(int(num_factor_iter)):
@@ -223,7 +222,6 @@ class GPSearch:
                 r = fit_models(Xn, Yn[active], [models[b] for b in active], maxiter=num_opt_iter, maxfun=num_opt_iter)
                 for key in ("f", "lml", "n_iter", "n_eval", "status"):
                     res[key][active] = r[key]
-                res["n_eval"] = res["n_eval"]
         self.iterating_penalization_factor = True
         return res, models
 

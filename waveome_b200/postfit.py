@@ -155,10 +155,12 @@ def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], masks: Opt
 
 
 def train_predictive_variance(X, Y, models: Sequence[GPR], engine=None, max_batch_bytes: float = 60e9) -> np.ndarray:
-    """``predict_y(X)[1]`` of gpflow GPR at the training inputs for B Gaussian models, [B, n]:
-    var f_i = sigma^2 - sigma^4 diag((K + sigma^2 I)^-1)_i, var y_i = var f_i + sigma^2."""
+    """``predict_y(X)[1]`` at the training inputs for B models, [B, n] (what ``penalization_factor=None`` iterates on,
+    waveome/model_search.py:333).  Gaussian (gpflow GPR): var f_i = sigma^2 - sigma^4 diag((K + sigma^2 I)^-1)_i,
+    var y_i = var f_i + sigma^2.  Other likelihoods: the likelihood's ``predict_mean_and_var`` of the latent posterior
+    q(f_i) = N(m_i, v_i) under the converged sites (``likelihood_predict_mean_and_var``)."""
     from .engine import Batch
-    from .model_fitting import get_engine
+    from .model_fitting import get_engine, likelihood_key
     engine = engine or get_engine()
     X = np.ascontiguousarray(X, dtype=np.float64)
     Y = np.ascontiguousarray(Y, dtype=np.float64)
@@ -178,16 +180,28 @@ def train_predictive_variance(X, Y, models: Sequence[GPR], engine=None, max_batc
     npad = ((n + 1 + 7) // 8 * 8 + 63) // 64 * 64
     chunk = max(1, int(max_batch_bytes // (2 * npad * npad * 8 + npad * 64 * 8)))
     out = np.empty((B, n))
-    for lo in range(0, B, chunk):
-        hi = min(B, lo + chunk)
-        batch = Batch(engine, X, Y[lo:hi], table, prog_id[lo:hi], P=P)
-        try:
-            batch.eval(x[lo:hi])
-            d = batch.kinv_diag()
-        finally:
-            batch.close()
-        s2 = np.array([float(m.likelihood.variance) for m in models[lo:hi]])[:, None]
-        out[lo:hi] = (s2 - s2 * s2 * d) + s2
+    groups = {}
+    for b, m in enumerate(models):
+        groups.setdefault(likelihood_key(m), []).append(b)
+    for (lik_name, lik_param), idx in groups.items():
+        idx = np.asarray(idx)
+        for lo in range(0, len(idx), chunk):
+            sel = idx[lo: lo + chunk]
+            batch = Batch(engine, X, Y[sel], table, prog_id[sel], P=P)
+            try:
+                if lik_name != "gaussian":
+                    batch.set_likelihood(lik_name, lik_param)
+                batch.eval(x[sel])
+                if lik_name == "gaussian":
+                    d = batch.kinv_diag()
+                    s2 = np.array([float(models[b].likelihood.variance) for b in sel])[:, None]
+                    out[sel] = (s2 - s2 * s2 * d) + s2
+                else:
+                    fm, fv = batch.latent()
+                    for i, b in enumerate(sel):
+                        out[b] = likelihood_predict_mean_and_var(models[b].likelihood, fm[i], fv[i])[1]
+            finally:
+                batch.close()
     return out
 
 
