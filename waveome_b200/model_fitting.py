@@ -4,7 +4,7 @@
                        (replaces one Ray task + one ``gpflow.optimizers.Scipy().minimize`` per model:
                        waveome/model_search.py:250-393, waveome/model_fitting.py:276-281)
 * ``kernel_test_reg``  drop-in for waveome/model_fitting.py:16-373 (exact GPR for "gaussian", the VGP branches for
-                       "poisson" / "gamma" / "bernoulli"): best-of-restarts MAP fit of one kernel, returns
+                       "exponential" / "poisson" / "gamma" / "bernoulli"): best-of-restarts MAP fit of one kernel, returns
                        ``(model, bic)``; failure -> ``(None, inf)``.
 """
 from __future__ import annotations
@@ -187,14 +187,14 @@ def kernel_test_reg(X, Y, k, num_restarts=5, random_init=True, verbose=False, li
                     lam=0, use_priors=True, max_iter=50000, keep_data=False, freeze_variances=False,
                     random_seed=None, engine=None, **unused):
     """waveome/model_fitting.py:16-373 without the lasso (SVPGPR) branch.  ``likelihood="gaussian"`` is the exact GPR
-    (:150-155); "poisson" / "gamma" / "bernoulli" are the reference's ``gpflow.models.VGP`` branches (:163-185, zero
-    mean), fitted on the engine's collapsed bound max_q ELBO.  The ``num_restarts`` restarts are
+    (:150-155); "exponential" / "poisson" / "gamma" / "bernoulli" are the reference's ``gpflow.models.VGP`` branches
+    (:156-185, zero mean), fitted on the engine's collapsed bound max_q ELBO.  The ``num_restarts`` restarts are
     one device batch (same y, different starts) instead of a Python loop."""
-    vgp_likelihoods = ("poisson", "gamma", "bernoulli")
+    vgp_likelihoods = ("exponential", "poisson", "gamma", "bernoulli")
     if lasso or likelihood not in ("gaussian",) + vgp_likelihoods:
         raise NotImplementedError("kernel_test_reg on the B200 engine covers likelihood='gaussian' (exact GPR) and "
-                                  "'poisson' / 'gamma' / 'bernoulli' (VGP) with lasso=False; the SVPGPR (lasso) and "
-                                  "'exponential' branches are not on the engine")
+                                  "'exponential' / 'poisson' / 'gamma' / 'bernoulli' (VGP) with lasso=False; the "
+                                  "SVPGPR (lasso) branch is not on the engine")
     from .utilities import freeze_variance_parameters
     X = np.asarray(X, dtype=np.float64)
     Y = np.asarray(Y, dtype=np.float64).reshape(-1)

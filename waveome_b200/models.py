@@ -89,6 +89,14 @@ class Gamma:
         return float(self.shape)
 
 
+class Exponential(Gamma):
+    """gpflow.likelihoods.Exponential (exp link, no parameters; waveome/model_fitting.py:156-162): p(y | f) is the Gamma
+    density with shape 1, so it runs as the engine's Gamma likelihood with the shape frozen at 1."""
+
+    def __init__(self):
+        super().__init__(shape=1.0, trainable=False)
+
+
 class ZeroInflatedNegativeBinomial:
     """waveome/likelihoods.py:96-139: NB with dispersion ``alpha`` and structural zeros with probability
     psi = km / (km + exp(f)) (Michaelis-Menten constant ``km``), both positive() parameters.  alpha rides in the
@@ -122,10 +130,12 @@ def make_likelihood(name, **kw):
         return Bernoulli()
     if name == "gamma":
         return Gamma(**kw)
+    if name == "exponential":
+        return Exponential()
     if name in ("zeroinflated_negativebinomial", "zero_inflated_negative_binomial", "zinb"):
         return ZeroInflatedNegativeBinomial(**kw)
     raise NotImplementedError(f"likelihood {name!r} is not covered by the B200 engine "
-                              "(gaussian, poisson, negative_binomial, bernoulli, gamma, zeroinflated_negativebinomial)")
+                              "(gaussian, poisson, negative_binomial, bernoulli, gamma, exponential, zeroinflated_negativebinomial)")
 
 
 class ConstantMean:
