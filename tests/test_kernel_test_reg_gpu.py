@@ -64,9 +64,9 @@ def test_gaussian_branch_matches_the_replayed_protocol(engine, lam):
     assert float(k.kernels[1].lengthscales) == 1.0
     assert abs(m.log_posterior_density() - ll) <= 1e-5 * max(1.0, abs(ll)), (m.log_posterior_density(), ll, fits)
     assert abs(bic - bic_o) <= 0.021, (bic, bic_o)
-    # BIC = round(2k - 2 log p, 2) with k = trainable Parameter objects (kernel 5 + noise; the mean is Zero)
-    assert len(m.trainable_parameters) == 6
-    assert bic == round(2 * 6 - 2 * m.log_posterior_density(), 2)
+    # BIC = round(2k - 2 log p, 2) with k = trainable Parameter objects (kernel 1 + 2 + (1 + 2), noise; the mean is Zero)
+    assert len(m.trainable_parameters) == 7
+    assert bic == round(2 * 7 - 2 * m.log_posterior_density(), 2)
     # lengthscales carry Uniform(0, 10) priors, variances Laplace(0, 1/lam) when lam > 0 (:198-242)
     d = m.parameter_dict()
     assert all(p.prior is not None for name, p in d.items() if "kernel" in name and "variance" not in name)
