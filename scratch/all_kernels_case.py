@@ -1,5 +1,5 @@
-"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck / initcheck):
-batched schedule (evaluation, a short L-BFGS fit, alpha / K^-1 diagonal / predictions, component masks), the large-n
+"""Small invocations of every kernel family in one process (written for compute-sanitizer, which is closed on this
+pool; still a quick all-kernels check): batched schedule (evaluation, a short L-BFGS fit, alpha / K^-1 diagonal / predictions, component masks), the large-n
 schedule forced at a small size, and the site iteration of the count likelihoods.  NumPy only (no torch import)."""
 import sys
 import numpy as np

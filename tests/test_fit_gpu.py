@@ -93,3 +93,38 @@ def test_readme_quickstart_iris_vs_oracle():
         m.update_kernel_name()
         assert got.kernel_name == m.kernel_name, (o, got.kernel_name, m.kernel_name)
         assert len(got.feature_importances) >= 2
+
+
+def test_concurrent_sub_batches_are_bit_identical():
+    """fit_models / fit_replicated split a large group over FIT_STREAMS engines (one CUDA stream and host thread each,
+    one buffer cache per device): the models are independent, so every result is bit-identical to the single-stream fit."""
+    from waveome_b200 import model_fitting as mf
+    X, y = helpers.make_data(100, seed=5)
+    rng = np.random.default_rng(12)
+    B = 600
+    Y = y[None, :] + 0.3 * rng.normal(size=(B, 100))
+    assert mf.split_for_streams(B, 10 ** 6, 4) == [(0, 150), (150, 300), (300, 450), (450, 600)]
+
+    def run(streams, replicated):
+        old, mf.FIT_STREAMS = mf.FIT_STREAMS, streams
+        try:
+            if replicated:
+                template = wb.GPR(helpers.saturated_kernel(hs=0.0), mean_function=wb.ConstantMean(0.0))
+                res, models = mf.fit_replicated(X, Y, template, maxiter=25)
+            else:
+                models = [wb.GPR(helpers.saturated_kernel(hs=0.0) if b % 2 else helpers.all_leaf_kernel(hs=0.0),
+                                 mean_function=wb.ConstantMean(0.0)) for b in range(B)]
+                res = mf.fit_models(X, Y, models, maxiter=25)
+            return res, models
+        finally:
+            mf.FIT_STREAMS = old
+
+    for replicated in (False, True):
+        r1, m1 = run(1, replicated)
+        r4, m4 = run(4, replicated)
+        for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
+            assert np.array_equal(r1[key], r4[key], equal_nan=True), key
+        assert r1["launches"] > 0 and r4["rounds"] >= r1["rounds"]
+        for a, b in zip(m1[:5], m4[:5]):
+            assert [float(p) for p in a.trainable_parameters] == [float(p) for p in b.trainable_parameters]
+    assert len(mf.get_engine_pool(4)) == 4 and mf.get_engine_pool(4)[0] is mf.get_engine()

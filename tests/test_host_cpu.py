@@ -159,3 +159,20 @@ def test_likelihood_key_ignores_trained_parameters():
     assert likelihood_key(z1) == likelihood_key(z2)
     assert likelihood_key(wb.GPR(k, likelihood=make_likelihood("poisson"))) == ("poisson", 0.0)
     assert likelihood_key(wb.GPR(k)) == ("gaussian", 0.0)
+
+
+def test_split_for_streams():
+    """Sub-batches of one fit (model_fitting.split_for_streams): contiguous cover, at most `chunk` models in flight over
+    all streams, no split below MIN_MODELS_PER_STREAM models per piece."""
+    from waveome_b200.model_fitting import MIN_MODELS_PER_STREAM, split_for_streams
+    for n, chunk, streams in [(2000, 9000, 4), (2000, 900, 4), (255, 9000, 4), (256, 9000, 4), (1, 5, 4), (1000, 9000, 1),
+                              (10254, 9000, 4), (513, 100, 8)]:
+        pieces = split_for_streams(n, chunk, streams)
+        assert pieces[0][0] == 0 and pieces[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+        sizes = [hi - lo for lo, hi in pieces]
+        k = max(1, min(streams, n // MIN_MODELS_PER_STREAM))
+        assert max(sizes) * k <= max(chunk, k) or max(sizes) == 1          # k concurrent pieces stay within the chunk
+        if n < 2 * MIN_MODELS_PER_STREAM and n <= chunk:
+            assert pieces == [(0, n)]
+    assert split_for_streams(2000, 9000, 4) == [(0, 500), (500, 1000), (1000, 1500), (1500, 2000)]

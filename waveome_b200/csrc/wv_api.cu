@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -37,34 +38,47 @@ static int wv_fail(const std::string& m) { g_err = m; return -1; }
     if (e_ != cudaSuccess) return wv_fail(std::string(#x) + ": " + cudaGetErrorString(e_));          \
   } while (0)
 
+// Device buffers of destroyed batches, kept for the next batch on the same GPU (oldest first): cudaMalloc / cudaFree of
+// the multi-GB workspaces costs 0.1 - 2 s each and every cudaFree of a small one synchronises the device, which is
+// visible next to a 4 s fit (fit -> post-fit batches, search levels).  Small buffers are binned to powers of two so that
+// batches of different sizes share them.  ONE cache per device, shared by all engines of the process (several engines
+// = several streams fitting sub-batches concurrently, model_fitting.fit_replicated): a buffer enters it only after its
+// batch's stream has been synchronised (wv_batch_destroy), so any engine may take it; a failed cudaMalloc flushes what
+// every engine of the device has parked.
+struct WvDeviceCache {
+  std::mutex mu;
+  std::vector<std::pair<size_t, void*>> cache;
+  size_t cache_bytes = 0;
+  int engines = 0;
+};
+static const int WV_MAX_DEVICES = 64;
+static WvDeviceCache g_dev_cache[WV_MAX_DEVICES];
+
 struct wv_engine {
   int device;
   cudaStream_t stream;
   WvAux aux;   // side stream / events of the large-n look-ahead schedule
-  // Device buffers of destroyed batches, kept for the next batch of the engine (oldest first): cudaMalloc / cudaFree
-  // of the multi-GB workspaces costs 0.1 - 2 s each and every cudaFree of a small one synchronises the device, which is
-  // visible next to a 4 s fit (fit -> post-fit batches, search levels).  Small buffers are binned to powers of two so
-  // that batches of different sizes share them.
-  std::vector<std::pair<size_t, void*>> cache;
-  size_t cache_bytes = 0;
+  WvDeviceCache* dc;
 };
 static const size_t WV_CACHE_SMALL_BYTES = (size_t)1 << 20;      // below: power-of-two bins
 static const size_t WV_CACHE_MAX_ENTRIES = 4096;    // small buffers are cheap to keep; evicting costs a device-wide sync
 static size_t WV_CACHE_MAX_BYTES = (size_t)110 << 30;      // of 180 GB (env WV_CACHE_MAX_GB); a failed cudaMalloc flushes the cache anyway
 
-static void wv_cache_flush(wv_engine* e) {
-  for (auto& c : e->cache) cudaFree(c.second);
-  e->cache.clear();
-  e->cache_bytes = 0;
+static void wv_cache_flush_locked(WvDeviceCache* dc) {
+  for (auto& c : dc->cache) cudaFree(c.second);
+  dc->cache.clear();
+  dc->cache_bytes = 0;
 }
 
 static void wv_cache_put(wv_engine* e, void* p, size_t bytes) {
-  e->cache.push_back({bytes, p});
-  e->cache_bytes += bytes;
-  while (!e->cache.empty() && (e->cache.size() > WV_CACHE_MAX_ENTRIES || e->cache_bytes > WV_CACHE_MAX_BYTES)) {
-    cudaFree(e->cache.front().second);
-    e->cache_bytes -= e->cache.front().first;
-    e->cache.erase(e->cache.begin());
+  WvDeviceCache* dc = e->dc;
+  std::lock_guard<std::mutex> lock(dc->mu);
+  dc->cache.push_back({bytes, p});
+  dc->cache_bytes += bytes;
+  while (!dc->cache.empty() && (dc->cache.size() > WV_CACHE_MAX_ENTRIES || dc->cache_bytes > WV_CACHE_MAX_BYTES)) {
+    cudaFree(dc->cache.front().second);
+    dc->cache_bytes -= dc->cache.front().first;
+    dc->cache.erase(dc->cache.begin());
   }
 }
 
@@ -97,8 +111,10 @@ template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
     while (bin < bytes) bin <<= 1;
     bytes = bin;
   }
-  {        // best fit from the engine's cache (at most 25 % larger than asked)
-    auto& cache = b->eng->cache;
+  {        // best fit from the device's cache (at most 25 % larger than asked)
+    WvDeviceCache* dc = b->eng->dc;
+    std::lock_guard<std::mutex> lock(dc->mu);
+    auto& cache = dc->cache;
     int best = -1;
     for (int i = 0; i < (int)cache.size(); ++i)
       if (cache[i].first >= bytes && cache[i].first <= bytes + bytes / 4 && (best < 0 || cache[i].first < cache[best].first))
@@ -106,15 +122,18 @@ template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
     if (best >= 0) {
       q = cache[best].second;
       bytes = cache[best].first;
-      b->eng->cache_bytes -= bytes;
+      dc->cache_bytes -= bytes;
       cache.erase(cache.begin() + best);
     }
   }
   if (!q) {
     cudaError_t e = cudaMalloc(&q, bytes);
-    if (e != cudaSuccess && !b->eng->cache.empty()) {     // give the cached buffers back and retry
+    if (e != cudaSuccess) {     // give the cached buffers back and retry
       cudaGetLastError();
-      wv_cache_flush(b->eng);
+      {
+        std::lock_guard<std::mutex> lock(b->eng->dc->mu);
+        wv_cache_flush_locked(b->eng->dc);
+      }
       e = cudaMalloc(&q, bytes);
     }
     if (e != cudaSuccess) return wv_fail(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
@@ -137,8 +156,14 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
                    "); waveome_b200 has no CPU fallback");
   if (device < 0 || device >= count) return wv_fail("wv_engine_create: bad device index");
   WV_CUDA(cudaSetDevice(device));
+  if (device >= WV_MAX_DEVICES) return wv_fail("wv_engine_create: device index beyond the cache table");
   wv_engine* eng = new wv_engine();
   eng->device = device;
+  eng->dc = &g_dev_cache[device];
+  {
+    std::lock_guard<std::mutex> lock(eng->dc->mu);
+    ++eng->dc->engines;
+  }
   // the main stream carries the serial chain of the factorisation (diagonal blocks, panels): it gets the highest
   // priority so that its few CTAs are placed ahead of the bulk trailing updates queued on the side stream
   int prio_lo = 0, prio_hi = 0;
@@ -164,7 +189,10 @@ extern "C" void wv_engine_destroy(wv_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  wv_cache_flush(e);
+  {        // the last engine of the device gives the parked buffers back
+    std::lock_guard<std::mutex> lock(e->dc->mu);
+    if (--e->dc->engines == 0) wv_cache_flush_locked(e->dc);
+  }
   cudaStreamDestroy(e->stream);
   if (e->aux.side) cudaStreamDestroy(e->aux.side);
   if (e->aux.ev_panel) cudaEventDestroy(e->aux.ev_panel);

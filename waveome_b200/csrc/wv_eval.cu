@@ -787,10 +787,14 @@ __global__ void __launch_bounds__(64 * WV_FIN_MAXG) wv_finalize_kernel(WvBatchDe
 // =============================================================================================
 static size_t wv_smem_gemm_bytes() { return sizeof(WvPanelSmem) > sizeof(WvDiagSmem) ? sizeof(WvPanelSmem) : sizeof(WvDiagSmem); }
 
-static bool g_attr_done = false;
+// dynamic shared-memory limits are a per-device function attribute; setting them twice (two host threads racing on the
+// first evaluation) is harmless
+static bool g_attr_done[64] = {};
 static cudaError_t wv_set_attrs() {
-  if (g_attr_done) return cudaSuccess;
-  cudaError_t e;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && g_attr_done[dev]) return cudaSuccess;
 #define WV_ATTR(k, bytes) \
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
   if (e != cudaSuccess) return e;
@@ -807,7 +811,7 @@ static cudaError_t wv_set_attrs() {
   WV_ATTR(wv_trtri_level_kernel<1>, sizeof(WvGemmSmem));
   WV_ATTR(wv_trtri_level_kernel<2>, sizeof(WvGemmSmem));
 #undef WV_ATTR
-  g_attr_done = true;
+  if (dev >= 0 && dev < 64) g_attr_done[dev] = true;
   return cudaSuccess;
 }
 
