@@ -235,16 +235,24 @@ def fit_replicated(X: np.ndarray, Y: np.ndarray, template: GPR, make_models=None
     t.start()
     try:
         models = make_models() if make_models is not None else [K.deepcopy(template) for _ in range(B)]
+        packed = [packed_parameters(m) for m in models]        # still behind the device fit
     finally:
         t.join()
     if err:
         raise err[0]
-    for b, m in enumerate(models):
-        for p, u in zip(packed_parameters(m), out["x"][b]):
-            p.assign(p.transform_fn(u))
-        m.log_marginal_likelihood_value = float(out["lml"][b])
-        m.log_posterior_density_value = float(-out["f"][b])
-        m.fit_info = dict(n_iter=int(out["n_iter"][b]), n_eval=int(out["n_eval"][b]), status=int(out["status"][b]))
+    # fitted values: the bijector of every packed position applied to its whole column (all copies share the template's
+    # transforms), then plain stores into the models' Parameter objects
+    values = np.empty((B, len(packed[0]) if packed else 0))
+    for j, p in enumerate(packed_parameters(template)):
+        values[:, j] = p.transform_fn(np.ascontiguousarray(out["x"][:, j]))
+    lml, lpd = out["lml"].tolist(), (-out["f"]).tolist()
+    nit, nev, st = out["n_iter"].tolist(), out["n_eval"].tolist(), out["status"].tolist()
+    for b, (m, ps, row) in enumerate(zip(models, packed, values.tolist())):
+        for p, v in zip(ps, row):
+            p._value = v
+        m.log_marginal_likelihood_value = lml[b]
+        m.log_posterior_density_value = lpd[b]
+        m.fit_info = dict(n_iter=nit[b], n_eval=nev[b], status=st[b])
     return out, models
 
 

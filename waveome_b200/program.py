@@ -93,10 +93,13 @@ class Program:
             p.assign(p.transform_fn(float(u)))
 
     def signature(self) -> tuple:
-        """Hashable identity of everything the device sees (used to share programs in a batch)."""
+        """Hashable identity of everything the device sees (used to share programs in a batch).  The device reads
+        ``slot_fixed`` of FROZEN slots only (trainable values travel in x), so the current values of trainable
+        parameters do not enter: fitted models of one structure share one device program."""
+        frozen_values = np.where(self.slot_xindex < 0, self.slot_fixed, 0.0)
         return tuple(a.tobytes() for a in (
             self.comp_start, self.leaf_type, self.leaf_dim, self.leaf_s_var, self.leaf_s_ls, self.leaf_s_aux,
-            self.leaf_degree, self.slot_transform, self.slot_xindex, self.slot_prior, self.slot_fixed,
+            self.leaf_degree, self.slot_transform, self.slot_xindex, self.slot_prior, frozen_values,
             self.slot_shift, self.slot_pa, self.slot_pb)) + (self.noise_slot, self.mean_slot, self.lik_slot2)
 
 
