@@ -114,7 +114,7 @@ def test_concurrent_sub_batches_are_bit_identical():
             else:
                 models = [wb.GPR(helpers.saturated_kernel(hs=0.0) if b % 2 else helpers.all_leaf_kernel(hs=0.0),
                                  mean_function=wb.ConstantMean(0.0)) for b in range(B)]
-                res = mf.fit_models(X, Y, models, maxiter=25)
+                res = mf.fit_models(X, Y, models, maxiter=25, streams=streams)
             return res, models
         finally:
             mf.FIT_STREAMS = old

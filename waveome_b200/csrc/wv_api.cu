@@ -59,6 +59,10 @@ struct wv_engine {
   cudaStream_t stream;
   WvAux aux;   // side stream / events of the large-n look-ahead schedule
   WvDeviceCache* dc;
+  // pinned scratch for the per-round counters the host reads back (active models, unconverged sites).  Owned by the
+  // engine, not the batch: cudaFreeHost waits for the whole device, which would park a finished sub-batch's host thread
+  // until every other stream has drained.  The batches of an engine are driven by one host thread, one call at a time.
+  int* h_count;
 };
 static const size_t WV_CACHE_SMALL_BYTES = (size_t)1 << 20;      // below: power-of-two bins
 static const size_t WV_CACHE_MAX_ENTRIES = 4096;    // small buffers are cheap to keep; evicting costs a device-wide sync
@@ -92,7 +96,7 @@ struct wv_batch {
   WvLbScalars* d_lbs;
   double* d_lbw;
   int lb_m_alloc;
-  int* h_count;   // pinned
+  int* h_count;   // the engine's pinned counters
   int64_t bytes, launches, rounds, model_evals;
   WvVgpState vgp;         // site-iteration state (variational path), arrays allocated by wv_batch_set_likelihood
   int *d_inner1, *d_inner2;
@@ -172,6 +176,7 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
   WV_CUDA(cudaStreamCreateWithPriority(&eng->aux.side, cudaStreamNonBlocking, prio_lo));
   WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_panel, cudaEventDisableTiming));
   WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_bulk, cudaEventDisableTiming));
+  WV_CUDA(cudaMallocHost((void**)&eng->h_count, 4 * sizeof(int)));
   if (const char* v = getenv("WV_BIG_NT")) eng->aux.big_nt = atoi(v) > 1 ? atoi(v) : 2;
   if (const char* v = getenv("WV_CACHE_MAX_GB")) WV_CACHE_MAX_BYTES = (size_t)(atof(v) > 0 ? atof(v) : 0) << 30;
   if (const char* v = getenv("WV_TRTRI_ROWS")) eng->aux.trtri_rows = atoi(v) != 0;
@@ -197,6 +202,7 @@ extern "C" void wv_engine_destroy(wv_engine* e) {
   if (e->aux.side) cudaStreamDestroy(e->aux.side);
   if (e->aux.ev_panel) cudaEventDestroy(e->aux.ev_panel);
   if (e->aux.ev_bulk) cudaEventDestroy(e->aux.ev_bulk);
+  if (e->h_count) cudaFreeHost(e->h_count);
   delete e;
 }
 
@@ -371,7 +377,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   step(cudaMemsetAsync(dY, 0, B * np * sizeof(double), st));
   step(cudaMemcpy2DAsync(dY, np * sizeof(double), yp.data(), (size_t)d->n * sizeof(double), (size_t)d->n * sizeof(double), B,
                          cudaMemcpyHostToDevice, st));
-  step(cudaMallocHost((void**)&b->h_count, 4 * sizeof(int)));
+  b->h_count = e->h_count;
   step(cudaStreamSynchronize(st));
   if (ce != cudaSuccess) {
     wv_batch_destroy(b);
@@ -387,7 +393,6 @@ extern "C" void wv_batch_destroy(wv_batch* b) {
   cudaStreamSynchronize(b->eng->stream);
   b->prof.destroy();
   for (auto& a : b->allocs) wv_cache_put(b->eng, a.first, a.second);
-  if (b->h_count) cudaFreeHost(b->h_count);
   delete b;
 }
 
