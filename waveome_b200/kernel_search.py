@@ -33,7 +33,7 @@ import numpy as np
 
 from . import kernels as K
 from .models import GPR, ConstantMean
-from .utilities import calc_bic, check_if_model_exists
+from .utilities import calc_bic, canonical_model_name, check_if_model_exists
 
 Candidate = Tuple[str, K.Kernel]                 # (name key, kernel to fit)
 Fitted = Tuple[Optional[GPR], float]             # (model or None if the fit failed, bic)
@@ -66,51 +66,76 @@ def _entry(kernel, model, bic, depth, parent):
     return {"kernel": kernel, "model": model, "bic": bic, "depth": depth, "parent": parent, "try_next": True}
 
 
+def _feature_kernel_names(f, kern_list, cat_vars, depth):
+    """Names of ``set_feature_kernels(f, ...)`` (+ the frozen first-level constant, :2387-2392) without building them."""
+    names = ["categorical"] if f in cat_vars else [x.name for x in kern_list]
+    if f == 0 and depth == 1:
+        names = names + ["constant"]
+    return names
+
+
 def loc_candidates(n_features, kern_list, base_kern=None, base_name=None, cat_vars=(), depth=0, operation="sum",
-                   prev_models=None) -> List[Candidate]:
-    """Candidate kernels of one ``loc_kernel_search`` call (:2347-2558), in the reference's order."""
-    prev_models = list(prev_models) if prev_models is not None else []
+                   prev_models=None, build=True) -> List[Candidate]:
+    """Candidate kernels of one ``loc_kernel_search`` call (:2347-2558), in the reference's order.
+
+    Which candidates exist depends on names only, so kernels are copied and composed only for the candidates that
+    survive the name checks (the reference deep-copies the base for every feature x kernel pair first);
+    ``build=False`` returns the names alone (kernel = None)."""
+    prev_set = {canonical_model_name(y) for y in prev_models} if prev_models is not None else set()
+    cat_vars = list(cat_vars)
     cands: List[Candidate] = []
-    for f in range(n_features):
-        k_list = set_feature_kernels(f, [K.deepcopy(x) for x in kern_list], list(cat_vars))
-        if f == 0 and depth == 1:
-            empty_kernel = K.Constant(variance=1e-6)
-            K.set_trainable(empty_kernel.variance, False)
-            k_list = k_list + [empty_kernel]
-        for k in k_list:
-            k_info = kernel_info(k)
-            if base_kern is None:
-                cands.append((k_info, k))
-                continue
-            base_kern_ = K.deepcopy(base_kern)
-            for p in base_kern_.trainable_parameters:
+    reset = []
+
+    def base_copy():
+        """deepcopy(base_kern) with every trainable parameter back at 1.0 (:2414-2416)"""
+        if not reset:
+            b = K.deepcopy(base_kern)
+            for p in b.trainable_parameters:
                 p.assign(1.0)
-            if operation == "sum":
+            reset.append(b)
+        return K.deepcopy(reset[0])
+
+    for f in range(n_features):
+        k_list: list = []
+
+        def leaf(j):
+            if not k_list:
+                k_list.extend(set_feature_kernels(f, [K.deepcopy(x) for x in kern_list], cat_vars))
+                if f == 0 and depth == 1:
+                    empty_kernel = K.Constant(variance=1e-6)
+                    K.set_trainable(empty_kernel.variance, False)
+                    k_list.append(empty_kernel)
+            return k_list[j]
+
+        for j, kname in enumerate(_feature_kernel_names(f, kern_list, cat_vars, depth)):
+            k_info = kname if kname == "constant" else kname + "[" + str(int(f)) + "]"
+            if base_kern is None:
+                cands.append((k_info, leaf(j) if build else None))
+                continue
+            if operation in ("sum", "product"):
                 if "categorical[" + str(f) + "]" in base_name:
                     continue
-                if base_name < k_info:
-                    k, k_info = K.Sum([base_kern_, k]), base_name + "+" + k_info
-                else:
-                    k, k_info = K.Sum([k, base_kern_]), k_info + "+" + base_name
-                if check_if_model_exists(k_info, prev_models):
+                if operation == "product" and "*" in base_name:               # two-way interactions only
                     continue
-                cands.append((k_info, k))
-            elif operation == "product":
-                if "categorical[" + str(f) + "]" in base_name:
+                sep, node = ("+", K.Sum) if operation == "sum" else ("*", K.Product)
+                base_first = base_name < k_info
+                name = base_name + sep + k_info if base_first else k_info + sep + base_name
+                if canonical_model_name(name) in prev_set:
                     continue
-                if "*" in base_name:               # two-way interactions only
+                if not build:
+                    cands.append((name, None))
                     continue
-                _freeze_new_factor(k)
-                if base_name < k_info:
-                    k, k_info = K.Product([base_kern_, k]), base_name + "*" + k_info
-                else:
-                    k, k_info = K.Product([k, base_kern_]), k_info + "*" + base_name
-                if check_if_model_exists(k_info, prev_models):
-                    continue
-                cands.append((k_info, k))
+                k = leaf(j)
+                if operation == "product":
+                    _freeze_new_factor(k)
+                cands.append((name, node([base_copy(), k]) if base_first else node([k, base_copy()])))
             elif operation == "split_product":
-                _freeze_new_factor(k)
-                cands += prod_kernel_candidates(base_kern_, base_name, k, prev_models)
+                def new_factor(j=j):
+                    k = leaf(j)
+                    _freeze_new_factor(k)
+                    return k
+                cands += _prod_candidates(len(base_kern.kernels), base_name, k_info, f, prev_set,
+                                          base_copy if build else None, new_factor)
             else:
                 raise ValueError(f"unknown operation {operation!r}")
     return cands
@@ -121,9 +146,12 @@ def loc_kernel_search(n_features, kern_list, base_kern=None, base_name=None, cat
     """:2347-2558 as a generator: yields ONE request with every candidate of this call that is not in ``cache``
     (name -> (kernel, (model, bic)) fitted ahead of time), returns the result dict (failed fits drop out, as the
     reference's ``except Exception: None`` does)."""
-    cands = loc_candidates(n_features, kern_list, base_kern, base_name, cat_vars, depth, operation, prev_models)
     parents = "None" if base_kern is None else base_name
     cache = cache if cache is not None else {}
+    cands = loc_candidates(n_features, kern_list, base_kern, base_name, cat_vars, depth, operation, prev_models,
+                           build=not cache)
+    if cache and any(c[0] not in cache for c in cands):       # a fit of the level failed: build what is still missing
+        cands = loc_candidates(n_features, kern_list, base_kern, base_name, cat_vars, depth, operation, prev_models)
     missing = [c for c in cands if c[0] not in cache]
     if missing:
         got = yield missing
@@ -138,33 +166,45 @@ def loc_kernel_search(n_features, kern_list, base_kern=None, base_name=None, cat
     return out
 
 
-def prod_kernel_candidates(base_kernel, base_name, new_kernel, prev_models) -> List[Candidate]:
-    """:2561-2664 — ``new_kernel`` times each additive component of the base.  When the new factor sorts before the
-    component, the reference moves the component's NAME inside the '+'-joined key but leaves the kernel in place;
-    later stages index names and kernels in parallel, so that is kept as it is."""
+def _prod_candidates(n_components, base_name, k_info, f, prev_set, base_copy, new_factor) -> List[Candidate]:
+    """:2561-2664 — the new factor ``k_info`` (on column ``f``) times each additive component of the base.  When the new
+    factor sorts before the component, the reference moves the component's NAME inside the '+'-joined key but leaves
+    the kernel in place; later stages index names and kernels in parallel, so that is kept as it is.
+    ``base_copy()`` -> a fresh copy of the base sum, ``new_factor()`` -> the new factor kernel; ``base_copy=None``
+    returns names only."""
     out: List[Candidate] = []
-    for feat in range(len(base_kernel.kernels)):
-        temp_kernel = K.deepcopy(base_kernel)
+    for feat in range(n_components):
         temp_name = base_name.split("+")
-        k_info = kernel_info(new_kernel)
-        if "categorical[" + str(int(new_kernel.active_dims[0])) + "]" in temp_name[feat]:
+        if "categorical[" + str(int(f)) + "]" in temp_name[feat]:
             continue
         if "*" in temp_name[feat]:
             continue
-        if temp_name[feat] < k_info:
+        comp_first = temp_name[feat] < k_info
+        if comp_first:
             temp_name[feat] = temp_name[feat] + "*" + k_info
-            temp_kernel.kernels[feat] = K.Product([temp_kernel.kernels[feat], new_kernel])
         else:
-            temp_kernel.kernels[feat] = K.Product([new_kernel, temp_kernel.kernels[feat]])
             later = [i for i, x in enumerate(temp_name) if k_info < x]
             new_idx = later[0] if later else len(temp_name) - 1
             cur_component_name = temp_name.pop(feat)
             temp_name.insert(new_idx, k_info + "*" + cur_component_name)
         name = "+".join(temp_name)
-        if check_if_model_exists(name, prev_models):
+        if canonical_model_name(name) in prev_set:
             continue
+        if base_copy is None:
+            out.append((name, None))
+            continue
+        temp_kernel, new_kernel = base_copy(), new_factor()
+        temp_kernel.kernels[feat] = K.Product([temp_kernel.kernels[feat], new_kernel] if comp_first
+                                              else [new_kernel, temp_kernel.kernels[feat]])
         out.append((name, temp_kernel))
     return out
+
+
+def prod_kernel_candidates(base_kernel, base_name, new_kernel, prev_models) -> List[Candidate]:
+    """:2561-2664 with the reference's arguments (``base_kernel``: a sum kernel; ``new_kernel``: the factor)."""
+    return _prod_candidates(len(base_kernel.kernels), base_name, kernel_info(new_kernel), int(new_kernel.active_dims[0]),
+                            {canonical_model_name(y) for y in prev_models}, lambda: K.deepcopy(base_kernel),
+                            lambda: new_kernel)
 
 
 def prod_kernel_creation(base_kernel, base_name, new_kernel, depth, prev_models=()):

@@ -170,6 +170,13 @@ def _fast_copy(obj, memo):
         return memo[oid]
     if obj is None or isinstance(obj, (bool, int, float, str, bytes, np.generic)):
         return obj
+    if type(obj) is Parameter:           # the bulk of every kernel tree: scalar fields + an optional prior object
+        new = object.__new__(Parameter)
+        memo[oid] = new
+        new.__dict__.update(obj.__dict__)
+        if obj.prior is not None:
+            new.prior = _fast_copy(obj.prior, memo)
+        return new
     if isinstance(obj, np.ndarray):
         return obj                       # data arrays are read-only on this path: shared, not duplicated
     if isinstance(obj, list):

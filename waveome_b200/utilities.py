@@ -4,6 +4,8 @@ freeze_variance_parameters (:977-986), find_variance_components (:1012-1062),
 keep_kernel_lengthscale_ (:1136-1153), search_through_kernel_list_ (:1156-1184)."""
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 from . import kernels as K
@@ -14,13 +16,17 @@ def calc_bic(loglik: float, n: int, k: int):
     return 2 * k - 2 * loglik
 
 
+@functools.lru_cache(maxsize=1 << 18)
+def canonical_model_name(model_name: str) -> frozenset:
+    """The form utilities.py:281-307 compares: the SET of '+'-separated terms, each with its characters sorted."""
+    return frozenset("".join(sorted(x)) for x in model_name.split("+"))
+
+
 def check_if_model_exists(model_name, model_list):
-    """Dedup by canonicalised name: split on '+', sort the characters of every term (utilities.py:281-307)."""
-    model_name_split = model_name.split("+")
-    model_list_split = [x.split("+") for x in model_list]
-    model_name_split_ordered = ["".join(sorted(x)) for x in model_name_split]
-    term_diff = [set(model_name_split_ordered) ^ set(["".join(sorted(x)) for x in y]) for y in model_list_split]
-    return set() in term_diff
+    """Dedup by canonicalised name: split on '+', sort the characters of every term, compare as sets
+    (utilities.py:281-307: ``set() in [set(a) ^ set(b) for b in ...]``)."""
+    canon = canonical_model_name(model_name)
+    return any(canon == canonical_model_name(y) for y in model_list)
 
 
 def print_kernel_names(kernel, with_idx=False):
