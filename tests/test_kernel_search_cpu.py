@@ -137,3 +137,35 @@ def test_full_search_with_oracle_fits():
     m = models[best2]["model"]
     assert len(m.trainable_parameters) == 5
     assert models[best2]["bic"] == round(2 * 5 - 2 * m.log_posterior_density_value, 2)
+
+
+def test_pipelined_lockstep_gives_the_same_search():
+    """run_lockstep with outcome groups (one group's batch on the fitter thread while the host advances the other):
+    same candidates, same results, same selected structures as the single-group driver."""
+    import zlib
+    from waveome_b200 import datasets
+    from waveome_b200.model_search import GPSearch
+
+    calls = []
+
+    def fake_fit(requests):
+        calls.append(len(requests))
+        out = []
+        for y, name, kernel in requests:
+            m = ks.candidate_model(kernel)
+            h = zlib.crc32((name + repr(float(y[0]))).encode()) % 10000 / 50.0
+            out.append((m, round(300.0 - 12.0 * min(name.count("+") + name.count("*"), 2) + h, 2)))
+        return out
+
+    X, Y = datasets.overview_synthetic(n_people=6, n_observations=4, n_outcomes=40)
+    res = {}
+    for groups in (1, 2, 3, None):
+        calls.clear()
+        gps = GPSearch(X, Y, unit_col="person_id", categorical_vars=["female"])
+        gps.run_search(max_depth=4, fit=fake_fit, pipeline_groups=groups)
+        res[groups] = ({o: gps.search_info[o]["best_model"] for o in gps.out_names},
+                       {o: sorted((k, v["bic"], v["depth"], v["try_next"]) for k, v in gps.search_info[o]["models"].items())
+                        for o in gps.out_names}, gps.fit_report["n_fits"], sum(calls))
+    for groups in (2, 3, None):
+        assert res[groups] == res[1], groups
+    assert len(set(res[1][0].values())) > 3          # the fake criterion does spread the outcomes over structures

@@ -91,3 +91,23 @@ def test_run_search_poisson_counts():
     m, bic = ks.kernel_test(X.to_numpy(), Y["flat"].to_numpy(), wb.Categorical(active_dims=[0]), likelihood="poisson",
                             num_restart=1)
     assert m.likelihood.name == "poisson" and np.isfinite(bic)
+
+
+def test_pipelined_run_search_matches_single_group():
+    """run_search with two outcome groups (device batch of one group behind the host work of the other, fits on a
+    worker thread) against the single-group driver: fits do not depend on the composition of their batch, so every
+    candidate's BIC and the selected structures are identical."""
+    X, Y = datasets.overview_synthetic(n_people=12, n_observations=5, n_outcomes=36)
+    out = {}
+    for groups in (1, 2):
+        gps = GPSearch(X, Y, unit_col="person_id", categorical_vars=["female"])
+        gps.run_search(kernels=[wb.SquaredExponential(), wb.Lin()], max_depth=3, pipeline_groups=groups)
+        out[groups] = gps
+    a, b = out[1], out[2]
+    assert a.fit_report["n_fits"] == b.fit_report["n_fits"]
+    for o in a.out_names:
+        assert a.search_info[o]["best_model"] == b.search_info[o]["best_model"], o
+        ma, mb = a.search_info[o]["models"], b.search_info[o]["models"]
+        assert list(ma.keys()) == list(mb.keys())
+        assert [v["bic"] for v in ma.values()] == [v["bic"] for v in mb.values()], o
+        np.testing.assert_array_equal(a.models[o].program().x0(), b.models[o].program().x0())

@@ -227,12 +227,15 @@ class GPSearch:
 
     # ------------------------------------------------------------------------------------------
     def run_search(self, kernels=None, max_depth=5, early_stopping=True, prune=True, keep_all=False, metric_diff=6,
-                   num_restart=1, random_seed=None, num_jobs=-1, verbose=False, debug=False, gather=True, fit=None):
+                   num_restart=1, random_seed=None, num_jobs=-1, verbose=False, debug=False, gather=True, fit=None,
+                   pipeline_groups=None):
         """Greedy compositional kernel search per outcome (waveome/model_search.py:1069-1250 -> full_kernel_search
         :2987-3272).  The searches of all outcomes (of this rank's shard) advance in lock-step; at every step the
         candidate kernels they ask for are fitted as ONE engine batch (kernel_search.run_lockstep).
         ``self.models[outcome]`` = best model, ``self.search_info[outcome]`` = {"models", "edges", "best_model"}.
-        ``num_jobs`` is accepted for signature compatibility.  ``fit`` replaces the engine fitter (tests)."""
+        ``num_jobs`` is accepted for signature compatibility.  ``fit`` replaces the engine fitter (tests).
+        ``pipeline_groups``: outcome groups of the lock-step driver (default one; with more, one group's device batch
+        overlaps the other's host work -- same result, measured slower on config 2, see ``kernel_search.run_lockstep``)."""
         from . import kernel_search as ks
         make_likelihood(self.likelihood)              # raises for likelihoods the engine does not cover
         self.model_selection_type = "stepwise"
@@ -260,7 +263,7 @@ class GPSearch:
         gens = {o: ks.full_kernel_search_gen(Xn.shape[1], kernels, cat_vars=self.cat_idx, max_depth=max_depth,
                                              keep_all=keep_all, metric_diff=metric_diff,
                                              early_stopping=early_stopping, prune=prune) for o in names}
-        info = ks.run_lockstep(gens, ys, counted)
+        info = ks.run_lockstep(gens, ys, counted, groups=pipeline_groups)
         local_models, local_info = {}, {}
         for o in names:
             best = info[o]["models"][info[o]["best_model"]]["model"]
