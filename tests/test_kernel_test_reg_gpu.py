@@ -112,3 +112,24 @@ def test_vgp_branches_match_the_replayed_protocol(engine, lik, olik):
     assert abs(bic - bic_o) <= 0.021, (bic, bic_o)
     n_par = 3 + (1 if lik == "gamma" else 0) + 2        # kernel + likelihood + (q_mu, q_sqrt) of the gpflow VGP
     assert bic == round(2 * n_par - 2 * m.log_posterior_density(), 2)
+
+
+def test_split_scores_the_holdout_rows(engine):
+    """split=True (:337-347): the criterion is minus the summed predictive log density of the held-out rows under the
+    best model fitted on the others; checked against the oracle's GPR predictive at the fitted hyper-parameters."""
+    X, y = helpers.make_data(100, seed=13)
+    tr, ho = np.arange(0, 80), np.arange(80, 100)
+    k = wb.Sum([wb.SquaredExponential(active_dims=[1]), wb.Categorical(active_dims=[3])])
+    m, bic = kernel_test_reg(X[tr], y[tr], k, num_restarts=2, random_seed=3, split=True, X_holdout=X[ho],
+                             Y_holdout=y[ho].reshape(-1, 1), engine=engine)
+    spec = copy.deepcopy(m.to_spec())
+    Kall, _ = go.kernel_K_and_grads(spec["kernel"], np.vstack([X[ho], X[tr]]), want_grads=False)
+    s2 = float(m.likelihood.variance)
+    Kss, Ksx, Kxx = Kall[:20, :20], Kall[:20, 20:], Kall[20:, 20:]
+    A = Kxx + s2 * np.eye(80)
+    mu = Ksx @ np.linalg.solve(A, y[tr])
+    var = np.diag(Kss) - np.einsum("ij,ij->i", Ksx, np.linalg.solve(A, Ksx.T).T) + s2
+    ref = -np.sum(-0.5 * (np.log(2 * np.pi) + np.log(var) + (y[ho] - mu) ** 2 / var))
+    assert abs(bic - round(ref, 2)) <= 0.011, (bic, ref)
+    with pytest.raises(ValueError):
+        kernel_test_reg(X[tr], y[tr], k, num_restarts=1, split=True, engine=engine)

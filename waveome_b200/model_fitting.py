@@ -261,12 +261,15 @@ def fit_replicated(X: np.ndarray, Y: np.ndarray, template: GPR, make_models=None
 
 
 def kernel_test_reg(X, Y, k, num_restarts=5, random_init=True, verbose=False, likelihood="gaussian", lasso=False,
-                    lam=0, use_priors=True, max_iter=50000, keep_data=False, freeze_variances=False,
-                    random_seed=None, engine=None, **unused):
+                    lam=0, use_priors=True, max_iter=50000, keep_data=False, X_holdout=None, Y_holdout=None,
+                    split=False, freeze_variances=False, random_seed=None, engine=None, **unused):
     """waveome/model_fitting.py:16-373 without the lasso (SVPGPR) branch.  ``likelihood="gaussian"`` is the exact GPR
     (:150-155); "exponential" / "poisson" / "gamma" / "bernoulli" are the reference's ``gpflow.models.VGP`` branches
     (:156-185, zero mean), fitted on the engine's collapsed bound max_q ELBO.  The ``num_restarts`` restarts are
-    one device batch (same y, different starts) instead of a Python loop."""
+    one device batch (same y, different starts) instead of a Python loop.  ``split=True`` scores the best model on
+    (``X_holdout``, ``Y_holdout``) instead: bic = round(-sum predict_log_density, 2) (:337-347).  The remaining
+    reference arguments (``gam``, ``base_variances``, ``freeze_inducing``, ``num_inducing_points``) belong to the lasso /
+    sparse branches and are ignored."""
     vgp_likelihoods = ("exponential", "poisson", "gamma", "bernoulli")
     if lasso or likelihood not in ("gaussian",) + vgp_likelihoods:
         raise NotImplementedError("kernel_test_reg on the B200 engine covers likelihood='gaussian' (exact GPR) and "
@@ -313,8 +316,15 @@ def kernel_test_reg(X, Y, k, num_restarts=5, random_init=True, verbose=False, li
         return None, -1 * best_loglik
     # :353-361: k = number of trainable Parameter objects; a gpflow VGP also carries q_mu and q_sqrt, which the
     # collapsed bound has maximised out
-    n_par = len(best_model.trainable_parameters) + (2 if likelihood in vgp_likelihoods else 0)
-    bic = round(calc_bic(loglik=best_loglik, n=X.shape[0], k=n_par), 2)
+    if split:
+        if X_holdout is None or Y_holdout is None:
+            raise ValueError("kernel_test_reg(split=True) needs X_holdout and Y_holdout")
+        held_out = best_model.predict_log_density((np.asarray(X_holdout, dtype=np.float64), Y_holdout),
+                                                  data=(X, Y.reshape(-1, 1)))
+        bic = round(-1 * float(np.sum(held_out)), 2)
+    else:
+        n_par = len(best_model.trainable_parameters) + (2 if likelihood in vgp_likelihoods else 0)
+        bic = round(calc_bic(loglik=best_loglik, n=X.shape[0], k=n_par), 2)
     if verbose:
         print(f"Model: {print_kernel_names(k)}, BIC: {bic}")
     best_model.data = (X, Y.reshape(-1, 1)) if keep_data else None
