@@ -183,7 +183,7 @@ def _kernel_and_mean(model, X, x):
 
 
 def vgp_elbo(model, lik, X, y, x, q_mu, q_sqrt):
-    """gpflow.models.VGP.elbo (whitened) + log prior of the hyper-parameters (none on this path by default)."""
+    """gpflow.models.VGP.elbo (whitened), without the log prior of the hyper-parameters (``vgp_collapsed`` reports it)."""
     model, K, c = _kernel_and_mean(model, X, x)
     lik = lik_of(model, lik)
     L = np.linalg.cholesky(K)

@@ -176,3 +176,93 @@ def test_split_for_streams():
         if n < 2 * MIN_MODELS_PER_STREAM and n <= chunk:
             assert pieces == [(0, n)]
     assert split_for_streams(2000, 9000, 4) == [(0, 500), (500, 1000), (1000, 1500), (1500, 2000)]
+
+
+def test_fit_models_reassembles_concurrent_sub_batches(monkeypatch):
+    """Host logic of the concurrent sub-batches without a GPU: ``engine.Batch`` and the engine pool are replaced by
+    fakes; fit_models(streams=4) must hand every model its own row of results whatever piece and thread fitted it,
+    group the models by likelihood, and re-raise a worker's exception on the calling thread."""
+    import threading
+    import time
+    import numpy as np
+    import waveome_b200 as wb
+    from waveome_b200 import engine as E, model_fitting as mf
+    from waveome_b200.models import make_likelihood
+
+    seen = []
+
+    class FakeBatch:
+        def __init__(self, eng, X, Y, table, prog_id=None, P=None):
+            self.eng, self.Y, self.P, self.lik = eng, np.asarray(Y), P, ("gaussian", 0.0)
+            self.B = self.Y.shape[0]
+
+        def set_likelihood(self, name, param):
+            self.lik = (name, param)
+
+        def fit(self, x0=None, **opts):
+            if self.Y[0, 0] < 0:
+                raise RuntimeError("boom")
+            seen.append((self.eng, threading.get_ident(), self.B, self.lik[0]))
+            time.sleep(0.05)                                          # a real fit leaves the other workers time to start
+            tag = self.Y[:, 0]                                        # every model is recognisable by its first y value
+            return dict(x=np.asarray(x0) + tag[:, None], f=-tag, lml=tag.copy(), n_iter=tag.astype(np.int32),
+                        n_eval=(2 * tag).astype(np.int32), status=np.zeros(self.B, np.int32))
+
+        def counters(self):
+            return dict(launches=10, rounds=1, model_evals=self.B)
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(E, "Batch", FakeBatch)
+    monkeypatch.setattr(mf, "get_engine", lambda device=None: "engine0")
+    monkeypatch.setattr(mf, "get_engine_pool", lambda k, device=None: ["engine%d" % i for i in range(k)])
+    B, n = 700, 12
+    X = np.zeros((n, 2))
+    Y = np.zeros((B, n))
+    Y[:, 0] = np.arange(B)
+    models = []
+    for b in range(B):
+        k = wb.SquaredExponential(active_dims=[1]) if b % 3 else wb.Sum([wb.SquaredExponential(active_dims=[1]), wb.Lin(active_dims=[1])])
+        lik = make_likelihood("poisson") if b >= 600 else None
+        models.append(wb.GPR(k, mean_function=wb.ConstantMean(0.0), likelihood=lik))
+    res = mf.fit_models(X, Y, models, streams=4)
+    np.testing.assert_array_equal(res["lml"], np.arange(B))
+    np.testing.assert_array_equal(res["n_eval"], 2 * np.arange(B))
+    for b in (0, 1, 299, 650, 699):
+        assert models[b].log_marginal_likelihood_value == b and models[b].fit_info["n_iter"] == b
+    # 600 Gaussian models -> 4 pieces of 150 on the pool; 100 Poisson models -> one piece (too few to split)
+    assert sorted(s[2] for s in seen) == [100, 150, 150, 150, 150]
+    assert {s[3] for s in seen if s[2] == 100} == {"poisson"} and res["rounds"] == 5 and res["launches"] == 50
+    assert len({s[0] for s in seen}) > 1 or len({s[1] for s in seen}) > 1          # more than one engine / thread took part
+    # default: one stream, everything on the process engine
+    seen.clear()
+    mf.fit_models(X, Y[:600], models[:600])
+    assert [s[2] for s in seen] == [600] and seen[0][0] == "engine0"
+    # a failing piece surfaces as the caller's exception
+    Y[300, 0] = -1.0
+    with pytest.raises(RuntimeError, match="boom"):
+        mf.fit_models(X, Y, models, streams=4)
+
+
+def test_program_signature_ignores_trainable_values():
+    """Models of one structure share one device program whatever their current (trainable) values -- the values travel
+    in x --, while frozen values, priors and structure are part of the identity."""
+    import helpers
+    import waveome_b200 as wb
+    a = wb.GPR(helpers.saturated_kernel(), mean_function=wb.ConstantMean(0.1))
+    b = wb.GPR(helpers.saturated_kernel(), mean_function=wb.ConstantMean(0.3))
+    b.kernel.kernels[2].lengthscales.assign(0.3)
+    b.likelihood.variance.assign(0.2)
+    assert a.program().signature() == b.program().signature()
+    assert not np.array_equal(a.program().x0(), b.program().x0())
+    wb.set_trainable(b.kernel.kernels[2].lengthscales, False)                    # frozen at 0.3
+    assert a.program().signature() != b.program().signature()
+    c = wb.GPR(helpers.saturated_kernel(), mean_function=wb.ConstantMean(0.1))
+    wb.set_trainable(c.kernel.kernels[2].lengthscales, False)
+    c.kernel.kernels[2].lengthscales.assign(0.3)
+    assert b.program().signature() == c.program().signature()
+    c.kernel.kernels[2].lengthscales.assign(0.4)                                 # another frozen value
+    assert b.program().signature() != c.program().signature()
+    d = wb.GPR(helpers.saturated_kernel(hs=2.0), mean_function=wb.ConstantMean(0.1))   # another prior scale
+    assert a.program().signature() != d.program().signature()

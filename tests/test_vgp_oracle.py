@@ -154,3 +154,29 @@ def test_objective_b_collapses_to_objective_a_for_the_gaussian_likelihood():
     for _ in range(5):
         dq, dS = 1e-3 * rng.normal(size=n), 1e-3 * np.tril(rng.normal(size=(n, n)))
         assert vo.vgp_elbo(model, lik, X, y, x, q_mu + dq, q_sqrt + dS) < e
+
+
+def test_collapsed_objective_with_hyperparameter_priors():
+    """MAP objective of the VGP branches (waveome/model_fitting.py:236-242 puts Uniform(0, 10) on the non-variance kernel
+    parameters; penalised models carry horseshoe priors on the variances): f = -(F + log prior), gradient checked by
+    finite differences, and equal to the whitened ELBO + log prior at the optimal q."""
+    model, X, y, x, rng = _setup(seed=3)
+    kerns = model["kernel"]["kernels"]
+    kerns[0]["params"]["variance"]["prior"] = {"type": "horseshoe", "scale": 0.5}
+    kerns[1]["params"]["variance"]["prior"] = {"type": "laplace", "loc": 0.0, "scale": 2.0}
+    kerns[1]["params"]["lengthscales"]["prior"] = {"type": "uniform", "low": 0.0, "high": 10.0}
+    lik = {"type": "poisson"}
+    r = vo.vgp_collapsed(model, lik, X, y, x)
+    assert r["log_prior"] != 0.0 and abs(r["f"] + r["F"] + r["log_prior"]) <= 1e-12 * abs(r["f"])
+    q_mu, q_sqrt = vo.q_from_sites(model, X, y, x, r["sites"])
+    assert abs(vo.vgp_elbo(model, lik, X, y, x, q_mu, q_sqrt) + r["log_prior"] + r["f"]) <= 1e-10 * abs(r["f"])
+    h, fd = 1e-5, []
+    for i in range(len(x)):
+        xp, xm = x.copy(), x.copy()
+        xp[i] += h; xm[i] -= h
+        fd.append((vo.vgp_collapsed(model, lik, X, y, xm, want_grad=False)["f"]
+                   - vo.vgp_collapsed(model, lik, X, y, xp, want_grad=False)["f"]) / (2 * h))
+    np.testing.assert_allclose(r["grad"], fd, rtol=2e-7)
+    # the fit minimises f: it ends at a point where the prior terms are part of the stationarity condition
+    ro = vo.fit(model, lik, X, y)
+    assert abs(ro["f"] + ro["F"] + ro["log_prior"]) <= 1e-12 * abs(ro["f"]) and ro["f"] <= r["f"]
