@@ -169,3 +169,36 @@ def test_pipelined_lockstep_gives_the_same_search():
     for groups in (2, 3, None):
         assert res[groups] == res[1], groups
     assert len(set(res[1][0].values())) > 3          # the fake criterion does spread the outcomes over structures
+
+
+def test_fitter_threads_get_their_own_engines(monkeypatch):
+    """run_lockstep(groups > 1) with WV_SEARCH_FITTERS fitter threads: every fitter thread resolves to its own engine of
+    the device pool (never the process engine, never a shared one), and the pool does not grow from search to search."""
+    import threading
+    import time
+    from waveome_b200 import model_fitting as mf
+    monkeypatch.setenv("WV_SEARCH_FITTERS", "2")
+    monkeypatch.setattr(mf, "get_engine", lambda device=None: "engine0")
+    monkeypatch.setattr(mf, "get_engine_pool", lambda k, device=None: ["engine%d" % i for i in range(k)])
+    used = []
+
+    def fit(requests):
+        used.append((threading.get_ident(), ks._thread_engine()))
+        time.sleep(0.02)
+        return [(None, np.inf)] * len(requests)
+
+    def gen():
+        for _ in range(3):
+            yield [("a", None)]
+        return {}
+
+    assert ks._thread_engine() == "engine0"                     # the calling thread keeps the process engine
+    for _ in range(2):                                          # (thread ids may be reused from one search to the next)
+        used.clear()
+        ks.run_lockstep({o: gen() for o in "abcd"}, {o: np.zeros(3) for o in "abcd"}, fit, groups=4)
+        by_thread = {}
+        for tid, eng in used:
+            by_thread.setdefault(tid, set()).add(eng)
+        assert len(used) == 12 and all(len(v) == 1 for v in by_thread.values())
+        assert {e for _t, e in used} == {"engine1", "engine2"}
+    assert ks._thread_engine() == "engine0"

@@ -414,22 +414,17 @@ def candidate_bic(model: GPR, log_posterior_density: float) -> float:
     return round(calc_bic(loglik=log_posterior_density, n=0, k=len(model.trainable_parameters)), 2)
 
 
-_THREAD_ENGINES: Dict[int, object] = {}
-_THREAD_ENGINES_LOCK = __import__("threading").Lock()
+_FITTER_SLOT = __import__("threading").local()      # .slot = index of a run_lockstep fitter thread (unset elsewhere)
 
 
 def _thread_engine():
-    """The process engine on the main thread, one engine (stream) of the device pool per other thread: an engine is
-    driven by one host thread at a time."""
-    import threading
+    """The process engine, except on a ``run_lockstep`` fitter thread: fitter i drives engine i + 1 of the device pool
+    (an engine is driven by one host thread at a time; the pool is reused by later searches)."""
     from .model_fitting import get_engine, get_engine_pool
-    if threading.current_thread() is threading.main_thread():
+    slot = getattr(_FITTER_SLOT, "slot", None)
+    if slot is None:
         return get_engine()
-    tid = threading.get_ident()
-    with _THREAD_ENGINES_LOCK:
-        if tid not in _THREAD_ENGINES:
-            _THREAD_ENGINES[tid] = get_engine_pool(len(_THREAD_ENGINES) + 2)[-1]
-        return _THREAD_ENGINES[tid]
+    return get_engine_pool(slot + 2)[slot + 1]
 
 
 def engine_fitter(X: np.ndarray, engine=None, num_restart=1, random_seed=None, max_iter=50000,
@@ -518,7 +513,16 @@ def run_lockstep(searches: Dict[str, object], ys: Dict[str, np.ndarray], fit: Ca
             rounds += 1
             advance(0, results)
     else:
-        with ThreadPoolExecutor(max_workers=int(os.environ.get("WV_SEARCH_FITTERS", "1"))) as pool:
+        import itertools
+        import threading
+        slots, slot_lock = itertools.count(), threading.Lock()
+
+        def take_slot():
+            with slot_lock:
+                _FITTER_SLOT.slot = next(slots)
+
+        with ThreadPoolExecutor(max_workers=max(1, int(os.environ.get("WV_SEARCH_FITTERS", "1"))),
+                                initializer=take_slot) as pool:
             pending = deque()
             for g in range(groups):
                 if waiting[g]:
