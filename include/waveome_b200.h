@@ -164,6 +164,21 @@ int wv_batch_predict_mean(wv_batch* b, const double* Xnew, int32_t m, double* me
  * jitter I + diag(1 / lam) (gpflow VGP.predict_f at the optimal q). */
 int wv_batch_predict_f(wv_batch* b, const double* Xnew, int32_t m, double* mean, double* var);
 
+/* Run-time specialised element-wise kernels.  The Gram builder and the gradient reduction normally interpret the flat
+ * kernel program; for a batch whose models all share one program structure the host (waveome_b200/specialize.py) can
+ * generate straight-line CUDA text for that structure.  wv_batch_specialize compiles it with NVRTC for sm_100a (cached
+ * per process under `key`, a hash of the text), loads it and routes the batch's Gram / gradient launches to the two
+ * named kernels (dynamic shared memory sizes as given); src = NULL returns the batch to the interpreter kernels.  Both
+ * paths compute the same quantities (reference: the GPflow kernel-tree ops behind waveome/regularization.py:14-189).
+ * wv_rtc_check only compiles (no GPU needed) and returns the cubin size, or < 0 with the compiler log in `log`. */
+int wv_batch_specialize(wv_batch* b, const char* key, const char* src, const char* gram_name, const char* grad_name,
+                        int32_t gram_smem, int32_t grad_smem);
+int wv_rtc_check(const char* src, char* log, int log_len);
+/* Disk cache of compiled texts (<dir>/<key>.cubin; NULL or "" = none): looked up before NVRTC is invoked, written after.
+ * wv_rtc_precompile_text fills it without a GPU (0 = compiled, 1 = already there). */
+void wv_rtc_set_cache(const char* dir);
+int wv_rtc_precompile_text(const char* key, const char* src);
+
 /* counters since batch creation: kernels launched, batched evaluation rounds, model evaluations */
 void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t* rounds, int64_t* model_evals);
 

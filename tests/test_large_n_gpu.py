@@ -96,3 +96,25 @@ def test_config4_full_size_properties(engine):
     ana = np.sum(g * d, axis=1)
     np.testing.assert_allclose(num, ana, rtol=1e-5)
     batch.close()
+
+
+def test_config4_full_size_vs_oracle(engine):
+    """n = 8192 (BASELINE configs[3]) against the oracle itself: LML and gradient to rel 1e-9.  The NumPy side costs a
+    Cholesky, one triangular inverse and one n^3 product (about a minute on the box's host cores, ~6 GB)."""
+    from waveome_b200 import datasets
+    from waveome_b200.engine import Batch
+    X, Y = datasets.large_gpr(512, 16)
+    Xn = X.to_numpy().copy()
+    Xn[:, 1] = (Xn[:, 1] - Xn[:, 1].mean()) / Xn[:, 1].std()
+    y = Y.to_numpy()[:, 0]
+    model = _config4_model()
+    batch = Batch(engine, Xn, y[None, :], [model.program()])
+    x = batch.x0() + 0.1 * np.random.default_rng(5).normal(size=(1, batch.P))
+    f, g, lml, st = batch.eval(x)
+    batch.close()
+    assert st[0] == 0
+    fo, go, lo, _ = oracle.objective(copy.deepcopy(model.to_spec()), Xn, y, x[0])
+    print("n=8192 lml", lml[0], lo, "rel", abs(lml[0] - lo) / abs(lo), "grad rel", np.max(np.abs(g[0] - go)) / np.max(np.abs(go)))
+    assert abs(lml[0] - lo) <= RTOL * abs(lo), (lml[0], lo)
+    assert abs(f[0] - fo) <= RTOL * abs(fo), (f[0], fo)
+    assert np.max(np.abs(g[0] - go)) <= RTOL * np.max(np.abs(go)), (g[0], go)

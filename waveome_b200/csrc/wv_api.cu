@@ -12,14 +12,17 @@
 #include "../../include/waveome_b200.h"
 #include "wv_kernels.cuh"
 #include "wv_lbfgsb.h"
+#include "wv_rtc.h"
 
 int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
-                    double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf, const WvAux* aux);
+                    double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf, const WvAux* aux,
+                    const WvSpecLaunch* spec);
 
 int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, cudaStream_t st,
-                      WvProfiler* pf, const WvAux* aux);
+                      WvProfiler* pf, const WvAux* aux, const WvSpecLaunch* spec);
 int wv_enqueue_grad_finalize(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
-                             double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf);
+                             double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf,
+                             const WvSpecLaunch* spec);
 int wv_enqueue_site_sweep(const WvBatchDev& bd, const WvVgpState& vs, const int* d_list, int n_list, const double* d_x,
                           int* d_next, int* d_count, cudaStream_t st, WvProfiler* pf);
 int wv_enqueue_vgp_begin(const WvVgpState& vs, const int* d_list, int n_list, cudaStream_t st);
@@ -104,6 +107,9 @@ struct wv_batch {
   const double* last_x;   // device pointer of the parameters of the last full evaluation (alpha belongs to them)
   WvProfiler prof;
   std::vector<int> perm;   // device row i holds caller row perm[i] (rows sorted by their categorical columns)
+  WvSpecLaunch spec;       // run-time specialised Gram / gradient kernels of the batch's program (wv_batch_specialize)
+  bool has_spec = false;
+  int n_programs = 0;
 };
 
 template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
@@ -287,6 +293,7 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
     smax = progs[i].n_slots > smax ? progs[i].n_slots : smax;
   }
   bd.n_slots_max = smax;
+  b->n_programs = d->n_programs;
   for (int i = 0; i < d->B; ++i)
     if (d->prog_id[i] < 0 || d->prog_id[i] >= d->n_programs) { delete b; return wv_fail("wv_batch_create: bad prog_id"); }
   const size_t np = bd.npad, B = d->B;
@@ -394,6 +401,47 @@ extern "C" void wv_batch_destroy(wv_batch* b) {
   b->prof.destroy();
   for (auto& a : b->allocs) wv_cache_put(b->eng, a.first, a.second);
   delete b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// run-time specialised element-wise kernels (waveome_b200/specialize.py generates the text)
+// ---------------------------------------------------------------------------------------------
+extern "C" int wv_rtc_check(const char* src, char* log, int log_len) {
+  if (!src) return wv_fail("wv_rtc_check: null source");
+  std::vector<char> cubin;
+  std::string lg;
+  const int rc = wv_rtc_compile(src, &cubin, &lg);
+  if (log && log_len > 0) { strncpy(log, lg.c_str(), (size_t)log_len - 1); log[log_len - 1] = 0; }
+  if (rc != 0) return wv_fail("wv_rtc_check: " + lg);
+  return (int)cubin.size();
+}
+
+extern "C" void wv_rtc_set_cache(const char* dir) { wv_rtc_set_cache_dir(dir); }
+
+extern "C" int wv_rtc_precompile_text(const char* key, const char* src) {
+  if (!key || !src) return wv_fail("wv_rtc_precompile_text: null argument");
+  std::string err;
+  const int rc = wv_rtc_precompile(key, src, &err);
+  if (rc < 0) return wv_fail("wv_rtc_precompile_text: " + err);
+  return rc;
+}
+
+extern "C" int wv_batch_specialize(wv_batch* b, const char* key, const char* src, const char* gram_name,
+                                   const char* grad_name, int32_t gram_smem, int32_t grad_smem) {
+  if (!b) return wv_fail("wv_batch_specialize: null batch");
+  if (!src) { b->has_spec = false; return 0; }        // back to the interpreter kernels
+  if (!key || !gram_name || !grad_name) return wv_fail("wv_batch_specialize: null argument");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  WvSpecLaunch sp;
+  std::string err;
+  if (wv_rtc_get_kernels(key, src, gram_name, grad_name, &sp, &err) != 0) return wv_fail("wv_batch_specialize: " + err);
+  if (wv_rtc_exp2_table(b->eng->device, &sp.tab12, &err) != 0) return wv_fail("wv_batch_specialize: " + err);
+  sp.gram_smem = gram_smem; sp.grad_smem = grad_smem;
+  WV_CUDA(cudaFuncSetAttribute(sp.gram, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem));
+  WV_CUDA(cudaFuncSetAttribute(sp.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, grad_smem));
+  b->spec = sp;
+  b->has_spec = true;
+  return 0;
 }
 
 extern "C" void wv_batch_profile_enable(wv_batch* b, int on) {
@@ -526,7 +574,8 @@ static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g,
   b->eng->aux.epoch += 1;
   cudaStream_t st = b->eng->stream;
   if (b->bd.lik == 0) {
-    int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, &b->prof, &b->eng->aux);
+    int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, &b->prof, &b->eng->aux,
+                            b->has_spec ? &b->spec : nullptr);
     if (l < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     b->launches += l; b->rounds += 1; b->model_evals += n_active;
     return 0;
@@ -541,7 +590,7 @@ static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g,
   for (int sweep = 0; sweep < b->vgp.max_sweeps + 2 && n_in > 0; ++sweep) {
     b->eng->aux.epoch += 1;
     WV_CUDA(cudaMemsetAsync(b->bd.chol_fail, 0, sizeof(int) * b->bd.B, st));
-    int l1 = wv_enqueue_factor(b->bd, cur, n_in, d_x, st, &b->prof, &b->eng->aux);
+    int l1 = wv_enqueue_factor(b->bd, cur, n_in, d_x, st, &b->prof, &b->eng->aux, b->has_spec ? &b->spec : nullptr);
     int l2 = l1 < 0 ? -1 : wv_enqueue_site_sweep(b->bd, b->vgp, cur, n_in, d_x, bufs[which], b->d_count + 1, st, &b->prof);
     if (l1 < 0 || l2 < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     l += l1 + l2;
@@ -554,7 +603,8 @@ static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g,
     which ^= 1;
   }
   WvProfiler none;
-  int l3 = wv_enqueue_grad_finalize(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, &b->prof);
+  int l3 = wv_enqueue_grad_finalize(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, &b->prof,
+                                    b->has_spec ? &b->spec : nullptr);
   int l4 = l3 < 0 ? -1 : wv_enqueue_vgp_status(b->vgp, d_active, n_active, d_status, st);
   if (l3 < 0 || l4 < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   b->launches += l + l3 + l4; b->rounds += 1; b->model_evals += n_active;

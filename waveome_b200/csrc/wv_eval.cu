@@ -1,5 +1,6 @@
 // waveome_b200 — kernels of one batched LML+gradient evaluation.  See wv_kernels.cuh for the plan.
 #include "wv_kernels.cuh"
+#include "wv_rtc.h"
 
 // dynamic shared memory is carved by hand; the GEMM pipeline and the epilogue tiles alias each other.
 extern __shared__ __align__(16) unsigned char wv_smem_raw[];
@@ -1193,8 +1194,15 @@ __global__ void wv_vgp_status_kernel(WvVgpState vs, const int* __restrict__ list
 }
 
 // Gram + Cholesky + L^{-T} + alpha + K^{-1} of the listed models.  Returns launches or -1.
+// launch of a run-time specialised element-wise kernel (same grid as the interpreter kernel it replaces)
+static cudaError_t wv_launch_spec(const void* kern, int smem, const double* tab12, const WvBatchDev& bd, const int* d_active,
+                                  int n_active, const double* d_x, int ntiles, int tpc, cudaStream_t st) {
+  void* args[] = {(void*)&bd, (void*)&d_active, (void*)&d_x, (void*)&tab12, (void*)&ntiles, (void*)&tpc};
+  return cudaLaunchKernel(kern, dim3((ntiles + tpc - 1) / tpc, n_active), dim3(WV_ELEM_THREADS), args, (size_t)smem, st);
+}
+
 int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, cudaStream_t st,
-                      WvProfiler* pf, const WvAux* aux) {
+                      WvProfiler* pf, const WvAux* aux, const WvSpecLaunch* spec) {
   if (n_active <= 0) return 0;
   if (wv_set_attrs() != cudaSuccess || !aux) return -1;
   int launches = 0;
@@ -1202,8 +1210,13 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
   const int ntiles = nt * (nt + 1) / 2;
   pf->mark(-1, st);
   const int tpc = wv_elem_tpc((long)ntiles * n_active);
-  wv_gram_kernel<<<dim3((ntiles + tpc - 1) / tpc, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
-      bd, d_active, d_x, ntiles, tpc);
+  if (spec && spec->gram) {
+    if (wv_launch_spec(spec->gram, spec->gram_smem, spec->tab12, bd, d_active, n_active, d_x, ntiles, tpc, st) != cudaSuccess)
+      return -1;
+  } else {
+    wv_gram_kernel<<<dim3((ntiles + tpc - 1) / tpc, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
+        bd, d_active, d_x, ntiles, tpc);
+  }
   pf->mark(WV_K_GRAM, st);
   ++launches;
   if (aux->side && nt >= aux->big_nt) {
@@ -1234,13 +1247,19 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
 
 // gradient reduction + objective of the listed models (after wv_enqueue_factor)
 int wv_enqueue_grad_finalize(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
-                             double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf) {
+                             double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf,
+                             const WvSpecLaunch* spec) {
   if (n_active <= 0) return 0;
   const int nt = bd.nt;
   const int ntiles = nt * (nt + 1) / 2;
   const int tpc = wv_elem_tpc((long)ntiles * n_active);
-  wv_grad_kernel<<<dim3((ntiles + tpc - 1) / tpc, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
-      bd, d_active, d_x, ntiles, tpc);
+  if (spec && spec->grad) {
+    if (wv_launch_spec(spec->grad, spec->grad_smem, spec->tab12, bd, d_active, n_active, d_x, ntiles, tpc, st) != cudaSuccess)
+      return -1;
+  } else {
+    wv_grad_kernel<<<dim3((ntiles + tpc - 1) / tpc, n_active), WV_ELEM_THREADS, sizeof(WvElemSmem), st>>>(
+        bd, d_active, d_x, ntiles, tpc);
+  }
   pf->mark(WV_K_GRAD, st);
   wv_finalize_kernel<<<dim3(n_active), ntiles > 128 ? 64 * WV_FIN_MAXG : 64, 0, st>>>(bd, d_active, d_x, ntiles, d_f, d_g,
                                                                                   d_lml, d_status);
@@ -1269,14 +1288,15 @@ int wv_enqueue_vgp_status(const WvVgpState& vs, const int* d_list, int n_list, i
 
 // Returns the number of kernel launches enqueued (for bench.py's gpu_launches), or -1 on error.
 int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
-                    double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf, const WvAux* aux) {
+                    double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf, const WvAux* aux,
+                    const WvSpecLaunch* spec) {
   if (n_active <= 0) return 0;
   WvProfiler none;
   if (!pf) pf = &none;
   cudaMemsetAsync(bd.chol_fail, 0, sizeof(int) * bd.B, st);
-  const int l1 = wv_enqueue_factor(bd, d_active, n_active, d_x, st, pf, aux);
+  const int l1 = wv_enqueue_factor(bd, d_active, n_active, d_x, st, pf, aux, spec);
   if (l1 < 0) return -1;
-  const int l2 = wv_enqueue_grad_finalize(bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, pf);
+  const int l2 = wv_enqueue_grad_finalize(bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, pf, spec);
   if (l2 < 0) return -1;
   return l1 + l2;
 }

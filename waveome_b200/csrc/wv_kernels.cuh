@@ -14,7 +14,9 @@
 //   Dinv[nt][64x64]  row-major inverses of the diagonal Cholesky blocks
 // Rows/cols in (n, npad) carry an identity so that no kernel needs ragged-edge special cases.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #include "wv_common.cuh"
 
 #define WV_NB 64
@@ -79,6 +81,7 @@ struct WvVgpState {
 enum WvKernelClass { WV_K_GRAM = 0, WV_K_CHOL_DIAG, WV_K_CHOL_PANEL, WV_K_TRTRI, WV_K_EXTRACT, WV_K_KINV, WV_K_GRAD,
                      WV_K_FINALIZE, WV_K_LBFGS, WV_K_CHOL_SYRK, WV_K_SITES, WV_K_NCLASS };
 
+#ifndef __CUDACC_RTC__     // host-side launch bookkeeping: not part of the NVRTC prelude
 // second stream + events of the large-n path (look-ahead: the next panel is factorised while the bulk of the trailing
 // update of the current one still runs), and the tile count from which that path is taken
 struct WvAux {
@@ -119,6 +122,7 @@ struct WvProfiler {
   }
   void destroy() { for (int i = 0; i < n_alloc; ++i) cudaEventDestroy(ev[i]); n_alloc = 0; n_ev = 0; }
 };
+#endif  // __CUDACC_RTC__
 
 // ---------------------------------------------------------------------------------------------
 // small helpers

@@ -50,6 +50,7 @@ class _LbfgsOpts(C.Structure):
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
     "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_likelihood", "wv_batch_set_likelihood2", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
+    "wv_batch_specialize", "wv_rtc_check", "wv_rtc_set_cache", "wv_rtc_precompile_text",
     "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_get_kinv_diag", "wv_batch_predict_mean", "wv_batch_predict_f", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
 KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk", "sites"]
@@ -92,6 +93,19 @@ def load_library():
     lib.wv_batch_predict_f.argtypes = [vp, _f64p, C.c_int32, _f64p, _f64p]; lib.wv_batch_predict_f.restype = C.c_int
     lib.wv_batch_profile_enable.argtypes = [vp, C.c_int]; lib.wv_batch_profile_enable.restype = None
     lib.wv_batch_profile_read.argtypes = [vp, _f64p, C.POINTER(C.c_int64), C.c_int]; lib.wv_batch_profile_read.restype = C.c_int
+    lib.wv_batch_specialize.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32]
+    lib.wv_batch_specialize.restype = C.c_int
+    lib.wv_rtc_check.argtypes = [C.c_char_p, C.c_char_p, C.c_int]; lib.wv_rtc_check.restype = C.c_int
+    lib.wv_rtc_set_cache.argtypes = [C.c_char_p]; lib.wv_rtc_set_cache.restype = None
+    lib.wv_rtc_precompile_text.argtypes = [C.c_char_p, C.c_char_p]; lib.wv_rtc_precompile_text.restype = C.c_int
+    # compiled specialisations are kept next to the library (in-tree: they travel with it), WV_RTC_CACHE overrides
+    cache = os.environ.get("WV_RTC_CACHE", os.path.join(os.path.dirname(_LIB_PATH), "rtc_cache"))
+    if cache:
+        try:
+            os.makedirs(cache, exist_ok=True)
+        except OSError:
+            cache = ""
+    lib.wv_rtc_set_cache(cache.encode() if cache else None)
     lib.wv_last_error.argtypes = []; lib.wv_last_error.restype = C.c_char_p
     lib.wv_version.argtypes = []; lib.wv_version.restype = C.c_char_p
     _lib = lib
@@ -119,6 +133,40 @@ def _i32(a):
 #: with 50000 at waveome/model_classes.py:310-315 and maxiter at waveome/model_fitting.py:280.
 DEFAULT_LBFGS = dict(maxcor=10, maxiter=15000, maxfun=15000, maxls=20, ftol=2.220446049250313e-09, gtol=1e-05,
                      on_chol_fail="nan")
+
+
+#: Batches of at least this many models that share ONE program structure get run-time specialised Gram / gradient
+#: kernels (specialize.py -> NVRTC); smaller or mixed batches stay on the interpreter kernels.  WV_SPECIALIZE=0 turns the
+#: specialisation off, WV_SPECIALIZE=1 forces it for every single-structure batch.
+SPECIALIZE_MIN_MODELS = 64
+_spec_warned = False
+
+
+def rtc_check(source: str) -> int:
+    """Compile CUDA text with NVRTC for sm_100a (no GPU needed); returns the cubin size or raises with the log."""
+    lib = load_library()
+    log = C.create_string_buffer(1 << 16)
+    rc = lib.wv_rtc_check(source.encode(), log, len(log))
+    if rc < 0:
+        raise EngineError("NVRTC: " + (log.value.decode(errors="replace") or lib.wv_last_error().decode()))
+    return rc
+
+
+def rtc_precompile(programs) -> int:
+    """Compile the specialised kernels of the given programs into the disk cache (no GPU needed); returns how many texts
+    were compiled now.  ``__graft_entry__.build()`` does this for the benchmark's kernel structure."""
+    from . import specialize as sp
+    lib = load_library()
+    done = 0
+    for p in programs:
+        s = sp.generate(p)
+        if s is None:
+            continue
+        rc = lib.wv_rtc_precompile_text(s.key.encode(), s.source.encode())
+        if rc < 0:
+            raise EngineError(lib.wv_last_error().decode())
+        done += rc == 0
+    return done
 
 
 class Engine:
@@ -157,7 +205,7 @@ class Batch:
     """B independent GP models on shared covariates X: y_b ~ GP(mean_b, k_b) + noise."""
 
     def __init__(self, engine: Engine, X: np.ndarray, Y: np.ndarray, programs: Sequence[Program],
-                 prog_id: Optional[Sequence[int]] = None, P: Optional[int] = None):
+                 prog_id: Optional[Sequence[int]] = None, P: Optional[int] = None, specialize=None):
         self.engine = engine
         self.lib = engine.lib
         X = np.ascontiguousarray(X, dtype=np.float64)
@@ -186,8 +234,50 @@ class Batch:
         h = C.c_void_p()
         _check(self.lib.wv_batch_create(engine.handle, C.byref(bd), C.byref(h)), "wv_batch_create")
         self.handle = h
+        self.specialized = False
+        mode = os.environ.get("WV_SPECIALIZE", "auto") if specialize is None else specialize
+        if mode in (True, "1", 1) or (mode == "auto" and self.B >= SPECIALIZE_MIN_MODELS):
+            self.specialize(X, strict=mode in (True, "1", 1) and specialize is not None)
 
     # ------------------------------------------------------------------------------------------
+    def specialize(self, X: Optional[np.ndarray] = None, strict: bool = False) -> bool:
+        """Route the batch's Gram / gradient passes to run-time specialised kernels (specialize.generate -> NVRTC) when
+        all its programs share one structure the generator covers; returns whether it happened.  ``strict`` raises
+        instead of staying on the interpreter kernels."""
+        global _spec_warned
+        from . import specialize as sp
+        srcs = [sp.generate(p) for p in self.programs]
+        why = None
+        if any(s is None for s in srcs):
+            why = "a program uses a leaf the generator does not cover"
+        elif len({s.key for s in srcs}) != 1:
+            why = "the batch mixes program structures"
+        elif X is not None:
+            cat_dims = {int(d) for p in self.programs for t, d in zip(p.leaf_type, p.leaf_dim) if int(t) == sp.CAT}
+            if cat_dims and not np.all(np.abs(np.rint(np.asarray(X)[:, sorted(cat_dims)])) < 2 ** 31 - 1):
+                why = "categorical codes do not fit int32"
+        if why is None:
+            s = srcs[0]
+            rc = self.lib.wv_batch_specialize(self.handle, s.key.encode(), s.source.encode(), s.gram_name.encode(),
+                                              s.grad_name.encode(), s.gram_smem, s.grad_smem)
+            if rc == 0:
+                self.specialized = True
+                return True
+            why = self.lib.wv_last_error().decode()
+            if not _spec_warned:
+                _spec_warned = True
+                import sys
+                print(f"waveome_b200: element-wise kernels not specialised ({why}); interpreter kernels stay in charge",
+                      file=sys.stderr)
+        if strict:
+            raise EngineError(f"Batch.specialize: {why}")
+        return False
+
+    def unspecialize(self):
+        """Back to the interpreter kernels (tests compare the two paths on identical inputs)."""
+        _check(self.lib.wv_batch_specialize(self.handle, None, None, None, None, 0, 0), "wv_batch_specialize")
+        self.specialized = False
+
     def x0(self) -> np.ndarray:
         """[B, P] unconstrained start vectors from the programs' current parameter values."""
         x = np.zeros((self.B, self.P))
