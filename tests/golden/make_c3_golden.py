@@ -3,7 +3,13 @@ kernel, P = 17): the workload generator of bench.py at N outcomes, every outcome
 L-BFGS-B, the restatement of gpflow.optimizers.Scipy().minimize at waveome/model_fitting.py:276-281), then pruned with
 ``cut_kernel_components`` (waveome/model_classes.py:1029-1079).
 
-    python tests/golden/make_c3_golden.py [N=64] [procs=8]      ->  tests/golden/c3_fits.json
+    python tests/golden/make_c3_golden.py [N=64] [procs=8]            ->  tests/golden/c3_fits.json
+    python tests/golden/make_c3_golden.py 64 8 perturb                ->  tests/golden/c3_fits_perturbed.json
+
+The second file is the ORACLE'S OWN sensitivity: the same fits with every y multiplied by (1 +- 2^-50) (a last-bits change
+of the input).  Most fits of this workload run into the horseshoe's singular regime (its log-density grows without bound as
+a variance goes to 0), where the stopping point of L-BFGS-B depends on the last bits of every evaluation; the spread between
+the two oracle runs is the yardstick for the spread between the engine and the oracle.
 
 tests/test_c3_parity_gpu.py fits the same outcomes on the engine and compares objective, parameters and the pruned
 structure; tests/test_c3_golden_cpu.py re-runs a few entries on the oracle so that the fixture cannot drift.
@@ -62,9 +68,13 @@ def main():
     import numpy as np
     n_out = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     procs = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    perturb = len(sys.argv) > 3 and sys.argv[3] == "perturb"
     gps, model = c3_setup(n_out)
     spec = model.to_spec()
     Xn, Yn = gps.X.to_numpy(dtype=np.float64), gps.Y.to_numpy(dtype=np.float64)
+    if perturb:
+        sign = np.where(np.arange(Yn.shape[0]) % 2 == 0, 1.0, -1.0)[:, None]
+        Yn = Yn * (1.0 + sign * 2.0 ** -50)
     with ProcessPoolExecutor(max_workers=procs, mp_context=mp.get_context("spawn")) as ex:
         fits = list(ex.map(_fit_one, [(spec, Xn, Yn[:, c].copy()) for c in range(n_out)]))
     for c, r in enumerate(fits):
@@ -74,7 +84,11 @@ def main():
     out = {"config": "BASELINE configs[2]: datasets.ihmp_scale(120, 5, n_outcomes, seed=2024), standardised, saturated kernel "
                      "(9 components, P = 17), horseshoe pf = 1.0, L-BFGS-B maxiter = maxfun = 50000",
            "n": int(Xn.shape[0]), "n_outcomes": n_out, "fits": fits}
-    with open(os.path.join(ROOT, "tests", "golden", "c3_fits.json"), "w") as fh:
+    if perturb:
+        out["config"] += "; y perturbed by a factor (1 +- 2^-50)"
+        for r in fits:
+            del r["y_checksum"]
+    with open(os.path.join(ROOT, "tests", "golden", "c3_fits_perturbed.json" if perturb else "c3_fits.json"), "w") as fh:
         json.dump(out, fh, indent=0)
     st = [r["status"] for r in fits]
     print("statuses", {s: st.count(s) for s in set(st)}, "mean nfev", np.mean([r["nfev"] for r in fits]),

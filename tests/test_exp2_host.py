@@ -56,30 +56,30 @@ SRC12 = r'''
 #include <vector>
 #include "%s/waveome_b200/csrc/wv_common.cuh"
 int main() {
-  std::vector<double> tab(WV_EXP2_TAB12);
-  for (int j = 0; j < WV_EXP2_TAB12; ++j) tab[j] = (double)exp2l((long double)j / WV_EXP2_TAB12);
+  std::vector<double> tab(WV_EXP2_BIG_TAB);
+  for (int j = 0; j < WV_EXP2_BIG_TAB; ++j) tab[j] = (double)exp2l((long double)j / WV_EXP2_BIG_TAB);
   std::mt19937_64 g(2);
   std::uniform_real_distribution<double> U(-1020.0, 30.0), V(-3.0, 1.0);
   double maxulp = 0;
   for (int i = 0; i < 2000000; ++i) {
     double u = (i & 1) ? U(g) : V(g);
-    double r = wv_exp2_12_lo(u, tab.data());
+    double r = wv_exp2_big_lo(u, tab.data());
     long double ref = exp2l((long double)u);
     double ulp = fabs((double)((r - ref) / ldexpl(1.0L, ilogbl(ref) - 52)));
     if (ulp > maxulp) maxulp = ulp;
   }
   printf("%%.4f\n", maxulp);
-  if (wv_exp2_12_lo(0.0, tab.data()) != 1.0 || wv_exp2_12_lo(-0.0, tab.data()) != 1.0 || wv_exp2_12_lo(3.0, tab.data()) != 8.0) return 3;
-  if (!std::isnan(wv_exp2_12_lo(NAN, tab.data()))) return 4;
-  if (!(wv_exp2_12_lo(-INFINITY, tab.data()) < 1e-307) || !(wv_exp2_12_lo(-1e300, tab.data()) < 1e-307)) return 5;
-  if (!(wv_exp2_12_lo(-INFINITY, tab.data()) > 0.0)) return 6;
+  if (wv_exp2_big_lo(0.0, tab.data()) != 1.0 || wv_exp2_big_lo(-0.0, tab.data()) != 1.0 || wv_exp2_big_lo(3.0, tab.data()) != 8.0) return 3;
+  if (!std::isnan(wv_exp2_big_lo(NAN, tab.data()))) return 4;
+  if (!(wv_exp2_big_lo(-INFINITY, tab.data()) < 1e-307) || !(wv_exp2_big_lo(-1e300, tab.data()) < 1e-307)) return 5;
+  if (!(wv_exp2_big_lo(-INFINITY, tab.data()) > 0.0)) return 6;
   return 0;
 }
 '''
 
 
-def test_exp2_12bit_table_accuracy(tmp_path):
-    """wv_exp2_12_lo: the 2^u of the run-time specialised kernels (4096-entry table, degree-3 polynomial)."""
+def test_exp2_bigtable_table_accuracy(tmp_path):
+    """wv_exp2_big_lo: the 2^u of the run-time specialised kernels (2048-entry table, degree-3 polynomial)."""
     src = tmp_path / "exp2_12_test.cpp"
     src.write_text(SRC12 % ROOT)
     exe = tmp_path / "exp2_12_test"

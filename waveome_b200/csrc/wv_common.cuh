@@ -171,40 +171,40 @@ WV_HD double wv_exp2_lo(double u, const double* __restrict__ tab) {
 #endif
 }
 
-// The same 2^u with a 4096-entry table of 2^(j/4096) (32 KB, staged in shared memory from a per-device copy) and a
-// degree-3 polynomial on |f| <= 2^-13 (truncation f^4 ln2^4 / 24 < 2.2e-18): 7 FP64 operations instead of 9.  Used by the
+// The same 2^u with a 2048-entry table of 2^(j/2048) (16 KB, staged in shared memory from a per-device copy) and a
+// degree-3 polynomial on |f| <= 2^-12 (truncation (f ln2)^4 / 24 < 3.4e-17): 7 FP64 operations instead of 9.  Used by the
 // run-time specialised element-wise kernels (wv_spec.cuh), whose squared-exponential leaves are bound by the FP64 pipe.
 // u < 1024; below -1021 (and -inf) the result is ~2^-1021 instead of 0; NaN propagates.
-#define WV_EXP2_BITS12 12
-#define WV_EXP2_TAB12 (1 << WV_EXP2_BITS12)
-WV_HD double wv_exp2_12_core(double u, const double* __restrict__ tab) {
-  const double M = 1.5 * 1099511627776.0;                  // 1.5 * 2^40: adding it rounds u to a multiple of 2^-12
+#define WV_EXP2_BIG_BITS 11
+#define WV_EXP2_BIG_TAB (1 << WV_EXP2_BIG_BITS)
+WV_HD double wv_exp2_big_core(double u, const double* __restrict__ tab) {
+  const double M = 1.5 * 2199023255552.0;                  // 1.5 * 2^41: adding it rounds u to a multiple of 2^-11
   const double tb = u + M;
-  const double f = u - (tb - M);                           // |f| <= 2^-13
+  const double f = u - (tb - M);                           // |f| <= 2^-12
   double p = fma(f, 5.5504108664821580e-02, 2.4022650695910071e-01);   // ln2^3/6, ln2^2/2
   p = fma(f, p, 6.9314718055994531e-01);                                // ln2
   p = f * p;
 #ifdef __CUDA_ARCH__
   const int ki = __double2loint(tb);
-  const double T = tab[ki & (WV_EXP2_TAB12 - 1)];
+  const double T = tab[ki & (WV_EXP2_BIG_TAB - 1)];
   const double r = fma(T, p, T);
-  return __hiloint2double(__double2hiint(r) + ((ki >> WV_EXP2_BITS12) << 20), __double2loint(r));
+  return __hiloint2double(__double2hiint(r) + ((ki >> WV_EXP2_BIG_BITS) << 20), __double2loint(r));
 #else
   long long bits;
   memcpy(&bits, &tb, 8);
   const int ki = (int)(bits & 0xffffffffLL);
-  const double T = tab[ki & (WV_EXP2_TAB12 - 1)];
+  const double T = tab[ki & (WV_EXP2_BIG_TAB - 1)];
   double r = fma(T, p, T);
   memcpy(&bits, &r, 8);
-  bits += (long long)(ki >> WV_EXP2_BITS12) << 52;
+  bits += (long long)(ki >> WV_EXP2_BIG_BITS) << 52;
   memcpy(&r, &bits, 8);
   return r;
 #endif
 }
-WV_HD double wv_exp2_12_lo(double u, const double* __restrict__ tab) {
+WV_HD double wv_exp2_big_lo(double u, const double* __restrict__ tab) {
 #ifdef __CUDA_ARCH__
   const unsigned hi = min((unsigned)__double2hiint(u), 0xC08FE800u);          // clamp at -1021.0 (see wv_exp2_lo)
-  return wv_exp2_12_core(__hiloint2double((int)hi, __double2loint(u)), tab);
+  return wv_exp2_big_core(__hiloint2double((int)hi, __double2loint(u)), tab);
 #else
   unsigned long long bits;
   memcpy(&bits, &u, 8);
@@ -212,7 +212,7 @@ WV_HD double wv_exp2_12_lo(double u, const double* __restrict__ tab) {
   if (hi > 0xC08FE800u) hi = 0xC08FE800u;
   bits = ((unsigned long long)hi << 32) | (bits & 0xffffffffULL);
   memcpy(&u, &bits, 8);
-  return wv_exp2_12_core(u, tab);
+  return wv_exp2_big_core(u, tab);
 #endif
 }
 

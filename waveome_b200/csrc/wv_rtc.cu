@@ -189,13 +189,13 @@ int wv_rtc_precompile(const char* key, const char* src, std::string* err) {
   return 0;
 }
 
-// 2^(j/4096), j = 0..4095, correctly rounded from long double; one copy per device, never freed
+// 2^(j/2048), j = 0..2047, correctly rounded from long double; one copy per device, never freed
 int wv_rtc_exp2_table(int device, const double** out, std::string* err) {
   std::lock_guard<std::mutex> lock(g_mu);
   if (device < 0 || device >= 64) { *err = "device index beyond the table cache"; return -1; }
   if (!g_tab12[device]) {
-    std::vector<double> h(WV_EXP2_TAB12);
-    for (int j = 0; j < WV_EXP2_TAB12; ++j) h[j] = (double)exp2l((long double)j / WV_EXP2_TAB12);
+    std::vector<double> h(WV_EXP2_BIG_TAB);
+    for (int j = 0; j < WV_EXP2_BIG_TAB; ++j) h[j] = (double)exp2l((long double)j / WV_EXP2_BIG_TAB);
     double* d = nullptr;
     cudaError_t e = cudaMalloc(&d, h.size() * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice);

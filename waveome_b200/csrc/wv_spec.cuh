@@ -14,8 +14,7 @@
 #include "wv_kernels.cuh"
 
 #define WVS_THREADS 256
-#define WVS_MR 4
-#define WVS_NE 16
+#define WVS_TPC_MAX 8      // tiles per CTA (wv_elem_tpc)
 
 extern __shared__ __align__(16) unsigned char wvs_smem_raw[];
 
@@ -30,22 +29,20 @@ __device__ __forceinline__ void wvs_stage_theta(const WvBatchDev& bd, int b, con
   }
 }
 
-// 2^(j/4096) table: per-device copy in global memory (L2 resident) -> shared memory
+// 2^(j/2048) table: per-device copy in global memory (L2 resident) -> shared memory
 __device__ __forceinline__ void wvs_load_tab(double* __restrict__ tab, const double* __restrict__ gtab) {
   const double2* src = reinterpret_cast<const double2*>(gtab);
   double2* dst = reinterpret_cast<double2*>(tab);
-  for (int i = threadIdx.x; i < WV_EXP2_TAB12 / 2; i += WVS_THREADS) dst[i] = src[i];
+  for (int i = threadIdx.x; i < WV_EXP2_BIG_TAB / 2; i += WVS_THREADS) dst[i] = src[i];
 }
 
-// thread -> micro-tile (same map as wv_elem_coords): warp w owns rows (w>>1) * 16 .., cols (w&1) * 32 ..; lane l the
-// 4 x 4 micro-tile at (+ (l>>3) 4, + (l&7) 4)
-__device__ __forceinline__ void wvs_coords(int& r_off, int& c_off, bool& above_diag, bool diag_tile) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = (warp >> 1) * 16, wc = (warp & 1) * 32;
-  r_off = wr + (lane >> 3) * 4;
-  c_off = wc + (lane & 7) * 4;
-  above_diag = diag_tile && wc > wr + 15;
-}
+// Work decomposition: a CTA owns `tpc` consecutive lower tiles of one model; inside every tile warp w owns the 16 x 32
+// region at rows (w>>1) * 16, columns (w&1) * 32, lane l the 4 x 4 micro-tile at (+ (l>>3) 4, + (l&7) 4), walked row by
+// row.  The warps are AUTONOMOUS: each stages the covariates of its own 16 rows and 32 columns (indices 0..15 and 16..47
+// of its private arrays) and synchronises with __syncwarp only, so a warp whose categorical masks let it skip most of
+// the squared exponentials moves on to its next tile instead of waiting at a CTA barrier (24 % of the stall samples of
+// the barrier version, profiles/r02c).
+#define WVS_STAGE 48
 
 __device__ __forceinline__ void wvs_ld4(const double* __restrict__ p, double (&v)[4]) {
   const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
@@ -101,16 +98,12 @@ __device__ __forceinline__ void wvs_periodic(double xi, double xj, double ell, d
   q_per = (ss * cs) * arg;
 }
 
-// fixed-order reduction of per-thread sums over the CTA: red[k][tid] holds sum k of thread tid; warp w reduces the sums
-// k = w, w + 8, ...: lane l adds red[k][l + 32 j], j = 0..7, in that order, then a shuffle tree; lane 0 writes out[k]
-__device__ __forceinline__ void wvs_reduce_sums(const double* __restrict__ red, int nsum, double* __restrict__ out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = warp; k < nsum; k += WVS_THREADS / 32) {
-    const double* r = red + (size_t)k * WVS_THREADS + lane;
-    double s = r[0];
-#pragma unroll
-    for (int j = 1; j < WVS_THREADS / 32; ++j) s += r[32 * j];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[k] = s;
-  }
+// fixed-order reduction of the lanes' sums inside one warp: lane l holds sum k in red[k * 33 + l] (stride 33: the
+// transposed read below is conflict free); lane k adds the 32 entries of row k in order
+__device__ __forceinline__ double wvs_warp_row_sum(const double* __restrict__ red, int k) {
+  const double* r = red + k * 33;
+  double s = r[0];
+#pragma unroll 8
+  for (int j = 1; j < 32; ++j) s += r[j];
+  return s;
 }

@@ -84,6 +84,8 @@ def _softplus(u):
 
 
 def _softplus_inv(y):
+    if y <= 0.0:            # a variance that underflowed to 0 during a fit (TFP's softplus inverse gives -inf as well)
+        return -math.inf if y == 0.0 else math.nan
     return y + math.log(-math.expm1(-y))
 
 
@@ -129,7 +131,7 @@ class Parameter:
         if self.transform == "softplus_shift":
             return _softplus_inv(v - self.shift)
         if self.transform == "exp":
-            return math.log(v)
+            return math.log(v) if v > 0.0 else (-math.inf if v == 0.0 else math.nan)
         return v
 
     def transform_fn(self, u):

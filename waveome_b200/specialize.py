@@ -33,6 +33,10 @@ _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 _PRELUDE_FILES = ("wv_common.cuh", "wv_kernels.cuh", "wv_spec.cuh")
 _prelude_cache: Optional[str] = None
 
+#: resident CTAs per SM the register allocation of the generated kernels aims for (measured on config 3, profiles/r02*)
+GRAM_MIN_CTAS = int(os.environ.get("WV_SPEC_GRAM_MINB", "4"))
+GRAD_MIN_CTAS = int(os.environ.get("WV_SPEC_GRAD_MINB", "2"))     # 3 CTAs (80 registers) spill the gradient sums: 4.6 ms vs 3.4 ms
+
 SE_SCALE = "0.84932180028801907"        # sqrt(log2(e) / 2): exp(-r2 / 2) = 2^(-(s (x - x'))^2), s = SE_SCALE / lengthscale
 TWO_LN2 = "1.3862943611198906"          # r2 = 2 ln2 (s d)^2
 
@@ -113,28 +117,24 @@ def _prod(terms: List[str]) -> str:
     return " * ".join(terms) if terms else "1.0"
 
 
-def _mask_expr(cp: _Comp, a: str, b: str) -> str:
-    return " && ".join(f"kr{k}[{a}] == kc{k}[{b}]" for k in cp.cats)
+def _mask_expr(cp: _Comp, b: str) -> str:
+    return " && ".join(f"kr{k} == kc{k}[{b}]" for k in cp.cats)
 
 
-def _emit_loads(cp: _Comp, need_q: bool) -> List[str]:
+def _emit_loads(cp: _Comp, ind: str) -> List[str]:
+    """covariates of one micro-tile ROW (row r of the tile, columns c_off .. c_off + 3) for the leaves of a component;
+    the categorical codes are loaded once per row for all components (see ``cat_loads``)"""
     out = []
-    for k in cp.cats:
-        out.append(f"      int kr{k}[4], kc{k}[4]; wvs_ld4i(&sm.cr[{k}][r_off], kr{k}); wvs_ld4i(&sm.cc[{k}][c_off], kc{k});")
     ids = [a for a, _ in cp.se] + [o["arr"] for o in cp.other]
     for a in dict.fromkeys(ids):
-        out.append(f"      double xi{a}[4], xj{a}[4]; wvs_ld4(&sm.ar[{a}][r_off], xi{a}); wvs_ld4(&sm.ac[{a}][c_off], xj{a});")
+        out.append(f"{ind}const double xi{a} = sw.a[{a}][r]; double xj{a}[4]; wvs_ld4(&sw.a[{a}][c_off], xj{a});")
     return out
 
 
-def _warp_skip_open(cp: _Comp) -> List[str]:
-    """whole warps skip the transcendental factors of a product whose categorical mask is zero for the warp"""
-    return ["      bool any_ = false;",
-            "#pragma unroll",
-            "      for (int a = 0; a < 4; ++a)",
-            "#pragma unroll",
-            f"        for (int b = 0; b < 4; ++b) any_ |= ({_mask_expr(cp, 'a', 'b')});",
-            "      if (__any_sync(0xffffffffu, any_)) {"]
+def _warp_skip_open(cp: _Comp, ind: str) -> List[str]:
+    """whole warps skip the transcendental factors of a product whose categorical mask is zero for the warp's row group"""
+    any_ = " || ".join(f"({_mask_expr(cp, str(b))})" for b in range(4))
+    return [f"{ind}if (__any_sync(0xffffffffu, {any_})) {{"]
 
 
 def generate(p: Program) -> Optional[SpecSource]:
@@ -192,22 +192,39 @@ def generate(p: Program) -> Optional[SpecSource]:
                              ns)).encode()).hexdigest()[:12]
     gram_name, grad_name = f"wvs_gram_{tag}", f"wvs_grad_{tag}"
 
+    red_doubles = nsum * 33
+    stage_bytes = 8 * 48 * na + 4 * 48 * ncat                 # one warp's staged covariates
+    warp_union = max(stage_bytes, 8 * red_doubles)
+    warp_union += (-warp_union) % 16
+
     def smem_struct(name, with_red):
+        """shared memory of one CTA; returns its size in bytes"""
+        w(f"struct {name}Warp {{")
+        if with_red:
+            w("  union {")
+            w(f"    struct {{ double a[{na}][WVS_STAGE]; int c[{ncat}][WVS_STAGE]; }};")
+            w(f"    double red[{warp_union // 8}];      // the lanes' sums, after the rows are done with the staged columns")
+            w("  };")
+            w("  double al[WVS_STAGE];")
+            per_warp = warp_union + 8 * 48
+        else:
+            w(f"  double a[{na}][WVS_STAGE];")
+            w(f"  int c[{ncat}][WVS_STAGE];")
+            per_warp = stage_bytes + (-stage_bytes) % 16
+            if per_warp != stage_bytes:
+                w(f"  int pad_[{(per_warp - stage_bytes) // 4}];")
+        w("};")
         w(f"struct {name} {{")
         w(f"  double theta[{ns + (ns & 1)}];")
         w(f"  double kc[{nkc + (nkc & 1)}];")
-        w("  double tab[WV_EXP2_TAB12];")
-        w(f"  double ar[{na}][64];")
-        w(f"  double ac[{na}][64];")
-        w(f"  int cr[{ncat}][64];")
-        w(f"  int cc[{ncat}][64];")
+        w("  double tab[WV_EXP2_BIG_TAB];")
+        w(f"  {name}Warp w[WVS_THREADS / 32];")
+        size = 8 * (ns + (ns & 1)) + 8 * (nkc + (nkc & 1)) + 8 * 2048 + 8 * per_warp
         if with_red:
-            w(f"  double red[{nsum}][WVS_THREADS];")
-            w(f"  double sums[{nsum + (nsum & 1)}];")
+            w(f"  double wsum[WVS_TPC_MAX][WVS_THREADS / 32][{nsum}];    // per tile and warp, combined in fixed order")
+            w(f"  double sums[WVS_TPC_MAX][{nsum}];")
+            size += 8 * 8 * 8 * nsum + 8 * 8 * nsum
         w("};")
-        size = 8 * (ns + (ns & 1)) + 8 * (nkc + (nkc & 1)) + 8 * 4096 + 2 * 8 * 64 * na + 2 * 4 * 64 * ncat
-        if with_red:
-            size += 8 * 256 * nsum + 8 * (nsum + (nsum & 1))
         w(f"static_assert(sizeof({name}) == {size}, \"shared-memory layout\");")
         return size
 
@@ -219,29 +236,30 @@ def generate(p: Program) -> Optional[SpecSource]:
         w("  __syncthreads();")
         for i, e in enumerate(kc_expr):
             w(f"  if (threadIdx.x == {i % 256}) sm.kc[{i}] = {e};")
+        w("  __syncthreads();")
         w("  const int n = bd.n, ld = bd.npad;")
-        w("  const int t1 = min(ntiles, (int)(blockIdx.x + 1) * tpc);")
+        w("  const int t0 = blockIdx.x * tpc, t1 = min(ntiles, t0 + tpc);")
+        w("  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;")
+        w("  const int wr = (warp >> 1) * 16, wc = (warp & 1) * 32;          // the warp's region inside every tile")
+        w("  const int r_loc = (lane >> 3) * 4, c_off = 16 + (lane & 7) * 4;  // the lane's rows / columns in the staged arrays")
+        w("  auto& sw = sm.w[warp];")
 
-    def stage_tile():
-        w("    int ti, tj;")
-        w("    wv_tile_from_linear(t, ti, tj);")
-        w("    __syncthreads();      // previous tile done with the staged columns; sm.kc visible")
-        w("    if (threadIdx.x < 128) {")
-        w("      const int r = threadIdx.x & 63, col = threadIdx.x >> 6;")
-        w("      const size_t g = (size_t)(col ? tj : ti) * 64 + r;")
+    def stage_warp(with_alpha):
+        w("    __syncwarp();       // the previous tile's rows are done with the staged columns")
+        w("    for (int i = lane; i < WVS_STAGE; i += 32) {")
+        w("      const size_t g = i < 16 ? (size_t)ti * 64 + wr + i : (size_t)tj * 64 + wc + (i - 16);")
         dims = sorted({d for (_, d, _) in arrays} | set(cats))
         for d in dims:
             w(f"      const double x{d} = bd.Xt[(size_t){d} * ld + g];")
         for (kind, dim, slot), a in arrays.items():
             sc = f" * sm.kc[{arr_scale[a]}]" if a in arr_scale else ""
-            w(f"      (col ? sm.ac : sm.ar)[{a}][r] = x{dim}{sc};")
+            w(f"      sw.a[{a}][i] = x{dim}{sc};")
         for dim, k in cats.items():
-            w(f"      (col ? sm.cc : sm.cr)[{k}][r] = (int)rint(x{dim});")
+            w(f"      sw.c[{k}][i] = (int)rint(x{dim});")
+        if with_alpha:
+            w("      sw.al[i] = al[g];")
         w("    }")
-        w("    __syncthreads();")
-        w("    int r_off, c_off;")
-        w("    bool above;")
-        w("    wvs_coords(r_off, c_off, above, ti == tj);")
+        w("    __syncwarp();")
 
     def value_terms(cp: _Comp, a: str, b: str, grads: bool) -> List[str]:
         """statements that multiply the unit-variance values of the non-SE leaves into `v` (and set their q's)"""
@@ -249,24 +267,31 @@ def generate(p: Program) -> Optional[SpecSource]:
         for i, o in enumerate(cp.other):
             x = o["arr"]
             if o["type"] == LINEAR:
-                out.append(f"v *= xi{x}[{a}] * xj{x}[{b}];")
+                out.append(f"v *= xi{x} * xj{x}[{b}];")
             elif o["type"] in (M12, M32, M52):
                 if grads and f"ls{i}" in cp.sums:
-                    out.append(f"double E{i}, q{i}; wvs_matern<{o['type']}>(xi{x}[{a}], xj{x}[{b}], E{i}, q{i}); v *= E{i};")
+                    out.append(f"double E{i}, q{i}; wvs_matern<{o['type']}>(xi{x}, xj{x}[{b}], E{i}, q{i}); v *= E{i};")
                 else:
-                    out.append(f"v *= wvs_matern_value<{o['type']}>(xi{x}[{a}], xj{x}[{b}]);")
+                    out.append(f"v *= wvs_matern_value<{o['type']}>(xi{x}, xj{x}[{b}]);")
             elif o["type"] == PERIODIC:
                 if grads and (f"ls{i}" in cp.sums or f"aux{i}" in cp.sums):
-                    out.append(f"double E{i}, q{i}, qa{i}; wvs_periodic(xi{x}[{a}], xj{x}[{b}], sm.theta[{o['ls']}], "
+                    out.append(f"double E{i}, q{i}, qa{i}; wvs_periodic(xi{x}, xj{x}[{b}], sm.theta[{o['ls']}], "
                                f"sm.theta[{o['aux']}], E{i}, q{i}, qa{i}); v *= E{i};")
                 else:
-                    out.append(f"v *= wvs_periodic_value(xi{x}[{a}], xj{x}[{b}], sm.theta[{o['ls']}], sm.theta[{o['aux']}]);")
+                    out.append(f"v *= wvs_periodic_value(xi{x}, xj{x}[{b}], sm.theta[{o['ls']}], sm.theta[{o['aux']}]);")
         return out
 
+    def cat_loads(ind):
+        for k in range(len(cats)):
+            w(f"{ind}const int kr{k} = sw.c[{k}][r]; int kc{k}[4]; wvs_ld4i(&sw.c[{k}][c_off], kc{k});")
+
+    # The micro-tile is walked ROW BY ROW in a rolled loop: the text of one row (4 elements per component) is a quarter
+    # of the fully unrolled micro-tile -- the unrolled kernels stalled on instruction fetch (22 % of the warp stall
+    # samples, profiles/r02b) -- and the live state is one row, so four CTAs fit on an SM instead of two.
     # =============================================================================== gram
     w("// ---------------- generated: Gram builder")
     gram_smem = smem_struct("WvsGramSmem", False)
-    w(f"extern \"C\" __global__ void __launch_bounds__(WVS_THREADS, 2) {gram_name}(WvBatchDev bd, const int* __restrict__ active,")
+    w(f"extern \"C\" __global__ void __launch_bounds__(WVS_THREADS, {GRAM_MIN_CTAS}) {gram_name}(WvBatchDev bd, const int* __restrict__ active,")
     w("    const double* __restrict__ xall, const double* __restrict__ gtab, int ntiles, int tpc) {")
     w("  WvsGramSmem& sm = *reinterpret_cast<WvsGramSmem*>(wvs_smem_raw);")
     stage_model()
@@ -274,59 +299,61 @@ def generate(p: Program) -> Optional[SpecSource]:
     w("  const double* yb = bd.Y + (size_t)b * ld;")
     w("  const double* lam = bd.site_lam ? bd.site_lam + (size_t)b * ld : nullptr;")
     w("  const double* eta = bd.site_eta ? bd.site_eta + (size_t)b * ld : nullptr;")
-    w("  for (int t = blockIdx.x * tpc; t < t1; ++t) {")
-    stage_tile()
-    w("    if (above) continue;                  // the strict upper part of a diagonal tile is never read")
-    w("    double acc[WVS_NE];")
-    w("#pragma unroll")
-    w("    for (int e = 0; e < WVS_NE; ++e) acc[e] = 0.0;")
-    for c, cp in enumerate(comps):
-        expensive = bool(cp.se or cp.other)
-        w(f"    if (cmask & {1 << c}u) {{      // component {c}")
-        for s in _emit_loads(cp, False):
-            w(s)
-        skip = bool(cp.cats) and expensive
-        if skip:
-            for s in _warp_skip_open(cp):
-                w(s)
-        w(f"      const double k_ = sm.kc[{comp_kc[c]}];")
-        w("#pragma unroll")
-        w("      for (int a = 0; a < 4; ++a)")
-        w("#pragma unroll")
-        w("        for (int b = 0; b < 4; ++b) {")
-        if cp.se:
-            w("          double u = k_;")
-            for (x, _) in cp.se:
-                w(f"          {{ const double d = xi{x}[a] - xj{x}[b]; u = fma(-d, d, u); }}")
-            w("          double v = wv_exp2_12_lo(u, sm.tab);")
-        else:
-            w("          double v = k_;")
-        for s in value_terms(cp, "a", "b", False):
-            w("          " + s)
-        if cp.cats:
-            w(f"          if ({_mask_expr(cp, 'a', 'b')}) acc[a * 4 + b] += v;")
-        else:
-            w("          acc[a * 4 + b] += v;")
-        w("        }")
-        if skip:
-            w("      }")
-        w("    }")
+    w("  for (int t = t0; t < t1; ++t) {")
+    w("    int ti, tj;")
+    w("    wv_tile_from_linear(t, ti, tj);")
+    w("    if (ti == tj && wc > wr + 15) continue;      // the strict upper part of a diagonal tile is never read")
+    stage_warp(False)
     w("    const double s2 = sm.theta[%d];" % int(p.noise_slot))
     w("    const double cmean = %s;" % (f"sm.theta[{int(p.mean_slot)}]" if int(p.mean_slot) >= 0 else "0.0"))
-    w("""#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int gi = ti * 64 + r_off + a;
+    w("#pragma unroll 1")
+    w("    for (int a = 0; a < 4; ++a) {")
+    w("      const int r = r_loc + a;")
+    w("      double acc[4] = {0.0, 0.0, 0.0, 0.0};")
+    cat_loads("      ")
+    for c, cp in enumerate(comps):
+        expensive = bool(cp.se or cp.other)
+        w(f"      if (cmask & {1 << c}u) {{      // component {c}")
+        skip = bool(cp.cats) and expensive
+        ind = "        "
+        if skip:
+            for s_ in _warp_skip_open(cp, ind):
+                w(s_)
+            ind += "  "
+        for s_ in _emit_loads(cp, ind):
+            w(s_)
+        w(f"{ind}const double k_ = sm.kc[{comp_kc[c]}];")
+        w("#pragma unroll")
+        w(f"{ind}for (int j = 0; j < 4; ++j) {{")
+        if cp.se:
+            w(f"{ind}  double u = k_;")
+            for (x, _) in cp.se:
+                w(f"{ind}  {{ const double d = xi{x} - xj{x}[j]; u = fma(-d, d, u); }}")
+            w(f"{ind}  double v = wv_exp2_big_lo(u, sm.tab);")
+        else:
+            w(f"{ind}  double v = k_;")
+        for s_ in value_terms(cp, "a", "j", False):
+            w(f"{ind}  " + s_)
+        if cp.cats:
+            w(f"{ind}  if ({_mask_expr(cp, 'j')}) acc[j] += v;")
+        else:
+            w(f"{ind}  acc[j] += v;")
+        w(f"{ind}}}")
+        if skip:
+            w("        }")
+        w("      }")
+    w("""      const int gi = ti * 64 + wr + r, gj0 = tj * 64 + wc + (c_off - 16);
       double out[4];
 #pragma unroll
       for (int bb = 0; bb < 4; ++bb) {
-        const int gj = tj * 64 + c_off + bb;
+        const int gj = gj0 + bb;
         double v;
-        if (gi < n && gj < n) v = acc[a * 4 + bb] + (gi == gj ? (lam ? bd.jitter + 1.0 / lam[gi] : s2) : 0.0);
+        if (gi < n && gj < n) v = acc[bb] + (gi == gj ? (lam ? bd.jitter + 1.0 / lam[gi] : s2) : 0.0);
         else if (gi == n && gj < n) v = (lam ? eta[gj] / lam[gj] : yb[gj]) - cmean;     // RHS row d^T
         else v = (gi == gj) ? 1.0 : 0.0;                     // identity padding (incl. A[n][n] = 1)
         out[bb] = v;
       }
-      double2* dst = reinterpret_cast<double2*>(Ab + (size_t)gi * ld + tj * 64 + c_off);
+      double2* dst = reinterpret_cast<double2*>(Ab + (size_t)gi * ld + gj0);
       dst[0] = make_double2(out[0], out[1]);
       dst[1] = make_double2(out[2], out[3]);
     }
@@ -337,90 +364,109 @@ def generate(p: Program) -> Optional[SpecSource]:
     # =============================================================================== grad
     w("// ---------------- generated: gradient reduction")
     grad_smem = smem_struct("WvsGradSmem", True)
-    w(f"extern \"C\" __global__ void __launch_bounds__(WVS_THREADS, 2) {grad_name}(WvBatchDev bd, const int* __restrict__ active,")
+    w(f"extern \"C\" __global__ void __launch_bounds__(WVS_THREADS, {GRAD_MIN_CTAS}) {grad_name}(WvBatchDev bd, const int* __restrict__ active,")
     w("    const double* __restrict__ xall, const double* __restrict__ gtab, int ntiles, int tpc) {")
     w("  WvsGradSmem& sm = *reinterpret_cast<WvsGradSmem*>(wvs_smem_raw);")
     stage_model()
     w("  const double* Kb = bd.A + (size_t)b * ld * ld;")
     w("  const double* al = bd.alpha + (size_t)b * ld;")
-    w("  for (int t = blockIdx.x * tpc; t < t1; ++t) {")
-    stage_tile()
-    w("""    double w[WVS_NE];
-    double trw = 0.0;
-    if (!above) {
-      double aj[4];
+    sum_names = [(c, k) for c, cp in enumerate(comps) for k in cp.sums]
+    w("  for (int t = t0; t < t1; ++t) {")
+    w("    int ti, tj;")
+    w("    wv_tile_from_linear(t, ti, tj);")
+    w("    if (ti == tj && wc > wr + 15) {             // strictly above the diagonal: contributes nothing")
+    w(f"      for (int k = lane; k < {nsum}; k += 32) sm.wsum[t - t0][warp][k] = 0.0;")
+    w("      continue;")
+    w("    }")
+    stage_warp(True)
+    w("    double trw = 0.0;")
+    if sum_names:
+        w("    double " + ", ".join(f"s{c}_{k} = 0.0" for c, k in sum_names) + ";")
+    w("    {")
+    w("      double aj[4];")
+    w("      wvs_ld4(&sw.al[c_off], aj);")
+    w("      const int gj0 = tj * 64 + wc + (c_off - 16);")
+    w("      const double* Krow = Kb + (size_t)(ti * 64 + wr + r_loc) * ld + gj0;")
+    w("      double2 n01 = *reinterpret_cast<const double2*>(Krow), n23 = *reinterpret_cast<const double2*>(Krow + 2);")
+    w("#pragma unroll 1")
+    w("      for (int a = 0; a < 4; ++a) {")
+    w("        const int r = r_loc + a;")
+    w("""        double w[4];
+        {
+          const double kin[4] = {n01.x, n01.y, n23.x, n23.y};
+          if (a < 3) {       // next row's K^-1 entries: in flight while this row is reduced
+            n01 = *reinterpret_cast<const double2*>(Krow + (size_t)(a + 1) * ld);
+            n23 = *reinterpret_cast<const double2*>(Krow + (size_t)(a + 1) * ld + 2);
+          }
+          const int gi = ti * 64 + wr + r;
+          const double ai = sw.al[r];
 #pragma unroll
-      for (int bb = 0; bb < 4; ++bb) aj[bb] = al[tj * 64 + c_off + bb];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int gi = ti * 64 + r_off + a;
-        const double2* src = reinterpret_cast<const double2*>(Kb + (size_t)gi * ld + tj * 64 + c_off);
-        const double2 k01 = src[0], k23 = src[1];
-        const double kin[4] = {k01.x, k01.y, k23.x, k23.y};
-        const double ai = al[gi];
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const int gj = tj * 64 + c_off + bb;
-          const double wv = ai * aj[bb] - kin[bb];
-          const bool in = gi < n && gj < n;
-          w[a * 4 + bb] = in ? (gi > gj ? 2.0 * wv : (gi == gj ? wv : 0.0)) : 0.0;
-          if (gi == gj && gi < n) trw += wv;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < WVS_NE; ++e) w[e] = 0.0;
-    }""")
-    w(f"    sm.red[{trw_sum}][threadIdx.x] = trw;")
+          for (int bb = 0; bb < 4; ++bb) {
+            const int gj = gj0 + bb;
+            const double wv = ai * aj[bb] - kin[bb];
+            const bool in = gi < n && gj < n;
+            w[bb] = in ? (gi > gj ? 2.0 * wv : (gi == gj ? wv : 0.0)) : 0.0;
+            if (gi == gj && gi < n) trw += wv;
+          }
+        }""")
+    cat_loads("        ")
     for c, cp in enumerate(comps):
         if not cp.sums:
             continue
-        names = list(cp.sums)
-        w(f"    {{      // component {c}: sums {', '.join(f'{k} -> {v}' for k, v in cp.sums.items())}")
-        w("      double " + ", ".join(f"s_{k} = 0.0" for k in names) + ";")
-        w(f"      if (!above && (cmask & {1 << c}u)) {{")
-        for s in _emit_loads(cp, True):
-            w("  " + s)
-        skip = bool(cp.cats)
+        w(f"        if (cmask & {1 << c}u) {{      // component {c}: sums {', '.join(f'{k} -> {v}' for k, v in cp.sums.items())}")
+        ind = "          "
+        skip = bool(cp.cats) and bool(cp.se or cp.other)
         if skip:
-            for s in _warp_skip_open(cp):
-                w("  " + s)
+            for s_ in _warp_skip_open(cp, ind):
+                w(s_)
+            ind += "  "
+        for s_ in _emit_loads(cp, ind):
+            w(s_)
         w("#pragma unroll")
-        w("        for (int a = 0; a < 4; ++a)")
-        w("#pragma unroll")
-        w("          for (int b = 0; b < 4; ++b) {")
-        w("            double v = w[a * 4 + b];")
+        w(f"{ind}for (int j = 0; j < 4; ++j) {{")
+        w(f"{ind}  double v = w[j];")
         if cp.cats:
-            w(f"            if (!({_mask_expr(cp, 'a', 'b')})) v = 0.0;")
+            w(f"{ind}  if (!({_mask_expr(cp, 'j')})) v = 0.0;")
         if cp.se:
-            first = True
             for i, (x, _) in enumerate(cp.se):
-                w(f"            const double d{i} = xi{x}[a] - xj{x}[b], u{i} = d{i} * d{i};")
-                w(f"            {'double un = -u0;' if first else f'un -= u{i};'}")
-                first = False
-            w("            v *= wv_exp2_12_lo(un, sm.tab);")
-        for s in value_terms(cp, "a", "b", True):
-            w("            " + s)
+                w(f"{ind}  const double d{i} = xi{x} - xj{x}[j], u{i} = d{i} * d{i};")
+                w(f"{ind}  {'double un = -u0;' if i == 0 else f'un -= u{i};'}")
+            w(f"{ind}  v *= wv_exp2_big_lo(un, sm.tab);")
+        for s_ in value_terms(cp, "a", "j", True):
+            w(f"{ind}  " + s_)
         if "S" in cp.sums:
-            w("            s_S += v;")
+            w(f"{ind}  s{c}_S += v;")
         for i in range(len(cp.se)):
             if f"se{i}" in cp.sums:
-                w(f"            s_se{i} = fma(v, u{i}, s_se{i});")
+                w(f"{ind}  s{c}_se{i} = fma(v, u{i}, s{c}_se{i});")
         for i, o in enumerate(cp.other):
             if f"ls{i}" in cp.sums:
-                w(f"            s_ls{i} = fma(v, q{i}, s_ls{i});")
+                w(f"{ind}  s{c}_ls{i} = fma(v, q{i}, s{c}_ls{i});")
             if f"aux{i}" in cp.sums:
-                w(f"            s_aux{i} = fma(v, qa{i}, s_aux{i});")
-        w("          }")
+                w(f"{ind}  s{c}_aux{i} = fma(v, qa{i}, s{c}_aux{i});")
+        w(f"{ind}}}")
         if skip:
-            w("        }")
-        w("      }")
-        for k in names:
-            w(f"      sm.red[{cp.sums[k]}][threadIdx.x] = s_{k};")
-        w("    }")
-    w("    __syncthreads();")
-    w(f"    wvs_reduce_sums(&sm.red[0][0], {nsum}, sm.sums);")
-    w("    __syncthreads();")
+            w("          }")
+        w("        }")
+    w("      }")
+    w("    }")
+    w("    __syncwarp();       // every lane is done with the staged columns: `red` aliases them")
+    w(f"    sw.red[{trw_sum} * 33 + lane] = trw;")
+    for c, cp in enumerate(comps):
+        for k, idx in cp.sums.items():
+            w(f"    sw.red[{idx} * 33 + lane] = s{c}_{k};")
+    w("    __syncwarp();")
+    w(f"    for (int k = lane; k < {nsum}; k += 32) sm.wsum[t - t0][warp][k] = wvs_warp_row_sum(sw.red, k);")
+    w("  }")
+    w("  __syncthreads();")
+    w(f"  for (int i = threadIdx.x; i < (t1 - t0) * {nsum}; i += WVS_THREADS) {{")
+    w(f"    const int tl = i / {nsum}, k = i % {nsum};")
+    w("    double s_ = sm.wsum[tl][0][k];")
+    w("#pragma unroll")
+    w("    for (int q = 1; q < WVS_THREADS / 32; ++q) s_ += sm.wsum[tl][q][k];")
+    w("    sm.sums[tl][k] = s_;")
+    w("  }")
+    w("  __syncthreads();")
     # ---- scalar epilogue: partial[slot] = sum of (reduced sum) x (scalar coefficient)
     contrib: Dict[int, List[str]] = {s: [] for s in range(ns)}
     for cp in comps:
@@ -431,26 +477,27 @@ def generate(p: Program) -> Optional[SpecSource]:
         if "S" in cp.sums:
             for k, s in enumerate(cp.var_slots):
                 if trainable[s]:
-                    contrib[s].append(f"sm.sums[{cp.sums['S']}] * ({_prod(th[:k] + th[k + 1:])})")
+                    contrib[s].append(f"S[{cp.sums['S']}] * ({_prod(th[:k] + th[k + 1:])})")
         for i, (_, sl) in enumerate(cp.se):
             if f"se{i}" in cp.sums:
-                contrib[sl].append(f"sm.sums[{cp.sums[f'se{i}']}] * ({var_all}) * ({TWO_LN2} / sm.theta[{sl}])")
+                contrib[sl].append(f"S[{cp.sums[f'se{i}']}] * ({var_all}) * ({TWO_LN2} / sm.theta[{sl}])")
         for i, o in enumerate(cp.other):
             if f"ls{i}" in cp.sums:
-                contrib[o["ls"]].append(f"sm.sums[{cp.sums[f'ls{i}']}] * ({var_all}) / sm.theta[{o['ls']}]")
+                contrib[o["ls"]].append(f"S[{cp.sums[f'ls{i}']}] * ({var_all}) / sm.theta[{o['ls']}]")
             if f"aux{i}" in cp.sums:
-                contrib[o["aux"]].append(f"sm.sums[{cp.sums[f'aux{i}']}] * ({var_all}) / (sm.theta[{o['ls']}] * sm.theta[{o['aux']}])")
-    contrib[int(p.noise_slot)].append(f"sm.sums[{trw_sum}]")
-    w(f"    if (threadIdx.x < {ns}) {{")
-    w("      double v = 0.0;")
-    w("      switch (threadIdx.x) {")
-    for s in range(ns):
-        if contrib[s]:
-            w(f"        case {s}: v = {' + '.join(contrib[s])}; break;")
-    w("        default: break;")
-    w("      }")
-    w("      bd.partial[((size_t)b * ntiles + t) * bd.n_slots_max + threadIdx.x] = v;")
+                contrib[o["aux"]].append(f"S[{cp.sums[f'aux{i}']}] * ({var_all}) / (sm.theta[{o['ls']}] * sm.theta[{o['aux']}])")
+    contrib[int(p.noise_slot)].append(f"S[{trw_sum}]")
+    w(f"  for (int i = threadIdx.x; i < (t1 - t0) * {ns}; i += WVS_THREADS) {{")
+    w(f"    const int tl = i / {ns}, slot = i % {ns};")
+    w("    const double* S = sm.sums[tl];")
+    w("    double v = 0.0;")
+    w("    switch (slot) {")
+    for s_ in range(ns):
+        if contrib[s_]:
+            w(f"      case {s_}: v = {' + '.join(contrib[s_])}; break;")
+    w("      default: break;")
     w("    }")
+    w("    bd.partial[((size_t)b * ntiles + t0 + tl) * bd.n_slots_max + slot] = v;")
     w("  }")
     w("}")
 
