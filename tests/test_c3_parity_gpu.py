@@ -51,7 +51,7 @@ def _rel_f(a, b):
 
 
 def _param_dev(xa, xb):
-    """max over the 17 parameters of |constrained difference| / (1e-5 + 1e-5 |value|): <= 1 means "to 1e-5""""
+    """max over the 17 parameters of |constrained difference| / (1e-5 + 1e-5 |value|): <= 1 means 'to 1e-5'"""
     ca, cb = _constrained(np.asarray(xa, dtype=np.float64)), _constrained(np.asarray(xb, dtype=np.float64))
     return float(np.max(np.abs(ca - cb) / (1e-5 + 1e-5 * np.abs(cb))))
 
