@@ -215,7 +215,7 @@ def main():
     lo, hi = shard_bounds(args.outcomes * world, rank, world)
     Xn = gps.X.to_numpy(dtype=np.float64)
     Yn = np.ascontiguousarray(gps.Y.iloc[:, lo:hi].to_numpy(dtype=np.float64).T)
-    batch = Batch(eng, Xn, Yn, [model.program()])
+    batch = Batch(eng, Xn, Yn, [model.program()], specialize=True)     # as penalized_optimization asks for this job size
     x0 = batch.x0()
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
     opts = dict(maxiter=50000, maxfun=50000)

@@ -16,7 +16,7 @@ for path, p in k.named_parameters():
 m = wb.GPR(k, mean_function=wb.ConstantMean())
 eng = Engine(0)
 t0 = time.time()
-bt = Batch(eng, Xs.to_numpy(), Ys.to_numpy().T.copy(), [m.program()])
+bt = Batch(eng, Xs.to_numpy(), Ys.to_numpy().T.copy(), [m.program()], specialize=True)
 print("batch create %.2fs workspace %.2f GB" % (time.time() - t0, bt.workspace_bytes / 1e9), flush=True)
 x = bt.x0()
 bt.profile(True)

@@ -32,7 +32,8 @@ def c3(engine):
     Yn = np.ascontiguousarray(gps.Y.to_numpy(dtype=np.float64).T)
     for r in gold["fits"]:      # the fixture belongs to exactly this data
         assert abs(float(np.sum(Yn[r["outcome"]] * np.arange(1, Yn.shape[1] + 1))) - r["y_checksum"]) < 1e-9
-    batch = Batch(engine, Xn, Yn, [model.program()])
+    batch = Batch(engine, Xn, Yn, [model.program()], specialize=True)      # as penalized_optimization runs this job size
+    assert batch.specialized
     res = batch.fit(maxiter=50000, maxfun=50000)
     batch.close()
     names = [pruned_name(model, res["x"][b], Xn) for b in range(B)]

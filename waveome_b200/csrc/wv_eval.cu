@@ -436,13 +436,16 @@ __device__ __forceinline__ void wv_panel_body(const WvBatchDev& bd, int b, int s
   // (n + 1) - 64 (nt - 1) real rows; a warp whose 32 rows / columns are all padding produces zeros that are already in
   // memory (gram rewrites the identity padding, Mt's padding columns are never non-zero)
   const int real_last = bd.n + 1 - (bd.nt - 1) * WV_NB;
-  const int warp_ = threadIdx.x >> 5;
+  const int warp_ = wv_warp_role();
   bool dead;
   if (MODE == 0) dead = (step + 1 + tile == bd.nt - 1) && real_last <= 32 && (warp_ >> 1) == 1;
   else dead = (step == bd.nt - 1) && real_last <= 32 && (warp_ & 1) == 1;
   double acc[4][4][2];
   wv_zero_acc(acc);
-  if (k1 > k0) wv_gemm_nt_64(sm.g, Ag, Bg, ld, k0, k1, acc, dead);
+  if (k1 > k0) {
+    if (MODE == 1) wv_gemm_nt_64_tria(sm.g, Ag, Bg, ld, k0, k1, acc, dead);     // Mt[j,j] is upper triangular
+    else wv_gemm_nt_64(sm.g, Ag, Bg, ld, k0, k1, acc, dead);
+  }
   int r0, c0;
   wv_frag_origin(r0, c0);
   // T = C_in - acc  (or -acc ... the sign is applied at the end for trtri) -> smem as the A operand of the 2nd product
@@ -607,9 +610,10 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_kinv_kernel(WvBatchDev bd,
   // rows / columns beyond n of K^-1 are never read (the gradient pass masks them): padding warps of the last tile
   // row / column skip their products
   const int real_last = bd.n + 1 - (bd.nt - 1) * WV_NB;
-  const int warp_ = threadIdx.x >> 5;
+  const int warp_ = wv_warp_role();
   const bool dead = real_last <= 32 && ((ti == bd.nt - 1 && (warp_ >> 1) == 1) || (tj == bd.nt - 1 && (warp_ & 1) == 1));
-  wv_gemm_nt_64(sm, Mb + (size_t)ti * WV_NB * ld, Mb + (size_t)tj * WV_NB * ld, ld, ti * WV_NB, bd.n8, acc, dead);
+  // the first k-tile of the A operand is Mt[ti,ti], upper triangular
+  wv_gemm_nt_64_tria(sm, Mb + (size_t)ti * WV_NB * ld, Mb + (size_t)tj * WV_NB * ld, ld, ti * WV_NB, bd.n8, acc, dead);
   if (dead) return;
   int r0, c0;
   wv_frag_origin(r0, c0);

@@ -165,6 +165,14 @@ __device__ __forceinline__ bool wv_leaf_is_cheap(int type) {
   return type == WV_LEAF_CAT || type == WV_LEAF_CONST || type == WV_LEAF_LINEAR || type == WV_LEAF_EMPTY;
 }
 
+// Role of a warp inside the 2 x 2 warp grid of a 64x64 tile product.  Hardware places warp w of every CTA on SM
+// sub-partition w mod 4, and the roles are not equally heavy: the padding ("dead") half of a model's last tile row and
+// the zero half of a triangular operand always fall on the same roles.  Flipping the row role with the CTA's parity
+// spreads the light roles over all four tensor pipes of the SM.
+__device__ __forceinline__ int wv_warp_role() {
+  return (int)(threadIdx.x >> 5) ^ ((int)((blockIdx.x + blockIdx.y) & 1u) << 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // 64x64 NT tile GEMM on the FP64 tensor pipe:
 //   acc[m][n] = sum_{k in [k0,k1)} Ag[m*ld + k] * Bg[n*ld + k],  k0 % 16 == 0, k1 % 8 == 0
@@ -205,11 +213,36 @@ __device__ __forceinline__ void wv_gemm_issue(WvGemmSmem& sm, int stage, const d
 // `dead`: this warp's 32x32 part of the tile is padding (rows / columns beyond the model's n + 1): it keeps staging
 // operands and meeting the barriers but issues no DMMA, which frees the tensor pipe for the other warps of the SM
 // (the last tile row / column of a model holds (n + 1) mod 64 real rows -- 25 of 64 at n = 600).
-template <bool BNN>
+// One 16-deep chunk of a product whose A operand is the UPPER TRIANGULAR diagonal tile of Mt = L^{-T} (row m is zero for
+// k < m): the 8-row group mi of row role WM needs the 4-deep step at k = 16 C + kk only if 16 C + kk + 4 > 32 WM + 8 mi.
+// C and WM are template constants, so the skipped DMMAs cost nothing -- 44 % of the tile product.
+template <int C, int WM>
+__device__ __forceinline__ void wv_chunk_tri_a(const double* __restrict__ as, const double* __restrict__ bs,
+                                               double (&acc)[4][4][2]) {
+#pragma unroll
+  for (int kk = 0; kk < WV_BK; kk += 4) {
+    if (16 * C + kk + 4 <= 32 * WM) continue;
+    double af[4], bf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      af[i] = (16 * C + kk + 4 > 32 * WM + 8 * i) ? as[i * 8 * WV_LDS + kk] : 0.0;
+      bf[i] = bs[i * 8 * WV_LDS + kk];
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+      if (16 * C + kk + 4 > 32 * WM + 8 * mi) {
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) wv_dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+      }
+  }
+}
+
+// TRIA: the first 64 k-columns of the A operand (k0 is a tile boundary) are an upper triangular tile
+template <bool BNN, bool TRIA = false>
 __device__ __forceinline__ void wv_gemm_64(WvGemmSmem& sm, const double* __restrict__ Ag,
                                            const double* __restrict__ Bg, int ld, int k0, int k1,
                                            double (&acc)[4][4][2], bool dead = false) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = wv_warp_role();
   const int wm = warp >> 1, wn = warp & 1;
   const int fr = lane >> 2, fk = lane & 3;
   const int nchunks = (k1 - k0 + WV_BK - 1) / WV_BK;
@@ -230,6 +263,18 @@ __device__ __forceinline__ void wv_gemm_64(WvGemmSmem& sm, const double* __restr
     const double* as = sm.a[c % WV_STAGES] + (wm * 32 + fr) * WV_LDS + fk;
     const double* bs = BNN ? sm.b[c % WV_STAGES] + fk * WV_LDN + wn * 32 + fr
                            : sm.b[c % WV_STAGES] + (wn * 32 + fr) * WV_LDS + fk;
+    if (TRIA && !BNN && c < 4) {
+      if (wm == 0) {
+        if (c == 0) wv_chunk_tri_a<0, 0>(as, bs, acc);
+        else if (c == 1) wv_chunk_tri_a<1, 0>(as, bs, acc);
+        else if (c == 2) wv_chunk_tri_a<2, 0>(as, bs, acc);
+        else wv_chunk_tri_a<3, 0>(as, bs, acc);
+      } else {
+        if (c == 2) wv_chunk_tri_a<2, 1>(as, bs, acc);
+        else if (c == 3) wv_chunk_tri_a<3, 1>(as, bs, acc);       // chunks 0, 1: rows 32.. are zero for k < 32
+      }
+      continue;
+    }
 #pragma unroll
     for (int kk = 0; kk < WV_BK; kk += 4) {
       double af[4], bf[4];
@@ -251,6 +296,12 @@ __device__ __forceinline__ void wv_gemm_nt_64(WvGemmSmem& sm, const double* __re
                                               const double* __restrict__ Bg, int ld, int k0, int k1,
                                               double (&acc)[4][4][2], bool dead = false) {
   wv_gemm_64<false>(sm, Ag, Bg, ld, k0, k1, acc, dead);
+}
+// A's first k-tile is the upper triangular diagonal tile of Mt (trtri, kinv)
+__device__ __forceinline__ void wv_gemm_nt_64_tria(WvGemmSmem& sm, const double* __restrict__ Ag,
+                                                   const double* __restrict__ Bg, int ld, int k0, int k1,
+                                                   double (&acc)[4][4][2], bool dead = false) {
+  wv_gemm_64<false, true>(sm, Ag, Bg, ld, k0, k1, acc, dead);
 }
 
 // Packed lower-triangular 64x64 block (the inverse of a Cholesky diagonal block) in shared memory: the 8 rows of row
@@ -277,7 +328,7 @@ __device__ __forceinline__ void wv_dp_load(double* __restrict__ Dp, const double
 __device__ __forceinline__ void wv_gemm_nt_smem64(const double* __restrict__ Ts, const double* __restrict__ Dp,
                                                   double (&acc)[4][4][2], bool dead = false) {
   if (dead) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = wv_warp_role();
   const int wm = warp >> 1, wn = warp & 1;
   const int fr = lane >> 2, fk = lane & 3;
   const double* as = Ts + (wm * 32 + fr) * WV_LDT + fk;
@@ -304,7 +355,7 @@ __device__ __forceinline__ void wv_gemm_nt_smem64(const double* __restrict__ Ts,
 
 // accumulator fragment coordinates of this thread: row = r0 + mi*8, col = c0 + ni*8 (+0,+1)
 __device__ __forceinline__ void wv_frag_origin(int& r0, int& c0) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = wv_warp_role();
   r0 = (warp >> 1) * 32 + (lane >> 2);
   c0 = (warp & 1) * 32 + (lane & 3) * 2;
 }

@@ -135,9 +135,10 @@ DEFAULT_LBFGS = dict(maxcor=10, maxiter=15000, maxfun=15000, maxls=20, ftol=2.22
                      on_chol_fail="nan")
 
 
-#: Batches of at least this many models that share ONE program structure get run-time specialised Gram / gradient
-#: kernels (specialize.py -> NVRTC); smaller or mixed batches stay on the interpreter kernels.  WV_SPECIALIZE=0 turns the
-#: specialisation off, WV_SPECIALIZE=1 forces it for every single-structure batch.
+#: Jobs of at least this many models that share ONE program structure (GPSearch.penalized_optimization: every outcome x
+#: the saturated kernel) ask for run-time specialised Gram / gradient kernels (specialize.py -> NVRTC, ~4 s once per
+#: structure and machine, then a disk cache); the decision is taken on the WHOLE job, not per shard or sub-batch.
+#: WV_SPECIALIZE=0 turns the specialisation off, WV_SPECIALIZE=1 forces it for every single-structure batch.
 SPECIALIZE_MIN_MODELS = 64
 _spec_warned = False
 
@@ -234,10 +235,14 @@ class Batch:
         h = C.c_void_p()
         _check(self.lib.wv_batch_create(engine.handle, C.byref(bd), C.byref(h)), "wv_batch_create")
         self.handle = h
+        # Run-time specialised element-wise kernels are the CALLER's choice, never a function of the batch size: a model's
+        # result must not depend on how many neighbours share its batch (specialised and interpreter kernels agree to
+        # ~1e-13, not bit for bit).  WV_SPECIALIZE=0 / 1 overrides every caller.
         self.specialized = False
-        mode = os.environ.get("WV_SPECIALIZE", "auto") if specialize is None else specialize
-        if mode in (True, "1", 1) or (mode == "auto" and self.B >= SPECIALIZE_MIN_MODELS):
-            self.specialize(X, strict=mode in (True, "1", 1) and specialize is not None)
+        env = os.environ.get("WV_SPECIALIZE", "")
+        want = bool(specialize) and env != "0" or env == "1"
+        if want:
+            self.specialize(X)
 
     # ------------------------------------------------------------------------------------------
     def specialize(self, X: Optional[np.ndarray] = None, strict: bool = False) -> bool:

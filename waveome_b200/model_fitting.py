@@ -69,7 +69,8 @@ def run_fit_jobs(jobs: List[dict], engine=None, streams: Optional[int] = None, *
     streams = FIT_STREAMS if streams is None else max(1, int(streams))
 
     def run_one(eng, job):
-        batch = Batch(eng, job["X"], job["Y"], job["table"], job.get("prog_id"), P=job["P"])
+        batch = Batch(eng, job["X"], job["Y"], job["table"], job.get("prog_id"), P=job["P"],
+                      specialize=job.get("specialize", False))
         try:
             if job["lik_name"] != "gaussian":
                 batch.set_likelihood(job["lik_name"], job["lik_param"])
@@ -125,7 +126,8 @@ def likelihood_key(model) -> tuple:
 
 
 def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional[np.ndarray] = None,
-               engine=None, max_batch_bytes: float = 60e9, streams: int = 1, **lbfgs_opts) -> dict:
+               engine=None, max_batch_bytes: float = 60e9, streams: int = 1, specialize: bool = False,
+               **lbfgs_opts) -> dict:
     """MAP-fit ``models[b]`` to outcome ``Y[b]`` (Y is [B, n]); all models share X [n, D].
 
     Models with identical kernel programs share one device program.  Fitted values are written back into the
@@ -134,7 +136,9 @@ def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional
 
     ``streams``: concurrent sub-batches per group (``run_fit_jobs``).  Default 1: the mixed batches of the kernel search
     (hundreds of structures, a few hundred models per piece) measured 5 % SLOWER on 4 streams (config 2: 24.8 s against
-    23.5 s); ``fit_replicated`` -- one structure, thousands of models -- is where the split pays."""
+    23.5 s); ``fit_replicated`` -- one structure, thousands of models -- is where the split pays.
+    ``specialize``: ask for run-time specialised element-wise kernels (engine.Batch); only pieces whose models share one
+    program structure get them."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     Y = np.ascontiguousarray(Y, dtype=np.float64)
     B = len(models)
@@ -172,7 +176,7 @@ def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional
             sel = idx[lo:hi]
             sels.append(sel)
             jobs.append(dict(X=X, Y=Y[sel], table=table, prog_id=prog_id[sel], P=P, lik_name=lik_name,
-                             lik_param=lik_param, starts=starts[sel]))
+                             lik_param=lik_param, starts=starts[sel], specialize=specialize))
     for sel, (r, c) in zip(sels, run_fit_jobs(jobs, engine=engine, streams=streams, **lbfgs_opts)):
         for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
             out[key][sel] = r[key]
@@ -202,7 +206,7 @@ def packed_parameters(model: GPR):
 
 
 def fit_replicated(X: np.ndarray, Y: np.ndarray, template: GPR, make_models=None, engine=None,
-                   max_batch_bytes: float = 60e9, **lbfgs_opts):
+                   max_batch_bytes: float = 60e9, specialize: bool = False, **lbfgs_opts):
     """MAP-fit B copies of ONE model structure (same kernel tree, priors and start values) to the B outcomes Y[b]:
     what GPSearch.penalized_optimization does (waveome/model_search.py:302-329 builds the same PSVGP for every
     outcome).  The device fit runs on a worker thread (the C call releases the GIL) while ``make_models()`` -- the
@@ -225,8 +229,8 @@ def fit_replicated(X: np.ndarray, Y: np.ndarray, template: GPR, make_models=None
     def work():
         try:
             pieces = split_for_streams(B, chunk, 1 if engine is not None else None)
-            jobs = [dict(X=X, Y=Y[lo:hi], table=[prog], P=P, lik_name=lik_name, lik_param=lik_param)
-                    for lo, hi in pieces]
+            jobs = [dict(X=X, Y=Y[lo:hi], table=[prog], P=P, lik_name=lik_name, lik_param=lik_param,
+                         specialize=specialize) for lo, hi in pieces]
             for (lo, hi), (r, c) in zip(pieces, run_fit_jobs(jobs, engine=engine, **lbfgs_opts)):
                 for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
                     out[key][lo:hi] = r[key]

@@ -136,6 +136,10 @@ class GPSearch:
         n_fits = max(1, int(num_restart)) if num_restart else 1
         if verbose and rank == 0:
             print(f"Building {len(self.out_names)} models on {world} GPU(s)...")
+        # one kernel structure for every outcome: worth run-time specialised Gram / gradient kernels when the JOB (all
+        # outcomes, not this rank's shard) is large enough to pay for their compilation
+        from .engine import SPECIALIZE_MIN_MODELS
+        self._specialize = len(self.out_names) >= SPECIALIZE_MIN_MODELS
         if penalization_factor is None:
             res, models = self._iterated_factor_fit(full_kernel, mean_function, names, Xn, Yn, num_factor_iter, num_opt_iter,
                                                     verbose and rank == 0)
@@ -149,7 +153,7 @@ class GPSearch:
                 for m in models:
                     for p in m.trainable_parameters:
                         p.assign(p.transform_fn(rs.normal(loc=0.0, scale=1.0)))
-                res = fit_models(Xn, Yn, models, maxiter=num_opt_iter, maxfun=num_opt_iter)
+                res = fit_models(Xn, Yn, models, maxiter=num_opt_iter, maxfun=num_opt_iter, specialize=self._specialize)
                 if best is None:
                     best = {k: np.array(v) for k, v in res.items() if isinstance(v, np.ndarray)}
                 else:
@@ -162,7 +166,7 @@ class GPSearch:
         else:
             # one structure for every outcome: the device fit overlaps the construction of the model objects
             res, models = fit_replicated(Xn, Yn, template, make_models=make_models, maxiter=num_opt_iter,
-                                         maxfun=num_opt_iter)
+                                         maxfun=num_opt_iter, specialize=self._specialize)
         for m in models:
             m.cut_kernel_components(Xn)
             m.update_kernel_name()
@@ -201,7 +205,8 @@ class GPSearch:
             models.append(PenalizedGPR(K.deepcopy(full_kernel), mean_function=K.deepcopy(mean_function),
                                        penalization_factor=2 * 1.1 * sigma_hat * np.sqrt(n) * z,
                                        likelihood=make_likelihood(self.likelihood)))
-        res = fit_models(Xn, Yn, models, maxiter=num_opt_iter, maxfun=num_opt_iter)
+        spec = getattr(self, "_specialize", False)
+        res = fit_models(Xn, Yn, models, maxiter=num_opt_iter, maxfun=num_opt_iter, specialize=spec)
         active = list(range(len(models)))
         for _ in range(int(num_factor_iter)):
             if not active:
@@ -219,7 +224,8 @@ class GPSearch:
             if verbose:
                 print(f"penalization factor iteration: {len(active)} outcomes continue")
             if active:
-                r = fit_models(Xn, Yn[active], [models[b] for b in active], maxiter=num_opt_iter, maxfun=num_opt_iter)
+                r = fit_models(Xn, Yn[active], [models[b] for b in active], maxiter=num_opt_iter, maxfun=num_opt_iter,
+                               specialize=spec)
                 for key in ("f", "lml", "n_iter", "n_eval", "status"):
                     res[key][active] = r[key]
         self.iterating_penalization_factor = True
