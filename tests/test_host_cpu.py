@@ -192,7 +192,7 @@ def test_fit_models_reassembles_concurrent_sub_batches(monkeypatch):
     seen = []
 
     class FakeBatch:
-        def __init__(self, eng, X, Y, table, prog_id=None, P=None):
+        def __init__(self, eng, X, Y, table, prog_id=None, P=None, specialize=False):
             self.eng, self.Y, self.P, self.lik = eng, np.asarray(Y), P, ("gaussian", 0.0)
             self.B = self.Y.shape[0]
 
