@@ -80,7 +80,7 @@ def _cpu_fit_one(args):
     r = gp_oracle.fit(spec, X, y, maxiter=50000, maxfun=50000)
     if ctx is not None:
         ctx.restore_original_limits()
-    return r["nfev"], r["status"], time.perf_counter() - t0, float(r["f"]), int(r["nit"])
+    return r["nfev"], r["status"], time.perf_counter() - t0, float(r["f"]), int(r["nit"]), [float(v) for v in r["x"]]
 
 
 def cpu_reference_step(spec, Xn, Yn, cols, cores):
@@ -131,6 +131,108 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
+# measurements of the other BASELINE configs and of the strong-scaling point, reported next to the headline
+# ------------------------------------------------------------------------------------------------
+def measure_extras(args, rank, world, local_rank, eng, barrier, reduce_max, torch):
+    """Each entry carries its own device-clock time: CUDA events on the engine stream, recorded after a barrier +
+    synchronize and read after the call returned (every entry point below synchronises its streams before returning),
+    max over ranks.  A failing entry reports its error instead of taking the headline line down."""
+    import numpy as np
+    import waveome_b200 as wb
+    from waveome_b200 import datasets
+    from waveome_b200.engine import Batch
+    from waveome_b200.model_search import GPSearch, shard_bounds
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
+    out = {}
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        r = fn()
+        e1.record(stream)
+        barrier()
+        return reduce_max(e0.elapsed_time(e1)) * 1e-3, r
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:                       # noqa: BLE001 -- reported in the line
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            barrier()
+
+    # ---- configs[2] as BASELINE.json words it: 2000 outcomes IN TOTAL, sharded over the ranks (strong scaling)
+    def strong():
+        total = args.outcomes
+        X, Y = make_workload(total, seed=2024)
+        gps = make_search(X, Y)
+        model = build_model(gps)
+        lo, hi = shard_bounds(total, rank, world)
+        Xn = gps.X.to_numpy(dtype=np.float64)
+        Yn = np.ascontiguousarray(gps.Y.iloc[:, lo:hi].to_numpy(dtype=np.float64).T)
+        batch = Batch(eng, Xn, Yn, [model.program()], specialize=True)
+        x0 = batch.x0()
+        batch.fit(x0, maxiter=50000, maxfun=50000)
+        steps = max(1, min(args.steps, 3))
+        secs, _ = timed(lambda: [batch.fit(x0, maxiter=50000, maxfun=50000) for _ in range(steps)])
+        batch.close()
+        return {"outcomes_total": total, "outcomes_per_gpu": hi - lo, "steps": steps, "value": total * steps / secs,
+                "unit": "fits/s", "ms_per_step": 1e3 * secs / steps, "scaling": "strong"}
+    if world > 1:
+        guarded("strong_scaling", strong)
+
+    # ---- configs[1]: full kernel search, 200 outcomes x depth 5 (outcomes sharded over the ranks by run_search)
+    def config2():
+        X, Y = datasets.overview_synthetic(n_people=50, n_observations=10, n_outcomes=200)
+        gps = GPSearch(X, Y, unit_col="person_id", categorical_vars=["female"])
+        secs, _ = timed(lambda: gps.run_search(max_depth=5, gather=False))
+        return {"outcomes": 200, "max_depth": 5, "search_s": secs, "fits_this_rank": int(gps.fit_report["n_fits"]),
+                "batches_this_rank": int(gps.fit_report["batches"]), "outcomes_per_s": 200 / secs}
+    guarded("config2_search", config2)
+
+    # ---- configs[3]: one n = 8192 GPR (large-n schedule); replicas only -- every rank runs its own copy
+    def config4():
+        X, Y = datasets.large_gpr(512, 16)
+        Xn = X.to_numpy().copy()
+        Xn[:, 1] = (Xn[:, 1] - Xn[:, 1].mean()) / Xn[:, 1].std()
+        y = Y.to_numpy()[:, 0]
+        cat = wb.Categorical(active_dims=[0]); wb.set_trainable(cat.variance, False)
+        k = wb.Sum([wb.Product([cat, wb.SquaredExponential(active_dims=[1], lengthscales=0.5)]),
+                    wb.Periodic(wb.SquaredExponential(active_dims=[1]), period=0.9)])
+        model = wb.GPR(k, mean_function=wb.ConstantMean(), noise_variance=0.1)
+        batch = Batch(eng, Xn, y[None, :], [model.program()])
+        x = batch.x0()
+        batch.eval(x)
+        batch.profile(True)
+        reps = 3
+        secs, _ = timed(lambda: [batch.eval(x) for _ in range(reps)])
+        prof = batch.profile_read()
+        batch.close()
+        n = float(len(y))
+        chol_ms = (prof["chol_diag"][0] + prof["chol_panel"][0] + prof["chol_syrk"][0]) / reps
+        tf = n ** 3 / 3 / (chol_ms * 1e-3) / 1e12
+        return {"n": int(n), "eval_ms": 1e3 * secs / reps, "evals_per_s": reps / secs, "cholesky_ms": chol_ms,
+                "cholesky_tflops": tf, "cholesky_frac_of_fp64_peak": tf / FP64_PEAK_TFLOPS,
+                "class_ms": {k_: round(v[0] / reps, 3) for k_, v in prof.items() if v[0] > 0}, "parallelism": "replicas only"}
+    guarded("config4_large_gpr", config4)
+
+    # ---- configs[4]: 1000 count outcomes (n = 500), variational bound, through the public API
+    def config5():
+        res = {}
+        for fam in ("poisson", "negative_binomial"):
+            X, Y = datasets.count_microbiome(n_outcomes=1000, family=fam)
+            def run():
+                g = GPSearch(X, Y, unit_col="subject", outcome_likelihood=fam)
+                g.penalized_optimization(gather=False)
+                return g
+            secs, g = timed(run)
+            res[fam] = {"outcomes": 1000, "n": int(len(X)), "seconds": secs, "fits_per_s": 1000 / secs}
+        return res
+    guarded("config5_counts", config5)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -140,6 +242,7 @@ def main():
     ap.add_argument("--outcomes", type=int, default=2000, help="outcomes (models) per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="outcomes in the CPU baseline sample (0 = one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-config measurements next to the headline")
     args = ap.parse_args()
 
     # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner under torchrun,
@@ -202,6 +305,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_max(v):
+        t_ = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
 
     from waveome_b200.engine import Batch
     from waveome_b200.model_fitting import get_engine
@@ -272,6 +381,16 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = fits_total / float(t.item())
+    # the API default gather=True on top (every rank ends with the fitted models of ALL outcomes: one all_gather_object
+    # of pickled models); one step
+    e2e_gather_value = None
+    if world > 1:
+        barrier()
+        t0 = time.perf_counter()
+        g = make_search(X, Y)
+        g.penalized_optimization(penalization_factor=1.0, gather=True)
+        barrier()
+        e2e_gather_value = args.outcomes * world / reduce_max(time.perf_counter() - t0)
     h2d = Xn.nbytes + Yn.nbytes + x0.nbytes
     d2h = x0.nbytes + args.outcomes * (8 + 8 + 4 + 4 + 4)
 
@@ -330,6 +449,7 @@ def main():
     }
     groups["class_hbm_frac"] = {k: (v / peaks["hbm_gbs"] if v else None) for k, v in groups["class_hbm_gbs"].items()}
 
+    extras = {} if args.no_extras else measure_extras(args, rank, world, local_rank, eng, barrier, reduce_max, torch)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -349,24 +469,37 @@ def main():
                 if o[1] == 0 and int(r["status"][i]) == 0 and o[0] == int(r["n_eval"][i]) and o[4] == int(r["n_iter"][i])]
         fin = [i for i, o in enumerate(cpu_reference_step.last) if np.isfinite(o[3]) and np.isfinite(r["f"][i])]
         rel = [abs(float(r["f"][i]) - cpu_reference_step.last[i][3]) / max(1.0, abs(cpu_reference_step.last[i][3])) for i in fin]
+        def pruned(xv):          # selected structure: cut_kernel_components at the fitted values
+            m = wb_kernels.deepcopy(model)
+            m.program().assign(np.asarray(xv, dtype=np.float64))
+            m.cut_kernel_components(Xn)
+            m.update_kernel_name()
+            return m.kernel_name
+        from waveome_b200 import kernels as wb_kernels
+        last = cpu_reference_step.last
+        structure_identical = sum(1 for i, o in enumerate(last) if pruned(o[5]) == pruned(r["x"][i]))
+        status_agree = sum(1 for i, o in enumerate(last) if (o[1] == 0) == (int(r["status"][i]) == 0))
         cpu["parity_sample"] = {
-            "outcomes": ncols, "converged_on_both_with_identical_nit_nfev": len(same),
+            "outcomes": ncols, "structure_identical": structure_identical, "status_agree": status_agree,
+            "converged_on_both_with_identical_nit_nfev": len(same),
             "max_rel_objective_diff_identical_trajectories":
                 max([abs(float(r["f"][i]) - cpu_reference_step.last[i][3]) / max(1.0, abs(cpu_reference_step.last[i][3]))
                      for i in same], default=None),
             "median_rel_objective_diff_all": float(np.median(rel)) if rel else None,
             "max_rel_objective_diff_all": max(rel, default=None),
             "note": "fits that enter the horseshoe's non-finite regime end ABNORMAL on both sides and are chaotic in the "
-                    "last bits (DESIGN.md section 5): they agree in objective value, not iteration by iteration"}
+                    "last bits (DESIGN.md section 5): they agree in selected structure and objective value, not iteration by "
+                    "iteration; tests/test_c3_parity_gpu.py compares the spread with the oracle's own last-bit sensitivity"}
 
     line = {"metric": "gp_model_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "lml_grad_evals_per_sec": evals_total / (ms_max * 1e-3),
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "GPSearch.penalized_optimization (pandas in, fitted models out)"},
+                    "api": "GPSearch.penalized_optimization (pandas in, fitted models out; gather=False)",
+                    "value_gather_true": e2e_gather_value},
             "gpu_launches": int(launches_total), "clocks": clocks, "roofline": roof, "roofline_groups": groups,
-            "cpu_baseline": cpu, "fit_status_hist": status_hist}
+            "cpu_baseline": cpu, "fit_status_hist": status_hist, "other_configs": extras}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

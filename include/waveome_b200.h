@@ -39,6 +39,7 @@ enum { WVT_IDENTITY = 0, WVT_SOFTPLUS = 1, WVT_SOFTPLUS_SHIFT = 2, WVT_EXP = 3 }
 enum { WVP_NONE = 0, WVP_HORSESHOE = 1, WVP_LAPLACE = 2, WVP_UNIFORM = 3 };
 /* per-model status bits */
 enum { WVS_OK = 0, WVS_CHOL_FAIL = 1, WVS_NONFINITE = 2, WVS_MAXITER = 4, WVS_LINESEARCH = 8, WVS_INNER_CAP = 16,
+       WVS_RESTORED = 64 /* wv_batch_fit_adam: a step hit a failed factorisation, the last checkpoint was restored */,
        WVS_SITE_BOUND = 32 /* ZINB: a site precision sits at its lower bound (1e-6): the value is a valid lower bound,
                               the envelope-theorem gradient is approximate */ };
 
@@ -147,6 +148,29 @@ int wv_batch_eval_device(wv_batch* b, const double* d_x, double* d_f, double* d_
  * f, lml [B] are evaluated at the returned x; n_iter, n_eval, status [B]. */
 int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* opts, double* f, double* lml,
                        int32_t* n_iter, int32_t* n_eval, int32_t* status);
+
+/* Adam with the schedule of the reference's default optimiser (BaseGP.optimize_params "adam/gradient" branch,
+ * waveome/model_classes.py:344-462; kernel_test calls it, waveome/model_search.py:2284-2297): Keras Adam steps on the
+ * unconstrained hyper-parameters; every `check_every` steps the loss after the step is recorded, the parameters are
+ * snapshotted and (every `decay_every` steps) the learning rate becomes learning_rate * decay_rate^(i / decay_every); a
+ * model stops when the loss fell by less than `convergence_threshold` between two checkpoints, after `max_iter` steps
+ * (WVS_MAXITER), on a NaN checkpoint loss (WVS_NONFINITE; upstream stops with the NaN values in place, the engine returns
+ * the last finite snapshot), or when a step meets a failed factorisation (WVS_RESTORED: the last snapshot is returned,
+ * upstream's InvalidArgumentError branch).
+ * The natural-gradient half of the upstream step acts on (q_mu, q_sqrt); the engine's objective is the bound maximised
+ * over q, so that half is exact here (its gamma = 1 limit for the Gaussian likelihood).  x HOST [B, P] in / out. */
+typedef struct wv_adam_opts {
+  double learning_rate;          /* upstream default 0.1 */
+  double decay_rate;             /* 0.96 */
+  double beta1, beta2, epsilon;  /* Keras Adam defaults 0.9, 0.999, 1e-7 */
+  double convergence_threshold;  /* 1e-9 */
+  int32_t max_iter;              /* num_opt_iter, 50000 */
+  int32_t check_every;           /* 100 */
+  int32_t decay_every;           /* 500 */
+  int32_t reserved;
+} wv_adam_opts;
+int wv_batch_fit_adam(wv_batch* b, double* x, const wv_adam_opts* opts, double* f, double* lml, int32_t* n_iter,
+                      int32_t* status);
 
 /* Post-fit quantities of the last evaluation (wv_batch_eval / wv_batch_eval_device / the final evaluation of
  * wv_batch_fit_lbfgs): alpha = (K + sigma^2 I)^{-1} (y - c), HOST [B, n] in the caller's row order, and the posterior

@@ -513,6 +513,32 @@ def log_posterior_density(model, X, y):
     return lml + lp
 
 
+def predict_f(model, X, y, Xnew):
+    """gpflow GPR.predict_f(Xnew, full_cov=False) at the model's current parameter values: (mean [m], var [m])."""
+    import scipy.linalg as sla
+    X = np.asarray(X, dtype=np.float64)
+    Xnew = np.asarray(Xnew, dtype=np.float64)
+    n = X.shape[0]
+    Kall, _ = kernel_K_and_grads(model["kernel"], np.vstack([Xnew, X]), want_grads=False)
+    m = Xnew.shape[0]
+    Kss, Ksx, Kxx = Kall[:m, :m], Kall[:m, m:], Kall[m:, m:]
+    s2 = model["likelihood_variance"]["value"]
+    c = model["mean"]["c"]["value"] if model["mean"]["type"] == "constant" else 0.0
+    L = np.linalg.cholesky(Kxx + s2 * np.eye(n))
+    A = sla.solve_triangular(L, Ksx.T, lower=True)                       # [n, m]
+    v = sla.solve_triangular(L, np.asarray(y, dtype=np.float64).reshape(-1) - c, lower=True)
+    return c + A.T @ v, np.diag(Kss) - np.sum(A * A, axis=0)
+
+
+def predict_log_density(model, X, y, Xnew, ynew):
+    """gpflow GPModel.predict_log_density((Xnew, ynew)) for the Gaussian likelihood: log N(ynew; mean, var_f + sigma^2)
+    per point (what waveome/model_classes.py:930-945 averages over the held-out rows)."""
+    mu, var = predict_f(model, X, y, Xnew)
+    vy = var + model["likelihood_variance"]["value"]
+    ynew = np.asarray(ynew, dtype=np.float64).reshape(-1)
+    return -0.5 * (LOG2PI + np.log(vy) + (ynew - mu) ** 2 / vy)
+
+
 # --------------------------------------------------------------------------------------
 # small builders used by tests / bench
 # --------------------------------------------------------------------------------------

@@ -847,6 +847,150 @@ extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o
 }
 
 // ---------------------------------------------------------------------------------------------
+// device-resident Adam with the reference's schedule (waveome/model_classes.py:344-462, the optimiser kernel_test uses by
+// default, waveome/model_search.py:2284-2297): Adam(learning_rate) steps on the unconstrained hyper-parameters, a
+// checkpoint every `check_every` steps (loss after the step; parameter snapshot; learning-rate decay
+// lr0 * decay^(i / decay_every) every `decay_every` steps), stop when the loss decreased by less than
+// `convergence_threshold` between two checkpoints, or -- restoring the last snapshot -- on a NaN checkpoint loss (the
+// reference stops there with the NaN values in place; the engine returns the last finite checkpoint) or when a step
+// hits a failed factorisation (TensorFlow's InvalidArgumentError there).  The reference alternates each Adam step
+// with a natural-gradient step of size gamma on (q_mu, q_sqrt); the engine's objective is the bound already maximised
+// over q, i.e. the gamma = 1 limit for a Gaussian likelihood, and the exact inner maximisation for the others.
+// One thread per model; the loss after step i is the value of the evaluation that opens step i + 1.
+// ---------------------------------------------------------------------------------------------
+struct WvAdamState {
+  double lr, prev_loss;
+  int it, n_loss, done, why;      // why: 0 converged, 1 maxiter, 2 NaN loss, 3 restored after a failed factorisation
+};
+
+__global__ void wv_adam_init_kernel(int B, int P, double lr0, WvAdamState* st, double* m, double* v, double* xprev,
+                                    const double* __restrict__ x, int* task) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  st[b].lr = lr0; st[b].prev_loss = 0.0; st[b].it = 0; st[b].n_loss = 0; st[b].done = 0; st[b].why = 0;
+  for (int k = 0; k < P; ++k) { m[(size_t)b * P + k] = 0.0; v[(size_t)b * P + k] = 0.0; xprev[(size_t)b * P + k] = x[(size_t)b * P + k]; }
+  task[b] = WV_LB_FG;
+}
+
+__global__ void wv_adam_step_kernel(const int* __restrict__ active, int n_active, const int* __restrict__ nx_of_model,
+                                    int P, wv_adam_opts o, WvAdamState* st, double* m, double* v, double* xprev, double* x,
+                                    const double* __restrict__ g, const double* __restrict__ f,
+                                    const int* __restrict__ status, int* task) {
+  const int i_ = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i_ >= n_active) return;
+  const int b = active[i_];
+  WvAdamState s = st[b];
+  if (s.done) return;                             // stopped since the last compaction of the active list
+  const int nx = nx_of_model[b];
+  double* xb = x + (size_t)b * P;
+  double* xp = xprev + (size_t)b * P;
+  const double fb = f[b];
+  bool stop = false;
+  if (status[b] & WV_STATUS_CHOL_FAIL) {          // the step that would start here raises in the reference
+    for (int k = 0; k < nx; ++k) xb[k] = xp[k];
+    s.why = 3; stop = true;
+  } else {
+    const int i = s.it;                           // steps done so far; fb is the loss after step i - 1
+    if (i >= 1 && (i - 1) % o.check_every == 0) {
+      if (fb != fb) {                             // NaN loss: back to the last finite checkpoint
+        for (int k = 0; k < nx; ++k) xb[k] = xp[k];
+        s.why = 2; stop = true;
+      } else {
+        for (int k = 0; k < nx; ++k) xp[k] = xb[k];
+        if ((i - 1) % o.decay_every == 0) s.lr = o.learning_rate * pow(o.decay_rate, (double)(i - 1) / o.decay_every);
+        if (s.n_loss >= 1 && s.prev_loss - fb < o.convergence_threshold) { s.why = 0; stop = true; }
+        s.prev_loss = fb;
+        s.n_loss += 1;
+      }
+    }
+    if (!stop && i >= o.max_iter) { s.why = 1; stop = true; }
+    if (!stop) {
+      const double t = (double)(i + 1);
+      const double alpha = s.lr * sqrt(1.0 - pow(o.beta2, t)) / (1.0 - pow(o.beta1, t));
+      const double* gb = g + (size_t)b * P;
+      double* mb = m + (size_t)b * P;
+      double* vb = v + (size_t)b * P;
+      for (int k = 0; k < nx; ++k) {
+        const double gk = gb[k];
+        mb[k] = o.beta1 * mb[k] + (1.0 - o.beta1) * gk;
+        vb[k] = o.beta2 * vb[k] + (1.0 - o.beta2) * gk * gk;
+        xb[k] -= alpha * mb[k] / (sqrt(vb[k]) + o.epsilon);
+      }
+      s.it = i + 1;
+    }
+  }
+  s.done = stop ? 1 : 0;
+  st[b] = s;
+  task[b] = stop ? WV_LB_CONV_F : WV_LB_FG;
+}
+
+__global__ void wv_adam_report_kernel(int B, const WvAdamState* st, const int* eval_status, int* n_iter, int* status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  n_iter[b] = st[b].it;
+  int s = eval_status[b];
+  if (st[b].why == 1) s |= WV_STATUS_MAXITER;
+  if (st[b].why == 2) s |= WV_STATUS_NONFINITE;
+  if (st[b].why == 3) s |= WV_STATUS_RESTORED;
+  status[b] = s;
+}
+
+extern "C" int wv_batch_fit_adam(wv_batch* b, double* x, const wv_adam_opts* o, double* f, double* lml, int32_t* n_iter,
+                                 int32_t* status) {
+  if (!b || !x || !o || !f || !lml || !n_iter || !status) return wv_fail("wv_batch_fit_adam: null argument");
+  if (o->max_iter < 1 || o->check_every < 1 || o->decay_every < 1) return wv_fail("wv_batch_fit_adam: bad schedule");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const int B = b->bd.B, P = b->bd.P;
+  cudaStream_t st = b->eng->stream;
+  WvAdamState* d_st = nullptr;
+  double *d_m = nullptr, *d_v = nullptr, *d_xp = nullptr;
+  if (wv_alloc(b, &d_st, (size_t)B) || wv_alloc(b, &d_m, (size_t)B * P) || wv_alloc(b, &d_v, (size_t)B * P) ||
+      wv_alloc(b, &d_xp, (size_t)B * P))
+    return -1;
+  const int tb = 64, gb = (B + tb - 1) / tb;
+  WV_CUDA(cudaMemcpyAsync(b->d_x, x, (size_t)B * P * sizeof(double), cudaMemcpyHostToDevice, st));
+  wv_nx_kernel<<<gb, tb, 0, st>>>(b->bd.programs, b->bd.prog_id, B, b->d_nx);
+  wv_adam_init_kernel<<<gb, tb, 0, st>>>(B, P, o->learning_rate, d_st, d_m, d_v, d_xp, b->d_x, b->d_task);
+  wv_iota_kernel<<<(B + 255) / 256, 256, 0, st>>>(b->d_active, B);
+  b->launches += 3;
+  int n_active = B;
+  int* cur = b->d_active;
+  int* nxt = b->d_active2;
+  // the active list is compacted (one host sync) at the checkpoints only: between them every model takes the same steps
+  for (long round = 0; n_active > 0 && round <= (long)o->max_iter + 1; ++round) {
+    if (wv_eval_all(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status, cur, n_active) != 0) return -1;
+    wv_adam_step_kernel<<<(n_active + tb - 1) / tb, tb, 0, st>>>(cur, n_active, b->d_nx, P, *o, d_st, d_m, d_v, d_xp, b->d_x,
+                                                               b->d_g, b->d_f, b->d_status, b->d_task);
+    b->prof.mark(WV_K_LBFGS, st);
+    b->launches += 1;
+    const bool sync_now = round == 0 || (round - 1) % o->check_every == 0 || b->bd.lik != 0 || round >= o->max_iter;
+    if (sync_now) {
+      wv_compact_kernel<<<1, 1024, 0, st>>>(b->d_task, B, nxt, b->d_count);
+      b->launches += 1;
+      WV_CUDA(cudaMemcpyAsync(b->h_count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+      WV_CUDA(cudaStreamSynchronize(st));
+      b->prof.resolve();
+      n_active = b->h_count[0];
+      int* tmp = cur; cur = nxt; nxt = tmp;
+    }
+  }
+  wv_iota_kernel<<<(B + 255) / 256, 256, 0, st>>>(b->d_active, B);
+  b->launches += 1;
+  if (wv_eval_all(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status, b->d_active, B) != 0) return -1;
+  b->last_x = b->d_x;
+  wv_adam_report_kernel<<<gb, tb, 0, st>>>(B, d_st, b->d_status, b->d_iter, b->d_st2);
+  b->launches += 1;
+  WV_CUDA(cudaMemcpyAsync(x, b->d_x, (size_t)B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(f, b->d_f, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(lml, b->d_lml, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(n_iter, b->d_iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(status, b->d_st2, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaStreamSynchronize(st));
+  WV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // post-fit: alpha and posterior means (gpflow GPR.predict_f mean; waveome/utilities.py:614-707 consumes predict_y means)
 // ---------------------------------------------------------------------------------------------
 extern "C" int wv_batch_get_alpha(wv_batch* b, double* alpha) {

@@ -45,6 +45,7 @@ enum WvPrior : int32_t { WV_PRIOR_NONE = 0, WV_PRIOR_HORSESHOE = 1, WV_PRIOR_LAP
 #define WV_STATUS_MAXITER 4
 #define WV_STATUS_LINESEARCH 8
 #define WV_STATUS_INNER_CAP 16    // variational path: the site iteration hit its sweep cap
+#define WV_STATUS_RESTORED 64     // Adam: a step ran into a failed factorisation, the last checkpoint was restored
 #define WV_STATUS_SITE_BOUND 32   // variational path (ZINB): a site precision sits at its lower bound; the value is a valid
                                  // bound, the gradient omits those sites' non-stationarity term
 

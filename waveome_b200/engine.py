@@ -47,10 +47,16 @@ class _LbfgsOpts(C.Structure):
                 ("ftol", C.c_double), ("gtol", C.c_double), ("chol_fail_policy", C.c_int32), ("reserved", C.c_int32)]
 
 
+class _AdamOpts(C.Structure):
+    _fields_ = [("learning_rate", C.c_double), ("decay_rate", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("epsilon", C.c_double), ("convergence_threshold", C.c_double), ("max_iter", C.c_int32),
+                ("check_every", C.c_int32), ("decay_every", C.c_int32), ("reserved", C.c_int32)]
+
+
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
     "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_likelihood", "wv_batch_set_likelihood2", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
-    "wv_batch_specialize", "wv_rtc_check", "wv_rtc_set_cache", "wv_rtc_precompile_text",
+    "wv_batch_fit_adam", "wv_batch_specialize", "wv_rtc_check", "wv_rtc_set_cache", "wv_rtc_precompile_text",
     "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_get_kinv_diag", "wv_batch_predict_mean", "wv_batch_predict_f", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
 KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk", "sites"]
@@ -85,6 +91,8 @@ def load_library():
     lib.wv_batch_eval_device.argtypes = [vp, vp, vp, vp, vp, vp]; lib.wv_batch_eval_device.restype = C.c_int
     lib.wv_batch_fit_lbfgs.argtypes = [vp, _f64p, C.POINTER(_LbfgsOpts), _f64p, _f64p, _i32p, _i32p, _i32p]
     lib.wv_batch_fit_lbfgs.restype = C.c_int
+    lib.wv_batch_fit_adam.argtypes = [vp, _f64p, C.POINTER(_AdamOpts), _f64p, _f64p, _i32p, _i32p]
+    lib.wv_batch_fit_adam.restype = C.c_int
     lib.wv_batch_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.wv_batch_counters.restype = None
     lib.wv_batch_get_alpha.argtypes = [vp, _f64p]; lib.wv_batch_get_alpha.restype = C.c_int
@@ -168,6 +176,11 @@ def rtc_precompile(programs) -> int:
             raise EngineError(lib.wv_last_error().decode())
         done += rc == 0
     return done
+
+
+#: BaseGP.optimize_params defaults (waveome/model_classes.py:236-246) + Keras Adam's
+DEFAULT_ADAM = dict(learning_rate=0.1, decay_rate=0.96, beta1=0.9, beta2=0.999, epsilon=1e-7, convergence_threshold=1e-9,
+                    max_iter=50000, check_every=100, decay_every=500)
 
 
 class Engine:
@@ -359,6 +372,24 @@ class Batch:
         _check(self.lib.wv_batch_fit_lbfgs(self.handle, _f64(x), C.byref(co), _f64(f), _f64(lml), _i32(nit), _i32(nev),
                                            _i32(st)), "wv_batch_fit_lbfgs")
         return dict(x=x, f=f, lml=lml, n_iter=nit, n_eval=nev, status=st)
+
+    def fit_adam(self, x0: Optional[np.ndarray] = None, **opts):
+        """Batched Adam with the reference's schedule (BaseGP.optimize_params, waveome/model_classes.py:344-462; the
+        natural-gradient half is the engine's exact inner maximisation).  Options: learning_rate 0.1, decay_rate 0.96,
+        beta1 0.9, beta2 0.999, epsilon 1e-7, convergence_threshold 1e-9, max_iter 50000, check_every 100, decay_every 500.
+        Returns dict(x, f, lml, n_iter, n_eval, status)."""
+        o = dict(DEFAULT_ADAM); o.update(opts)
+        x = self.x0() if x0 is None else np.array(x0, dtype=np.float64, order="C", copy=True)
+        if x.shape != (self.B, self.P):
+            raise ValueError(f"x0 must be [{self.B}, {self.P}]")
+        co = _AdamOpts(float(o["learning_rate"]), float(o["decay_rate"]), float(o["beta1"]), float(o["beta2"]),
+                       float(o["epsilon"]), float(o["convergence_threshold"]), int(o["max_iter"]), int(o["check_every"]),
+                       int(o["decay_every"]), 0)
+        f = np.empty(self.B); lml = np.empty(self.B)
+        nit = np.empty(self.B, np.int32); st = np.empty(self.B, np.int32)
+        _check(self.lib.wv_batch_fit_adam(self.handle, _f64(x), C.byref(co), _f64(f), _f64(lml), _i32(nit), _i32(st)),
+               "wv_batch_fit_adam")
+        return dict(x=x, f=f, lml=lml, n_iter=nit, n_eval=nit + 1, status=st)
 
     def alpha(self) -> np.ndarray:
         """[B, n] alpha = (K + sigma^2 I)^{-1} (y - c) of the last evaluation, in the caller's row order."""

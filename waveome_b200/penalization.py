@@ -74,6 +74,7 @@ def penalization_search_batch(X, Y, kernel, mean_function=None, penalization_fac
     F, R = len(factors), max(1, int(num_restart))
     folds = make_folds(X, unit_col, k_fold, random_seed)
     results = np.full((B, F, len(folds)), np.nan)
+    selected = {}            # (outcome, factor index, fold) -> the model whose held-out score was recorded
     for k, hold in enumerate(folds):
         train = np.setdiff1d(np.arange(n), hold)
         Xt, Xh = X[train], X[hold]
@@ -110,6 +111,10 @@ def penalization_search_batch(X, Y, kernel, mean_function=None, penalization_fac
                 s2 = float(models[i].likelihood.variance)
                 vy = var[i] + s2
                 results[b, fi, k] = np.mean(-0.5 * (np.log(2 * np.pi) + np.log(vy) + (Y[b, hold] - mu[i]) ** 2 / vy))
+                models[i].log_posterior_density_value = float(-r["f"][i])
+                models[i].log_marginal_likelihood_value = float(r["lml"][i])
+                models[i].fit_info = dict(n_iter=int(r["n_iter"][i]), n_eval=int(r["n_eval"][i]), status=int(r["status"][i]))
+                selected[(b, fi, k)] = models[i]
     # best factor per outcome (:961-975): mean over folds, minus one standard error when selection_type == "se"
     best_factor = np.empty(B)
     for b in range(B):
@@ -121,7 +126,7 @@ def penalization_search_batch(X, Y, kernel, mean_function=None, penalization_fac
             if cur_val > max_val:
                 max_factor, max_val = pf, cur_val
         best_factor[b] = max_factor
-    out = dict(best_factor=best_factor, results=results, folds=folds, factors=factors, models=None)
+    out = dict(best_factor=best_factor, results=results, folds=folds, factors=factors, models=None, fold_models=selected)
     if fit_best:
         final = []
         for b in range(B):
