@@ -106,6 +106,12 @@ void* wv_engine_stream(wv_engine* e);
 int wv_engine_set_large_n_tiles(wv_engine* e, int nt);
 
 int wv_batch_create(wv_engine* e, const wv_batch_desc* desc, wv_batch** out);
+/* Same with flags.  WV_BATCH_KEEP_ROW_ORDER: device rows stay in the caller's order (by default the rows are sorted by the
+ * categorical columns the programs use -- the marginal likelihood is invariant, the element-wise kernels skip whole
+ * zero blocks).  Needed by wv_batch_eval_elbo, whose whitened variational parameters refer to chol(K) in the caller's
+ * row order. */
+enum { WV_BATCH_KEEP_ROW_ORDER = 1 };
+int wv_batch_create2(wv_engine* e, const wv_batch_desc* desc, int32_t flags, wv_batch** out);
 void wv_batch_destroy(wv_batch* b);
 /* bytes of device workspace held by the batch */
 int64_t wv_batch_workspace_bytes(const wv_batch* b);
@@ -148,6 +154,19 @@ int wv_batch_eval_device(wv_batch* b, const double* d_x, double* d_f, double* d_
  * f, lml [B] are evaluated at the returned x; n_iter, n_eval, status [B]. */
 int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* opts, double* f, double* lml,
                        int32_t* n_iter, int32_t* n_eval, int32_t* status);
+
+/* Objective (B) at GIVEN variational parameters: the whitened bound of gpflow.models.VGP / SVGP with Z = X that the live
+ * reference API optimises (PSVGP: waveome/model_classes.py:1082-1126; bound: gpflow SVGP.elbo, in-repo mirror
+ * waveome/model_types_DEPR.py:126-158; VGP branches: waveome/model_fitting.py:158-185):
+ *     L L^T = K + jitter I,  f_mean = c + L q_mu,  f_var_i = |(L tril(q_sqrt))_i|^2,
+ *     elbo = sum_i E_{N(f_mean_i, f_var_i)} log p(y_i | f_i) - KL[N(q_mu, q_sqrt q_sqrt^T) || N(0, I)]
+ * with the batch's likelihood (wv_batch_set_likelihood; Gaussian: the programs' noise slot).  f = -(elbo + log prior) is
+ * what training_loss hands to the optimisers.  HOST buffers: x [B, P], q_mu [B, n], q_sqrt [B, n, n] row-major (the lower
+ * triangle is read); jitter = gpflow's default_jitter() = 1e-6.  The batch must have been created with
+ * WV_BATCH_KEEP_ROW_ORDER.  wv_batch_eval / wv_batch_fit_* evaluate the same bound MAXIMISED over (q_mu, q_sqrt); this
+ * entry point exists to check that statement and to score externally optimised variational parameters. */
+int wv_batch_eval_elbo(wv_batch* b, const double* x, const double* q_mu, const double* q_sqrt, double jitter,
+                       double* elbo, double* f, int32_t* status);
 
 /* Adam with the schedule of the reference's default optimiser (BaseGP.optimize_params "adam/gradient" branch,
  * waveome/model_classes.py:344-462; kernel_test calls it, waveome/model_search.py:2284-2297): Keras Adam steps on the

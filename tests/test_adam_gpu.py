@@ -29,42 +29,57 @@ def test_adam_matches_the_numpy_restatement(engine):
     rng = np.random.default_rng(1)
     Y = np.stack([y, np.sin(2 * X[:, 1]) + 0.2 * rng.normal(size=n)])
     model = wb.GPR(helpers.saturated_kernel(hs=0.0), mean_function=wb.ConstantMean(0.0))
+    # Identical trajectories while rounding has had no time to act (learning rate 0.1: Adam's iterates on this objective
+    # separate exponentially -- 2e-13 after 450 steps, 2e-7 after 1050, O(0.1) after 1150, measured): every prefix of the
+    # schedule, incl. the checkpoints at steps 0, 100, ... with their learning-rate decay, must reproduce the NumPy run.
+    for steps in (50, 150, 250, 450):
+        batch = Batch(engine, X, Y, [model.program()])
+        r = batch.fit_adam(max_iter=steps)
+        batch.close()
+        for b in range(2):
+            ref = so.fit_adam_collapsed(model.to_spec(), X, Y[b], max_iter=steps)
+            assert int(r["n_iter"][b]) == steps == ref["n_iter"] and (int(r["status"][b]) & 4) and ref["why"] == "maxiter"
+            np.testing.assert_allclose(r["x"][b], ref["x"], rtol=1e-8, atol=1e-8)
+            assert abs(r["f"][b] - ref["f"]) <= 1e-9 * max(1.0, abs(ref["f"]))
+    # The stopping rule (loss fell by < 1e-9 between two checkpoints 100 steps apart) fires on the first checkpoint at
+    # which Adam's oscillating loss happens to be higher than at the previous one, so WHERE a run stops is a property of
+    # its last bits; both runs must stop at a checkpoint (or the step limit) in the flat region of the same optimum.
     batch = Batch(engine, X, Y, [model.program()])
     r = batch.fit_adam(max_iter=3000)
     batch.close()
     for b in range(2):
         ref = so.fit_adam_collapsed(model.to_spec(), X, Y[b], max_iter=3000)
-        # stop decisions are taken at checkpoints every 100 steps on a 1e-9 loss difference: the same checkpoint, or
-        # a neighbouring one when the difference sits at the threshold
-        assert abs(int(r["n_iter"][b]) - ref["n_iter"]) in (0, 100), (r["n_iter"][b], ref["n_iter"], ref["why"])
-        assert abs(r["f"][b] - ref["f"]) <= 1e-7 * max(1.0, abs(ref["f"])), (r["f"][b], ref["f"])
-        if int(r["n_iter"][b]) == ref["n_iter"]:
-            np.testing.assert_allclose(r["x"][b], ref["x"], rtol=1e-5, atol=1e-5)
-    # the first 50 steps, where rounding has not had time to act: identical trajectories
-    batch = Batch(engine, X, Y, [model.program()])
-    r50 = batch.fit_adam(max_iter=50)
-    batch.close()
-    ref50 = so.fit_adam_collapsed(model.to_spec(), X, Y[0], max_iter=50)
-    assert int(r50["n_iter"][0]) == 50 and ref50["n_iter"] == 50 and (int(r50["status"][0]) & 4)
-    np.testing.assert_allclose(r50["x"][0], ref50["x"], rtol=1e-9, atol=1e-9)
+        assert int(r["n_iter"][b]) == 3000 or int(r["n_iter"][b]) % 100 == 1, r["n_iter"][b]
+        assert ref["n_iter"] == 3000 or ref["n_iter"] % 100 == 1
+        assert abs(r["f"][b] - ref["f"]) <= 5e-2 * max(1.0, abs(ref["f"])), (r["f"][b], ref["f"])
 
 
 def test_objective_b_structures_reproduced_by_the_collapsed_objective(engine):
-    from make_adam_golden import cases, pruned_name
+    """kernel_test's candidate fits: the BIC ranking of the upstream algorithm on objective (B) (fixture) == the ranking
+    of the engine on objective (A) with L-BFGS-B and with Adam; the winner is the structure the reference's notebooks
+    report; the BICs themselves differ by the constant 4 (two variational Parameter objects in upstream's k), the 1e-6
+    jitter, and what Adam's stopping rule leaves on the table."""
+    from make_adam_golden import CANDIDATES, cases
     from waveome_b200.engine import Batch
     with open(os.path.join(GOLDEN, "adam_natgrad_fits.json")) as fh:
-        gold = {g["case"]: g for g in json.load(fh)["fits"]}
-    expected = {"penalized_regression": "categorical[4]+squared_exponential[0]",           # notebook cell 4
-                "overview_outcome1": "squared_exponential[1]",                               # waveome_overview.ipynb text
-                "overview_outcome2": "categorical[2]*squared_exponential[1]",
-                "overview_outcome3": "categorical[0]+lin[1]"}
-    for name, X, y, model in cases():
+        gold = {(g["case"], g["candidate"]): g for g in json.load(fh)["fits"]}
+    by_case = {}
+    for case, nm, X, y, model in cases():
         batch = Batch(engine, X, y[None, :], [model.program()])
         lb = batch.fit(maxiter=50000, maxfun=50000)
         ad = batch.fit_adam()
         batch.close()
-        s_lb, s_ad = pruned_name(model, lb["x"][0], X), pruned_name(model, ad["x"][0], X)
-        print(name, "| B adam/natgrad:", gold[name]["kernel_name"], gold[name]["n_iter"], gold[name]["why"],
-              "| A l-bfgs-b:", s_lb, "| A adam:", s_ad, int(ad["n_iter"][0]), int(ad["status"][0]))
-        assert gold[name]["kernel_name"] == expected[name]
-        assert s_lb == gold[name]["kernel_name"] and s_ad == gold[name]["kernel_name"]
+        k = len(model.trainable_parameters)
+        row = dict(b=gold[(case, nm)]["bic"] - 4.0, lbfgs=round(2 * k + 2 * float(lb["f"][0]), 2),
+                   adam=round(2 * k + 2 * float(ad["f"][0]), 2), adam_iter=int(ad["n_iter"][0]), b_iter=gold[(case, nm)]["n_iter"])
+        by_case.setdefault(case, {})[nm] = row
+        print(case, nm, row)
+    for case, rows in by_case.items():
+        documented = CANDIDATES[case][0]
+        for key in ("b", "lbfgs", "adam"):
+            best = min(rows, key=lambda nm: rows[nm][key])
+            assert best == documented, (case, key, best, rows)
+        for nm, row in rows.items():
+            # (A) is the collapsed form of (B): L-BFGS-B reaches its optimum, the Adam runs stop within their rule's slack
+            assert row["lbfgs"] <= row["b"] + 0.05 and row["lbfgs"] <= row["adam"] + 0.05, (case, nm, row)
+            assert abs(row["adam"] - row["b"]) <= max(1.0, 0.01 * abs(row["b"])), (case, nm, row)

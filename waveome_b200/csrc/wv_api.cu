@@ -19,7 +19,9 @@ int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, con
                     const WvSpecLaunch* spec);
 
 int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, cudaStream_t st,
-                      WvProfiler* pf, const WvAux* aux, const WvSpecLaunch* spec);
+                      WvProfiler* pf, const WvAux* aux, const WvSpecLaunch* spec, bool chol_only);
+int wv_enqueue_elbo(const WvBatchDev& bd, const double* d_x, const double* d_qmu, const double* d_qs, double* d_part,
+                    int nblk, double* d_logprior, cudaStream_t st);
 int wv_enqueue_grad_finalize(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
                              double* d_g, double* d_lml, int* d_status, cudaStream_t st, WvProfiler* pf,
                              const WvSpecLaunch* spec);
@@ -110,6 +112,7 @@ struct wv_batch {
   WvSpecLaunch spec;       // run-time specialised Gram / gradient kernels of the batch's program (wv_batch_specialize)
   bool has_spec = false;
   int n_programs = 0;
+  bool keep_row_order = false;   // WV_BATCH_KEEP_ROW_ORDER: device rows = caller rows (needed by wv_batch_eval_elbo)
 };
 
 template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
@@ -270,7 +273,12 @@ static int wv_build_program(const wv_program_desc& d, int D, WvProgram* p) {
   return 0;
 }
 
+extern "C" int wv_batch_create2(wv_engine* e, const wv_batch_desc* d, int32_t flags, wv_batch** out);
 extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** out) {
+  return wv_batch_create2(e, d, 0, out);
+}
+
+extern "C" int wv_batch_create2(wv_engine* e, const wv_batch_desc* d, int32_t flags, wv_batch** out) {
   if (!e || !d || !out) return wv_fail("wv_batch_create: null argument");
   if (d->n <= 0 || d->B <= 0 || d->D <= 0 || d->P <= 0 || d->n_programs <= 0)
     return wv_fail("wv_batch_create: n, D, B, P, n_programs must be positive");
@@ -340,7 +348,8 @@ extern "C" int wv_batch_create(wv_engine* e, const wv_batch_desc* d, wv_batch** 
   // transcendental factors of categorical x numeric products where the mask is zero.
   b->perm.resize(d->n);
   for (int i = 0; i < d->n; ++i) b->perm[i] = i;
-  {
+  b->keep_row_order = (flags & 1) != 0;
+  if (!b->keep_row_order) {
     std::set<int> cat;
     for (int p = 0; p < d->n_programs; ++p)
       for (int l = 0; l < d->programs[p].n_leaves; ++l)
@@ -590,7 +599,7 @@ static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g,
   for (int sweep = 0; sweep < b->vgp.max_sweeps + 2 && n_in > 0; ++sweep) {
     b->eng->aux.epoch += 1;
     WV_CUDA(cudaMemsetAsync(b->bd.chol_fail, 0, sizeof(int) * b->bd.B, st));
-    int l1 = wv_enqueue_factor(b->bd, cur, n_in, d_x, st, &b->prof, &b->eng->aux, b->has_spec ? &b->spec : nullptr);
+    int l1 = wv_enqueue_factor(b->bd, cur, n_in, d_x, st, &b->prof, &b->eng->aux, b->has_spec ? &b->spec : nullptr, false);
     int l2 = l1 < 0 ? -1 : wv_enqueue_site_sweep(b->bd, b->vgp, cur, n_in, d_x, bufs[which], b->d_count + 1, st, &b->prof);
     if (l1 < 0 || l2 < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     l += l1 + l2;
@@ -987,6 +996,60 @@ extern "C" int wv_batch_fit_adam(wv_batch* b, double* x, const wv_adam_opts* o, 
   WV_CUDA(cudaMemcpyAsync(status, b->d_st2, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   WV_CUDA(cudaStreamSynchronize(st));
   WV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// objective (B) at given variational parameters (validation entry point, see wv_elbo_rows_kernel)
+// ---------------------------------------------------------------------------------------------
+__global__ void wv_fill_kernel(double* p, size_t n, double v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+extern "C" int wv_batch_eval_elbo(wv_batch* b, const double* x, const double* q_mu, const double* q_sqrt, double jitter,
+                                  double* elbo, double* f, int32_t* status) {
+  if (!b || !x || !q_mu || !q_sqrt || !elbo || !f || !status) return wv_fail("wv_batch_eval_elbo: null argument");
+  if (!b->keep_row_order)
+    return wv_fail("wv_batch_eval_elbo: the batch must be created with WV_BATCH_KEEP_ROW_ORDER (wv_batch_create2): the "
+                   "whitened variational parameters refer to the Cholesky factor in the caller's row order");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  WvBatchDev bd = b->bd;                   // local copy: Gram of K + jitter I through the per-row-noise path, 1 / lam = 0
+  const size_t B = bd.B, n = bd.n, np = bd.npad;
+  const int nblk = (int)((n + 63) / 64);
+  cudaStream_t st = b->eng->stream;
+  double *d_qmu, *d_qs, *d_part, *d_lp, *d_inf, *d_zero;
+  if (wv_alloc(b, &d_qmu, B * n) || wv_alloc(b, &d_qs, B * n * n) || wv_alloc(b, &d_part, B * nblk) || wv_alloc(b, &d_lp, B) ||
+      wv_alloc(b, &d_inf, B * np) || wv_alloc(b, &d_zero, B * np))
+    return -1;
+  WV_CUDA(cudaMemcpyAsync(b->d_x, x, B * bd.P * sizeof(double), cudaMemcpyHostToDevice, st));
+  WV_CUDA(cudaMemcpyAsync(d_qmu, q_mu, B * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  WV_CUDA(cudaMemcpyAsync(d_qs, q_sqrt, B * n * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  wv_fill_kernel<<<(unsigned)((B * np + 255) / 256), 256, 0, st>>>(d_inf, B * np, INFINITY);
+  WV_CUDA(cudaMemsetAsync(d_zero, 0, B * np * sizeof(double), st));
+  bd.site_lam = d_inf; bd.site_eta = d_zero; bd.jitter = jitter;
+  wv_iota_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(b->d_active, (int)B);
+  WV_CUDA(cudaMemsetAsync(bd.chol_fail, 0, sizeof(int) * B, st));
+  b->eng->aux.epoch += 1;
+  const int l1 = wv_enqueue_factor(bd, b->d_active, (int)B, b->d_x, st, &b->prof, &b->eng->aux,
+                                   b->has_spec ? &b->spec : nullptr, true);
+  const int l2 = l1 < 0 ? -1 : wv_enqueue_elbo(bd, b->d_x, d_qmu, d_qs, d_part, nblk, d_lp, st);
+  if (l1 < 0 || l2 < 0) return wv_fail(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  b->launches += l1 + l2 + 2;
+  std::vector<double> part(B * nblk), lp(B);
+  std::vector<int> fail(B);
+  WV_CUDA(cudaMemcpyAsync(part.data(), d_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(lp.data(), d_lp, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(fail.data(), bd.chol_fail, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaStreamSynchronize(st));
+  for (size_t m = 0; m < B; ++m) {
+    double s = 0.0;
+    for (int k = 0; k < nblk; ++k) s += part[m * nblk + k];
+    elbo[m] = s;
+    f[m] = -(s + lp[m]);
+    status[m] = (fail[m] ? WV_STATUS_CHOL_FAIL : 0) | (std::isfinite(f[m]) ? 0 : WV_STATUS_NONFINITE);
+  }
+  b->last_x = nullptr;            // A holds L, not K^-1: the post-fit getters need a full evaluation first
   return 0;
 }
 

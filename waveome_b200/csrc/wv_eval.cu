@@ -822,7 +822,7 @@ static cudaError_t wv_set_attrs() {
 
 // Cholesky + L^{-T} of the large-n path (see the comment above wv_syrk_kernel).  Returns launches or -1.
 static int wv_enqueue_factor_big(const WvBatchDev& bd, const int* d_active, int n_active, cudaStream_t st,
-                                 WvProfiler* pf, const WvAux& aux) {
+                                 WvProfiler* pf, const WvAux& aux, bool chol_only = false) {
   const int nt = bd.nt;
   int launches = 0;
   bool bulk_pending = false;
@@ -856,6 +856,7 @@ static int wv_enqueue_factor_big(const WvBatchDev& bd, const int* d_active, int 
     ++launches;
   }
   if (bulk_pending) cudaStreamWaitEvent(st, aux.ev_bulk, 0);
+  if (chol_only) return launches;
   for (int m = 1; m < nt; m *= 2) {
     const int nblk = (nt + 2 * m - 1) / (2 * m);
     wv_trtri_level_kernel<1><<<dim3(nblk * m * m, n_active), WV_GEMM_THREADS, sizeof(WvGemmSmem), st>>>(bd, d_active, m);
@@ -1197,6 +1198,112 @@ __global__ void wv_vgp_status_kernel(WvVgpState vs, const int* __restrict__ list
   if (vs.at_bound[b]) status[b] |= WV_STATUS_SITE_BOUND;
 }
 
+// =============================================================================================
+// Objective (B) at GIVEN variational parameters: the whitened VGP / SVGP-with-Z = X bound the live reference API hands to
+// its optimisers (waveome/model_classes.py:1082-1126 PSVGP -> gpflow.models.SVGP.elbo; mirror
+// waveome/model_types_DEPR.py:126-158; VGP: waveome/model_fitting.py:158-185):
+//     L L^T = K + jitter I,  f_mean = c + L q_mu,  f_var_i = |(L tril(q_sqrt))_i|^2
+//     ELBO = sum_i E_{N(f_mean_i, f_var_i)}[log p(y_i | f_i)] - 1/2 (|q_mu|^2 + |tril(q_sqrt)|_F^2 - n - 2 sum log|q_sqrt_ii|)
+// L is read from the lower tiles of A after the Cholesky steps (rows in the CALLER's order: the batch must have been
+// created with keep_row_order, the whitening is not permutation invariant).  A validation entry point, not a hot path:
+// plain FP64 FMAs, grid (row blocks of 64, models), 256 threads; thread t owns the columns k = t, t + 256, ... of L S.
+// part[b][blk] = sum of E_i over the block's rows (block 0 adds -KL): the host adds the blocks in order.
+// =============================================================================================
+__global__ void __launch_bounds__(256) wv_elbo_rows_kernel(WvBatchDev bd, const double* __restrict__ xall,
+                                                           const double* __restrict__ qmu, const double* __restrict__ qs,
+                                                           double* __restrict__ part, int nblk) {
+  __shared__ double red[8];
+  __shared__ double s_row[2];
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int n = bd.n, ld = bd.npad;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const WvProgram* pg = bd.programs + bd.prog_id[b];
+  const double* x = xall + (size_t)b * bd.P;
+  auto slot_value = [&](int s_) {
+    const WvSlot& sl = pg->slots[s_];
+    return sl.xindex >= 0 ? wv_transform(sl.transform, x[sl.xindex], sl.shift) : sl.fixed;
+  };
+  const double cmean = pg->mean_slot >= 0 ? slot_value(pg->mean_slot) : 0.0;
+  const double p1 = slot_value(pg->noise_slot);                 // Gaussian variance | NB / ZINB alpha | Gamma shape
+  double lik_param = bd.lik_param, lik_param2 = bd.lik_param2;
+  if (bd.lik == 2 || bd.lik == 4 || bd.lik == 5) { if (pg->slots[pg->noise_slot].xindex >= 0) lik_param = p1; }
+  if (bd.lik == 5 && pg->lik_slot2 >= 0) lik_param2 = slot_value(pg->lik_slot2);
+  const double* Lb = bd.A + (size_t)b * ld * ld;
+  const double* mu = qmu + (size_t)b * n;
+  const double* S = qs + (size_t)b * n * n;
+  const double* yb = bd.Y + (size_t)b * ld;
+  double esum = 0.0;                       // thread 0 accumulates the block's E_i in row order
+  const int i1 = min(n, (blk + 1) * 64);
+  for (int i = blk * 64; i < i1; ++i) {
+    const double* Li = Lb + (size_t)i * ld;
+    double fm = 0.0, fv = 0.0;
+    for (int k = threadIdx.x; k <= i; k += blockDim.x) {
+      double s_ = 0.0;
+      for (int j = k; j <= i; ++j) s_ = fma(Li[j], S[(size_t)j * n + k], s_);
+      fv = fma(s_, s_, fv);
+      fm = fma(Li[k], mu[k], fm);
+    }
+    for (int o = 16; o > 0; o >>= 1) { fm += __shfl_xor_sync(0xffffffffu, fm, o); fv += __shfl_xor_sync(0xffffffffu, fv, o); }
+    __syncthreads();
+    if (lane == 0) red[warp] = fm;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; ++w) t += red[w]; s_row[0] = t; }
+    __syncthreads();
+    if (lane == 0) red[warp] = fv;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      const double m_ = cmean + s_row[0], v_ = t, y_ = yb[i];
+      double E;
+      if (bd.lik == 0) {
+        E = -0.5 * log(6.283185307179586 * p1) - ((y_ - m_) * (y_ - m_) + v_) / (2.0 * p1);
+      } else {
+        double g_, h_, da_, da2_;
+        wv_var_exp(bd.lik, lik_param, lik_param2, y_, lgamma(y_ + 1.0), m_, v_, E, g_, h_, da_, da2_);
+      }
+      esum += E;
+    }
+  }
+  if (blk == 0) {          // - KL[q(v) || N(0, I)]
+    double kl = 0.0;
+    for (size_t e = threadIdx.x; e < (size_t)n * n; e += blockDim.x) {
+      const size_t r = e / n, c = e % n;
+      if (c <= r) { const double sv = S[e]; kl += sv * sv; if (c == r) kl -= 2.0 * log(fabs(sv)); }
+    }
+    for (int k = threadIdx.x; k < n; k += blockDim.x) kl += mu[k] * mu[k];
+    for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = kl;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; ++w) t += red[w]; esum -= 0.5 * (t - n); }
+  }
+  if (threadIdx.x == 0) part[(size_t)b * nblk + blk] = esum;
+}
+
+// log prior of the trainable parameters of every model (the same wv_prior the finalize kernel uses)
+__global__ void wv_logprior_kernel(WvBatchDev bd, const double* __restrict__ xall, double* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bd.B) return;
+  const WvProgram* pg = bd.programs + bd.prog_id[b];
+  double lp = 0.0;
+  for (int s_ = 0; s_ < pg->n_slots; ++s_) {
+    const WvSlot sl = pg->slots[s_];
+    if (sl.xindex < 0) continue;
+    double l, d;
+    wv_prior(sl, wv_transform(sl.transform, xall[(size_t)b * bd.P + sl.xindex], sl.shift), &l, &d);
+    lp += l;
+  }
+  out[b] = lp;
+}
+
+int wv_enqueue_elbo(const WvBatchDev& bd, const double* d_x, const double* d_qmu, const double* d_qs, double* d_part,
+                    int nblk, double* d_logprior, cudaStream_t st) {
+  wv_elbo_rows_kernel<<<dim3(nblk, bd.B), 256, 0, st>>>(bd, d_x, d_qmu, d_qs, d_part, nblk);
+  wv_logprior_kernel<<<(bd.B + 63) / 64, 64, 0, st>>>(bd, d_x, d_logprior);
+  return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
 // Gram + Cholesky + L^{-T} + alpha + K^{-1} of the listed models.  Returns launches or -1.
 // launch of a run-time specialised element-wise kernel (same grid as the interpreter kernel it replaces)
 static cudaError_t wv_launch_spec(const void* kern, int smem, const double* tab12, const WvBatchDev& bd, const int* d_active,
@@ -1206,7 +1313,7 @@ static cudaError_t wv_launch_spec(const void* kern, int smem, const double* tab1
 }
 
 int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, cudaStream_t st,
-                      WvProfiler* pf, const WvAux* aux, const WvSpecLaunch* spec) {
+                      WvProfiler* pf, const WvAux* aux, const WvSpecLaunch* spec, bool chol_only) {
   if (n_active <= 0) return 0;
   if (wv_set_attrs() != cudaSuccess || !aux) return -1;
   int launches = 0;
@@ -1224,11 +1331,13 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
   pf->mark(WV_K_GRAM, st);
   ++launches;
   if (aux->side && nt >= aux->big_nt) {
-    int l = wv_enqueue_factor_big(bd, d_active, n_active, st, pf, *aux);
+    int l = wv_enqueue_factor_big(bd, d_active, n_active, st, pf, *aux, chol_only);
     if (l < 0) return -1;
     launches += l;
+    if (chol_only) return cudaGetLastError() == cudaSuccess ? launches : -1;
   } else {
     for (int j = 0; j < nt; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, 0, st, pf, *aux);
+    if (chol_only) return cudaGetLastError() == cudaSuccess ? launches : -1;
     if (aux->trtri_rows && nt > 1) {
       wv_trtri_rows_kernel<<<dim3(nt - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active);
       pf->mark(WV_K_TRTRI, st);
@@ -1298,7 +1407,7 @@ int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, con
   WvProfiler none;
   if (!pf) pf = &none;
   cudaMemsetAsync(bd.chol_fail, 0, sizeof(int) * bd.B, st);
-  const int l1 = wv_enqueue_factor(bd, d_active, n_active, d_x, st, pf, aux, spec);
+  const int l1 = wv_enqueue_factor(bd, d_active, n_active, d_x, st, pf, aux, spec, false);
   if (l1 < 0) return -1;
   const int l2 = wv_enqueue_grad_finalize(bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, pf, spec);
   if (l2 < 0) return -1;

@@ -56,7 +56,7 @@ class _AdamOpts(C.Structure):
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
     "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_likelihood", "wv_batch_set_likelihood2", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
-    "wv_batch_fit_adam", "wv_batch_specialize", "wv_rtc_check", "wv_rtc_set_cache", "wv_rtc_precompile_text",
+    "wv_batch_fit_adam", "wv_batch_create2", "wv_batch_eval_elbo", "wv_batch_specialize", "wv_rtc_check", "wv_rtc_set_cache", "wv_rtc_precompile_text",
     "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_get_kinv_diag", "wv_batch_predict_mean", "wv_batch_predict_f", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
 KERNEL_CLASSES = ["gram", "chol_diag", "chol_panel", "trtri", "extract", "kinv", "grad", "finalize", "lbfgs", "chol_syrk", "sites"]
@@ -80,6 +80,9 @@ def load_library():
     lib.wv_engine_stream.argtypes = [vp]; lib.wv_engine_stream.restype = vp
     lib.wv_engine_set_large_n_tiles.argtypes = [vp, C.c_int]; lib.wv_engine_set_large_n_tiles.restype = C.c_int
     lib.wv_batch_create.argtypes = [vp, C.POINTER(_BatchDesc), C.POINTER(vp)]; lib.wv_batch_create.restype = C.c_int
+    lib.wv_batch_create2.argtypes = [vp, C.POINTER(_BatchDesc), C.c_int32, C.POINTER(vp)]; lib.wv_batch_create2.restype = C.c_int
+    lib.wv_batch_eval_elbo.argtypes = [vp, _f64p, _f64p, _f64p, C.c_double, _f64p, _f64p, _i32p]
+    lib.wv_batch_eval_elbo.restype = C.c_int
     lib.wv_batch_destroy.argtypes = [vp]; lib.wv_batch_destroy.restype = None
     lib.wv_batch_workspace_bytes.argtypes = [vp]; lib.wv_batch_workspace_bytes.restype = C.c_int64
     lib.wv_batch_set_y.argtypes = [vp, _f64p]; lib.wv_batch_set_y.restype = C.c_int
@@ -219,7 +222,8 @@ class Batch:
     """B independent GP models on shared covariates X: y_b ~ GP(mean_b, k_b) + noise."""
 
     def __init__(self, engine: Engine, X: np.ndarray, Y: np.ndarray, programs: Sequence[Program],
-                 prog_id: Optional[Sequence[int]] = None, P: Optional[int] = None, specialize=None):
+                 prog_id: Optional[Sequence[int]] = None, P: Optional[int] = None, specialize=None,
+                 keep_row_order: bool = False):
         self.engine = engine
         self.lib = engine.lib
         X = np.ascontiguousarray(X, dtype=np.float64)
@@ -246,7 +250,7 @@ class Batch:
             d.lik_slot2 = getattr(p, "lik_slot2", -1)
         bd = _BatchDesc(self.n, self.D, self.B, self.P, _f64(X), _f64(Y), len(self.programs), descs, _i32(pid))
         h = C.c_void_p()
-        _check(self.lib.wv_batch_create(engine.handle, C.byref(bd), C.byref(h)), "wv_batch_create")
+        _check(self.lib.wv_batch_create2(engine.handle, C.byref(bd), 1 if keep_row_order else 0, C.byref(h)), "wv_batch_create2")
         self.handle = h
         # Run-time specialised element-wise kernels are the CALLER's choice, never a function of the batch size: a model's
         # result must not depend on how many neighbours share its batch (specialised and interpreter kernels agree to
@@ -372,6 +376,20 @@ class Batch:
         _check(self.lib.wv_batch_fit_lbfgs(self.handle, _f64(x), C.byref(co), _f64(f), _f64(lml), _i32(nit), _i32(nev),
                                            _i32(st)), "wv_batch_fit_lbfgs")
         return dict(x=x, f=f, lml=lml, n_iter=nit, n_eval=nev, status=st)
+
+    def eval_elbo(self, x: np.ndarray, q_mu: np.ndarray, q_sqrt: np.ndarray, jitter: float = 1e-6):
+        """Objective (B) at given variational parameters: (elbo [B], f = -(elbo + log prior) [B], status [B]) of the
+        whitened VGP / SVGP-with-Z = X bound (include/waveome_b200.h: wv_batch_eval_elbo).  q_mu [B, n], q_sqrt [B, n, n]
+        (lower triangles).  The batch must have been created with ``keep_row_order=True``."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        q_mu = np.ascontiguousarray(q_mu, dtype=np.float64)
+        q_sqrt = np.ascontiguousarray(q_sqrt, dtype=np.float64)
+        if x.shape != (self.B, self.P) or q_mu.shape != (self.B, self.n) or q_sqrt.shape != (self.B, self.n, self.n):
+            raise ValueError("x [B, P], q_mu [B, n], q_sqrt [B, n, n] expected")
+        elbo = np.empty(self.B); f = np.empty(self.B); st = np.empty(self.B, np.int32)
+        _check(self.lib.wv_batch_eval_elbo(self.handle, _f64(x), _f64(q_mu), _f64(q_sqrt), float(jitter), _f64(elbo), _f64(f),
+                                           _i32(st)), "wv_batch_eval_elbo")
+        return elbo, f, st
 
     def fit_adam(self, x0: Optional[np.ndarray] = None, **opts):
         """Batched Adam with the reference's schedule (BaseGP.optimize_params, waveome/model_classes.py:344-462; the
