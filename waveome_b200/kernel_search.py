@@ -428,7 +428,7 @@ def _thread_engine():
 
 
 def engine_fitter(X: np.ndarray, engine=None, num_restart=1, random_seed=None, max_iter=50000,
-                  likelihood="gaussian") -> Callable:
+                  likelihood="gaussian", optimizer="lbfgs") -> Callable:
     """Returns ``fit(requests) -> results`` where requests is a list of (y [n], name, kernel): all of them become one
     engine batch (restarts included: ``num_restart`` > 1 adds randomised starts as extra models of the batch,
     waveome/model_classes.py:472-524, seeds ``random_seed + 1 + r`` or ``r``)."""
@@ -448,7 +448,8 @@ def engine_fitter(X: np.ndarray, engine=None, num_restart=1, random_seed=None, m
                         p.assign(p.transform_fn(rs.normal(loc=0.0, scale=1.0)))
                 models.append(m)
                 ys.append(y)
-        res = fit_models(X, np.stack(ys), models, engine=engine or _thread_engine(), maxiter=max_iter, maxfun=max_iter)
+        res = fit_models(X, np.stack(ys), models, engine=engine or _thread_engine(), maxiter=max_iter, maxfun=max_iter,
+                         optimizer=optimizer)
         out = []
         for i in range(len(requests)):
             best, best_lpd = None, -np.inf
@@ -544,13 +545,15 @@ def _drive_single(gen, y, fit):
 
 
 def kernel_test(X, Y, k, mean_function=None, num_restart=5, random_init=True, random_seed=None, verbose=False,
-                likelihood="gaussian", engine=None, keep_data=False, **unused):
+                likelihood="gaussian", engine=None, keep_data=False, optimizer="lbfgs", **unused):
     """Drop-in for :2239-2334: (fitted model, bic).  ``likelihood``: any name ``models.make_likelihood`` covers (it
-    raises NotImplementedError for the others)."""
+    raises NotImplementedError for the others).  ``optimizer``: "lbfgs" (default: L-BFGS-B reaches the optimum of the
+    collapsed objective) or "adam" -- upstream's own choice here, ``optimize_params()`` with its "adam/gradient" default
+    (:2297), run on the device with the same schedule."""
     X = np.asarray(X, dtype=np.float64)
     y = np.asarray(Y, dtype=np.float64).reshape(-1)
     fit = engine_fitter(X, engine=engine, num_restart=num_restart if random_init else 1, random_seed=random_seed,
-                        likelihood=likelihood)
+                        likelihood=likelihood, optimizer=optimizer)
     (m, bic), = fit([(y, "", k)])
     if m is None:
         raise RuntimeError("kernel_test: the fit failed (Cholesky failure or non-finite objective at the start point)")

@@ -18,6 +18,7 @@ from .models import GPR, make_likelihood
 from .utilities import calc_bic, print_kernel_names
 
 _ENGINES: Dict[int, "object"] = {}
+DEFAULT_LBFGS_KEYS = ("maxcor", "maxiter", "maxfun", "maxls", "ftol", "gtol", "on_chol_fail")
 
 
 def get_engine(device: Optional[int] = None):
@@ -74,7 +75,16 @@ def run_fit_jobs(jobs: List[dict], engine=None, streams: Optional[int] = None, *
         try:
             if job["lik_name"] != "gaussian":
                 batch.set_likelihood(job["lik_name"], job["lik_param"])
-            r = batch.fit(job.get("starts"), **lbfgs_opts)
+            if job.get("optimizer", "lbfgs") in ("adam", "adam/gradient"):
+                # the reference's default optimiser for kernel_test (waveome/model_classes.py:344-462); num_opt_iter
+                # arrives as maxiter
+                adam = {k: v for k, v in lbfgs_opts.items() if k in ("learning_rate", "decay_rate", "convergence_threshold",
+                                                                    "check_every", "decay_every", "beta1", "beta2", "epsilon")}
+                if "maxiter" in lbfgs_opts:
+                    adam["max_iter"] = lbfgs_opts["maxiter"]
+                r = batch.fit_adam(job.get("starts"), **adam)
+            else:
+                r = batch.fit(job.get("starts"), **{k: v for k, v in lbfgs_opts.items() if k in DEFAULT_LBFGS_KEYS})
             return r, batch.counters()
         finally:
             batch.close()
@@ -127,7 +137,7 @@ def likelihood_key(model) -> tuple:
 
 def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional[np.ndarray] = None,
                engine=None, max_batch_bytes: float = 60e9, streams: int = 1, specialize: bool = False,
-               **lbfgs_opts) -> dict:
+               optimizer: str = "lbfgs", **lbfgs_opts) -> dict:
     """MAP-fit ``models[b]`` to outcome ``Y[b]`` (Y is [B, n]); all models share X [n, D].
 
     Models with identical kernel programs share one device program.  Fitted values are written back into the
@@ -138,7 +148,9 @@ def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional
     (hundreds of structures, a few hundred models per piece) measured 5 % SLOWER on 4 streams (config 2: 24.8 s against
     23.5 s); ``fit_replicated`` -- one structure, thousands of models -- is where the split pays.
     ``specialize``: ask for run-time specialised element-wise kernels (engine.Batch); only pieces whose models share one
-    program structure get them."""
+    program structure get them.
+    ``optimizer``: "lbfgs" (SciPy-compatible L-BFGS-B, default) or "adam" / "adam/gradient" (the schedule of
+    BaseGP.optimize_params, waveome/model_classes.py:344-462: ``Batch.fit_adam``; maxiter = num_opt_iter)."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     Y = np.ascontiguousarray(Y, dtype=np.float64)
     B = len(models)
@@ -176,7 +188,7 @@ def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional
             sel = idx[lo:hi]
             sels.append(sel)
             jobs.append(dict(X=X, Y=Y[sel], table=table, prog_id=prog_id[sel], P=P, lik_name=lik_name,
-                             lik_param=lik_param, starts=starts[sel], specialize=specialize))
+                             lik_param=lik_param, starts=starts[sel], specialize=specialize, optimizer=optimizer))
     for sel, (r, c) in zip(sels, run_fit_jobs(jobs, engine=engine, streams=streams, **lbfgs_opts)):
         for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
             out[key][sel] = r[key]

@@ -234,12 +234,13 @@ class GPSearch:
     # ------------------------------------------------------------------------------------------
     def run_search(self, kernels=None, max_depth=5, early_stopping=True, prune=True, keep_all=False, metric_diff=6,
                    num_restart=1, random_seed=None, num_jobs=-1, verbose=False, debug=False, gather=True, fit=None,
-                   pipeline_groups=None):
+                   pipeline_groups=None, optimizer="lbfgs"):
         """Greedy compositional kernel search per outcome (waveome/model_search.py:1069-1250 -> full_kernel_search
         :2987-3272).  The searches of all outcomes (of this rank's shard) advance in lock-step; at every step the
         candidate kernels they ask for are fitted as ONE engine batch (kernel_search.run_lockstep).
         ``self.models[outcome]`` = best model, ``self.search_info[outcome]`` = {"models", "edges", "best_model"}.
         ``num_jobs`` is accepted for signature compatibility.  ``fit`` replaces the engine fitter (tests).
+        ``optimizer``: "lbfgs" (default) or "adam" (upstream's schedule for the candidate fits, ``kernel_search.kernel_test``).
         ``pipeline_groups``: outcome groups of the lock-step driver (default one; with more, one group's device batch
         overlaps the other's host work -- same result, measured slower on config 2, see ``kernel_search.run_lockstep``)."""
         from . import kernel_search as ks
@@ -259,7 +260,8 @@ class GPSearch:
         if verbose and rank == 0:
             print(f"Building {len(self.out_names)} models on {world} GPU(s)...")
         counters = dict(fits=0, batches=0)
-        inner = fit or ks.engine_fitter(Xn, num_restart=num_restart, random_seed=random_seed, likelihood=self.likelihood)
+        inner = fit or ks.engine_fitter(Xn, num_restart=num_restart, random_seed=random_seed, likelihood=self.likelihood,
+                                        optimizer=optimizer)
 
         def counted(requests):
             counters["fits"] += len(requests) * max(1, int(num_restart))
@@ -295,6 +297,28 @@ class GPSearch:
         return None
 
     # ------------------------------------------------------------------------------------------
+    def multioutput_penalized_optimization(self, latent_kernels=None, penalization_factor=1.0, num_opt_iter=2000,
+                                           adam_learning_rate=0.01, nat_gradient_gamma=0.1, constraint_weight=1.0,
+                                           sparse_options=None, variational_options=None, verbose=False, random_seed=None,
+                                           kernel_options=None, device=None):
+        """Fit ONE linear-coregionalisation model to all outcomes (waveome/model_search.py:519-573):
+        ``self.models["multioutput"]`` = the fitted ``multioutput.MultiOutputPSVGP``."""
+        from .multioutput import MultiOutputPSVGP
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        variational_options = dict(variational_options or {})
+        variational_options["likelihood"] = self.likelihood
+        model = MultiOutputPSVGP(X=self.X.to_numpy(dtype=np.float64), Y=self.Y.to_numpy(dtype=np.float64),
+                                 latent_kernels=latent_kernels, penalization_factor=penalization_factor, verbose=verbose,
+                                 sparse_options=sparse_options or {}, variational_options=variational_options,
+                                 kernel_options=kernel_options if kernel_options is not None else {},
+                                 cat_vars=self.cat_idx, num_vars=self.cont_idx, unit_idx=self.unit_idx,
+                                 var_names=self.feat_names, device=device)
+        model.optimize_params(num_opt_iter=num_opt_iter, adam_learning_rate=adam_learning_rate,
+                              nat_gradient_gamma=nat_gradient_gamma, constraint_weight=constraint_weight)
+        self.models = {"multioutput": model}
+        return None
+
     def run_penalized_search(self, *args, **kwargs):
         """model_search.py:933-958: deprecated upstream, raises there as well."""
         raise NotImplementedError("run_penalized_search is deprecated, use penalized_optimization instead.")
