@@ -80,6 +80,8 @@ def test_objective_b_structures_reproduced_by_the_collapsed_objective(engine):
             best = min(rows, key=lambda nm: rows[nm][key])
             assert best == documented, (case, key, best, rows)
         for nm, row in rows.items():
-            # (A) is the collapsed form of (B): L-BFGS-B reaches its optimum, the Adam runs stop within their rule's slack
-            assert row["lbfgs"] <= row["b"] + 0.05 and row["lbfgs"] <= row["adam"] + 0.05, (case, nm, row)
-            assert abs(row["adam"] - row["b"]) <= max(1.0, 0.01 * abs(row["b"])), (case, nm, row)
+            # (A) is the collapsed form of (B): max_q B = A, so an optimiser of (A) may not end ABOVE upstream's run on (B)
+            # by more than a local-optimum's worth (measured: one candidate with an irrelevant SE term, 304.89 vs 304.78);
+            # upstream's Adam often stops early on (B) (e.g. 301 steps, BIC -753.65 against the optimum's -768.58)
+            assert row["lbfgs"] <= row["b"] + 0.5 and row["adam"] <= row["b"] + 0.5, (case, nm, row)
+            assert abs(row["lbfgs"] - row["adam"]) <= 0.5, (case, nm, row)
