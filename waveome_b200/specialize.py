@@ -35,6 +35,11 @@ _prelude_cache: Optional[str] = None
 
 #: resident CTAs per SM the register allocation of the generated kernels aims for (measured on config 3, profiles/r02*)
 GRAM_MIN_CTAS = int(os.environ.get("WV_SPEC_GRAM_MINB", "4"))
+#: per-component run-time mask checks (feature-importance batches switch components off).  Measured on config 3: WITHOUT
+#: them the kernels are slower (gram 3.28 vs 2.76 ms, grad 3.60 vs 3.37 ms per 2000-model evaluation): the uniform
+#: branches keep the compiler from interleaving components, which costs registers (gram spills at 64).  Kept on; the
+#: switch exists for that experiment only (a text generated without them ignores the masks).
+USE_CMASK = os.environ.get("WV_SPEC_CMASK", "1") == "1"
 GRAD_MIN_CTAS = int(os.environ.get("WV_SPEC_GRAD_MINB", "2"))     # 3 CTAs (80 registers) spill the gradient sums: 4.6 ms vs 3.4 ms
 
 SE_SCALE = "0.84932180028801907"        # sqrt(log2(e) / 2): exp(-r2 / 2) = 2^(-(s (x - x'))^2), s = SE_SCALE / lengthscale
@@ -232,7 +237,8 @@ def generate(p: Program) -> Optional[SpecSource]:
         w("  const int b = active[blockIdx.y];")
         w(f"  wvs_stage_theta(bd, b, xall, sm.theta, {ns});")
         w("  wvs_load_tab(sm.tab, gtab);")
-        w("  const unsigned cmask = bd.comp_mask[b];")
+        if USE_CMASK:
+            w("  const unsigned cmask = bd.comp_mask[b];")
         w("  __syncthreads();")
         for i, e in enumerate(kc_expr):
             w(f"  if (threadIdx.x == {i % 256}) sm.kc[{i}] = {e};")
@@ -313,7 +319,7 @@ def generate(p: Program) -> Optional[SpecSource]:
     cat_loads("      ")
     for c, cp in enumerate(comps):
         expensive = bool(cp.se or cp.other)
-        w(f"      if (cmask & {1 << c}u) {{      // component {c}")
+        w(f"      if (cmask & {1 << c}u) {{      // component {c}" if USE_CMASK else f"      {{      // component {c}")
         skip = bool(cp.cats) and expensive
         ind = "        "
         if skip:
@@ -413,7 +419,8 @@ def generate(p: Program) -> Optional[SpecSource]:
     for c, cp in enumerate(comps):
         if not cp.sums:
             continue
-        w(f"        if (cmask & {1 << c}u) {{      // component {c}: sums {', '.join(f'{k} -> {v}' for k, v in cp.sums.items())}")
+        w((f"        if (cmask & {1 << c}u) {{" if USE_CMASK else "        {") +
+          f"      // component {c}: sums {', '.join(f'{k} -> {v}' for k, v in cp.sums.items())}")
         ind = "          "
         skip = bool(cp.cats) and bool(cp.se or cp.other)
         if skip:
