@@ -57,6 +57,26 @@ def calc_deviance_loglik(y, model_mu, base_mu=None, likelihood="gaussian", alpha
     return base_ll, mod_ll, sat_ll
 
 
+def structure_key(model: GPR) -> tuple:
+    """Everything of a model the device program depends on EXCEPT the values of its trainable parameters: the kernel tree
+    with dims, per parameter its (trainable, transform, shift, prior, frozen value), likelihood, mean."""
+    ids = {}
+
+    def par(p):
+        pr = p.prior
+        return (ids.setdefault(id(p), len(ids)),        # sharing pattern: one Parameter object in several leaves
+                p.trainable, p.transform, p.shift, None if pr is None else tuple(sorted(pr.to_spec().items())),
+                None if p.trainable else float(p))
+
+    def tree(k):
+        if isinstance(k, (K.Sum, K.Product)):
+            return (k.name,) + tuple(tree(c) for c in k.kernels)
+        return (k.name, tuple(int(d) for d in k.active_dims), getattr(k, "degree", None)) + tuple(par(p) for p in k.parameters)
+    lik = model.likelihood
+    return (tree(model.kernel), getattr(lik, "name", "gaussian"), tuple(par(p) for p in getattr(lik, "parameters", [])),
+            getattr(model.mean_function, "name", "zero"), tuple(par(p) for p in model.mean_function.parameters))
+
+
 def _component_masks(model: GPR) -> List[int]:
     """Component masks of [full model] + [model without top-level additive component k for every k]: the reference
     pops the component and predicts again with the same parameter values (utilities.py:657-662).  A top-level
@@ -86,29 +106,33 @@ def fitted_means(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], masks: Opt
     X = np.ascontiguousarray(X, dtype=np.float64)
     Y = np.ascontiguousarray(Y, dtype=np.float64)
     B = len(models)
-    cache = {}
-    progs = []
-    for m in models:                       # the same model object may appear many times (once per mask)
-        if id(m) not in cache:
-            cache[id(m)] = m.program()
-        progs.append(cache[id(m)])
-    uniq, prog_id, table = {}, np.empty(B, np.int32), []
-    sig_of = {}
-    for b, p in enumerate(progs):
-        if id(p) not in sig_of:
-            sig_of[id(p)] = p.signature()
-        sig = sig_of[id(p)]
-        if sig not in uniq:
-            uniq[sig] = len(table)
-            table.append(p)
-        prog_id[b] = uniq[sig]
-    P = max(1, max(p.n_x for p in progs))
+    # Device programs: one per distinct structure.  Fitted models of one penalized_optimization call differ in their
+    # parameter VALUES and in which components survived the pruning; models that agree in structure_key() (component
+    # names, frozen flags and values, priors, likelihood, mean) share the first one's Program -- building 2000 Program
+    # objects cost more than the device evaluation -- and only contribute their packed parameter vector.
+    from .model_fitting import packed_parameters
+    by_model, by_key, table, uniq = {}, {}, [], {}
+    prog_id = np.empty(B, np.int32)
+    xs = [None] * B
+    for b, m in enumerate(models):                       # the same model object may appear many times (once per mask)
+        if id(m) not in by_model:
+            key = structure_key(m)
+            if key not in by_key:
+                p = m.program()
+                sig = p.signature()
+                if sig not in uniq:
+                    uniq[sig] = len(table)
+                    table.append(p)
+                by_key[key] = (uniq[sig], p.n_x)
+            pid, n_x = by_key[key]
+            x0 = np.array([q.unconstrained for q in packed_parameters(m)], dtype=np.float64)
+            assert x0.size == n_x, "structure_key does not determine the program"
+            by_model[id(m)] = (pid, x0)
+        prog_id[b], xs[b] = by_model[id(m)]
+    P = max(1, max(v.size for v in xs))
     x = np.zeros((B, P))
-    x0_of = {}
-    for b, p in enumerate(progs):
-        if id(p) not in x0_of:
-            x0_of[id(p)] = p.x0()
-        x[b, : p.n_x] = x0_of[id(p)]
+    for b, v in enumerate(xs):
+        x[b, : v.size] = v
     n = X.shape[0]
     npad = ((n + 1 + 7) // 8 * 8 + 63) // 64 * 64
     chunk = max(1, int(max_batch_bytes // (2 * npad * npad * 8 + npad * 64 * 8)))
@@ -224,18 +248,30 @@ def feature_importances_batch(X, Y, models: Sequence[GPR], return_value="log_bf"
         var_masks += ms
         rows += [b] * len(ms)
     means, status = fitted_means(X, Y[rows], var_models, masks=var_masks, engine=engine)
+    all_gaussian = all(getattr(m.likelihood, "name", "gaussian") == "gaussian" for m in models)
+    if all_gaussian and len(models):
+        # calc_deviance_loglik's Gaussian branch for every model and variant in three array operations
+        rows_a = np.asarray(rows)
+        y_var = np.var(Y, axis=1)
+        g_null = np.sum(gaussian_logdensity(Y, np.mean(Y, axis=1, keepdims=True), y_var[:, None]), axis=1)
+        g_sat = np.sum(gaussian_logdensity(Y, Y, y_var[:, None]), axis=1)
+        g_mod = np.sum(gaussian_logdensity(Y[rows_a], means, y_var[rows_a][:, None]), axis=1)
     out, pos = [], 0
     for b, m in enumerate(models):
         nv = 1 + (len(m.kernel.kernels) if m.kernel.name == "sum" else 0)
-        mu = means[pos: pos + nv]
-        pos += nv
-        y = Y[b]
-        lk = dict(likelihood=getattr(m.likelihood, "name", "gaussian"),
-                  alpha=float(getattr(m.likelihood, "engine_param", 1.0)) or 1.0)
-        # one vectorised call for the full model and every leave-one-component-out model (rows of mu)
-        null_lls, all_mod_lls, sat_lls = calc_deviance_loglik(y, mu, **lk)
-        null_sum, sat_sum = np.sum(null_lls), np.sum(sat_lls)
-        mod_sums = np.sum(np.atleast_2d(all_mod_lls), axis=-1)
+        if all_gaussian:
+            null_sum, sat_sum, mod_sums = g_null[b], g_sat[b], g_mod[pos: pos + nv]
+            pos += nv
+        else:
+            mu = means[pos: pos + nv]
+            pos += nv
+            y = Y[b]
+            lk = dict(likelihood=getattr(m.likelihood, "name", "gaussian"),
+                      alpha=float(getattr(m.likelihood, "engine_param", 1.0)) or 1.0)
+            # one vectorised call for the full model and every leave-one-component-out model (rows of mu)
+            null_lls, all_mod_lls, sat_lls = calc_deviance_loglik(y, mu, **lk)
+            null_sum, sat_sum = np.sum(null_lls), np.sum(sat_lls)
+            mod_sums = np.sum(np.atleast_2d(all_mod_lls), axis=-1)
         mod_sum = mod_sums[0]
         if sat_sum >= mod_sum and mod_sum >= null_sum:
             full_de = 1 - (-2 * (mod_sum - sat_sum) / (-2 * (null_sum - sat_sum)))
