@@ -1119,13 +1119,10 @@ extern "C" int wv_batch_predict_f(wv_batch* b, const double* Xnew, int32_t m, do
   cudaStream_t st = b->eng->stream;
   const size_t Bm = (size_t)bd.B * m;
   const int ntiles = bd.nt * (bd.nt + 1) / 2;
-  WV_CUDA(cudaMalloc(&d_xt, xt.size() * sizeof(double)));
-  cudaError_t e = cudaMalloc(&d_mean, Bm * sizeof(double) * (var ? 3 : 1));      // mean | prior | var
-  if (e == cudaSuccess && var) e = cudaMalloc(&d_part, Bm * ntiles * sizeof(double));
-  if (e != cudaSuccess) {
-    cudaFree(d_xt); cudaFree(d_mean);
-    return wv_fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
-  }
+  // workspaces come from (and return to, at wv_batch_destroy) the device's buffer cache like every other buffer of
+  // the batch: a cudaMalloc / cudaFree pair per call synchronises the device under the other streams' feet
+  if (wv_alloc(b, &d_xt, xt.size()) != 0 || wv_alloc(b, &d_mean, Bm * (var ? 3 : 1)) != 0) return -1;   // mean | prior | var
+  if (var && wv_alloc(b, &d_part, Bm * ntiles) != 0) return -1;
   int rc = 0;
   if (cudaMemcpyAsync(d_xt, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
   if (rc == 0 && wv_enqueue_cross_mean(bd, b->last_x, d_xt, m, mpad, d_mean, st) < 0) rc = -1;
@@ -1137,7 +1134,6 @@ extern "C" int wv_batch_predict_f(wv_batch* b, const double* Xnew, int32_t m, do
   }
   if (cudaStreamSynchronize(st) != cudaSuccess) rc = -1;
   b->launches += 1;
-  cudaFree(d_xt); cudaFree(d_mean); cudaFree(d_part);
   if (rc != 0) return wv_fail(std::string("wv_batch_predict_f: ") + cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
