@@ -190,10 +190,13 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
   if (const char* v = getenv("WV_CACHE_MAX_GB")) WV_CACHE_MAX_BYTES = (size_t)(atof(v) > 0 ? atof(v) : 0) << 30;
   if (const char* v = getenv("WV_TRTRI_ROWS")) eng->aux.trtri_rows = atoi(v) != 0;
   if (const char* v = getenv("WV_PANEL_TILES")) eng->aux.panel_tiles = atoi(v) > 0 ? atoi(v) : 4;
+  if (const char* v = getenv("WV_PANEL_FUSED")) eng->aux.panel_fused = atoi(v) != 0;
+  if (const char* v = getenv("WV_PANEL_CTAS")) eng->aux.panel_ctas = atoi(v) > 0 ? atoi(v) : 148;
   {
     cudaDeviceProp prop;
     WV_CUDA(cudaGetDeviceProperties(&prop, device));
     eng->aux.resident_ctas = 3 * prop.multiProcessorCount;
+    if (!getenv("WV_PANEL_CTAS")) eng->aux.panel_ctas = prop.multiProcessorCount;
   }
   *out = eng;
   return 0;
@@ -322,7 +325,7 @@ extern "C" int wv_batch_create2(wv_engine* e, const wv_batch_desc* d, int32_t fl
   WV_TRY(wv_alloc(b, &bd.quad, B));
   WV_TRY(wv_alloc(b, &bd.partial, B * ntiles * smax));
   WV_TRY(wv_alloc(b, &bd.chol_fail, B));
-  WV_TRY(wv_alloc(b, &bd.step_flag, B * bd.nt));
+  WV_TRY(wv_alloc(b, &bd.step_flag, 2 * B * bd.nt + 1));
   unsigned* dmask;
   WV_TRY(wv_alloc(b, &dmask, B));
   WV_TRY(wv_alloc(b, &b->d_x, B * d->P));
@@ -388,7 +391,7 @@ extern "C" int wv_batch_create2(wv_engine* e, const wv_batch_desc* d, int32_t fl
   step(cudaMemcpyAsync(b->d_active, ident.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
   step(cudaMemsetAsync(bd.A, 0, B * np * np * sizeof(double), st));
   step(cudaMemsetAsync(bd.Mt, 0, B * np * np * sizeof(double), st));
-  step(cudaMemsetAsync(bd.step_flag, 0, B * bd.nt * sizeof(int), st));
+  step(cudaMemsetAsync(bd.step_flag, 0, (2 * B * bd.nt + 1) * sizeof(int), st));
   step(cudaMemsetAsync(dmask, 0xff, B * sizeof(unsigned), st));
   step(cudaMemsetAsync(dY, 0, B * np * sizeof(double), st));
   step(cudaMemcpy2DAsync(dY, np * sizeof(double), yp.data(), (size_t)d->n * sizeof(double), (size_t)d->n * sizeof(double), B,

@@ -510,6 +510,70 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS, 4) wv_chol_panel_kernel(WvBat
   wv_panel_body<0>(bd, active[blockIdx.y], j, blockIdx.x, k0, epoch);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Large-n path: ALL column steps of one panel [p0, p1) in ONE launch.  With one launch per step the serial chain of the
+// factorisation pays, per 64 columns, a diagonal block (~30 us), the tail of that step's panel tiles and a launch
+// boundary (58 us per step measured at n = 8192: 7.4 of the 8.8 ms Cholesky).  Here the work items of the panel's steps --
+// per column j the diagonal block (x = 0) and the tiles (i, j), i > j -- form one grid in column order, and every
+// dependency is a flag in global memory:
+//   diagonal block j     waits until row j has received the panel's earlier columns   (row_done[j] >= j - p0)
+//   tile (i, j)          waits for rows i and j likewise, accumulates, then waits for the diagonal block's flag
+//                        (step_flag, inside wv_panel_body<0>) and publishes row_done[i] = j - p0 + 1
+// so the chain per column is  diagonal block -> ONE tile (j + 1, j) -> next diagonal block, while the other tiles of a
+// column overlap the next diagonal block.  CTAs are dispatched in linear block order and every flag is set by a block
+// with a smaller index, so a spinning CTA never waits for one that cannot become resident.  Tiles of a row complete in
+// column order (tile (i, j) reads tile (i, j - 1)), hence one counter per row suffices; its value carries a tag of
+// (evaluation epoch, panel) so that stale counts of earlier panels / evaluations never match.
+// grid (sum_j (nt - j), n_active), 128 threads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wv_wait_row(const int* row_done, int tag, int need) {
+  if (need <= 0) return;
+  const volatile int* f = reinterpret_cast<const volatile int*>(row_done);
+  for (;;) {
+    const int v = *f;
+    if ((v >> 3) == tag && (v & 7) >= need) break;
+    __nanosleep(40);
+  }
+}
+
+__global__ void __launch_bounds__(WV_GEMM_THREADS, 3) wv_chol_panel_fused_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                                              int n_active, int p0, int p1, int items,
+                                                                              int epoch, int tag) {
+  // PERSISTENT: a few CTAs per SM pull the work items in index order from a counter.  One CTA per item would fill every
+  // SM slot with spinning CTAs and starve the trailing update that runs beside this kernel on the side stream
+  // (measured: 8.54 ms per n = 8192 Cholesky with one CTA per item).  Items are taken in order, so the lowest unfinished
+  // item is always held by a running CTA and its dependencies -- all of lower index -- are finished: no deadlock.
+  __shared__ int s_item;
+  int* counter = bd.step_flag + 2 * (size_t)bd.B * bd.nt;
+  const int total = items * n_active;
+  for (;;) {
+    __syncthreads();                      // previous item done with the shared-memory tiles
+    if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= total) return;
+    const int b = active[it / items];
+    int j = p0, x = it % items;
+    while (x >= bd.nt - j) { x -= bd.nt - j; ++j; }          // work item -> (column j, x = 0 diagonal | tile j + x)
+    int* row_done = bd.step_flag + (size_t)bd.B * bd.nt + (size_t)b * bd.nt;
+    const int need = j - p0;
+    if (threadIdx.x == 0) {
+      wv_wait_row(row_done + j, tag, need);
+      if (x > 0) wv_wait_row(row_done + j + x, tag, need);
+      __threadfence();
+    }
+    __syncthreads();
+    if (x == 0) {
+      wv_diag_body(bd, b, j, p0 * WV_NB, epoch);
+      continue;
+    }
+    wv_panel_body<0>(bd, b, j, x - 1, p0 * WV_NB, epoch);
+    __threadfence();                       // the tile is visible device-wide before the row counter moves
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(row_done + j + x) = (tag << 3) | (need + 1);
+  }
+}
+
 // enqueue one Cholesky column step; fused into one launch iff all its CTAs can be resident at once
 static int wv_launch_chol_step(const WvBatchDev& bd, const int* d_active, int n_active, int j, int k0, cudaStream_t st,
                                WvProfiler* pf, const WvAux& aux) {
@@ -809,6 +873,7 @@ static cudaError_t wv_set_attrs() {
   WV_ATTR(wv_cross_var_kernel, sizeof(WvCrossVarSmem));
   WV_ATTR(wv_chol_step_kernel, wv_smem_gemm_bytes());
   WV_ATTR(wv_chol_panel_kernel, sizeof(WvPanelSmem));
+  WV_ATTR(wv_chol_panel_fused_kernel, wv_smem_gemm_bytes());
   WV_ATTR(wv_trtri_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_trtri_rows_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_kinv_kernel, sizeof(WvGemmSmem));
@@ -829,7 +894,20 @@ static int wv_enqueue_factor_big(const WvBatchDev& bd, const int* d_active, int 
   const int PT = aux.panel_tiles;
   for (int p0 = 0; p0 < nt; p0 += PT) {
     const int p1 = p0 + PT < nt ? p0 + PT : nt;
-    for (int j = p0; j < p1; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, p0 * WV_NB, st, pf, aux);
+    if (aux.panel_fused && p1 - p0 <= 6) {
+      int items = 0;
+      for (int j = p0; j < p1; ++j) items += nt - j;
+      const int tag = (aux.epoch * 256 + p0 / PT) & 0x0fffffff;
+      const long total = (long)items * n_active;
+      const int ctas = (int)(total < aux.panel_ctas ? total : aux.panel_ctas);
+      cudaMemsetAsync(bd.step_flag + 2 * (size_t)bd.B * bd.nt, 0, sizeof(int), st);      // the work counter
+      wv_chol_panel_fused_kernel<<<ctas, WV_GEMM_THREADS, wv_smem_gemm_bytes(), st>>>(bd, d_active, n_active, p0, p1, items,
+                                                                                   aux.epoch, tag);
+      pf->mark(WV_K_CHOL_PANEL, st);
+      ++launches;
+    } else {
+      for (int j = p0; j < p1; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, p0 * WV_NB, st, pf, aux);
+    }
     if (p1 >= nt) break;
     const int a_hi = p1 + PT < nt ? p1 + PT : nt;   // columns of the next panel
     cudaEventRecord(aux.ev_panel, st);

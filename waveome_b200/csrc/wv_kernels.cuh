@@ -49,7 +49,8 @@ struct WvBatchDev {
   double* partial;                  // [B][n_tiles][n_slots_max]
   int* chol_fail;                   // [B]
   const unsigned* comp_mask;        // [B] bit c = additive component c of the model's program takes part (default all)
-  int* step_flag;                   // [B][nt] epoch of the last finished diagonal block (fused Cholesky step)
+  int* step_flag;                   // [2][B][nt] + 1: epoch of the last finished diagonal block (fused Cholesky step), then the
+                                    // per-row column counters of the fused large-n panel (wv_chol_panel_fused_kernel), then its work counter
   // variational path for count likelihoods (nullptr / 0 on the Gaussian path), see wv_site_update_kernel:
   int lik;                          // 0 gaussian, 1 poisson (exp link), 2 negative binomial (log link, fixed alpha)
   double lik_param;                 // negative binomial: alpha when the programs' noise slot is frozen; a trainable
@@ -90,6 +91,8 @@ struct WvAux {
   int big_nt = 16;
   int panel_tiles = 4;       // tile columns per panel of the large-n right-looking Cholesky
   int resident_ctas = 444;   // 3 CTAs x 148 SMs: a Cholesky step is fused into one launch only if it fits
+  int panel_ctas = 148;      // persistent CTAs of that launch (WV_PANEL_CTAS; default one per SM)
+  int panel_fused = 1;       // large-n path: all column steps of a panel in one launch (flags instead of launch boundaries)
   int trtri_rows = 0;   // 1: the batched schedule's triangular inverse as one row-wise launch (wv_trtri_rows_kernel)
   int epoch = 0;   // evaluation counter of the engine: the value the diagonal CTAs publish in step_flag
 };
