@@ -600,12 +600,18 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_trtri_kernel(WvBatchDev bd
 // earlier tiles only), so CTA (j, model) walks its row left to right, i = j + 1 .. nt - 1.  The tiles it has just written
 // come back from L2 instead of DRAM and the nt - 1 dependent launches (and their tails) become one.  Heavy rows first
 // (j = 0 has nt - 1 tiles).  grid (nt - 1, n_active), 128 threads.
-__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_trtri_rows_kernel(WvBatchDev bd, const int* __restrict__ active) {
+__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_trtri_rows_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                                        int paired) {
   const int b = active[blockIdx.y];
-  const int j = blockIdx.x;
-  for (int i = j + 1; i < bd.nt; ++i) {
-    wv_panel_body<1>(bd, b, i, j, 0, 0);
-    __syncthreads();          // the tile just stored is an operand of the next one (block-scope ordering)
+  // paired: CTA p takes row p and then row nt - 2 - p (nt - 1 - p and p + 1 tiles: every CTA walks nt tiles) -- the
+  // load-balanced form of the one-launch inverse; unpaired: CTA j takes row j alone (grid nt - 1)
+  for (int half = 0; half < (paired ? 2 : 1); ++half) {
+    const int j = half == 0 ? (int)blockIdx.x : bd.nt - 2 - (int)blockIdx.x;
+    if (half == 1 && j <= (int)blockIdx.x) break;
+    for (int i = j + 1; i < bd.nt; ++i) {
+      wv_panel_body<1>(bd, b, i, j, 0, 0);
+      __syncthreads();          // the tile just stored is an operand of the next one (block-scope ordering)
+    }
   }
 }
 
@@ -1417,7 +1423,9 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
     for (int j = 0; j < nt; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, 0, st, pf, *aux);
     if (chol_only) return cudaGetLastError() == cudaSuccess ? launches : -1;
     if (aux->trtri_rows && nt > 1) {
-      wv_trtri_rows_kernel<<<dim3(nt - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active);
+      const int paired = aux->trtri_rows == 2;
+      wv_trtri_rows_kernel<<<dim3(paired ? nt / 2 : nt - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active,
+                                                                                                              paired);
       pf->mark(WV_K_TRTRI, st);
       ++launches;
     } else {
