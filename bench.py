@@ -405,12 +405,12 @@ def main():
         achieved = alg / (dom_ms * 1e-3) / 1e9
         roof = {"kernel": f"wv_{dom}_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": {"gram": 3.393e9, "grad": 3.483e9}[dom], "peak_kind": peak_kind + " copy bandwidth",
+                "traffic": {"gram": 3.397e9, "grad": 3.470e9}[dom], "peak_kind": peak_kind + " copy bandwidth",
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch with 2000 models in flight "
-                                "(profiles/r01i_ncu_set_full_summary.txt); algorithmic bytes of that launch: 5.8e9 "
+                                "(profiles/r02t_eval_dram_per_launch.csv); algorithmic bytes of that launch: 5.8e9 "
                                 "(8 n^2 per model, the kernel touches the lower tiles only)",
-                "note": "FP64-issue bound, not HBM bound: up to 6 squared-exponential leaves per matrix element for this "
-                        "kernel tree, each a table-driven 2^u of 9 FP64 operations (see DESIGN.md section 4)"}
+                "note": "issue bound, not HBM bound: up to 6 squared-exponential leaves per matrix element for this "
+                        "kernel tree, each a table-driven 2^u of 10 FP64 + 8 integer instructions (DESIGN.md section 4a')"}
     else:
         share = {"chol_diag": 1.0 / 3, "chol_panel": 1.0 / 3, "trtri": 1.0 / 3, "kinv": 1.0 / 3}.get(dom, 0.0)
         if dom in ("chol_diag", "chol_panel"):
@@ -418,15 +418,16 @@ def main():
             dom = "chol_diag+chol_panel"
         alg = share * float(n) ** 3 * model_evals
         achieved = alg / (dom_ms * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture with 2000 models in flight
-        # (profiles/r01i_ncu_set_full_summary.txt): trtri = its largest launch (step nt-1: 9 tiles per model, every Mt
-        # and L tile read once from DRAM), kinv = its single launch, Cholesky = step 4 (diagonal + 5 panel tiles)
-        traffic = {"trtri": 3.943e9, "kinv": 6.301e9, "chol_diag+chol_panel": 2.671e9}.get(dom)
+        # dram__bytes_read.sum + dram__bytes_write.sum over ALL launches of the class in one evaluation of 2000 models
+        # (ncu --metrics pass, profiles/r02t_eval_dram_per_launch.csv)
+        traffic = {"trtri": 16.86e9, "kinv": 6.31e9, "chol_diag+chol_panel": 20.82e9}.get(dom)
         roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
-                "traffic_note": "bytes of the class's largest launch at 2000 models (trtri step nt-1; kinv; Cholesky step 4), "
-                                "see profiles/r01i_ncu_set_full_summary.txt; achieved counts the algorithmic n^3/3 flops of the "
-                                "class, the kernels execute ~1.5x that (full diagonal tiles, inverse-block epilogues, padding)",
+                "traffic_note": "CLASS TOTAL per evaluation of 2000 models: dram__bytes_read.sum + dram__bytes_write.sum summed over "
+                                "all launches of the class in one evaluation (Cholesky: 10 diagonal + 9 panel launches, trtri: 9, "
+                                "kinv: 1), profiles/r02t_eval_dram_per_launch.csv; the lower tiles of the 2000 matrices are 3.5e9 "
+                                "bytes: the left-looking panel / trtri steps re-read the earlier tile columns (13.6 / 14.4e9 read). "
+                                "achieved counts the algorithmic n^3/3 flops of the class, the kernels execute 1.06-1.25x that",
                 "peak_kind": "measured cuBLAS DGEMM fp64 on this pool (not in MEASURED_PEAKS.json)"}
     roof["share_of_step"] = dom_ms / step_ms if step_ms else None
     roof["launches"] = dom_launches
