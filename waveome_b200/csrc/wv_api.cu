@@ -20,6 +20,7 @@ int wv_enqueue_eval(const WvBatchDev& bd, const int* d_active, int n_active, con
 
 int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, cudaStream_t st,
                       WvProfiler* pf, const WvAux* aux, const WvSpecLaunch* spec, bool chol_only);
+int wv_make_tmap_mt(const WvBatchDev& bd, void* out128);
 int wv_enqueue_elbo(const WvBatchDev& bd, const double* d_x, const double* d_qmu, const double* d_qs, double* d_part,
                     int nblk, double* d_logprior, cudaStream_t st);
 int wv_enqueue_grad_finalize(const WvBatchDev& bd, const int* d_active, int n_active, const double* d_x, double* d_f,
@@ -112,6 +113,8 @@ struct wv_batch {
   WvSpecLaunch spec;       // run-time specialised Gram / gradient kernels of the batch's program (wv_batch_specialize)
   bool has_spec = false;
   int n_programs = 0;
+  alignas(64) unsigned char tmap_mt[128];   // CUtensorMap over Mt (WV_KINV_TMA=1)
+  bool has_tmap = false;
   bool keep_row_order = false;   // WV_BATCH_KEEP_ROW_ORDER: device rows = caller rows (needed by wv_batch_eval_elbo)
 };
 
@@ -397,6 +400,8 @@ extern "C" int wv_batch_create2(wv_engine* e, const wv_batch_desc* d, int32_t fl
   step(cudaMemcpy2DAsync(dY, np * sizeof(double), yp.data(), (size_t)d->n * sizeof(double), (size_t)d->n * sizeof(double), B,
                          cudaMemcpyHostToDevice, st));
   b->h_count = e->h_count;
+  if (const char* v = getenv("WV_KINV_TMA"))
+    if (atoi(v) != 0 && bd.nt < e->aux.big_nt) b->has_tmap = wv_make_tmap_mt(bd, b->tmap_mt) == 0;
   step(cudaStreamSynchronize(st));
   if (ce != cudaSuccess) {
     wv_batch_destroy(b);
@@ -584,6 +589,7 @@ extern "C" void wv_batch_counters(const wv_batch* b, int64_t* launches, int64_t*
 static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g, double* d_lml, int* d_status,
                        const int* d_active, int n_active) {
   b->eng->aux.epoch += 1;
+  b->eng->aux.tmap_mt = b->has_tmap ? b->tmap_mt : nullptr;
   cudaStream_t st = b->eng->stream;
   if (b->bd.lik == 0) {
     int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, &b->prof, &b->eng->aux,

@@ -1,4 +1,5 @@
 // waveome_b200 — kernels of one batched LML+gradient evaluation.  See wv_kernels.cuh for the plan.
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "wv_kernels.cuh"
 #include "wv_rtc.h"
 
@@ -698,6 +699,163 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_kinv_kernel(WvBatchDev bd,
 }
 
 // =============================================================================================
+// kinv with a TMA operand ring (experiment, WV_KINV_TMA=1; result in DESIGN.md section 4): the two 64 x 16 fp64 operand
+// boxes of a k-chunk are fetched by ONE thread with cp.async.bulk.tensor.2d (tensor map over Mt as a [B npad, npad]
+// matrix, 128-byte swizzle) and land on an mbarrier; the other 127 threads issue no load instructions at all.
+// With 128-byte rows the DMMA fragment loads (8 rows x 4 k per operand) are bank-conflict free only if the 8 rows of a
+// fragment differ in (row & 7) in a way the XOR swizzle separates: fragment row fr of block mi is matrix row
+//     R(mi, fr) = 32 wm + 16 (mi >> 1) + 2 fr + (mi & 1)
+// (rows of stride 2: (R & 7) runs over {0,2,4,6} or {1,3,5,7} within a half-warp, so the two 16-byte chunks of the 4
+// k-values land in 8 distinct chunk slots).  Columns likewise; a thread then owns 4 adjacent output columns per (mi, ni
+// pair) and stores them as two double2.
+// =============================================================================================
+#ifndef WV_TMA_STAGES
+#define WV_TMA_STAGES 3
+#endif
+struct WvTmaSmem {
+  double a[WV_TMA_STAGES][WV_NB * WV_BK];      // 8 KB per box, 1024-byte aligned (swizzle atom)
+  double b[WV_TMA_STAGES][WV_NB * WV_BK];
+  unsigned long long bar[WV_TMA_STAGES];
+};
+
+__device__ __forceinline__ void wv_mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void wv_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void wv_mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void wv_tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// byte offset of element (row r, k) of a 64 x 16 fp64 box written with CU_TENSOR_MAP_SWIZZLE_128B
+__device__ __forceinline__ int wv_swz(int r, int k) { return r * 128 + ((((k >> 1) ^ (r & 7)) << 4) | ((k & 1) << 3)); }
+
+__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_kinv_tma_kernel(const __grid_constant__ CUtensorMap tmap, WvBatchDev bd,
+                                                                      const int* __restrict__ active) {
+  const int b = active[blockIdx.y];
+  const int ld = bd.npad;
+  int ti, tj;
+  wv_tile_from_linear(blockIdx.x, ti, tj);
+  const double* Mb = bd.Mt + (size_t)b * ld * ld;
+  if (ti == tj) {      // symmetric diagonal tile: the single-operand cp.async path of wv_kinv_kernel
+    WvGemmSmem& sm = *reinterpret_cast<WvGemmSmem*>(wv_smem_raw);
+    double sacc[10][2];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) sacc[q][0] = sacc[q][1] = 0.0;
+    wv_syrk_self_64(sm, Mb + (size_t)ti * WV_NB * ld, ld, ti * WV_NB, bd.n8, sacc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    double* Out = bd.A + (size_t)b * ld * ld + (size_t)ti * WV_NB * ld + ti * WV_NB;
+#define WV_X(q, i, j) \
+    *reinterpret_cast<double2*>(Out + (size_t)((i) * 8 + fr) * ld + (j) * 8 + 2 * fk) = make_double2(sacc[q][0], sacc[q][1]);
+    if (warp == 0) { WV_SYM_W0(WV_X) }
+    else if (warp == 1) { WV_SYM_W1(WV_X) }
+    else if (warp == 2) { WV_SYM_W2(WV_X) }
+    else { WV_SYM_W3(WV_X) }
+#undef WV_X
+    return;
+  }
+  WvTmaSmem& sm = *reinterpret_cast<WvTmaSmem*>((reinterpret_cast<uintptr_t>(wv_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int lane = threadIdx.x & 31, warp = wv_warp_role();
+  const int wm = warp >> 1, wn = warp & 1, fr = lane >> 2, fk = lane & 3;
+  const int real_last = bd.n + 1 - (bd.nt - 1) * WV_NB;
+  const bool dead = real_last <= 32 && ((ti == bd.nt - 1 && wm == 1) || (tj == bd.nt - 1 && wn == 1));
+  const int k0 = ti * WV_NB, nch = (bd.n8 - k0 + WV_BK - 1) / WV_BK;
+  const int row_a = b * ld + ti * WV_NB, row_b = b * ld + tj * WV_NB;
+  if (threadIdx.x == 0) {
+    for (int s_ = 0; s_ < WV_TMA_STAGES; ++s_) wv_mbar_init(&sm.bar[s_], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int s_ = 0; s_ < WV_TMA_STAGES && s_ < nch; ++s_) {
+      wv_mbar_expect_tx(&sm.bar[s_], 2 * WV_NB * WV_BK * 8);
+      wv_tma_load_2d(sm.a[s_], &tmap, &sm.bar[s_], k0 + s_ * WV_BK, row_a);
+      wv_tma_load_2d(sm.b[s_], &tmap, &sm.bar[s_], k0 + s_ * WV_BK, row_b);
+    }
+  double acc[4][4][2];
+  wv_zero_acc(acc);
+  for (int c = 0; c < nch; ++c) {
+    const int st = c % WV_TMA_STAGES;
+    wv_mbar_wait(&sm.bar[st], (c / WV_TMA_STAGES) & 1);
+    if (!dead) {
+      const char* as = reinterpret_cast<const char*>(sm.a[st]);
+      const char* bs = reinterpret_cast<const char*>(sm.b[st]);
+#pragma unroll
+      for (int kk = 0; kk < WV_BK; kk += 4) {
+        // Mt[ti,ti] (chunks 0..3) is upper triangular: rows >= r are zero for k < r; 16-row granularity here
+        const int kabs = c * WV_BK + kk;
+        const bool lo = !(c < 4 && kabs + 4 <= wm * 32), hi = !(c < 4 && kabs + 4 <= wm * 32 + 16);
+        if (!hi && !lo) continue;
+        double bf[4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          bf[ni] = *reinterpret_cast<const double*>(bs + wv_swz(wn * 32 + (ni >> 1) * 16 + 2 * fr + (ni & 1), kk + fk));
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          if (mi < 2 ? !lo : !hi) continue;
+          const double af = *reinterpret_cast<const double*>(as + wv_swz(wm * 32 + (mi >> 1) * 16 + 2 * fr + (mi & 1), kk + fk));
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) wv_dmma(acc[mi][ni][0], acc[mi][ni][1], af, bf[ni]);
+        }
+      }
+    }
+    __syncthreads();                                        // every warp is done with stage st
+    if (threadIdx.x == 0 && c + WV_TMA_STAGES < nch) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy reads before the async-proxy refill
+      wv_mbar_expect_tx(&sm.bar[st], 2 * WV_NB * WV_BK * 8);
+      wv_tma_load_2d(sm.a[st], &tmap, &sm.bar[st], k0 + (c + WV_TMA_STAGES) * WV_BK, row_a);
+      wv_tma_load_2d(sm.b[st], &tmap, &sm.bar[st], k0 + (c + WV_TMA_STAGES) * WV_BK, row_b);
+    }
+  }
+  if (dead) return;
+  double* Out = bd.A + (size_t)b * ld * ld + (size_t)ti * WV_NB * ld + tj * WV_NB;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    const int r = wm * 32 + (mi >> 1) * 16 + 2 * fr + (mi & 1);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {       // ni pair (2 np, 2 np + 1): columns 16 np + 4 fk .. + 3
+      double* o = Out + (size_t)r * ld + wn * 32 + np * 16 + 4 * fk;
+      *reinterpret_cast<double2*>(o) = make_double2(acc[mi][2 * np][0], acc[mi][2 * np + 1][0]);
+      *reinterpret_cast<double2*>(o + 2) = make_double2(acc[mi][2 * np][1], acc[mi][2 * np + 1][1]);
+    }
+  }
+}
+
+// tensor map of Mt as a row-major [B npad, npad] fp64 matrix, box 16 (k) x 64 (rows), 128-byte swizzle
+int wv_make_tmap_mt(const WvBatchDev& bd, void* out128) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)bd.npad, (cuuint64_t)bd.B * bd.npad};
+  const cuuint64_t strides[1] = {(cuuint64_t)bd.npad * sizeof(double)};
+  const cuuint32_t box[2] = {WV_BK, WV_NB};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out128), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)bd.Mt, dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -1;
+}
+
+// =============================================================================================
 // Large-n path (nt >= WvAux::big_nt, e.g. config 4: one n = 8192 model).  The left-looking batched scheme above has
 // one CTA per model on its critical path; for few, large models the factorisation is reorganised so that almost all
 // flops sit in wide launches of the same 64x64 DMMA tile GEMM:
@@ -883,6 +1041,7 @@ static cudaError_t wv_set_attrs() {
   WV_ATTR(wv_trtri_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_trtri_rows_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_kinv_kernel, sizeof(WvGemmSmem));
+  WV_ATTR(wv_kinv_tma_kernel, sizeof(WvTmaSmem) + 1024);
   WV_ATTR(wv_syrk_kernel, sizeof(WvGemmSmem));
   WV_ATTR(wv_trtri_level_kernel<1>, sizeof(WvGemmSmem));
   WV_ATTR(wv_trtri_level_kernel<2>, sizeof(WvGemmSmem));
@@ -1438,7 +1597,12 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
   }
   wv_extract_kernel<<<dim3(n_active), 256, 0, st>>>(bd, d_active);
   pf->mark(WV_K_EXTRACT, st);
-  wv_kinv_kernel<<<dim3(ntiles, n_active), WV_GEMM_THREADS, sizeof(WvGemmSmem), st>>>(bd, d_active);
+  if (aux->tmap_mt) {
+    wv_kinv_tma_kernel<<<dim3(ntiles, n_active), WV_GEMM_THREADS, sizeof(WvTmaSmem) + 1024, st>>>(
+        *reinterpret_cast<const CUtensorMap*>(aux->tmap_mt), bd, d_active);
+  } else {
+    wv_kinv_kernel<<<dim3(ntiles, n_active), WV_GEMM_THREADS, sizeof(WvGemmSmem), st>>>(bd, d_active);
+  }
   pf->mark(WV_K_KINV, st);
   launches += 2;
   return cudaGetLastError() == cudaSuccess ? launches : -1;

@@ -91,6 +91,7 @@ struct WvAux {
   int big_nt = 16;
   int panel_tiles = 4;       // tile columns per panel of the large-n right-looking Cholesky
   int resident_ctas = 444;   // 3 CTAs x 148 SMs: a Cholesky step is fused into one launch only if it fits
+  const void* tmap_mt = nullptr;   // CUtensorMap of the current batch's Mt (kinv through a TMA operand ring, WV_KINV_TMA=1)
   int panel_ctas = 148;      // persistent CTAs of that launch (WV_PANEL_CTAS; default one per SM)
   int panel_fused = 1;       // large-n path: all column steps of a panel in one launch (flags instead of launch boundaries)
   int trtri_rows = 0;   // 1: the batched schedule's triangular inverse as one row-wise launch (wv_trtri_rows_kernel)
