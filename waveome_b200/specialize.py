@@ -224,9 +224,10 @@ def generate(p: Program) -> Optional[SpecSource]:
         w(f"  double kc[{nkc + (nkc & 1)}];")
         w("  double tab[WV_EXP2_BIG_TAB];")
         w(f"  {name}Warp w[WVS_THREADS / 32];")
-        size = 8 * (ns + (ns & 1)) + 8 * (nkc + (nkc & 1)) + 8 * 2048 + 8 * per_warp
+        w("  int next_unit, pad_unit;         // work counter: (tile, region) units are pulled by whichever warp is free")
+        size = 8 * (ns + (ns & 1)) + 8 * (nkc + (nkc & 1)) + 8 * 2048 + 8 * per_warp + 8
         if with_red:
-            w(f"  double wsum[WVS_TPC_MAX][WVS_THREADS / 32][{nsum}];    // per tile and warp, combined in fixed order")
+            w(f"  double wsum[WVS_TPC_MAX][8][{nsum}];    // per tile and region, combined in fixed order")
             w(f"  double sums[WVS_TPC_MAX][{nsum}];")
             size += 8 * 8 * 8 * nsum + 8 * 8 * nsum
         w("};")
@@ -242,11 +243,16 @@ def generate(p: Program) -> Optional[SpecSource]:
         w("  __syncthreads();")
         for i, e in enumerate(kc_expr):
             w(f"  if (threadIdx.x == {i % 256}) sm.kc[{i}] = {e};")
+        w("  if (threadIdx.x == 255) sm.next_unit = 0;")
         w("  __syncthreads();")
         w("  const int n = bd.n, ld = bd.npad;")
         w("  const int t0 = blockIdx.x * tpc, t1 = min(ntiles, t0 + tpc);")
         w("  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;")
-        w("  const int wr = (warp >> 1) * 16, wc = (warp & 1) * 32;          // the warp's region inside every tile")
+        w("  // Work units = (tile, 16 x 32 region) pairs, pulled from a shared counter: warps whose regions are masked out")
+        w("  // (categorical x numeric products) or lie above the diagonal finish early and take the next unit instead of")
+        w("  // idling until the slowest warp of the CTA is done (13 % of the stall samples with a fixed warp -> region map).")
+        w("  // Results are indexed by unit, not by warp: sums stay bit-reproducible.")
+        w("  const int n_units = (t1 - t0) * 8;")
         w("  const int r_loc = (lane >> 3) * 4, c_off = 16 + (lane & 7) * 4;  // the lane's rows / columns in the staged arrays")
         w("  auto& sw = sm.w[warp];")
 
@@ -305,7 +311,13 @@ def generate(p: Program) -> Optional[SpecSource]:
     w("  const double* yb = bd.Y + (size_t)b * ld;")
     w("  const double* lam = bd.site_lam ? bd.site_lam + (size_t)b * ld : nullptr;")
     w("  const double* eta = bd.site_eta ? bd.site_eta + (size_t)b * ld : nullptr;")
-    w("  for (int t = t0; t < t1; ++t) {")
+    w("  for (;;) {")
+    w("    int unit = 0;")
+    w("    if (lane == 0) unit = atomicAdd(&sm.next_unit, 1);")
+    w("    unit = __shfl_sync(0xffffffffu, unit, 0);")
+    w("    if (unit >= n_units) break;")
+    w("    const int t = t0 + (unit >> 3), reg = unit & 7;")
+    w("    const int wr = (reg >> 1) * 16, wc = (reg & 1) * 32;          // the region inside tile t")
     w("    int ti, tj;")
     w("    wv_tile_from_linear(t, ti, tj);")
     w("    if (ti == tj && wc > wr + 15) continue;      // the strict upper part of a diagonal tile is never read")
@@ -377,11 +389,17 @@ def generate(p: Program) -> Optional[SpecSource]:
     w("  const double* Kb = bd.A + (size_t)b * ld * ld;")
     w("  const double* al = bd.alpha + (size_t)b * ld;")
     sum_names = [(c, k) for c, cp in enumerate(comps) for k in cp.sums]
-    w("  for (int t = t0; t < t1; ++t) {")
+    w("  for (;;) {")
+    w("    int unit = 0;")
+    w("    if (lane == 0) unit = atomicAdd(&sm.next_unit, 1);")
+    w("    unit = __shfl_sync(0xffffffffu, unit, 0);")
+    w("    if (unit >= n_units) break;")
+    w("    const int t = t0 + (unit >> 3), reg = unit & 7;")
+    w("    const int wr = (reg >> 1) * 16, wc = (reg & 1) * 32;          // the region inside tile t")
     w("    int ti, tj;")
     w("    wv_tile_from_linear(t, ti, tj);")
     w("    if (ti == tj && wc > wr + 15) {             // strictly above the diagonal: contributes nothing")
-    w(f"      for (int k = lane; k < {nsum}; k += 32) sm.wsum[t - t0][warp][k] = 0.0;")
+    w(f"      for (int k = lane; k < {nsum}; k += 32) sm.wsum[t - t0][reg][k] = 0.0;")
     w("      continue;")
     w("    }")
     stage_warp(True)
@@ -463,7 +481,7 @@ def generate(p: Program) -> Optional[SpecSource]:
         for k, idx in cp.sums.items():
             w(f"    sw.red[{idx} * 33 + lane] = s{c}_{k};")
     w("    __syncwarp();")
-    w(f"    for (int k = lane; k < {nsum}; k += 32) sm.wsum[t - t0][warp][k] = wvs_warp_row_sum(sw.red, k);")
+    w(f"    for (int k = lane; k < {nsum}; k += 32) sm.wsum[t - t0][reg][k] = wvs_warp_row_sum(sw.red, k);")
     w("  }")
     w("  __syncthreads();")
     w(f"  for (int i = threadIdx.x; i < (t1 - t0) * {nsum}; i += WVS_THREADS) {{")
