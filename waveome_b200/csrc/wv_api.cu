@@ -193,6 +193,8 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
   if (const char* v = getenv("WV_CACHE_MAX_GB")) WV_CACHE_MAX_BYTES = (size_t)(atof(v) > 0 ? atof(v) : 0) << 30;
   if (const char* v = getenv("WV_TRTRI_ROWS")) eng->aux.trtri_rows = atoi(v);      // 1: one CTA per row, 2: balanced row pairs
   if (const char* v = getenv("WV_PANEL_TILES")) eng->aux.panel_tiles = atoi(v) > 0 ? atoi(v) : 4;
+  if (const char* v = getenv("WV_CHOL_ALL")) eng->aux.chol_all = atoi(v) != 0;
+  if (const char* v = getenv("WV_CHOL_LAG")) eng->aux.chol_lag = atoi(v) > 0 ? atoi(v) : 640;
   if (const char* v = getenv("WV_PANEL_FUSED")) eng->aux.panel_fused = atoi(v) != 0;
   if (const char* v = getenv("WV_PANEL_CTAS")) eng->aux.panel_ctas = atoi(v) > 0 ? atoi(v) : 148;
   {

@@ -575,6 +575,86 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS, 3) wv_chol_panel_fused_kernel
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Many models of moderate n (the batched schedule, nt < big_nt): the WHOLE left-looking factorisation in ONE persistent
+// launch.  With one launch pair per column every CTA of the device runs the diagonal blocks at the same time -- a serial
+// 64x64 factorisation per CTA that leaves the tensor pipe idle (1.8 of the 7.7 ms Cholesky of 2000 models, n = 600) --
+// and then every CTA runs panel tiles.  Here the work items of all columns form one ordered list that a few CTAs per SM
+// pull from a counter, and the diagonal blocks of column j + 1 are INTERLEAVED with the panel tiles of column j:
+//   items [0, B)                              diagonal block (m, 0) of every model m
+//   super-step j = 0 .. nt-2, group q = 0 .. B + lag_j - 1, nt - j slots per group:
+//       slots 0 .. nt-j-2                     panel tiles (q, row j + 1 + slot, column j)              [if q < B]
+//       slot  nt-j-1                          diagonal block (q - lag_j, j + 1)                        [if q >= lag_j]
+// so at any time about one CTA in nt - j runs a diagonal block while the others keep the DMMA pipe busy.  lag_j models
+// (> the items in flight / slots per group) separate a diagonal block from the tile (j + 1, j) it depends on, so it
+// almost never waits.  Dependencies are the flags of the large-n panel kernel: step_flag[b][j] = epoch when diagonal
+// block j is done (waited for inside wv_panel_body<0>), row counter row_done[b][i] = (epoch, columns finished in row i).
+// Every dependency of an item has a lower index and items are pulled in order: the lowest unfinished item is always held by
+// a running CTA whose dependencies are finished -- no deadlock.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wv_wait_cols(const int* row_done, int ep, int need) {
+  if (need <= 0) return;
+  const volatile int* f = reinterpret_cast<const volatile int*>(row_done);
+  for (;;) {
+    const int v = *f;
+    if ((v >> 8) == ep && (v & 255) >= need) break;
+    __nanosleep(40);
+  }
+}
+
+__global__ void __launch_bounds__(WV_GEMM_THREADS, 3) wv_chol_all_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                                      int n_active, int lag_items, int epoch) {
+  __shared__ int s_item;
+  int* counter = bd.step_flag + 2 * (size_t)bd.B * bd.nt;
+  const int nt = bd.nt;
+  const int ep = epoch & 0x7fffff;
+  for (;;) {
+    __syncthreads();                      // previous item done with the shared-memory tiles
+    if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);
+    __syncthreads();
+    int it = s_item;
+    int m, j = 0, x = 0;
+    if (it < n_active) {
+      m = it;
+    } else {
+      it -= n_active;
+      int lag;
+      for (;; ++j) {
+        if (j >= nt - 1) return;
+        lag = (lag_items + nt - j - 1) / (nt - j);
+        const int sz = (n_active + lag) * (nt - j);
+        if (it < sz) break;
+        it -= sz;
+      }
+      const int gsz = nt - j;
+      const int q = it / gsz, sl = it - q * gsz;
+      if (sl < gsz - 1) {
+        if (q >= n_active) continue;
+        m = q; x = sl + 1;
+      } else {
+        if (q < lag) continue;
+        m = q - lag; j += 1;
+      }
+    }
+    const int b = active[m];
+    int* row_done = bd.step_flag + (size_t)bd.B * bd.nt + (size_t)b * bd.nt;
+    if (threadIdx.x == 0) {
+      wv_wait_cols(row_done + j, ep, j);
+      if (x > 0) wv_wait_cols(row_done + j + x, ep, j);
+      __threadfence();
+    }
+    __syncthreads();
+    if (x == 0) {
+      wv_diag_body(bd, b, j, 0, epoch);
+      continue;
+    }
+    wv_panel_body<0>(bd, b, j, x - 1, 0, epoch);
+    __threadfence();                       // the tile is visible device-wide before the row counter moves
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(row_done + j + x) = (ep << 8) | (j + 1);
+  }
+}
+
 // enqueue one Cholesky column step; fused into one launch iff all its CTAs can be resident at once
 static int wv_launch_chol_step(const WvBatchDev& bd, const int* d_active, int n_active, int j, int k0, cudaStream_t st,
                                WvProfiler* pf, const WvAux& aux) {
@@ -1038,6 +1118,7 @@ static cudaError_t wv_set_attrs() {
   WV_ATTR(wv_chol_step_kernel, wv_smem_gemm_bytes());
   WV_ATTR(wv_chol_panel_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_chol_panel_fused_kernel, wv_smem_gemm_bytes());
+  WV_ATTR(wv_chol_all_kernel, wv_smem_gemm_bytes());
   WV_ATTR(wv_trtri_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_trtri_rows_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_kinv_kernel, sizeof(WvGemmSmem));
@@ -1579,7 +1660,15 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
     launches += l;
     if (chol_only) return cudaGetLastError() == cudaSuccess ? launches : -1;
   } else {
-    for (int j = 0; j < nt; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, 0, st, pf, *aux);
+    if (aux->chol_all && nt >= 2 && nt < 200 && (long)n_active * nt > 2L * aux->resident_ctas) {
+      cudaMemsetAsync(bd.step_flag + 2 * (size_t)bd.B * bd.nt, 0, sizeof(int), st);      // the work counter
+      wv_chol_all_kernel<<<aux->resident_ctas, WV_GEMM_THREADS, wv_smem_gemm_bytes(), st>>>(bd, d_active, n_active,
+                                                                                         aux->chol_lag, aux->epoch);
+      pf->mark(WV_K_CHOL_PANEL, st);
+      ++launches;
+    } else {
+      for (int j = 0; j < nt; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, 0, st, pf, *aux);
+    }
     if (chol_only) return cudaGetLastError() == cudaSuccess ? launches : -1;
     if (aux->trtri_rows && nt > 1) {
       const int paired = aux->trtri_rows == 2;

@@ -53,7 +53,7 @@ struct WvLbScalars {
 
 // number of doubles of vector/matrix workspace per model
 WV_HD size_t wv_lb_work_doubles(int P, int m) {
-  return (size_t)4 * P + (size_t)2 * P * m + (size_t)3 * m * m + (size_t)4 * m * m + (size_t)2 * m;
+  return (size_t)4 * P + (size_t)2 * P * m + (size_t)4 * m * m + (size_t)4 * m * m + (size_t)2 * m;
 }
 
 struct WvLbState {
@@ -63,14 +63,15 @@ struct WvLbState {
   double *t, *r, *d, *z;                // [P]
   double *ws, *wy;                      // [P x m] column-major (column c at c*P)
   double *sy, *ss, *wt;                 // [m x m] column-major, leading dimension m
+  double *yy;                           // [m x m] y_i' y_j for i >= j (lower incl. diagonal), kept across iterations
   double *wn;                           // [2m x 2m] column-major, leading dimension 2m
   double *wv;                           // [2m]
   WV_HD void bind(WvLbScalars* sc, double* x_, double* g_, double* w, int P_, int m_) {
     P = P_; m = m_; s = sc;
     x = x_; g = g_; t = w; r = t + P; d = r + P; z = d + P;
     ws = z + P; wy = ws + (size_t)P * m;
-    sy = wy + (size_t)P * m; ss = sy + m * m; wt = ss + m * m;
-    wn = wt + m * m; wv = wn + 4 * m * m;
+    sy = wy + (size_t)P * m; ss = sy + m * m; wt = ss + m * m; yy = wt + m * m;
+    wn = yy + m * m; wv = wn + 4 * m * m;
   }
 };
 
@@ -272,22 +273,19 @@ WV_HD int wv_lb_formk(WvLbState& L) {
   WvLbScalars& S = *L.s;
   const int m = L.m, P = L.P, col = S.col, m2 = 2 * m;
   double* wn = L.wn;
-  // sy(i,j) = s_i' y_j is kept for i >= j (lower, incl. diagonal); the upper part of S'Y is recomputed here
+  (void)P;
+  // The inner products y_i'y_j (i >= j: yy) and s_i'y_j (i >= j: lower part of sy; i < j: its strict upper part) are
+  // formed ONCE, when a pair enters the memory (wv_lb_matupd, as the Fortran code keeps them in wn1), not recomputed from
+  // the vectors in every iteration: the same dot products, hence the same values, at a tenth of the work.
   for (int iy = 0; iy < col; ++iy) {
     const int is = col + iy;
-    const double* yi = L.wy + (size_t)wv_lb_ptr(S, m, iy) * P;
-    const double* si = L.ws + (size_t)wv_lb_ptr(S, m, iy) * P;
     for (int jy = 0; jy <= iy; ++jy) {
       const int js = col + jy;
-      const double* yj = L.wy + (size_t)wv_lb_ptr(S, m, jy) * P;
-      wn[jy + iy * m2] = wv_dot(yi, yj, P) / S.theta;     // Y'ZZ'Y / theta
+      wn[jy + iy * m2] = L.yy[iy + jy * m] / S.theta;      // Y'ZZ'Y / theta
       wn[js + is * m2] = 0.0;                               // S'AA'S * theta (no active variables)
     }
     for (int jy = 0; jy < iy; ++jy) wn[jy + is * m2] = 0.0; // -L_a' (no active variables)
-    for (int jy = iy; jy < col; ++jy) {
-      const double* yj = L.wy + (size_t)wv_lb_ptr(S, m, jy) * P;
-      wn[jy + is * m2] = wv_dot(si, yj, P);                 // R_z'
-    }
+    for (int jy = iy; jy < col; ++jy) wn[jy + is * m2] = L.sy[iy + jy * m];      // R_z' = s_iy' y_jy, jy >= iy
     wn[iy + iy * m2] += L.sy[iy + iy * m];
   }
   if (wv_dpofa(wn, m2, col) != 0) return -1;
@@ -330,19 +328,24 @@ WV_HD void wv_lb_matupd(WvLbState& L, double rr, double dr, double stp, double d
   for (int i = 0; i < P; ++i) { wsc[i] = L.d[i]; wyc[i] = L.r[i]; }
   S.theta = rr / dr;
   const int col = S.col;
-  if (S.iupdat > m) {   // shift old part of SS (upper) and SY (lower) one place up-left
+  if (S.iupdat > m) {   // shift the old part of SS (upper), SY (all of it) and YY (lower) one place up-left
     for (int j = 0; j < col - 1; ++j) {
       for (int i = 0; i <= j; ++i) L.ss[i + j * m] = L.ss[(i + 1) + (j + 1) * m];
-      for (int i = j; i < col - 1; ++i) L.sy[i + j * m] = L.sy[(i + 1) + (j + 1) * m];
+      for (int i = 0; i < col - 1; ++i) L.sy[i + j * m] = L.sy[(i + 1) + (j + 1) * m];
+      for (int i = j; i < col - 1; ++i) L.yy[i + j * m] = L.yy[(i + 1) + (j + 1) * m];
     }
   }
   for (int j = 0; j < col - 1; ++j) {
     const int p = wv_lb_ptr(S, m, j);
     L.sy[(col - 1) + j * m] = wv_dot(L.d, L.wy + (size_t)p * P, P);
     L.ss[j + (col - 1) * m] = wv_dot(L.ws + (size_t)p * P, L.d, P);
+    // for wv_lb_formk: s_j' y_new (upper part of S'Y) and y_new' y_j, operands in the order formk used to take them
+    L.sy[j + (col - 1) * m] = wv_dot(L.ws + (size_t)p * P, L.r, P);
+    L.yy[(col - 1) + j * m] = wv_dot(L.r, L.wy + (size_t)p * P, P);
   }
   L.ss[(col - 1) + (col - 1) * m] = (stp == 1.0) ? dtd : stp * stp * dtd;
   L.sy[(col - 1) + (col - 1) * m] = dr;
+  L.yy[(col - 1) + (col - 1) * m] = wv_dot(L.r, L.r, P);
 }
 
 // subsm (all variables free, no bounds): on entry L.d = r = -g; on exit L.z = x + Newton step
