@@ -193,6 +193,7 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
   if (const char* v = getenv("WV_CACHE_MAX_GB")) WV_CACHE_MAX_BYTES = (size_t)(atof(v) > 0 ? atof(v) : 0) << 30;
   if (const char* v = getenv("WV_TRTRI_ROWS")) eng->aux.trtri_rows = atoi(v);      // 1: one CTA per row, 2: balanced row pairs
   if (const char* v = getenv("WV_PANEL_TILES")) eng->aux.panel_tiles = atoi(v) > 0 ? atoi(v) : 4;
+  if (const char* v = getenv("WV_FEW_MODELS")) eng->aux.few_models = atoi(v) != 0;
   if (const char* v = getenv("WV_CHOL_ALL")) eng->aux.chol_all = atoi(v) != 0;
   if (const char* v = getenv("WV_CHOL_LAG")) eng->aux.chol_lag = atoi(v) > 0 ? atoi(v) : 640;
   if (const char* v = getenv("WV_PANEL_FUSED")) eng->aux.panel_fused = atoi(v) != 0;
@@ -702,9 +703,11 @@ __global__ void wv_lb_step_kernel(const int* __restrict__ active, int n_active, 
 }
 
 // The same step with the model's optimiser state staged in shared memory: one WARP per model copies workspace, iterate,
-// gradient and scalars in (coalesced), lane 0 runs the sequential state machine on them, the warp copies them back.
+// gradient and scalars in (coalesced), runs the state machine on them with the warp policy of wv_lbfgsb.h (lane 0 owns the
+// scalars, independent dot products / columns / right-hand sides go to different lanes), and copies them back.
 // The thread-per-model kernel above walks ~9 KB of private state per model through dependent, uncoalesced global loads
-// (0.46 ms per round at 2000 models, 3 % of a fit); the arithmetic is identical, so are the results.
+// (0.46 ms per round at 2000 models); lane 0 alone on the staged state took 156-170 us per round (round 1).  The
+// arithmetic of every value is identical in all three forms, so are the results (tests/test_lbfgs_warp_gpu.py).
 __global__ void wv_lb_step_warp_kernel(const int* __restrict__ active, int n_active, const int* __restrict__ nx_of_model,
                                        int Pstride, int m, WvLbOpts opts, WvLbScalars* sc, double* work, size_t wstride,
                                        double* x, double* g, const double* __restrict__ f,
@@ -727,7 +730,7 @@ __global__ void wv_lb_step_warp_kernel(const int* __restrict__ active, int n_act
   for (int k = lane; k < Pstride; k += 32) { sx[k] = gx[k]; sg[k] = gg[k]; }
   for (int k = lane; k < nsc; k += 32) ssc[k] = gsc[k];
   __syncwarp();
-  if (lane == 0) {
+  {
     WvLbScalars* ls = reinterpret_cast<WvLbScalars*>(ssc);
     WvLbState L;
     L.bind(ls, sx, sg, sw, nx_of_model[b], m);
@@ -735,14 +738,20 @@ __global__ void wv_lb_step_warp_kernel(const int* __restrict__ active, int n_act
     bool run = true;
     if (status[b] & WV_STATUS_CHOL_FAIL) {
       if (opts.chol_fail_policy == 1 || ls->first) {
-        task[b] = WV_LB_CHOLFAIL;
+        if (lane == 0) task[b] = WV_LB_CHOLFAIL;
         run = false;
       } else {
         fb = nan("");
-        for (int k = 0; k < L.P; ++k) L.g[k] = fb;
+        for (int k = lane; k < L.P; k += 32) L.g[k] = fb;
       }
     }
-    if (run) task[b] = wv_lb_step(L, opts, fb);
+    __syncwarp();
+    if (run) {
+      WvExWarp ex;
+      ex.ln = lane;
+      const int t = wv_lb_step(ex, L, opts, fb);
+      if (lane == 0) task[b] = t;
+    }
   }
   __syncwarp();
   for (size_t k = lane; k < wstride; k += 32) gw[k] = sw[k];
@@ -825,13 +834,16 @@ extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o
   int* nxt = b->d_active2;
   long guard = 0;
   const long guard_max = (long)o->maxfun + (long)o->maxiter + 1000;
+  // WV_LB_SERIAL=1: the thread-per-model form of the optimiser step (the tests compare the warp form against it)
+  const char* lb_env = getenv("WV_LB_SERIAL");
+  const bool lb_serial = lb_env && atoi(lb_env) != 0;
   while (n_active > 0) {
     if (wv_eval_all(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status, cur, n_active) != 0) return -1;
     {
       static_assert(sizeof(WvLbScalars) % sizeof(double) == 0, "WvLbScalars is copied as doubles");
       const size_t per = (wstride + 2 * (size_t)P + sizeof(WvLbScalars) / sizeof(double)) * sizeof(double);
       const int wpc = (int)std::min<size_t>(4, (48 * 1024) / per);     // warps (= models) per CTA within 48 KB
-      if (wpc >= 1)
+      if (wpc >= 1 && !lb_serial)
         wv_lb_step_warp_kernel<<<(n_active + wpc - 1) / wpc, wpc * 32, wpc * per, st>>>(
             cur, n_active, d_nx, P, m, opts, b->d_lbs, b->d_lbw, wstride, b->d_x, b->d_g, b->d_f, b->d_status, b->d_task);
       else      // very long memories: the state does not fit, one thread per model on global memory

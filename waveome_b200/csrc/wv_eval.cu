@@ -1660,17 +1660,23 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
     launches += l;
     if (chol_only) return cudaGetLastError() == cudaSuccess ? launches : -1;
   } else {
-    if (aux->chol_all && nt >= 2 && nt < 200 && (long)n_active * nt > 2L * aux->resident_ctas) {
+    // few models (the tail rounds of a fit, small searches): the device is empty and the evaluation is a chain of
+    // dependent launches -- one persistent launch for the whole factorisation (no lag: a diagonal block follows its
+    // model's tiles directly and spins for the one it needs) and one for the triangular inverse (a CTA per tile row)
+    const long tiles_all = (long)n_active * nt * (nt + 1) / 2;
+    const bool few = aux->few_models && nt >= 2 && nt < 200 && tiles_all <= aux->resident_ctas;
+    if (few || (aux->chol_all && nt >= 2 && nt < 200 && (long)n_active * nt > 2L * aux->resident_ctas)) {
       cudaMemsetAsync(bd.step_flag + 2 * (size_t)bd.B * bd.nt, 0, sizeof(int), st);      // the work counter
-      wv_chol_all_kernel<<<aux->resident_ctas, WV_GEMM_THREADS, wv_smem_gemm_bytes(), st>>>(bd, d_active, n_active,
-                                                                                         aux->chol_lag, aux->epoch);
+      const int ctas = few ? (int)tiles_all : aux->resident_ctas;
+      wv_chol_all_kernel<<<ctas, WV_GEMM_THREADS, wv_smem_gemm_bytes(), st>>>(bd, d_active, n_active,
+                                                                              few ? 0 : aux->chol_lag, aux->epoch);
       pf->mark(WV_K_CHOL_PANEL, st);
       ++launches;
     } else {
       for (int j = 0; j < nt; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, 0, st, pf, *aux);
     }
     if (chol_only) return cudaGetLastError() == cudaSuccess ? launches : -1;
-    if (aux->trtri_rows && nt > 1) {
+    if ((aux->trtri_rows || few) && nt > 1) {
       const int paired = aux->trtri_rows == 2;
       wv_trtri_rows_kernel<<<dim3(paired ? nt / 2 : nt - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active,
                                                                                                               paired);

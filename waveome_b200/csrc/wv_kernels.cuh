@@ -97,6 +97,7 @@ struct WvAux {
   int trtri_rows = 0;   // 1: the batched schedule's triangular inverse as one row-wise launch (wv_trtri_rows_kernel)
   int chol_all = 0;     // many models, nt < big_nt: the whole Cholesky in one persistent launch (wv_chol_all_kernel; WV_CHOL_ALL=1;
                         // measured slower than the launch pair per column, DESIGN.md section 4b: off)
+  int few_models = 1;   // few models in flight: one launch each for the Cholesky and the triangular inverse (WV_FEW_MODELS=0: off)
   int chol_lag = 640;   // work items between a panel tile (j + 1, j) and the diagonal block j + 1 that needs it (WV_CHOL_LAG)
   int epoch = 0;   // evaluation counter of the engine: the value the diagonal CTAs publish in step_flag
 };
