@@ -96,6 +96,10 @@ typedef struct wv_lbfgs_opts {
 } wv_lbfgs_opts;
 
 int wv_engine_create(int device, wv_engine** out);
+/* flags: WV_ENGINE_HIGH_PRIORITY -- the engine's stream is scheduled ahead of the default engines' (for the few straggler
+ * models of a batch that finish while the next batch already runs, see wv_batch_set_engine / wv_batch_fit_lbfgs_run). */
+#define WV_ENGINE_HIGH_PRIORITY 1
+int wv_engine_create2(int device, int flags, wv_engine** out);
 void wv_engine_destroy(wv_engine* e);
 /* CUDA stream the engine launches on (cudaStream_t as void*), for event timing by the caller */
 void* wv_engine_stream(wv_engine* e);
@@ -154,6 +158,20 @@ int wv_batch_eval_device(wv_batch* b, const double* d_x, double* d_f, double* d_
  * f, lml [B] are evaluated at the returned x; n_iter, n_eval, status [B]. */
 int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* opts, double* f, double* lml,
                        int32_t* n_iter, int32_t* n_eval, int32_t* status);
+
+/* The same fit in three calls, for callers that want the results of the finished models while a few stragglers keep
+ * iterating (kernel search: a level's batch lasts as long as its slowest model).
+ *   begin   upload the starts x (HOST [B, P]) and initialise every model's optimiser state
+ *   run     optimiser rounds while more than min_active models are still iterating; *n_active = how many are left
+ *   report  as wv_batch_fit_lbfgs's outputs; finished [B] (may be NULL): 1 where the model's fit has ended.  While models
+ *           are still iterating only the finished ones are evaluated: f / lml / status of the others are undefined.
+ * wv_batch_fit_lbfgs(...) == begin, run(min_active = 0), report. */
+int wv_batch_fit_lbfgs_begin(wv_batch* b, const double* x, const wv_lbfgs_opts* opts);
+/* Re-home a batch onto another engine (= stream) of the same device; no call on the batch may be in progress. */
+int wv_batch_set_engine(wv_batch* b, wv_engine* e);
+int wv_batch_fit_lbfgs_run(wv_batch* b, int32_t min_active, int32_t* n_active);
+int wv_batch_fit_lbfgs_report(wv_batch* b, double* x, double* f, double* lml, int32_t* n_iter, int32_t* n_eval,
+                              int32_t* status, int32_t* finished);
 
 /* Objective (B) at GIVEN variational parameters: the whitened bound of gpflow.models.VGP / SVGP with Z = X that the live
  * reference API optimises (PSVGP: waveome/model_classes.py:1082-1126; bound: gpflow SVGP.elbo, in-repo mirror

@@ -128,3 +128,31 @@ def test_concurrent_sub_batches_are_bit_identical():
         for a, b in zip(m1[:5], m4[:5]):
             assert [float(p) for p in a.trainable_parameters] == [float(p) for p in b.trainable_parameters]
     assert len(mf.get_engine_pool(4)) == 4 and mf.get_engine_pool(4)[0] is mf.get_engine()
+
+
+def test_fit_in_three_calls_matches_single_call(engine):
+    """wv_batch_fit_lbfgs_begin / _run(min_active) / _report: the models finished when control comes back already carry
+    their final results; running the stragglers to the end afterwards gives, for every model, exactly what the
+    single-call fit gives."""
+    from waveome_b200.engine import Batch
+    n = 120
+    X, y = helpers.make_data(n, seed=21)
+    rng = np.random.default_rng(4)
+    Y = np.stack([y + s * rng.normal(size=n) for s in np.linspace(0.0, 2.0, 24)])
+    model = wb.GPR(helpers.saturated_kernel(hs=0.0), mean_function=wb.ConstantMean(0.0))
+    batch = Batch(engine, X, Y, [model.program()])
+    full = batch.fit()
+    batch.fit_begin()
+    left = batch.fit_run(6)
+    part = batch.fit_report()
+    assert 0 < left <= 6 and int((~part["finished"]).sum()) == left
+    done = part["finished"]
+    for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
+        assert np.array_equal(part[key][done], full[key][done]), key
+    assert np.all(part["n_eval"][~done] < full["n_eval"][~done])
+    assert batch.fit_run(0) == 0
+    rest = batch.fit_report()
+    assert rest["finished"].all()
+    for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
+        assert np.array_equal(rest[key], full[key]), key
+    batch.close()

@@ -202,3 +202,78 @@ def test_fitter_threads_get_their_own_engines(monkeypatch):
         assert len(used) == 12 and all(len(v) == 1 for v in by_thread.values())
         assert {e for _t, e in used} == {"engine1", "engine2"}
     assert ks._thread_engine() == "engine0"
+
+
+def test_deferred_stragglers_give_the_same_search():
+    """run_lockstep with a fitter that hands back control while some requests are unfinished (the engine fitter with
+    ``tail`` > 0): outcomes without stragglers move on, the others rejoin later -- same candidates, same results, same
+    selected structures as the level-synchronous driver, every request fitted exactly once."""
+    import threading
+    import time
+    import zlib
+    from waveome_b200 import datasets
+    from waveome_b200.model_search import GPSearch
+
+    def result(y, name, kernel):
+        m = ks.candidate_model(kernel)
+        h = zlib.crc32((name + repr(float(y[0]))).encode()) % 10000 / 50.0
+        return (m, round(300.0 - 12.0 * min(name.count("+") + name.count("*"), 2) + h, 2))
+
+    def sync_fit(requests):
+        return [result(*r) for r in requests]
+
+    seen, threads, shapes = [], set(), []
+
+    def deferring_fit(requests, tail=0):
+        assert tail > 0
+        seen.extend((float(y[0]), name) for y, name, _k in requests)
+        full = [result(*r) for r in requests]
+        # every 7th request (by a hash of its identity) is a straggler
+        slow = [zlib.crc32((name + repr(float(y[0]))).encode()) % 7 == 0 for y, name, _k in requests]
+        shapes.append((len(requests), sum(slow)))
+        if not any(slow):
+            return full, None
+
+        def pending():
+            threads.add(threading.get_ident())
+            time.sleep(0.01)
+            return full
+
+        return [None if s else r for r, s in zip(full, slow)], pending
+
+    deferring_fit.supports_tail = True
+    X, Y = datasets.overview_synthetic(n_people=6, n_observations=4, n_outcomes=40)
+    res = {}
+    for label, fit in (("sync", sync_fit), ("deferred", deferring_fit)):
+        gps = GPSearch(X, Y, unit_col="person_id", categorical_vars=["female"])
+        gps.run_search(max_depth=4, fit=fit)
+        res[label] = ({o: gps.search_info[o]["best_model"] for o in gps.out_names},
+                      {o: sorted((k, v["bic"], v["depth"], v["try_next"]) for k, v in gps.search_info[o]["models"].items())
+                       for o in gps.out_names}, gps.fit_report["n_fits"])
+    assert res["deferred"] == res["sync"]
+    assert len(seen) == len(set(seen)) == res["sync"][2]            # nothing fitted twice, nothing dropped
+    assert threads and threading.get_ident() not in threads         # the stragglers finished on worker threads
+    assert sum(1 for _n, k in shapes if k) > 3                      # ... at several levels
+
+
+def test_engine_lease_hands_out_distinct_engines(monkeypatch):
+    from waveome_b200 import engine as E, model_fitting as mf
+    made = []
+
+    class FakeEngine:
+        def __init__(self, device, high_priority=False):
+            assert high_priority
+            made.append(self)
+
+    monkeypatch.setattr(E, "Engine", FakeEngine)
+    monkeypatch.setattr(mf, "_LEASED", {})
+    monkeypatch.setattr(mf, "_HP_POOLS", {})
+    a, ia = mf.lease_engine(0)
+    b, ib = mf.lease_engine(0)
+    assert a is not b and len(made) == 2
+    mf.release_engine(ia, 0)
+    c, ic = mf.lease_engine(0)
+    assert c is a and ic == ia and len(made) == 2          # returned engines are reused, the pool does not grow
+    mf.release_engine(ib, 0)
+    mf.release_engine(ic, 0)
+    assert mf._LEASED[0] == set()

@@ -111,3 +111,27 @@ def test_pipelined_run_search_matches_single_group():
         assert list(ma.keys()) == list(mb.keys())
         assert [v["bic"] for v in ma.values()] == [v["bic"] for v in mb.values()], o
         np.testing.assert_array_equal(a.models[o].program().x0(), b.models[o].program().x0())
+
+
+def test_deferred_stragglers_run_search_matches_level_synchronous(monkeypatch):
+    """run_search with the stragglers of a level finishing in the background (kernel_search.SEARCH_TAIL > 0: the fit
+    returns once at most that many models are still iterating, wv_batch_fit_lbfgs_begin / _run / _report) against the
+    level-synchronous driver: bit-identical fits, identical candidate sets, BICs and selected structures."""
+    X, Y = datasets.overview_synthetic(n_people=12, n_observations=5, n_outcomes=36)
+    out = {}
+    for tail in (0, 24):
+        monkeypatch.setattr(ks, "SEARCH_TAIL", tail)
+        gps = GPSearch(X, Y, unit_col="person_id", categorical_vars=["female"])
+        gps.run_search(max_depth=3)
+        out[tail] = gps
+    a, b = out[0], out[24]
+    assert a.fit_report["n_fits"] == b.fit_report["n_fits"]
+    assert b.fit_report["batches"] > a.fit_report["batches"]             # late outcomes did rejoin in later batches
+    for o in a.out_names:
+        assert a.search_info[o]["best_model"] == b.search_info[o]["best_model"], o
+        ma, mb = a.search_info[o]["models"], b.search_info[o]["models"]
+        assert list(ma.keys()) == list(mb.keys())
+        assert [v["bic"] for v in ma.values()] == [v["bic"] for v in mb.values()], o
+        np.testing.assert_array_equal(a.models[o].program().x0(), b.models[o].program().x0())
+    from waveome_b200 import model_fitting as mf
+    assert all(not v for v in mf._LEASED.values())                       # every engine lease was returned

@@ -102,6 +102,10 @@ struct wv_batch {
   WvLbScalars* d_lbs;
   double* d_lbw;
   int lb_m_alloc;
+  WvLbOpts lb_opts;              // the fit in progress (wv_batch_fit_lbfgs_begin / _run / _report)
+  int lb_n_active = 0;
+  int *lb_cur = nullptr, *lb_nxt = nullptr;
+  long lb_guard = 0, lb_guard_max = 0;
   int* h_count;   // the engine's pinned counters
   int64_t bytes, launches, rounds, model_evals;
   WvVgpState vgp;         // site-iteration state (variational path), arrays allocated by wv_batch_set_likelihood
@@ -163,7 +167,10 @@ template <typename T> static int wv_alloc(wv_batch* b, T** p, size_t count) {
 extern "C" const char* wv_last_error(void) { return g_err.c_str(); }
 extern "C" const char* wv_version(void) { return "waveome_b200 0.1 (sm_100a, fp64 DMMA)"; }
 
-extern "C" int wv_engine_create(int device, wv_engine** out) {
+extern "C" int wv_engine_create2(int device, int flags, wv_engine** out);
+extern "C" int wv_engine_create(int device, wv_engine** out) { return wv_engine_create2(device, 0, out); }
+
+extern "C" int wv_engine_create2(int device, int flags, wv_engine** out) {
   if (!out) return wv_fail("wv_engine_create: out is null");
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -182,9 +189,13 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
   }
   // the main stream carries the serial chain of the factorisation (diagonal blocks, panels): it gets the highest
   // priority so that its few CTAs are placed ahead of the bulk trailing updates queued on the side stream
+  // ... except behind the streams of WV_ENGINE_HIGH_PRIORITY engines: those carry the few straggler models of a batch
+  // whose other outcomes have moved on (kernel search), tiny dependent launches that must not queue behind the thousands
+  // of CTAs of the next level's batch
   int prio_lo = 0, prio_hi = 0;
   WV_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  WV_CUDA(cudaStreamCreateWithPriority(&eng->stream, cudaStreamNonBlocking, prio_hi));
+  const int prio_main = (prio_lo - prio_hi >= 2 && !(flags & 1)) ? prio_hi + 1 : prio_hi;
+  WV_CUDA(cudaStreamCreateWithPriority(&eng->stream, cudaStreamNonBlocking, prio_main));
   WV_CUDA(cudaStreamCreateWithPriority(&eng->aux.side, cudaStreamNonBlocking, prio_lo));
   WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_panel, cudaEventDisableTiming));
   WV_CUDA(cudaEventCreateWithFlags(&eng->aux.ev_bulk, cudaEventDisableTiming));
@@ -207,6 +218,10 @@ extern "C" int wv_engine_create(int device, wv_engine** out) {
   *out = eng;
   return 0;
 }
+
+// Re-home a batch: its later calls run on engine e's stream.  No call on the batch may be in progress; both engines must
+// be on the batch's device.  (Every entry point synchronises its stream before it returns, so nothing is in flight.)
+extern "C" int wv_batch_set_engine(wv_batch* b, wv_engine* e);
 
 extern "C" void wv_engine_destroy(wv_engine* e) {
   if (!e) return;
@@ -760,7 +775,7 @@ __global__ void wv_lb_step_warp_kernel(const int* __restrict__ active, int n_act
 }
 
 // ordered compaction of the models that still need an evaluation (single CTA, warp ballots)
-__global__ void wv_compact_kernel(const int* __restrict__ task, int B, int* out, int* count) {
+__global__ void wv_compact_kernel(const int* __restrict__ task, int B, int* out, int* count, int want_active = 1) {
   __shared__ int warp_tot[32];
   __shared__ int base;
   if (threadIdx.x == 0) base = 0;
@@ -768,7 +783,7 @@ __global__ void wv_compact_kernel(const int* __restrict__ task, int B, int* out,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int start = 0; start < B; start += blockDim.x) {
     int b = start + threadIdx.x;
-    bool act = b < B && task[b] == WV_LB_FG;
+    bool act = b < B && (task[b] == WV_LB_FG) == (want_active != 0);
     unsigned bal = __ballot_sync(0xffffffffu, act);
     if (lane == 0) warp_tot[warp] = __popc(bal);
     __syncthreads();
@@ -805,9 +820,26 @@ __global__ void wv_lb_report_kernel(int B, const WvLbScalars* sc, const int* tas
   status[b] = st;
 }
 
-extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o, double* f, double* lml,
-                                  int32_t* n_iter, int32_t* n_eval, int32_t* status) {
-  if (!b || !x || !o || !f || !lml || !n_iter || !n_eval || !status) return wv_fail("wv_batch_fit_lbfgs: null argument");
+extern "C" int wv_batch_set_engine(wv_batch* b, wv_engine* e) {
+  if (!b || !e) return wv_fail("wv_batch_set_engine: null argument");
+  if (e->device != b->eng->device) return wv_fail("wv_batch_set_engine: the engine is on another device");
+  WV_CUDA(cudaSetDevice(e->device));
+  WV_CUDA(cudaStreamSynchronize(b->eng->stream));
+  // the dependency flags in the batch's buffers carry evaluation epochs of the old engine: the new one must stay ahead
+  if (e->aux.epoch < b->eng->aux.epoch) e->aux.epoch = b->eng->aux.epoch;
+  b->eng = e;
+  b->h_count = e->h_count;
+  return 0;
+}
+
+// The fit in three calls, so that a caller can take the results of the models that are finished while a few stragglers
+// keep iterating (the kernel search: a level batch lasts as long as its slowest model, waveome_b200/kernel_search.py):
+//   begin   upload the starts, initialise every model's state machine
+//   run     rounds of {evaluate the active models, advance their state machines, compact} while more than `min_active`
+//           models are active
+//   report  objective / LML / status at the current iterates, counters, and which models are finished
+extern "C" int wv_batch_fit_lbfgs_begin(wv_batch* b, const double* x, const wv_lbfgs_opts* o) {
+  if (!b || !x || !o) return wv_fail("wv_batch_fit_lbfgs_begin: null argument");
   if (o->maxcor < 1 || o->maxcor > WV_LB_MAXCOR) return wv_fail("wv_batch_fit_lbfgs: maxcor must be in [1, 20]");
   if (o->maxls < 1) return wv_fail("wv_batch_fit_lbfgs: maxls must be positive");
   WV_CUDA(cudaSetDevice(b->eng->device));
@@ -819,25 +851,40 @@ extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o
     if (wv_alloc(b, &b->d_lbw, (size_t)B * wstride) != 0) return -1;
     b->lb_m_alloc = m;
   }
-  int *d_nx = b->d_nx, *d_iter = b->d_iter, *d_neval = b->d_neval, *d_st2 = b->d_st2;
-  WvLbOpts opts;
+  WvLbOpts& opts = b->lb_opts;
   opts.m = m; opts.maxiter = o->maxiter; opts.maxfun = o->maxfun; opts.maxls = o->maxls;
   opts.ftol = o->ftol; opts.pgtol = o->gtol; opts.chol_fail_policy = o->chol_fail_policy; opts.reserved = 0;
   const int tb = 64, gb = (B + tb - 1) / tb;
   WV_CUDA(cudaMemcpyAsync(b->d_x, x, (size_t)B * P * sizeof(double), cudaMemcpyHostToDevice, st));
-  wv_nx_kernel<<<gb, tb, 0, st>>>(b->bd.programs, b->bd.prog_id, B, d_nx);
+  wv_nx_kernel<<<gb, tb, 0, st>>>(b->bd.programs, b->bd.prog_id, B, b->d_nx);
   wv_lb_init_kernel<<<gb, tb, 0, st>>>(B, P, m, b->d_lbs, b->d_lbw, wstride, b->d_x, b->d_g, b->d_task);
   wv_iota_kernel<<<(B + 255) / 256, 256, 0, st>>>(b->d_active, B);
   b->launches += 3;
-  int n_active = B;
-  int* cur = b->d_active;
-  int* nxt = b->d_active2;
-  long guard = 0;
-  const long guard_max = (long)o->maxfun + (long)o->maxiter + 1000;
+  b->lb_n_active = B;
+  b->lb_cur = b->d_active;
+  b->lb_nxt = b->d_active2;
+  b->lb_guard = 0;
+  b->lb_guard_max = (long)o->maxfun + (long)o->maxiter + 1000;
+  // the pageable source has been consumed by the time cudaMemcpyAsync returns, but not a pinned one
+  WV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int wv_batch_fit_lbfgs_run(wv_batch* b, int32_t min_active, int32_t* n_active_out) {
+  if (!b || b->lb_m_alloc < 1 || !b->lb_cur) return wv_fail("wv_batch_fit_lbfgs_run: no fit in progress");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const int B = b->bd.B, P = b->bd.P, m = b->lb_opts.m;
+  cudaStream_t st = b->eng->stream;
+  const size_t wstride = wv_lb_work_doubles(P, m);
+  const WvLbOpts opts = b->lb_opts;
+  const int tb = 64;
+  int n_active = b->lb_n_active;
+  int* cur = b->lb_cur;
+  int* nxt = b->lb_nxt;
   // WV_LB_SERIAL=1: the thread-per-model form of the optimiser step (the tests compare the warp form against it)
   const char* lb_env = getenv("WV_LB_SERIAL");
   const bool lb_serial = lb_env && atoi(lb_env) != 0;
-  while (n_active > 0) {
+  while (n_active > (min_active > 0 ? min_active : 0)) {
     if (wv_eval_all(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status, cur, n_active) != 0) return -1;
     {
       static_assert(sizeof(WvLbScalars) % sizeof(double) == 0, "WvLbScalars is copied as doubles");
@@ -845,9 +892,9 @@ extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o
       const int wpc = (int)std::min<size_t>(4, (48 * 1024) / per);     // warps (= models) per CTA within 48 KB
       if (wpc >= 1 && !lb_serial)
         wv_lb_step_warp_kernel<<<(n_active + wpc - 1) / wpc, wpc * 32, wpc * per, st>>>(
-            cur, n_active, d_nx, P, m, opts, b->d_lbs, b->d_lbw, wstride, b->d_x, b->d_g, b->d_f, b->d_status, b->d_task);
+            cur, n_active, b->d_nx, P, m, opts, b->d_lbs, b->d_lbw, wstride, b->d_x, b->d_g, b->d_f, b->d_status, b->d_task);
       else      // very long memories: the state does not fit, one thread per model on global memory
-        wv_lb_step_kernel<<<(n_active + tb - 1) / tb, tb, 0, st>>>(cur, n_active, d_nx, P, m, opts, b->d_lbs, b->d_lbw,
+        wv_lb_step_kernel<<<(n_active + tb - 1) / tb, tb, 0, st>>>(cur, n_active, b->d_nx, P, m, opts, b->d_lbs, b->d_lbw,
                                                                   wstride, b->d_x, b->d_g, b->d_f, b->d_status, b->d_task);
     }
     wv_compact_kernel<<<1, 1024, 0, st>>>(b->d_task, B, nxt, b->d_count);
@@ -858,24 +905,58 @@ extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o
     b->prof.resolve();
     n_active = b->h_count[0];
     int* tmp = cur; cur = nxt; nxt = tmp;
-    if (++guard > guard_max) return wv_fail("wv_batch_fit_lbfgs: iteration guard tripped");
+    b->lb_n_active = n_active; b->lb_cur = cur; b->lb_nxt = nxt;
+    if (++b->lb_guard > b->lb_guard_max) return wv_fail("wv_batch_fit_lbfgs: iteration guard tripped");
   }
-  // objective, LML and status at the returned optimum (waveome/model_fitting.py:316 log_posterior_density)
-  wv_iota_kernel<<<(B + 255) / 256, 256, 0, st>>>(b->d_active, B);
+  if (n_active_out) *n_active_out = n_active;
+  return 0;
+}
+
+extern "C" int wv_batch_fit_lbfgs_report(wv_batch* b, double* x, double* f, double* lml, int32_t* n_iter, int32_t* n_eval,
+                                         int32_t* status, int32_t* finished) {
+  if (!b || !x || !f || !lml || !n_iter || !n_eval || !status) return wv_fail("wv_batch_fit_lbfgs_report: null argument");
+  if (b->lb_m_alloc < 1 || !b->lb_cur) return wv_fail("wv_batch_fit_lbfgs_report: no fit in progress");
+  WV_CUDA(cudaSetDevice(b->eng->device));
+  const int B = b->bd.B, P = b->bd.P;
+  cudaStream_t st = b->eng->stream;
+  const int tb = 64, gb = (B + tb - 1) / tb;
+  // objective, LML and status at the returned optimum (waveome/model_fitting.py:316 log_posterior_density); the active
+  // list is not touched (d_iter doubles as the list of models to evaluate).  f / lml / status of a model that is still
+  // iterating are not meaningful.
+  int n_list = B;
+  if (b->lb_n_active > 0) {     // mid-fit: the finished models only (an evaluation of the others would advance their sites)
+    wv_compact_kernel<<<1, 1024, 0, st>>>(b->d_task, B, b->d_iter, b->d_count, 0);
+    WV_CUDA(cudaMemcpyAsync(b->h_count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    WV_CUDA(cudaStreamSynchronize(st));
+    n_list = b->h_count[0];
+  } else {
+    wv_iota_kernel<<<(B + 255) / 256, 256, 0, st>>>(b->d_iter, B);
+  }
   b->launches += 1;
-  if (wv_eval_all(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status, b->d_active, B) != 0) return -1;
+  if (n_list > 0 && wv_eval_all(b, b->d_x, b->d_f, b->d_g, b->d_lml, b->d_status, b->d_iter, n_list) != 0) return -1;
   b->last_x = b->d_x;
-  wv_lb_report_kernel<<<gb, tb, 0, st>>>(B, b->d_lbs, b->d_task, b->d_status, d_iter, d_neval, d_st2);
+  wv_lb_report_kernel<<<gb, tb, 0, st>>>(B, b->d_lbs, b->d_task, b->d_status, b->d_iter, b->d_neval, b->d_st2);
   b->launches += 1;
   WV_CUDA(cudaMemcpyAsync(x, b->d_x, (size_t)B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
   WV_CUDA(cudaMemcpyAsync(f, b->d_f, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
   WV_CUDA(cudaMemcpyAsync(lml, b->d_lml, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  WV_CUDA(cudaMemcpyAsync(n_iter, d_iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  WV_CUDA(cudaMemcpyAsync(n_eval, d_neval, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  WV_CUDA(cudaMemcpyAsync(status, d_st2, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(n_iter, b->d_iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(n_eval, b->d_neval, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  WV_CUDA(cudaMemcpyAsync(status, b->d_st2, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (finished) WV_CUDA(cudaMemcpyAsync(finished, b->d_task, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   WV_CUDA(cudaStreamSynchronize(st));
+  if (finished)
+    for (int i = 0; i < B; ++i) finished[i] = finished[i] != WV_LB_FG;
   WV_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int wv_batch_fit_lbfgs(wv_batch* b, double* x, const wv_lbfgs_opts* o, double* f, double* lml,
+                                  int32_t* n_iter, int32_t* n_eval, int32_t* status) {
+  if (!b || !x || !o || !f || !lml || !n_iter || !n_eval || !status) return wv_fail("wv_batch_fit_lbfgs: null argument");
+  if (wv_batch_fit_lbfgs_begin(b, x, o) != 0) return -1;
+  if (wv_batch_fit_lbfgs_run(b, 0, nullptr) != 0) return -1;
+  return wv_batch_fit_lbfgs_report(b, x, f, lml, n_iter, n_eval, status, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -54,8 +54,9 @@ class _AdamOpts(C.Structure):
 
 
 EXPORTED_SYMBOLS = [
-    "wv_engine_create", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
+    "wv_engine_create", "wv_engine_create2", "wv_batch_set_engine", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
     "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_likelihood", "wv_batch_set_likelihood2", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
+    "wv_batch_fit_lbfgs_begin", "wv_batch_fit_lbfgs_run", "wv_batch_fit_lbfgs_report",
     "wv_batch_fit_adam", "wv_batch_create2", "wv_batch_eval_elbo", "wv_batch_specialize", "wv_rtc_check", "wv_rtc_set_cache", "wv_rtc_precompile_text",
     "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_get_kinv_diag", "wv_batch_predict_mean", "wv_batch_predict_f", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
 ]
@@ -76,6 +77,8 @@ def load_library():
     lib = C.CDLL(_LIB_PATH)
     vp = C.c_void_p
     lib.wv_engine_create.argtypes = [C.c_int, C.POINTER(vp)]; lib.wv_engine_create.restype = C.c_int
+    lib.wv_engine_create2.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]; lib.wv_engine_create2.restype = C.c_int
+    lib.wv_batch_set_engine.argtypes = [vp, vp]; lib.wv_batch_set_engine.restype = C.c_int
     lib.wv_engine_destroy.argtypes = [vp]; lib.wv_engine_destroy.restype = None
     lib.wv_engine_stream.argtypes = [vp]; lib.wv_engine_stream.restype = vp
     lib.wv_engine_set_large_n_tiles.argtypes = [vp, C.c_int]; lib.wv_engine_set_large_n_tiles.restype = C.c_int
@@ -94,6 +97,12 @@ def load_library():
     lib.wv_batch_eval_device.argtypes = [vp, vp, vp, vp, vp, vp]; lib.wv_batch_eval_device.restype = C.c_int
     lib.wv_batch_fit_lbfgs.argtypes = [vp, _f64p, C.POINTER(_LbfgsOpts), _f64p, _f64p, _i32p, _i32p, _i32p]
     lib.wv_batch_fit_lbfgs.restype = C.c_int
+    lib.wv_batch_fit_lbfgs_begin.argtypes = [vp, _f64p, C.POINTER(_LbfgsOpts)]
+    lib.wv_batch_fit_lbfgs_begin.restype = C.c_int
+    lib.wv_batch_fit_lbfgs_run.argtypes = [vp, C.c_int32, C.POINTER(C.c_int32)]
+    lib.wv_batch_fit_lbfgs_run.restype = C.c_int
+    lib.wv_batch_fit_lbfgs_report.argtypes = [vp, _f64p, _f64p, _f64p, _i32p, _i32p, _i32p, _i32p]
+    lib.wv_batch_fit_lbfgs_report.restype = C.c_int
     lib.wv_batch_fit_adam.argtypes = [vp, _f64p, C.POINTER(_AdamOpts), _f64p, _f64p, _i32p, _i32p]
     lib.wv_batch_fit_adam.restype = C.c_int
     lib.wv_batch_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -189,10 +198,12 @@ DEFAULT_ADAM = dict(learning_rate=0.1, decay_rate=0.96, beta1=0.9, beta2=0.999, 
 class Engine:
     """One per GPU / host thread; owns the CUDA stream the batches launch on."""
 
-    def __init__(self, device: int = 0, large_n_tiles: Optional[int] = None):
+    def __init__(self, device: int = 0, large_n_tiles: Optional[int] = None, high_priority: bool = False):
+        """``high_priority``: the stream is scheduled ahead of the default engines' streams (stragglers of a search
+        level that finish while the next level's batch runs, ``Batch.move_to``)."""
         self.lib = load_library()
         h = C.c_void_p()
-        _check(self.lib.wv_engine_create(int(device), C.byref(h)), "wv_engine_create")
+        _check(self.lib.wv_engine_create2(int(device), 1 if high_priority else 0, C.byref(h)), "wv_engine_create2")
         self.handle = h
         self.device = int(device)
         if large_n_tiles is not None:
@@ -376,6 +387,41 @@ class Batch:
         _check(self.lib.wv_batch_fit_lbfgs(self.handle, _f64(x), C.byref(co), _f64(f), _f64(lml), _i32(nit), _i32(nev),
                                            _i32(st)), "wv_batch_fit_lbfgs")
         return dict(x=x, f=f, lml=lml, n_iter=nit, n_eval=nev, status=st)
+
+    def move_to(self, engine: "Engine"):
+        """Re-home the batch: later calls run on ``engine``'s stream (same device; no call may be in progress)."""
+        _check(self.lib.wv_batch_set_engine(self.handle, engine.handle), "wv_batch_set_engine")
+        self.engine = engine
+
+    def fit_begin(self, x0: Optional[np.ndarray] = None, **opts):
+        """First of the three calls ``fit`` consists of (include/waveome_b200.h: wv_batch_fit_lbfgs_begin / _run /
+        _report): upload the starts.  Then ``fit_run(min_active)`` iterates while more than ``min_active`` models are
+        unfinished and ``fit_report()`` returns ``fit``'s dict plus ``finished`` [B] (bool) at any point in between."""
+        o = dict(DEFAULT_LBFGS); o.update(opts)
+        x = self.x0() if x0 is None else np.array(x0, dtype=np.float64, order="C", copy=True)
+        if x.shape != (self.B, self.P):
+            raise ValueError(f"x0 must be [{self.B}, {self.P}]")
+        if o["on_chol_fail"] not in ("nan", "abort"):
+            raise ValueError("on_chol_fail must be 'nan' (failed trial = non-finite value) or 'abort'")
+        co = _LbfgsOpts(int(o["maxcor"]), int(o["maxiter"]), int(o["maxfun"]), int(o["maxls"]), float(o["ftol"]),
+                        float(o["gtol"]), 1 if o["on_chol_fail"] == "abort" else 0, 0)
+        _check(self.lib.wv_batch_fit_lbfgs_begin(self.handle, _f64(x), C.byref(co)), "wv_batch_fit_lbfgs_begin")
+
+    def fit_run(self, min_active: int = 0) -> int:
+        """Optimiser rounds while more than ``min_active`` models are still iterating; returns how many are left."""
+        left = C.c_int32(0)
+        _check(self.lib.wv_batch_fit_lbfgs_run(self.handle, int(min_active), C.byref(left)), "wv_batch_fit_lbfgs_run")
+        return int(left.value)
+
+    def fit_report(self):
+        """dict(x, f, lml, n_iter, n_eval, status, finished) of the fit in progress; f / lml / status are meaningful for
+        the finished models only."""
+        x = np.empty((self.B, self.P)); f = np.empty(self.B); lml = np.empty(self.B)
+        nit = np.empty(self.B, np.int32); nev = np.empty(self.B, np.int32); st = np.empty(self.B, np.int32)
+        fin = np.empty(self.B, np.int32)
+        _check(self.lib.wv_batch_fit_lbfgs_report(self.handle, _f64(x), _f64(f), _f64(lml), _i32(nit), _i32(nev), _i32(st),
+                                                  _i32(fin)), "wv_batch_fit_lbfgs_report")
+        return dict(x=x, f=f, lml=lml, n_iter=nit, n_eval=nev, status=st, finished=fin != 0)
 
     def eval_elbo(self, x: np.ndarray, q_mu: np.ndarray, q_sqrt: np.ndarray, jitter: float = 1e-6):
         """Objective (B) at given variational parameters: (elbo [B], f = -(elbo + log prior) [B], status [B]) of the

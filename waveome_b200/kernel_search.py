@@ -414,6 +414,9 @@ def candidate_bic(model: GPR, log_posterior_density: float) -> float:
     return round(calc_bic(loglik=log_posterior_density, n=0, k=len(model.trainable_parameters)), 2)
 
 
+#: run_lockstep: a level's fit hands back control once at most this many models are still iterating; the stragglers finish
+#: in the background while the other outcomes go on (0 / WV_SEARCH_TAIL=0: every level waits for its slowest model)
+SEARCH_TAIL = max(0, int(os.environ.get("WV_SEARCH_TAIL", "32")))
 _FITTER_SLOT = __import__("threading").local()      # .slot = index of a run_lockstep fitter thread (unset elsewhere)
 
 
@@ -434,9 +437,28 @@ def engine_fitter(X: np.ndarray, engine=None, num_restart=1, random_seed=None, m
     waveome/model_classes.py:472-524, seeds ``random_seed + 1 + r`` or ``r``)."""
     from .model_fitting import fit_models
 
-    def fit(requests):
+    def collect(requests, models, res, R, which=None):
+        out = []
+        for i in range(len(requests)):
+            if which is not None and not which[i]:
+                out.append(None)
+                continue
+            best, best_lpd = None, -np.inf
+            for r in range(R):
+                b = i * R + r
+                ok = not (int(res["status"][b]) & 1) and np.isfinite(res["f"][b])
+                if ok and -float(res["f"][b]) > best_lpd:
+                    best, best_lpd = models[b], -float(res["f"][b])
+            out.append((None, np.inf) if best is None else (best, candidate_bic(best, best_lpd)))
+        return out
+
+    def fit(requests, tail=0):
+        """results = [(model, bic)] per request.  ``tail`` > 0 (run_lockstep): returns (results, pending) as soon as at
+        most ``tail`` models are still iterating -- results[i] is None for a request with an unfinished model, and
+        ``pending()`` (callable from a worker thread; None when nothing is left) finishes them and returns the complete
+        list."""
         if not requests:
-            return []
+            return ([], None) if tail else []
         R = max(1, int(num_restart))
         models, ys = [], []
         for y, _name, kernel in requests:
@@ -448,19 +470,19 @@ def engine_fitter(X: np.ndarray, engine=None, num_restart=1, random_seed=None, m
                         p.assign(p.transform_fn(rs.normal(loc=0.0, scale=1.0)))
                 models.append(m)
                 ys.append(y)
+        if not tail:
+            res = fit_models(X, np.stack(ys), models, engine=engine or _thread_engine(), maxiter=max_iter, maxfun=max_iter,
+                             optimizer=optimizer)
+            return collect(requests, models, res, R)
         res = fit_models(X, np.stack(ys), models, engine=engine or _thread_engine(), maxiter=max_iter, maxfun=max_iter,
-                         optimizer=optimizer)
-        out = []
-        for i in range(len(requests)):
-            best, best_lpd = None, -np.inf
-            for r in range(R):
-                b = i * R + r
-                ok = not (int(res["status"][b]) & 1) and np.isfinite(res["f"][b])
-                if ok and -float(res["f"][b]) > best_lpd:
-                    best, best_lpd = models[b], -float(res["f"][b])
-            out.append((None, np.inf) if best is None else (best, candidate_bic(best, best_lpd)))
-        return out
+                         optimizer=optimizer, tail=tail)
+        if res["pending"] is None:
+            return collect(requests, models, res, R), None
+        done = res["finished"].reshape(len(requests), R).all(axis=1)
+        finish = res["pending"]
+        return collect(requests, models, res, R, which=done), lambda: collect(requests, models, finish(), R)
 
+    fit.supports_tail = optimizer == "lbfgs"
     return fit
 
 
@@ -508,7 +530,47 @@ def run_lockstep(searches: Dict[str, object], ys: Dict[str, np.ndarray], fit: Ca
                 done[o] = e.value
         waiting[g] = nxt
 
-    if groups == 1:
+    tail = SEARCH_TAIL if getattr(fit, "supports_tail", False) else 0
+    if groups == 1 and tail > 0:
+        # A level's batch lasts as long as its slowest model (config 2: one candidate of 1931 needs 5019 evaluations, the
+        # others at most 386).  The fit returns once at most `tail` models are still iterating; the outcomes whose
+        # candidates are all fitted move on to their next level at once, the stragglers finish on a worker thread (their
+        # batch stays open on its own engine) and their outcomes rejoin whatever batch is formed next.  Every outcome still
+        # sees exactly the results it would see alone, so the search result does not depend on the grouping (tested).
+        from concurrent.futures import FIRST_COMPLETED, wait
+        with ThreadPoolExecutor(max_workers=8) as pool:
+            ready = waiting[0]
+            late = []                               # (future, {outcome: (candidates, first request, count)})
+
+            def step(o, results):
+                try:
+                    ready[o] = searches[o].send(results)
+                except StopIteration as e:
+                    done[o] = e.value
+
+            while ready or late:
+                if ready:
+                    cur, ready = ready, {}
+                    results, pending = fit([(ys[o], name, k) for o, cands in cur.items() for name, k in cands], tail=tail)
+                    rounds += 1
+                    pos, held = 0, {}
+                    for o, cands in cur.items():
+                        r = results[pos: pos + len(cands)]
+                        if any(x is None for x in r):
+                            held[o] = (pos, len(cands))
+                        else:
+                            step(o, r)
+                        pos += len(cands)
+                    if pending is not None:
+                        late.append((pool.submit(pending), held))
+                if late and not ready:
+                    wait([f for f, _ in late], return_when=FIRST_COMPLETED)
+                for item in [it for it in late if it[0].done()]:
+                    late.remove(item)
+                    full = item[0].result()
+                    for o, (pos, k) in item[1].items():
+                        step(o, full[pos: pos + k])
+    elif groups == 1:
         while waiting[0]:
             results = fit(flatten(0))
             rounds += 1

@@ -61,6 +61,54 @@ def split_for_streams(n_models: int, chunk: int, streams: Optional[int] = None) 
     return [(lo, min(n_models, lo + piece)) for lo in range(0, n_models, piece)]
 
 
+def _open_batch(eng, job):
+    """The engine batch of one fit job (dict X, Y, table, prog_id, P, lik_name, lik_param, specialize)."""
+    from .engine import Batch
+    batch = Batch(eng, job["X"], job["Y"], job["table"], job.get("prog_id"), P=job["P"],
+                  specialize=job.get("specialize", False))
+    try:
+        if job["lik_name"] != "gaussian":
+            batch.set_likelihood(job["lik_name"], job["lik_param"])
+    except BaseException:
+        batch.close()
+        raise
+    return batch
+
+
+# High-priority engines for the stragglers of a deferred fit (fit_models(tail=...)): the batch moves onto one of them when
+# control goes back to the caller, so the caller's engine is free again and the stragglers' tiny launches are scheduled
+# ahead of whatever batch runs next.  An engine is driven by ONE host thread at a time: leased, then returned.
+_LEASE_LOCK = __import__("threading").Lock()
+_HP_POOLS: Dict[int, list] = {}
+_LEASED: Dict[int, set] = {}
+
+
+def lease_engine(device: Optional[int] = None):
+    """(engine, index): the first high-priority engine of the device nobody has leased (the pool grows on demand)."""
+    import os
+    from .engine import Engine
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    with _LEASE_LOCK:
+        used = _LEASED.setdefault(device, set())
+        pool = _HP_POOLS.setdefault(device, [])
+        idx = 0
+        while idx in used:
+            idx += 1
+        while len(pool) <= idx:
+            pool.append(Engine(device, high_priority=True))
+        used.add(idx)
+        return pool[idx], idx
+
+
+def release_engine(idx: int, device: Optional[int] = None):
+    import os
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    with _LEASE_LOCK:
+        _LEASED.setdefault(device, set()).discard(idx)
+
+
 def run_fit_jobs(jobs: List[dict], engine=None, streams: Optional[int] = None, **lbfgs_opts) -> List[tuple]:
     """Fit every job (dict X, Y, table, prog_id, P, lik_name, lik_param, starts) as one engine batch; up to ``streams``
     jobs at a time, each on its own engine and host thread (the C call releases the GIL).  Returns [(result dict,
@@ -70,11 +118,8 @@ def run_fit_jobs(jobs: List[dict], engine=None, streams: Optional[int] = None, *
     streams = FIT_STREAMS if streams is None else max(1, int(streams))
 
     def run_one(eng, job):
-        batch = Batch(eng, job["X"], job["Y"], job["table"], job.get("prog_id"), P=job["P"],
-                      specialize=job.get("specialize", False))
+        batch = _open_batch(eng, job)
         try:
-            if job["lik_name"] != "gaussian":
-                batch.set_likelihood(job["lik_name"], job["lik_param"])
             if job.get("optimizer", "lbfgs") in ("adam", "adam/gradient"):
                 # the reference's default optimiser for kernel_test (waveome/model_classes.py:344-462); num_opt_iter
                 # arrives as maxiter
@@ -137,7 +182,7 @@ def likelihood_key(model) -> tuple:
 
 def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional[np.ndarray] = None,
                engine=None, max_batch_bytes: float = 60e9, streams: int = 1, specialize: bool = False,
-               optimizer: str = "lbfgs", **lbfgs_opts) -> dict:
+               optimizer: str = "lbfgs", tail: int = 0, **lbfgs_opts) -> dict:
     """MAP-fit ``models[b]`` to outcome ``Y[b]`` (Y is [B, n]); all models share X [n, D].
 
     Models with identical kernel programs share one device program.  Fitted values are written back into the
@@ -149,6 +194,12 @@ def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional
     23.5 s); ``fit_replicated`` -- one structure, thousands of models -- is where the split pays.
     ``specialize``: ask for run-time specialised element-wise kernels (engine.Batch); only pieces whose models share one
     program structure get them.
+    ``tail`` > 0 (needs ``engine``; L-BFGS, one batch): return as soon as at most ``tail`` models are still iterating.
+    The result then carries ``finished`` [B] (bool; results and write-back are complete for those models) and
+    ``pending``: a callable that runs the stragglers to the end (from any ONE thread; the batch has moved to a leased
+    high-priority engine, ``engine`` itself is free again), completes the arrays and the write-back and returns the
+    same dict.
+    Otherwise ``finished`` is all True and ``pending`` None.
     ``optimizer``: "lbfgs" (SciPy-compatible L-BFGS-B, default) or "adam" / "adam/gradient" (the schedule of
     BaseGP.optimize_params, waveome/model_classes.py:344-462: ``Batch.fit_adam``; maxiter = num_opt_iter)."""
     X = np.ascontiguousarray(X, dtype=np.float64)
@@ -189,16 +240,72 @@ def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional
             sels.append(sel)
             jobs.append(dict(X=X, Y=Y[sel], table=table, prog_id=prog_id[sel], P=P, lik_name=lik_name,
                              lik_param=lik_param, starts=starts[sel], specialize=specialize, optimizer=optimizer))
+    def write_back(which):
+        for b in which:
+            m, p = models[b], progs[b]
+            p.assign(out["x"][b, : p.n_x])
+            m.log_marginal_likelihood_value = float(out["lml"][b])
+            m.log_posterior_density_value = float(-out["f"][b])
+            m.fit_info = dict(n_iter=int(out["n_iter"][b]), n_eval=int(out["n_eval"][b]), status=int(out["status"][b]))
+
+    out["finished"] = np.ones(B, bool)
+    out["pending"] = None
+    if int(tail) > 0 and engine is not None and optimizer == "lbfgs" and len(jobs) == 1:
+        sel, job = sels[0], jobs[0]
+        opts = {k: v for k, v in lbfgs_opts.items() if k in DEFAULT_LBFGS_KEYS}
+        batch = _open_batch(engine, job)
+        try:
+            batch.fit_begin(job.get("starts"), **opts)
+            left = batch.fit_run(int(tail))
+            r = batch.fit_report()
+        except BaseException:
+            batch.close()
+            raise
+        for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
+            out[key][sel] = r[key]
+        out["finished"][sel] = r["finished"]
+        write_back(sel[r["finished"]])
+        if left == 0:
+            c = batch.counters()
+            batch.close()
+            out["launches"] += c["launches"]
+            out["rounds"] += c["rounds"]
+            return out
+        late = sel[~r["finished"]]
+        hp, lease = lease_engine(engine.device)
+        try:
+            batch.move_to(hp)
+        except BaseException:
+            release_engine(lease, engine.device)
+            batch.close()
+            raise
+
+        def pending():
+            try:
+                batch.fit_run(0)
+                r2 = batch.fit_report()
+                c = batch.counters()
+            finally:
+                batch.close()
+                release_engine(lease, engine.device)
+            keep = ~r["finished"]
+            for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
+                out[key][late] = r2[key][keep]
+            out["launches"] += c["launches"]
+            out["rounds"] += c["rounds"]
+            write_back(late)
+            out["finished"][:] = True
+            out["pending"] = None
+            return out
+
+        out["pending"] = pending
+        return out
     for sel, (r, c) in zip(sels, run_fit_jobs(jobs, engine=engine, streams=streams, **lbfgs_opts)):
         for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
             out[key][sel] = r[key]
         out["launches"] += c["launches"]
         out["rounds"] += c["rounds"]
-    for b, (m, p) in enumerate(zip(models, progs)):
-        p.assign(out["x"][b, : p.n_x])
-        m.log_marginal_likelihood_value = float(out["lml"][b])
-        m.log_posterior_density_value = float(-out["f"][b])
-        m.fit_info = dict(n_iter=int(out["n_iter"][b]), n_eval=int(out["n_eval"][b]), status=int(out["status"][b]))
+    write_back(range(B))
     return out
 
 

@@ -263,10 +263,12 @@ class GPSearch:
         inner = fit or ks.engine_fitter(Xn, num_restart=num_restart, random_seed=random_seed, likelihood=self.likelihood,
                                         optimizer=optimizer)
 
-        def counted(requests):
+        def counted(requests, **kw):
             counters["fits"] += len(requests) * max(1, int(num_restart))
             counters["batches"] += 1
-            return inner(requests)
+            return inner(requests, **kw)
+
+        counted.supports_tail = getattr(inner, "supports_tail", False)      # run_lockstep: stragglers finish in the background
 
         gens = {o: ks.full_kernel_search_gen(Xn.shape[1], kernels, cat_vars=self.cat_idx, max_depth=max_depth,
                                              keep_all=keep_all, metric_diff=metric_diff,
