@@ -596,8 +596,8 @@ __device__ __forceinline__ void wv_wait_cols(const int* row_done, int ep, int ne
   if (need <= 0) return;
   const volatile int* f = reinterpret_cast<const volatile int*>(row_done);
   for (;;) {
-    const int v = *f;
-    if ((v >> 8) == ep && (v & 255) >= need) break;
+    const int w = -*f - 1;               // this kernel's counters are stored negated: never mistaken for (or by) the
+    if (w >= 0 && (w >> 8) == ep && (w & 255) >= need) break;      // large-n panel kernel's, which share the array
     __nanosleep(40);
   }
 }
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS, 3) wv_chol_all_kernel(WvBatch
   __shared__ int s_item;
   int* counter = bd.step_flag + 2 * (size_t)bd.B * bd.nt;
   const int nt = bd.nt;
-  const int ep = epoch & 0x7fffff;
+  const int ep = epoch & 0x3fffff;
   for (;;) {
     __syncthreads();                      // previous item done with the shared-memory tiles
     if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS, 3) wv_chol_all_kernel(WvBatch
     wv_panel_body<0>(bd, b, j, x - 1, 0, epoch);
     __threadfence();                       // the tile is visible device-wide before the row counter moves
     __syncthreads();
-    if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(row_done + j + x) = (ep << 8) | (j + 1);
+    if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(row_done + j + x) = -((ep << 8) | (j + 1)) - 1;
   }
 }
 
