@@ -417,6 +417,9 @@ def candidate_bic(model: GPR, log_posterior_density: float) -> float:
 #: run_lockstep: a level's fit hands back control once at most this many models are still iterating; the stragglers finish
 #: in the background while the other outcomes go on (0 / WV_SEARCH_TAIL=0: every level waits for its slowest model)
 SEARCH_TAIL = max(0, int(os.environ.get("WV_SEARCH_TAIL", "32")))
+#: ... and this many level fits are in flight at a time (one group of outcomes each, on fitter threads with their own
+#: engines): the device works on one group while the host advances the other's generators (WV_SEARCH_LANES)
+SEARCH_LANES = max(1, int(os.environ.get("WV_SEARCH_LANES", "2")))
 _FITTER_SLOT = __import__("threading").local()      # .slot = index of a run_lockstep fitter thread (unset elsewhere)
 
 
@@ -533,14 +536,30 @@ def run_lockstep(searches: Dict[str, object], ys: Dict[str, np.ndarray], fit: Ca
     tail = SEARCH_TAIL if getattr(fit, "supports_tail", False) else 0
     if groups == 1 and tail > 0:
         # A level's batch lasts as long as its slowest model (config 2: one candidate of 1931 needs 5019 evaluations, the
-        # others at most 386).  The fit returns once at most `tail` models are still iterating; the outcomes whose
-        # candidates are all fitted move on to their next level at once, the stragglers finish on a worker thread (their
-        # batch stays open on its own engine) and their outcomes rejoin whatever batch is formed next.  Every outcome still
-        # sees exactly the results it would see alone, so the search result does not depend on the grouping (tested).
+        # others at most 386), and while the host advances the generators the device has nothing to do.  So:
+        #  * a fit returns once at most `tail` models are still iterating; the outcomes whose candidates are all fitted move
+        #    on at once, the stragglers finish on a worker thread (their batch re-homed onto a high-priority engine) and
+        #    their outcomes rejoin whatever batch is formed next;
+        #  * SEARCH_LANES fits are in flight at a time, each on a fitter thread with its own engine (the C call releases
+        #    the GIL): the outcomes start as that many groups, and while one group's batch is on the device the host
+        #    advances the generators of the group that has just come back.
+        # Every outcome still sees exactly the results it would see alone, so the search result does not depend on the
+        # grouping (tested).
+        import itertools
+        import threading
         from concurrent.futures import FIRST_COMPLETED, wait
-        with ThreadPoolExecutor(max_workers=8) as pool:
-            ready = waiting[0]
-            late = []                               # (future, {outcome: (candidates, first request, count)})
+        slots, slot_lock = itertools.count(), threading.Lock()
+
+        def take_lane_slot():
+            with slot_lock:
+                _FITTER_SLOT.slot = next(slots)
+
+        lanes = max(1, min(SEARCH_LANES, len(waiting[0]) or 1))
+        with ThreadPoolExecutor(max_workers=lanes, initializer=take_lane_slot) as main_pool, \
+                ThreadPoolExecutor(max_workers=8) as late_pool:
+            ready = dict(waiting[0])
+            inflight = {}                           # future -> ("main", {outcome: candidates}) | ("late", {outcome: (pos, count)})
+            n_main = 0
 
             def step(o, results):
                 try:
@@ -548,28 +567,41 @@ def run_lockstep(searches: Dict[str, object], ys: Dict[str, np.ndarray], fit: Ca
                 except StopIteration as e:
                     done[o] = e.value
 
-            while ready or late:
-                if ready:
-                    cur, ready = ready, {}
-                    results, pending = fit([(ys[o], name, k) for o, cands in cur.items() for name, k in cands], tail=tail)
-                    rounds += 1
-                    pos, held = 0, {}
-                    for o, cands in cur.items():
-                        r = results[pos: pos + len(cands)]
-                        if any(x is None for x in r):
-                            held[o] = (pos, len(cands))
-                        else:
-                            step(o, r)
-                        pos += len(cands)
-                    if pending is not None:
-                        late.append((pool.submit(pending), held))
-                if late and not ready:
-                    wait([f for f, _ in late], return_when=FIRST_COMPLETED)
-                for item in [it for it in late if it[0].done()]:
-                    late.remove(item)
-                    full = item[0].result()
-                    for o, (pos, k) in item[1].items():
-                        step(o, full[pos: pos + k])
+            def launch(first=False):
+                nonlocal n_main
+                while ready and n_main < lanes:
+                    names_now = list(ready)
+                    if first:                       # the initial split: one group per lane
+                        names_now = names_now[: -(-len(names_now) // (lanes - n_main))]
+                    cur = {o: ready.pop(o) for o in names_now}
+                    reqs = [(ys[o], name, k) for o, cands in cur.items() for name, k in cands]
+                    inflight[main_pool.submit(fit, reqs, tail=tail)] = ("main", cur)
+                    n_main += 1
+
+            launch(first=True)
+            while inflight:
+                finished, _ = wait(list(inflight), return_when=FIRST_COMPLETED)
+                for fut in finished:
+                    kind, info = inflight.pop(fut)
+                    if kind == "main":
+                        n_main -= 1
+                        results, pending = fut.result()
+                        rounds += 1
+                        pos, held = 0, {}
+                        for o, cands in info.items():
+                            r = results[pos: pos + len(cands)]
+                            if any(x is None for x in r):
+                                held[o] = (pos, len(cands))
+                            else:
+                                step(o, r)
+                            pos += len(cands)
+                        if pending is not None:
+                            inflight[late_pool.submit(pending)] = ("late", held)
+                    else:
+                        full = fut.result()
+                        for o, (pos, k) in info.items():
+                            step(o, full[pos: pos + k])
+                    launch()
     elif groups == 1:
         while waiting[0]:
             results = fit(flatten(0))
