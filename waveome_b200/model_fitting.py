@@ -250,7 +250,8 @@ def fit_models(X: np.ndarray, Y: np.ndarray, models: Sequence[GPR], x0: Optional
 
     out["finished"] = np.ones(B, bool)
     out["pending"] = None
-    if int(tail) > 0 and engine is not None and optimizer == "lbfgs" and len(jobs) == 1:
+    # (a batch that is not several times larger than `tail` has no bulk to separate from its stragglers: fitted in one go)
+    if int(tail) > 0 and B >= 4 * int(tail) and engine is not None and optimizer == "lbfgs" and len(jobs) == 1:
         sel, job = sels[0], jobs[0]
         opts = {k: v for k, v in lbfgs_opts.items() if k in DEFAULT_LBFGS_KEYS}
         batch = _open_batch(engine, job)
