@@ -266,3 +266,80 @@ def test_program_signature_ignores_trainable_values():
     assert b.program().signature() != c.program().signature()
     d = wb.GPR(helpers.saturated_kernel(hs=2.0), mean_function=wb.ConstantMean(0.1))   # another prior scale
     assert a.program().signature() != d.program().signature()
+
+
+def test_fit_models_deferred_tail_bookkeeping(monkeypatch):
+    """fit_models(tail=...): the finished models are written back when control returns, the batch moves to a leased
+    high-priority engine, ``pending()`` completes arrays and write-back, closes the batch and returns the lease; small
+    batches and multi-job fits are not deferred.  (Host logic on a fake batch; the device side is tests/test_fit_gpu.py.)"""
+    import waveome_b200 as wb
+    from waveome_b200 import engine as E, model_fitting as mf
+    log = []
+
+    class FakeEngine:
+        def __init__(self, device=0, high_priority=False):
+            self.device, self.high_priority = device, high_priority
+
+    class FakeBatch:
+        def __init__(self, eng, X, Y, table, prog_id=None, P=None, specialize=False):
+            self.engine, self.B, self.P, self.tag = eng, np.asarray(Y).shape[0], P, np.asarray(Y)[:, 0].copy()
+            self.slow = self.tag % 10 == 0                     # every tenth model is a straggler
+            self.done_all = False
+
+        def fit_begin(self, x0=None, **opts):
+            self.x0 = np.asarray(x0).copy()
+            log.append(("begin", self.engine.high_priority))
+
+        def fit_run(self, min_active=0):
+            if min_active == 0:
+                self.done_all = True
+                log.append(("finish", self.engine.high_priority))
+                return 0
+            return int(self.slow.sum())
+
+        def fit_report(self):
+            fin = np.ones(self.B, bool) if self.done_all else ~self.slow
+            return dict(x=self.x0 + self.tag[:, None], f=np.where(fin, -self.tag, np.nan), lml=np.where(fin, self.tag, np.nan),
+                        n_iter=self.tag.astype(np.int32), n_eval=(2 * self.tag).astype(np.int32),
+                        status=np.zeros(self.B, np.int32), finished=fin)
+
+        def fit(self, x0=None, **opts):
+            log.append(("sync", self.B))
+            return dict(x=np.asarray(x0) + self.tag[:, None], f=-self.tag, lml=self.tag.copy(), n_iter=self.tag.astype(np.int32),
+                        n_eval=(2 * self.tag).astype(np.int32), status=np.zeros(self.B, np.int32))
+
+        def move_to(self, eng):
+            self.engine = eng
+            log.append(("move", eng.high_priority))
+
+        def counters(self):
+            return dict(launches=7, rounds=3, model_evals=self.B)
+
+        def close(self):
+            log.append(("close",))
+
+    monkeypatch.setattr(E, "Batch", FakeBatch)
+    monkeypatch.setattr(E, "Engine", FakeEngine)
+    monkeypatch.setattr(mf, "_LEASED", {})
+    monkeypatch.setattr(mf, "_HP_POOLS", {})
+    B, n = 200, 12
+    X = np.zeros((n, 2))
+    Y = np.zeros((B, n))
+    Y[:, 0] = np.arange(B)
+    models = [wb.GPR(wb.SquaredExponential(active_dims=[1]), mean_function=wb.ConstantMean(0.0)) for _ in range(B)]
+    main = FakeEngine()
+    res = mf.fit_models(X, Y, models, engine=main, tail=16)
+    slow = np.arange(B) % 10 == 0
+    assert np.array_equal(res["finished"], ~slow) and callable(res["pending"])
+    assert log == [("begin", False), ("move", True)] and mf._LEASED[0] == {0}
+    assert models[7].fit_info["n_iter"] == 7 and not getattr(models[10], "fit_info", None)      # stragglers: not written yet
+    out = res["pending"]()
+    assert out is res and res["finished"].all() and res["pending"] is None
+    assert log[2:] == [("finish", True), ("close",)] and mf._LEASED[0] == set()
+    np.testing.assert_array_equal(res["lml"], np.arange(B))
+    assert models[10].fit_info["n_eval"] == 20 and models[190].log_marginal_likelihood_value == 190.0
+    assert res["launches"] == 7 and res["rounds"] == 3
+    # a batch that is not several times the tail is fitted in one go
+    log.clear()
+    small = mf.fit_models(X, Y[:40], models[:40], engine=main, tail=16)
+    assert small["pending"] is None and small["finished"].all() and log[0] == ("sync", 40)
