@@ -171,6 +171,7 @@ def measure_extras(args, rank, world, local_rank, eng, barrier, reduce_max, torc
         Xn = gps.X.to_numpy(dtype=np.float64)
         Yn = np.ascontiguousarray(gps.Y.iloc[:, lo:hi].to_numpy(dtype=np.float64).T)
         batch = Batch(eng, Xn, Yn, [model.program()], specialize=True)
+        batch.set_solo(True)            # one batch per GPU, nothing beside it (what fit_models does for a single job)
         x0 = batch.x0()
         batch.fit(x0, maxiter=50000, maxfun=50000)
         steps = max(1, min(args.steps, 3))
@@ -325,6 +326,7 @@ def main():
     Xn = gps.X.to_numpy(dtype=np.float64)
     Yn = np.ascontiguousarray(gps.Y.iloc[:, lo:hi].to_numpy(dtype=np.float64).T)
     batch = Batch(eng, Xn, Yn, [model.program()], specialize=True)     # as penalized_optimization asks for this job size
+    batch.set_solo(True)                # one batch per GPU, nothing beside it (what fit_models does for a single job)
     x0 = batch.x0()
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
     opts = dict(maxiter=50000, maxfun=50000)

@@ -146,6 +146,11 @@ int wv_batch_get_latent(wv_batch* b, double* fmean, double* fvar);
  * evaluate (waveome/utilities.py:657-662 pops the component and predicts again): one program, B masks. HOST [B]. */
 int wv_batch_set_component_mask(wv_batch* b, const uint32_t* mask);
 
+/* Scheduling hint: solo != 0 says that nothing else runs on the device while this batch's calls run (one batch, one
+ * stream).  Mid-size batches (n_active * tiles-per-side <= 10 000) then factorise in one persistent launch per evaluation
+ * instead of a launch pair per tile column; results are bit-identical either way.  Default 0. */
+int wv_batch_set_solo(wv_batch* b, int solo);
+
 /* One LML+gradient evaluation of every model.  HOST buffers:
  *   x [B, P] unconstrained parameters; f [B] = -(lml + log prior); grad [B, P] = df/dx; lml [B]; status [B]. */
 int wv_batch_eval(wv_batch* b, const double* x, double* f, double* grad, double* lml, int32_t* status);

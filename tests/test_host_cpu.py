@@ -190,6 +190,7 @@ def test_fit_models_reassembles_concurrent_sub_batches(monkeypatch):
     from waveome_b200.models import make_likelihood
 
     seen = []
+    solo_flags = []
 
     class FakeBatch:
         def __init__(self, eng, X, Y, table, prog_id=None, P=None, specialize=False):
@@ -198,6 +199,9 @@ def test_fit_models_reassembles_concurrent_sub_batches(monkeypatch):
 
         def set_likelihood(self, name, param):
             self.lik = (name, param)
+
+        def set_solo(self, solo=True):
+            solo_flags.append(bool(solo))
 
         def fit(self, x0=None, **opts):
             if self.Y[0, 0] < 0:
@@ -235,10 +239,11 @@ def test_fit_models_reassembles_concurrent_sub_batches(monkeypatch):
     assert sorted(s[2] for s in seen) == [100, 150, 150, 150, 150]
     assert {s[3] for s in seen if s[2] == 100} == {"poisson"} and res["rounds"] == 5 and res["launches"] == 50
     assert len({s[0] for s in seen}) > 1 or len({s[1] for s in seen}) > 1          # more than one engine / thread took part
-    # default: one stream, everything on the process engine
+    assert solo_flags == []                                            # concurrent pieces never declare themselves alone
+    # default: one stream, everything on the process engine -- and the batch says it has the device to itself
     seen.clear()
     mf.fit_models(X, Y[:600], models[:600])
-    assert [s[2] for s in seen] == [600] and seen[0][0] == "engine0"
+    assert [s[2] for s in seen] == [600] and seen[0][0] == "engine0" and solo_flags == [True]
     # a failing piece surfaces as the caller's exception
     Y[300, 0] = -1.0
     with pytest.raises(RuntimeError, match="boom"):
@@ -312,6 +317,9 @@ def test_fit_models_deferred_tail_bookkeeping(monkeypatch):
             self.engine = eng
             log.append(("move", eng.high_priority))
 
+        def set_solo(self, solo=True):
+            log.append(("solo", bool(solo)))
+
         def counters(self):
             return dict(launches=7, rounds=3, model_evals=self.B)
 
@@ -342,4 +350,4 @@ def test_fit_models_deferred_tail_bookkeeping(monkeypatch):
     # a batch that is not several times the tail is fitted in one go
     log.clear()
     small = mf.fit_models(X, Y[:40], models[:40], engine=main, tail=16)
-    assert small["pending"] is None and small["finished"].all() and log[0] == ("sync", 40)
+    assert small["pending"] is None and small["finished"].all() and log[:2] == [("solo", True), ("sync", 40)]

@@ -119,6 +119,7 @@ struct wv_batch {
   int n_programs = 0;
   alignas(64) unsigned char tmap_mt[128];   // CUtensorMap over Mt (WV_KINV_TMA=1)
   bool has_tmap = false;
+  int solo = 0;                  // wv_batch_set_solo: nothing else runs on the device beside this batch's calls
   bool keep_row_order = false;   // WV_BATCH_KEEP_ROW_ORDER: device rows = caller rows (needed by wv_batch_eval_elbo)
 };
 
@@ -205,7 +206,8 @@ extern "C" int wv_engine_create2(int device, int flags, wv_engine** out) {
   if (const char* v = getenv("WV_TRTRI_ROWS")) eng->aux.trtri_rows = atoi(v);      // 1: one CTA per row, 2: balanced row pairs
   if (const char* v = getenv("WV_PANEL_TILES")) eng->aux.panel_tiles = atoi(v) > 0 ? atoi(v) : 4;
   if (const char* v = getenv("WV_FEW_MODELS")) eng->aux.few_models = atoi(v) != 0;
-  if (const char* v = getenv("WV_CHOL_ALL")) eng->aux.chol_all = atoi(v) != 0;
+  if (const char* v = getenv("WV_CHOL_ALL")) eng->aux.chol_all = atoi(v);
+  if (const char* v = getenv("WV_CHOL_ALL_MAX")) eng->aux.chol_all_max = atol(v);
   if (const char* v = getenv("WV_CHOL_LAG")) eng->aux.chol_lag = atoi(v) > 0 ? atoi(v) : 640;
   if (const char* v = getenv("WV_PANEL_FUSED")) eng->aux.panel_fused = atoi(v) != 0;
   if (const char* v = getenv("WV_PANEL_CTAS")) eng->aux.panel_ctas = atoi(v) > 0 ? atoi(v) : 148;
@@ -588,6 +590,12 @@ extern "C" int wv_batch_get_latent(wv_batch* b, double* fmean, double* fvar) {
   return 0;
 }
 
+extern "C" int wv_batch_set_solo(wv_batch* b, int solo) {
+  if (!b) return wv_fail("wv_batch_set_solo: null batch");
+  b->solo = solo != 0;
+  return 0;
+}
+
 extern "C" int wv_batch_set_component_mask(wv_batch* b, const uint32_t* mask) {
   if (!b || !mask) return wv_fail("wv_batch_set_component_mask: null argument");
   WV_CUDA(cudaSetDevice(b->eng->device));
@@ -608,6 +616,7 @@ static int wv_eval_all(wv_batch* b, const double* d_x, double* d_f, double* d_g,
                        const int* d_active, int n_active) {
   b->eng->aux.epoch += 1;
   b->eng->aux.tmap_mt = b->has_tmap ? b->tmap_mt : nullptr;
+  b->eng->aux.solo = b->solo;
   cudaStream_t st = b->eng->stream;
   if (b->bd.lik == 0) {
     int l = wv_enqueue_eval(b->bd, d_active, n_active, d_x, d_f, d_g, d_lml, d_status, st, &b->prof, &b->eng->aux,

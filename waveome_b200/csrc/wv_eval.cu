@@ -1665,7 +1665,15 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
     // model's tiles directly and spins for the one it needs) and one for the triangular inverse (a CTA per tile row)
     const long tiles_all = (long)n_active * nt * (nt + 1) / 2;
     const bool few = aux->few_models && nt >= 2 && nt < 200 && tiles_all <= aux->resident_ctas;
-    if (few || (aux->chol_all && nt >= 2 && nt < 200 && (long)n_active * nt > 2L * aux->resident_ctas)) {
+    // ... and the same persistent launch (with the lag) for batches of up to about a thousand models that have the device
+    // to themselves: it removes the launch pair per column and hides the diagonal chains behind panel tiles, which
+    // outweighs its lower panel occupancy (3 instead of 4 CTAs per SM) until the batch fills every launch several times
+    // over.  Beside other streams' work the persistent CTAs hold every slot and the streams stop filling each other's
+    // gaps (measured: DESIGN.md, the section on the one-launch Cholesky)
+    const long cols_all = (long)n_active * nt;
+    const bool mid = nt >= 2 && nt < 200 && cols_all > 2L * aux->resident_ctas &&
+                     (aux->chol_all == 1 || (aux->chol_all == 2 && aux->solo && cols_all <= aux->chol_all_max));
+    if (few || mid) {
       cudaMemsetAsync(bd.step_flag + 2 * (size_t)bd.B * bd.nt, 0, sizeof(int), st);      // the work counter
       const int ctas = few ? (int)tiles_all : aux->resident_ctas;
       wv_chol_all_kernel<<<ctas, WV_GEMM_THREADS, wv_smem_gemm_bytes(), st>>>(bd, d_active, n_active,

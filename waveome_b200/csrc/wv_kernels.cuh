@@ -95,8 +95,11 @@ struct WvAux {
   int panel_ctas = 148;      // persistent CTAs of that launch (WV_PANEL_CTAS; default one per SM)
   int panel_fused = 1;       // large-n path: all column steps of a panel in one launch (flags instead of launch boundaries)
   int trtri_rows = 0;   // 1: the batched schedule's triangular inverse as one row-wise launch (wv_trtri_rows_kernel)
-  int chol_all = 0;     // many models, nt < big_nt: the whole Cholesky in one persistent launch (wv_chol_all_kernel; WV_CHOL_ALL=1;
-                        // measured slower than the launch pair per column, DESIGN.md section 4b: off)
+  int chol_all = 2;     // nt < big_nt: the whole Cholesky in one persistent launch (wv_chol_all_kernel).  0: never (beyond the
+                        // few-models case), 1: always, 2: for a batch that has the device to itself (wv_batch_set_solo)
+                        // while n_active * nt <= chol_all_max (WV_CHOL_ALL, WV_CHOL_ALL_MAX)
+  long chol_all_max = 10000;
+  int solo = 0;         // the batch being evaluated declared itself alone on the device
   int few_models = 1;   // few models in flight: one launch each for the Cholesky and the triangular inverse (WV_FEW_MODELS=0: off)
   int chol_lag = 640;   // work items between a panel tile (j + 1, j) and the diagonal block j + 1 that needs it (WV_CHOL_LAG)
   int epoch = 0;   // evaluation counter of the engine: the value the diagonal CTAs publish in step_flag

@@ -55,7 +55,7 @@ class _AdamOpts(C.Structure):
 
 EXPORTED_SYMBOLS = [
     "wv_engine_create", "wv_engine_create2", "wv_batch_set_engine", "wv_engine_destroy", "wv_engine_stream", "wv_engine_set_large_n_tiles", "wv_batch_create", "wv_batch_destroy",
-    "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_likelihood", "wv_batch_set_likelihood2", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
+    "wv_batch_workspace_bytes", "wv_batch_set_y", "wv_batch_set_component_mask", "wv_batch_set_solo", "wv_batch_set_likelihood", "wv_batch_set_likelihood2", "wv_batch_get_latent", "wv_batch_eval", "wv_batch_eval_device", "wv_batch_fit_lbfgs",
     "wv_batch_fit_lbfgs_begin", "wv_batch_fit_lbfgs_run", "wv_batch_fit_lbfgs_report",
     "wv_batch_fit_adam", "wv_batch_create2", "wv_batch_eval_elbo", "wv_batch_specialize", "wv_rtc_check", "wv_rtc_set_cache", "wv_rtc_precompile_text",
     "wv_batch_counters", "wv_batch_get_alpha", "wv_batch_get_kinv_diag", "wv_batch_predict_mean", "wv_batch_predict_f", "wv_batch_profile_enable", "wv_batch_profile_read", "wv_last_error", "wv_version",
@@ -79,6 +79,7 @@ def load_library():
     lib.wv_engine_create.argtypes = [C.c_int, C.POINTER(vp)]; lib.wv_engine_create.restype = C.c_int
     lib.wv_engine_create2.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]; lib.wv_engine_create2.restype = C.c_int
     lib.wv_batch_set_engine.argtypes = [vp, vp]; lib.wv_batch_set_engine.restype = C.c_int
+    lib.wv_batch_set_solo.argtypes = [vp, C.c_int]; lib.wv_batch_set_solo.restype = C.c_int
     lib.wv_engine_destroy.argtypes = [vp]; lib.wv_engine_destroy.restype = None
     lib.wv_engine_stream.argtypes = [vp]; lib.wv_engine_stream.restype = vp
     lib.wv_engine_set_large_n_tiles.argtypes = [vp, C.c_int]; lib.wv_engine_set_large_n_tiles.restype = C.c_int
@@ -387,6 +388,10 @@ class Batch:
         _check(self.lib.wv_batch_fit_lbfgs(self.handle, _f64(x), C.byref(co), _f64(f), _f64(lml), _i32(nit), _i32(nev),
                                            _i32(st)), "wv_batch_fit_lbfgs")
         return dict(x=x, f=f, lml=lml, n_iter=nit, n_eval=nev, status=st)
+
+    def set_solo(self, solo: bool = True):
+        """Scheduling hint (wv_batch_set_solo): this batch has the device to itself while its calls run."""
+        _check(self.lib.wv_batch_set_solo(self.handle, 1 if solo else 0), "wv_batch_set_solo")
 
     def move_to(self, engine: "Engine"):
         """Re-home the batch: later calls run on ``engine``'s stream (same device; no call may be in progress)."""

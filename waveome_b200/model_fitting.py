@@ -21,15 +21,19 @@ _ENGINES: Dict[int, "object"] = {}
 DEFAULT_LBFGS_KEYS = ("maxcor", "maxiter", "maxfun", "maxls", "ftol", "gtol", "on_chol_fail")
 
 
+_ENGINE_LOCK = __import__("threading").RLock()      # engines are created lazily, possibly from several fitter threads at once
+
+
 def get_engine(device: Optional[int] = None):
     """One engine per GPU per process (LOCAL_RANK picks the GPU under torchrun)."""
     import os
     from .engine import Engine
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
-    if device not in _ENGINES:
-        _ENGINES[device] = Engine(device)
-    return _ENGINES[device]
+    with _ENGINE_LOCK:
+        if device not in _ENGINES:
+            _ENGINES[device] = Engine(device)
+        return _ENGINES[device]
 
 
 _POOLS: Dict[int, list] = {}
@@ -46,10 +50,13 @@ def get_engine_pool(k: int, device: Optional[int] = None) -> list:
     from .engine import Engine
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
-    pool = _POOLS.setdefault(device, [get_engine(device)])
-    while len(pool) < k:
-        pool.append(Engine(device))
-    return pool[:k]
+    with _ENGINE_LOCK:
+        if device not in _POOLS:
+            _POOLS[device] = [get_engine(device)]
+        pool = _POOLS[device]
+        while len(pool) < k:
+            pool.append(Engine(device))
+        return pool[:k]
 
 
 def split_for_streams(n_models: int, chunk: int, streams: Optional[int] = None) -> List[tuple]:
@@ -67,6 +74,8 @@ def _open_batch(eng, job):
     batch = Batch(eng, job["X"], job["Y"], job["table"], job.get("prog_id"), P=job["P"],
                   specialize=job.get("specialize", False))
     try:
+        if job.get("solo"):
+            batch.set_solo(True)
         if job["lik_name"] != "gaussian":
             batch.set_likelihood(job["lik_name"], job["lik_param"])
     except BaseException:
@@ -136,7 +145,10 @@ def run_fit_jobs(jobs: List[dict], engine=None, streams: Optional[int] = None, *
 
     if engine is not None or streams == 1 or len(jobs) <= 1:
         eng = engine or get_engine()
-        return [run_one(eng, j) for j in jobs]
+        # one batch at a time on this process's device -- unless this is one of several fitter threads of a search
+        from .kernel_search import _FITTER_SLOT
+        alone = getattr(_FITTER_SLOT, "slot", None) is None
+        return [run_one(eng, dict(j, solo=alone)) for j in jobs]
     engines = get_engine_pool(min(streams, len(jobs)))
     out: List[Optional[tuple]] = [None] * len(jobs)
     err: list = []
