@@ -18,6 +18,8 @@ eng = Engine(0)
 t0 = time.time()
 bt = Batch(eng, Xs.to_numpy(), Ys.to_numpy().T.copy(), [m.program()], specialize=True)
 print("batch create %.2fs workspace %.2f GB" % (time.time() - t0, bt.workspace_bytes / 1e9), flush=True)
+import os
+if os.environ.get("SOLO"): bt.set_solo(True)
 x = bt.x0()
 bt.profile(True)
 st = torch.cuda.ExternalStream(eng.stream)

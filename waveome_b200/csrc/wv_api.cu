@@ -208,6 +208,7 @@ extern "C" int wv_engine_create2(int device, int flags, wv_engine** out) {
   if (const char* v = getenv("WV_FEW_MODELS")) eng->aux.few_models = atoi(v) != 0;
   if (const char* v = getenv("WV_CHOL_ALL")) eng->aux.chol_all = atoi(v);
   if (const char* v = getenv("WV_CHOL_ALL_MAX")) eng->aux.chol_all_max = atol(v);
+  if (const char* v = getenv("WV_CHOL_ALL_MIN")) eng->aux.chol_all_min = atol(v);
   if (const char* v = getenv("WV_CHOL_LAG")) eng->aux.chol_lag = atoi(v) > 0 ? atoi(v) : 640;
   if (const char* v = getenv("WV_PANEL_FUSED")) eng->aux.panel_fused = atoi(v) != 0;
   if (const char* v = getenv("WV_PANEL_CTAS")) eng->aux.panel_ctas = atoi(v) > 0 ? atoi(v) : 148;

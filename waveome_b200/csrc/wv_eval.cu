@@ -1671,13 +1671,14 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
     // over.  Beside other streams' work the persistent CTAs hold every slot and the streams stop filling each other's
     // gaps (measured: DESIGN.md, the section on the one-launch Cholesky)
     const long cols_all = (long)n_active * nt;
-    const bool mid = nt >= 2 && nt < 200 && cols_all > 2L * aux->resident_ctas &&
-                     (aux->chol_all == 1 || (aux->chol_all == 2 && aux->solo && cols_all <= aux->chol_all_max));
+    const bool mid = nt >= 2 && nt < 200 &&
+                     ((aux->chol_all == 1 && cols_all > 2L * aux->resident_ctas) ||
+                      (aux->chol_all == 2 && aux->solo && cols_all <= aux->chol_all_max && cols_all > aux->chol_all_min));
     if (few || mid) {
       cudaMemsetAsync(bd.step_flag + 2 * (size_t)bd.B * bd.nt, 0, sizeof(int), st);      // the work counter
       const int ctas = few ? (int)tiles_all : aux->resident_ctas;
       wv_chol_all_kernel<<<ctas, WV_GEMM_THREADS, wv_smem_gemm_bytes(), st>>>(bd, d_active, n_active,
-                                                                              few ? 0 : aux->chol_lag, aux->epoch);
+                                                                              few ? 0 : (int)(cols_all / 2 < aux->chol_lag ? cols_all / 2 : aux->chol_lag), aux->epoch);
       pf->mark(WV_K_CHOL_PANEL, st);
       ++launches;
     } else {

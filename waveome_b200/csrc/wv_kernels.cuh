@@ -99,6 +99,7 @@ struct WvAux {
                         // few-models case), 1: always, 2: for a batch that has the device to itself (wv_batch_set_solo)
                         // while n_active * nt <= chol_all_max (WV_CHOL_ALL, WV_CHOL_ALL_MAX)
   long chol_all_max = 10000;
+  long chol_all_min = 300;   // (WV_CHOL_ALL_MIN) below: the fused launch per column
   int solo = 0;         // the batch being evaluated declared itself alone on the device
   int few_models = 1;   // few models in flight: one launch each for the Cholesky and the triangular inverse (WV_FEW_MODELS=0: off)
   int chol_lag = 640;   // work items between a panel tile (j + 1, j) and the diagonal block j + 1 that needs it (WV_CHOL_LAG)
