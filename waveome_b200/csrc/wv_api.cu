@@ -209,6 +209,8 @@ extern "C" int wv_engine_create2(int device, int flags, wv_engine** out) {
   if (const char* v = getenv("WV_CHOL_ALL")) eng->aux.chol_all = atoi(v);
   if (const char* v = getenv("WV_CHOL_ALL_MAX")) eng->aux.chol_all_max = atol(v);
   if (const char* v = getenv("WV_CHOL_ALL_MIN")) eng->aux.chol_all_min = atol(v);
+  if (const char* v = getenv("WV_TRTRI_ALL")) eng->aux.trtri_all = atoi(v);
+  if (const char* v = getenv("WV_TRTRI_ALL_MAX")) eng->aux.trtri_all_max = atol(v);
   if (const char* v = getenv("WV_CHOL_LAG")) eng->aux.chol_lag = atoi(v) > 0 ? atoi(v) : 640;
   if (const char* v = getenv("WV_PANEL_FUSED")) eng->aux.panel_fused = atoi(v) != 0;
   if (const char* v = getenv("WV_PANEL_CTAS")) eng->aux.panel_ctas = atoi(v) > 0 ? atoi(v) : 148;
@@ -217,6 +219,8 @@ extern "C" int wv_engine_create2(int device, int flags, wv_engine** out) {
     WV_CUDA(cudaGetDeviceProperties(&prop, device));
     eng->aux.resident_ctas = 3 * prop.multiProcessorCount;
     if (!getenv("WV_PANEL_CTAS")) eng->aux.panel_ctas = prop.multiProcessorCount;
+    eng->aux.trtri_ctas = 4 * prop.multiProcessorCount;
+    if (const char* v = getenv("WV_TRTRI_CTAS")) eng->aux.trtri_ctas = atoi(v) > 0 ? atoi(v) : eng->aux.trtri_ctas;
   }
   *out = eng;
   return 0;

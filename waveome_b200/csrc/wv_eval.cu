@@ -696,6 +696,45 @@ __global__ void __launch_bounds__(WV_GEMM_THREADS) wv_trtri_rows_kernel(WvBatchD
   }
 }
 
+// The triangular inverse as ONE persistent launch for a batch that has the device to itself: the tiles (j, i) of all
+// steps i = 1 .. nt-1 form one list in step order, pulled from the work counter of wv_chol_all_kernel by a few CTAs per SM.
+// Tile (j, i) needs the earlier tiles of its own row (j, j+1 .. i-1) -- a per-row counter, kept in the row counters of the
+// Cholesky kernel with an offset of 128 so that a leftover Cholesky count never satisfies a wait -- and L / Linv, which are
+// final.  Dependencies have lower indices and items are pulled in order: no deadlock.  Unlike the row-per-CTA form
+// (wv_trtri_rows_kernel) the load is balanced, and the nine launch boundaries with their tails are gone.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WV_GEMM_THREADS) wv_trtri_all_kernel(WvBatchDev bd, const int* __restrict__ active,
+                                                                     int n_active, int epoch) {
+  __shared__ int s_item;
+  int* counter = bd.step_flag + 2 * (size_t)bd.B * bd.nt;
+  const int nt = bd.nt;
+  const int ep = epoch & 0x3fffff;
+  for (;;) {
+    __syncthreads();                      // previous item done with the shared-memory tiles
+    if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);
+    __syncthreads();
+    int it = s_item, i = 1;
+    for (;; ++i) {
+      if (i >= nt) return;
+      const int sz = n_active * i;
+      if (it < sz) break;
+      it -= sz;
+    }
+    const int m = it / i, j = it - m * i;
+    const int b = active[m];
+    int* row_done = bd.step_flag + (size_t)bd.B * bd.nt + (size_t)b * bd.nt;
+    if (threadIdx.x == 0) {
+      if (i - 1 > j) wv_wait_cols(row_done + j, ep, 128 + (i - 1 - j));
+      __threadfence();
+    }
+    __syncthreads();
+    wv_panel_body<1>(bd, b, i, j, 0, 0);
+    __threadfence();                       // the tile is visible device-wide before the row counter moves
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(row_done + j) = -((ep << 8) | (128 + i - j)) - 1;
+  }
+}
+
 // =============================================================================================
 // extract: alpha_j = -Mt[j][n], quad = |L[n][0:n]|^2 = |L^{-1} d|^2 ; then clear column n of Mt so that
 // kinv = Mt Mt^T excludes the augmented row.  grid (n_active), 256 threads.
@@ -1121,6 +1160,7 @@ static cudaError_t wv_set_attrs() {
   WV_ATTR(wv_chol_all_kernel, wv_smem_gemm_bytes());
   WV_ATTR(wv_trtri_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_trtri_rows_kernel, sizeof(WvPanelSmem));
+  WV_ATTR(wv_trtri_all_kernel, sizeof(WvPanelSmem));
   WV_ATTR(wv_kinv_kernel, sizeof(WvGemmSmem));
   WV_ATTR(wv_kinv_tma_kernel, sizeof(WvTmaSmem) + 1024);
   WV_ATTR(wv_syrk_kernel, sizeof(WvGemmSmem));
@@ -1685,7 +1725,15 @@ int wv_enqueue_factor(const WvBatchDev& bd, const int* d_active, int n_active, c
       for (int j = 0; j < nt; ++j) launches += wv_launch_chol_step(bd, d_active, n_active, j, 0, st, pf, *aux);
     }
     if (chol_only) return cudaGetLastError() == cudaSuccess ? launches : -1;
-    if ((aux->trtri_rows || few) && nt > 1) {
+    const long tri_tiles = (long)n_active * nt * (nt - 1) / 2;
+    if (aux->trtri_all && aux->solo && !few && nt > 1 && nt < 120 && tri_tiles > aux->resident_ctas &&
+        cols_all <= aux->trtri_all_max) {
+      cudaMemsetAsync(bd.step_flag + 2 * (size_t)bd.B * bd.nt, 0, sizeof(int), st);      // the work counter
+      const int ctas = aux->trtri_ctas;
+      wv_trtri_all_kernel<<<ctas, WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active, n_active, aux->epoch);
+      pf->mark(WV_K_TRTRI, st);
+      ++launches;
+    } else if ((aux->trtri_rows || few) && nt > 1) {
       const int paired = aux->trtri_rows == 2;
       wv_trtri_rows_kernel<<<dim3(paired ? nt / 2 : nt - 1, n_active), WV_GEMM_THREADS, sizeof(WvPanelSmem), st>>>(bd, d_active,
                                                                                                               paired);

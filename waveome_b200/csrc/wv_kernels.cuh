@@ -101,6 +101,9 @@ struct WvAux {
   long chol_all_max = 10000;
   long chol_all_min = 300;   // (WV_CHOL_ALL_MIN) below: the fused launch per column
   int solo = 0;         // the batch being evaluated declared itself alone on the device
+  int trtri_all = 1;    // solo batches: the triangular inverse as one persistent launch (wv_trtri_all_kernel; WV_TRTRI_ALL)
+  long trtri_all_max = 5000;       // ... while n_active * nt <= this (WV_TRTRI_ALL_MAX; measured crossover ~600 models at nt = 10)
+  int trtri_ctas = 592; // its persistent CTAs (4 per SM; WV_TRTRI_CTAS)
   int few_models = 1;   // few models in flight: one launch each for the Cholesky and the triangular inverse (WV_FEW_MODELS=0: off)
   int chol_lag = 640;   // work items between a panel tile (j + 1, j) and the diagonal block j + 1 that needs it (WV_CHOL_LAG)
   int epoch = 0;   // evaluation counter of the engine: the value the diagonal CTAs publish in step_flag
