@@ -122,6 +122,11 @@ def _prod(terms: List[str]) -> str:
     return " * ".join(terms) if terms else "1.0"
 
 
+#: Gram pass: add a masked-out value as ``+ 0.0`` through a select instead of branching around the addition (the sums
+#: start at +0.0 and every value is positive, so the bits are the same).  WV_SPEC_MASK_SELECT=0 restores the branch.
+MASK_SELECT = os.environ.get("WV_SPEC_MASK_SELECT", "1") != "0"
+
+
 def _mask_expr(cp: _Comp, b: str) -> str:
     return " && ".join(f"kr{k} == kc{k}[{b}]" for k in cp.cats)
 
@@ -353,7 +358,7 @@ def generate(p: Program) -> Optional[SpecSource]:
         for s_ in value_terms(cp, "a", "j", False):
             w(f"{ind}  " + s_)
         if cp.cats:
-            w(f"{ind}  if ({_mask_expr(cp, 'j')}) acc[j] += v;")
+            w(f"{ind}  acc[j] += ({_mask_expr(cp, 'j')}) ? v : 0.0;" if MASK_SELECT else f"{ind}  if ({_mask_expr(cp, 'j')}) acc[j] += v;")
         else:
             w(f"{ind}  acc[j] += v;")
         w(f"{ind}}}")
