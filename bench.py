@@ -182,6 +182,20 @@ def measure_extras(args, rank, world, local_rank, eng, barrier, reduce_max, torc
     if world > 1:
         guarded("strong_scaling", strong)
 
+    # ---- configs[0]: the README quick-start (iris: 150 rows, 2 outcomes) -- a latency-bound job; single-GPU runs only
+    def config1():
+        X, Y = datasets.iris()
+        def run():
+            gps = GPSearch(X, Y, categorical_vars=["species"])
+            gps.penalized_optimization(gather=False)
+            return gps
+        run()                                    # warm-up (buffers)
+        secs, gps = timed(run)
+        return {"outcomes": int(Y.shape[1]), "n": int(X.shape[0]), "seconds": secs,
+                "structures": {o: m.kernel_name for o, m in gps.models.items()}}
+    if world == 1:
+        guarded("config1_iris", config1)
+
     # ---- configs[1]: full kernel search, 200 outcomes x depth 5 (outcomes sharded over the ranks by run_search)
     def config2():
         X, Y = datasets.overview_synthetic(n_people=50, n_observations=10, n_outcomes=200)
