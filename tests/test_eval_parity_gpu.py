@@ -187,3 +187,27 @@ def test_device_pointer_entry(engine):
     torch.cuda.ExternalStream(engine.stream).synchronize()
     assert np.array_equal(fd.cpu().numpy(), f_h) and np.array_equal(gd.cpu().numpy(), g_h)
     batch.close()
+
+
+def test_one_launch_factorisation_paths_are_bit_identical(engine):
+    """A batch that declares itself alone on the device (wv_batch_set_solo) factorises mid-size batches with the persistent
+    one-launch kernels (wv_chol_all_kernel, wv_trtri_all_kernel) instead of a launch pair per tile column and a launch per
+    inverse step: same tile bodies, same arithmetic -- every value, gradient and status must agree BIT FOR BIT, for two- and
+    ten-tile models, with and without the full active list."""
+    from waveome_b200.engine import Batch
+    rng = np.random.default_rng(3)
+    for n, B in ((100, 320), (600, 60)):
+        X, y = helpers.make_data(n, seed=n)
+        Y = y[None, :] + 0.3 * rng.normal(size=(B, n))
+        model = wb.GPR(helpers.saturated_kernel(hs=0.0), mean_function=wb.ConstantMean(0.0))
+        out = []
+        for solo in (False, True):
+            batch = Batch(engine, X, Y, [model.program()])
+            batch.set_solo(solo)
+            x = batch.x0() + 0.1 * np.random.default_rng(1).normal(size=(B, batch.P))
+            out.append(batch.eval(x))
+            fit = batch.fit(maxiter=12)              # the active list shrinks: both forms see ragged lists too
+            out[-1] = out[-1] + (fit["x"], fit["f"], fit["n_eval"])
+            batch.close()
+        for a, b in zip(*out):
+            assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
