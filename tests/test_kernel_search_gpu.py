@@ -135,3 +135,23 @@ def test_deferred_stragglers_run_search_matches_level_synchronous(monkeypatch):
         np.testing.assert_array_equal(a.models[o].program().x0(), b.models[o].program().x0())
     from waveome_b200 import model_fitting as mf
     assert all(not v for v in mf._LEASED.values())                       # every engine lease was returned
+
+
+def test_split_kernel_search_engine_vs_oracle(engine):
+    """split_kernel_search (waveome/model_search.py:3275-3532) on the engine -- training fits by the device L-BFGS-B, hold-out
+    scores through wv_batch_predict_f -- against the same search with the oracle's fits and the oracle's predictive
+    density: same split, same candidates, same hold-out criteria (to their two printed decimals), same selection."""
+    import gp_oracle as oracle
+    X, y = _toy()
+    kl = lambda: [wb.SquaredExponential(), wb.Lin()]
+    a = ks.split_kernel_search(X, y, kl(), unit_idx=0, cat_vars=[0, 2], max_depth=2, random_seed=4, engine=engine,
+                               num_restart=1, keep_only_best=False)
+    tr = np.isin(X[:, 0], np.unique(a["X"][:, 0]))
+    b = ks.split_kernel_search(X, y, kl(), unit_idx=0, cat_vars=[0, 2], max_depth=2, random_seed=4, keep_only_best=False,
+                               fit=oracle_fitter(X[tr]),
+                               log_density=lambda m, Xt, yt, Xh, yh: oracle.predict_log_density(m.to_spec(), Xt, yt, Xh, yh))
+    np.testing.assert_array_equal(a["X"], b["X"])
+    np.testing.assert_array_equal(a["X_holdout"], b["X_holdout"])
+    assert a["best_model"] == b["best_model"] and set(a["models"]) == set(b["models"]) and a["edges"] == b["edges"]
+    for k in a["models"]:
+        assert abs(a["models"][k]["bic"] - b["models"][k]["bic"]) <= 0.011, (k, a["models"][k]["bic"], b["models"][k]["bic"])

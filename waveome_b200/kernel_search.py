@@ -334,11 +334,44 @@ def _best_of_depth(search_dict, d):
     return min((i["bic"], i["depth"], k) for k, i in search_dict.items() if i["depth"] == d)[2]
 
 
+def softmax_kernel_selection(bic_list, name_list):
+    """:3535-3567 — draw ONE model name with probability softmax of the min-max normalised negated criteria (models whose
+    criterion is inf are left out; a single candidate is returned as it is).  Draws from ``np.random`` like the reference."""
+    name_list = [name_list[x] for x in range(len(bic_list)) if bic_list[x] != np.inf]
+    bic_list = [x for x in bic_list if x != np.inf]
+    if len(bic_list) == 1:
+        return name_list[0]
+    neg = np.array([-x for x in bic_list])
+    norm = (neg - min(neg)) / (max(neg) - min(neg))
+    prob = np.exp(norm) / sum(np.exp(norm))
+    return name_list[np.random.choice(a=np.arange(len(prob)), p=prob)]
+
+
+class BicRequests(list):
+    """Fit requests whose results must be scored by BIC on the training data even in a hold-out (split) search: the
+    reference prunes with ``prune_best_model2(...)`` WITHOUT the hold-out arguments (:3441-3449, :3483-3491)."""
+
+
+def _scored_by_bic(gen):
+    """Re-yield the requests of ``gen`` as BicRequests."""
+    try:
+        req = next(gen)
+        while True:
+            req = gen.send((yield BicRequests(req)))
+    except StopIteration as e:
+        return e.value
+
+
 def full_kernel_search_gen(n_features, kern_list, cat_vars=(), max_depth=5, keep_all=False, metric_diff=6,
-                           early_stopping=True, prune=True, keep_only_best=True, softmax_select=False):
-    """:2987-3272 as a generator over fit requests; returns {"models", "edges", "best_model", "var_exp"}."""
-    if softmax_select:
-        raise NotImplementedError("softmax_select draws from np.random per outcome; not part of the batched search")
+                           early_stopping=True, prune=True, keep_only_best=True, softmax_select=False, split=False):
+    """:2987-3272 as a generator over fit requests; returns {"models", "edges", "best_model", "var_exp"}.
+
+    ``split`` = True gives the level logic of ``split_kernel_search`` (:3338-3500) instead: the criterion the fitter returns
+    is the negated hold-out log density, ``keep_top_k`` uses its log window, there is no stop at a constant best model,
+    and pruning happens once -- when the search stops early or reaches ``max_depth`` -- scored by BIC (BicRequests).
+    ``softmax_select`` (:3190-3204, :3467-3481): after ``keep_top_k`` one model of the whole dictionary is drawn by
+    ``softmax_kernel_selection`` and only it stays expandable at this depth (draws from ``np.random``: per-outcome
+    results then depend on the order in which the generators are advanced)."""
     search_dict: Dict[str, dict] = {}
     edge_list = []
     for d in range(1, max_depth + 1):
@@ -380,17 +413,27 @@ def full_kernel_search_gen(n_features, kern_list, cat_vars=(), max_depth=5, keep
         if not any(i["depth"] == d for i in search_dict.values()):
             break          # (the reference raises on the empty min(); nothing left to expand)
         best_model_name = _best_of_depth(search_dict, d)
-        if best_model_name == "constant":
+        if best_model_name == "constant" and not split:
             break
         if early_stopping and d > 1:
             if not check_if_better_metric(search_dict, d):
                 if prune:
-                    search_dict = yield from prune_best_model2(search_dict, depth=d)
+                    search_dict = yield from (_scored_by_bic(prune_best_model2(search_dict, depth=d)) if split
+                                              else prune_best_model2(search_dict, depth=d))
                 break
-        if d != max_depth and not keep_all:
-            search_dict = keep_top_k(search_dict, depth=d, metric_diff=metric_diff)
-        if prune:
+        if d != max_depth:
+            if not keep_all:
+                search_dict = keep_top_k(search_dict, depth=d, metric_diff=metric_diff, split=split)
+            if softmax_select:
+                info = [(i["bic"], k) for k, i in search_dict.items()]
+                chosen = softmax_kernel_selection([x[0] for x in info], [x[1] for x in info])
+                for k, v in search_dict.items():
+                    if v["depth"] == d and k != chosen:
+                        v["try_next"] = False
+        if prune and not split:
             search_dict = yield from prune_best_model2(search_dict, depth=d)
+        elif prune and d == max_depth:
+            search_dict = yield from _scored_by_bic(prune_best_model2(search_dict, depth=d))
     best_model_name = min((i["bic"], i["depth"], k) for k, i in search_dict.items())[2]
     if keep_only_best:
         search_dict = {best_model_name: search_dict[best_model_name]}
@@ -678,3 +721,88 @@ def full_kernel_search(X, Y, kern_list, cat_vars=(), max_depth=5, keep_all=False
                                  metric_diff=metric_diff, early_stopping=early_stopping, prune=prune,
                                  keep_only_best=keep_only_best, softmax_select=softmax_select)
     return _drive_single(gen, y, fit)
+
+
+
+def holdout_fitter(fit: Callable, X_train: np.ndarray, X_holdout: np.ndarray, y_holdout: np.ndarray,
+                   log_density: Optional[Callable] = None) -> Callable:
+    """Wrap a fitter ``fit(requests) -> [(model, bic)]`` (models fitted on the training rows) so that the criterion becomes
+    what ``kernel_test(split=True)`` reports (:2299-2308): round(-sum of the predictive log density of the hold-out rows, 2).
+    Requests that arrive as BicRequests keep their BIC.  ``log_density(model, X_train, y_train, X_holdout, y_holdout)`` ->
+    [m] overrides the engine's ``model.predict_log_density`` (the CPU tests score with the oracle)."""
+    if log_density is None:
+        def log_density(m, Xt, yt, Xh, yh):
+            return m.predict_log_density((Xh, yh), data=(Xt, np.asarray(yt).reshape(-1, 1)))
+
+    def scored(requests, **kw):
+        res = fit(requests, **kw)
+        if isinstance(requests, BicRequests):
+            return res
+        out = []
+        for (y, _name, _k), (m, bic) in zip(requests, res):
+            if m is None:
+                out.append((None, np.inf))
+                continue
+            lp = log_density(m, X_train, np.asarray(y), X_holdout, y_holdout)
+            out.append((m, round(-float(np.sum(lp)), 2)))
+        return out
+    return scored
+
+
+def split_kernel_search(X, Y, kern_list, unit_idx, training_percent=0.7, cat_vars=(), max_depth=5, keep_all=False,
+                        metric_diff=1, early_stopping=True, prune=True, num_restart=5, lik="gaussian", scale_value=None,
+                        verbose=False, debug=False, keep_only_best=True, softmax_select=False, random_seed=None,
+                        engine=None, fit=None, log_density=None, **unused):
+    """Drop-in for :3275-3532: the kernel search of one outcome with the units split into a training part
+    (``training_percent`` of the unit ids, drawn with ``np.random.choice`` after ``np.random.seed(random_seed)``) and a
+    hold-out part; candidates are fitted on the training rows and ranked by the negated hold-out log density.  Returns the
+    reference's dictionary (models, edges, best_model, var_exp, X_holdout, Y_holdout, X, Y).  ``fit`` overrides the engine
+    fitter for the TRAINING fits and ``log_density`` the hold-out scorer (the CPU tests pass the oracle for both)."""
+    if random_seed is not None:
+        np.random.seed(random_seed)
+    Xn = X.to_numpy() if hasattr(X, "to_numpy") else np.asarray(X)
+    Xn = np.asarray(Xn, dtype=np.float64).reshape(len(Xn), -1)
+    Yn = Y.to_numpy() if hasattr(Y, "to_numpy") else np.asarray(Y)
+    y = np.asarray(Yn, dtype=np.float64).reshape(-1)
+    ok = ~np.isnan(Xn).any(axis=1) & ~np.isnan(y)
+    Xn, y = Xn[ok], y[ok]
+    unique_ids = np.unique(Xn[:, unit_idx])
+    train_ids = np.random.choice(unique_ids, size=round(training_percent * len(unique_ids)), replace=False)
+    tr = np.isin(Xn[:, unit_idx], train_ids)
+    X_tr, y_tr, X_ho, y_ho = Xn[tr], y[tr], Xn[~tr], y[~tr]
+    base = fit or engine_fitter(X_tr, engine=engine, num_restart=num_restart, random_seed=random_seed, likelihood=lik)
+    scored = holdout_fitter(base, X_tr, X_ho, y_ho, log_density=log_density)
+    gen = full_kernel_search_gen(Xn.shape[1], kern_list, cat_vars=cat_vars, max_depth=max_depth, keep_all=keep_all,
+                                 metric_diff=metric_diff, early_stopping=early_stopping, prune=prune,
+                                 keep_only_best=keep_only_best, softmax_select=softmax_select, split=True)
+    # one outcome: a plain request / reply loop (the BicRequests marker must reach the fitter unflattened)
+    try:
+        req = next(gen)
+        while True:
+            tagged = type(req)((y_tr, name, k) for name, k in req)
+            req = gen.send(scored(tagged))
+    except StopIteration as e:
+        out = e.value
+    out.update(X_holdout=X_ho, Y_holdout=y_ho.reshape(-1, 1), X=X_tr, Y=y_tr.reshape(-1, 1))
+    return out
+
+
+def softmax_kernel_search(X, Y, kern_list, num_trials=5, cat_vars=(), max_depth=5, lik="gaussian", verbose=False,
+                          engine=None, fit=None, **unused):
+    """:3570-3627 — ``num_trials`` full searches with the softmax exploration step (``keep_all=True``, no early stopping,
+    no pruning), the trial whose best model has the lowest BIC wins.  Returns the reference's 5-tuple (models of the best
+    trial, its edges, its best model's name, var_exp, {trial: models}).  (Upstream unpacks ``full_kernel_search``'s
+    dictionary as a tuple there and cannot run as written; this is what the code sets out to do.)"""
+    best_bic, best = np.inf, ({}, [], "", None)
+    search_book = {}
+    for i in range(num_trials):
+        out = full_kernel_search(X, Y, kern_list, cat_vars=cat_vars, max_depth=max_depth, keep_all=True,
+                                 early_stopping=False, prune=False, lik=lik, verbose=verbose, keep_only_best=False,
+                                 softmax_select=True, engine=engine, fit=fit)
+        search_book[i] = out["models"]
+        bic = out["models"][out["best_model"]]["bic"]
+        if verbose:
+            print(out["best_model"], bic)
+        if bic < best_bic:
+            best_bic, best = bic, (out["models"], out["edges"], out["best_model"], out["var_exp"])
+    return best + (search_book,)
