@@ -167,3 +167,29 @@ def test_component_predictions(engine):
     np.testing.assert_array_equal(mu[:, 0], parts[1][0])
     with pytest.raises(ValueError):
         individual_kernel_predictions(model, 5, data=(X, y), X=Xnew)
+
+
+def test_post_fit_work_behind_the_fit_gives_the_same_models():
+    """penalized_optimization fits a large job as concurrent pieces and does the post-fit work of a piece (pruning, feature
+    importances on an engine of its own) while the others are still on the device: names, fitted values and importances must
+    be those of the single-piece run."""
+    from waveome_b200 import datasets, model_fitting as mf
+    from waveome_b200.model_search import GPSearch
+    X, Y = datasets.overview_synthetic(n_people=10, n_observations=5, n_outcomes=600)
+    out = {}
+    for streams in (1, 4):
+        old, mf.FIT_STREAMS = mf.FIT_STREAMS, streams
+        try:
+            g = GPSearch(X, Y, unit_col="person_id", categorical_vars=["female"])
+            g.penalized_optimization(num_restart=0, optimization_options={"num_opt_iter": 30})
+        finally:
+            mf.FIT_STREAMS = old
+        out[streams] = g
+    a, b = out[1], out[4]
+    assert all(not v for v in mf._LEASED.values())
+    for o in a.out_names:
+        ma, mb = a.models[o], b.models[o]
+        assert ma.kernel_name == mb.kernel_name
+        assert [float(p) for p in ma.trainable_parameters] == [float(p) for p in mb.trainable_parameters]
+        np.testing.assert_array_equal(np.asarray(ma.feature_importances, dtype=float),
+                                      np.asarray(mb.feature_importances, dtype=float))

@@ -9,7 +9,7 @@
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -118,10 +118,12 @@ def release_engine(idx: int, device: Optional[int] = None):
         _LEASED.setdefault(device, set()).discard(idx)
 
 
-def run_fit_jobs(jobs: List[dict], engine=None, streams: Optional[int] = None, **lbfgs_opts) -> List[tuple]:
+def run_fit_jobs(jobs: List[dict], engine=None, streams: Optional[int] = None, on_done: Optional[Callable] = None,
+                 **lbfgs_opts) -> List[tuple]:
     """Fit every job (dict X, Y, table, prog_id, P, lik_name, lik_param, starts) as one engine batch; up to ``streams``
     jobs at a time, each on its own engine and host thread (the C call releases the GIL).  Returns [(result dict,
-    counters)] in job order.  With a caller-supplied ``engine`` or a single job everything runs on that one engine."""
+    counters)] in job order.  With a caller-supplied ``engine`` or a single job everything runs on that one engine.
+    ``on_done(i, (result, counters))`` is called, on the thread that ran it, as soon as job i has finished."""
     import threading
     from .engine import Batch
     streams = FIT_STREAMS if streams is None else max(1, int(streams))
@@ -148,7 +150,12 @@ def run_fit_jobs(jobs: List[dict], engine=None, streams: Optional[int] = None, *
         # one batch at a time on this process's device -- unless this is one of several fitter threads of a search
         from .kernel_search import _FITTER_SLOT
         alone = getattr(_FITTER_SLOT, "slot", None) is None
-        return [run_one(eng, dict(j, solo=alone)) for j in jobs]
+        res = []
+        for i, j in enumerate(jobs):
+            res.append(run_one(eng, dict(j, solo=alone)))
+            if on_done is not None:
+                on_done(i, res[-1])
+        return res
     engines = get_engine_pool(min(streams, len(jobs)))
     out: List[Optional[tuple]] = [None] * len(jobs)
     err: list = []
@@ -164,6 +171,8 @@ def run_fit_jobs(jobs: List[dict], engine=None, streams: Optional[int] = None, *
                 return
             try:
                 out[i] = run_one(eng, jobs[i])
+                if on_done is not None:
+                    on_done(i, out[i])
             except BaseException as e:       # re-raised on the calling thread
                 err.append(e)
 
@@ -338,12 +347,18 @@ def packed_parameters(model: GPR):
 
 
 def fit_replicated(X: np.ndarray, Y: np.ndarray, template: GPR, make_models=None, engine=None,
-                   max_batch_bytes: float = 60e9, specialize: bool = False, **lbfgs_opts):
+                   max_batch_bytes: float = 60e9, specialize: bool = False, post: Optional[Callable] = None,
+                   **lbfgs_opts):
     """MAP-fit B copies of ONE model structure (same kernel tree, priors and start values) to the B outcomes Y[b]:
     what GPSearch.penalized_optimization does (waveome/model_search.py:302-329 builds the same PSVGP for every
-    outcome).  The device fit runs on a worker thread (the C call releases the GIL) while ``make_models()`` -- the
+    outcome).  The device fit runs on worker threads (the C calls release the GIL) while ``make_models()`` -- the
     per-outcome model objects the caller wants back -- is evaluated on the calling thread.  Returns (raw result dict,
-    models); the fitted values are written into the models' parameters."""
+    models); the fitted values are written into the models' parameters.
+
+    The outcomes are fitted as concurrent pieces (``split_for_streams``).  As each piece finishes, the calling thread
+    writes its values into its models and calls ``post(lo, hi, models[lo:hi])`` -- the caller's post-fit work on that
+    piece (pruning, feature importances) then runs behind the pieces that are still on the device."""
+    import queue
     import threading
     X = np.ascontiguousarray(X, dtype=np.float64)
     Y = np.ascontiguousarray(Y, dtype=np.float64)
@@ -357,42 +372,59 @@ def fit_replicated(X: np.ndarray, Y: np.ndarray, template: GPR, make_models=None
     out = dict(x=np.empty((B, P)), f=np.empty(B), lml=np.empty(B), n_iter=np.empty(B, np.int32),
                n_eval=np.empty(B, np.int32), status=np.empty(B, np.int32), launches=0, rounds=0)
     err = []
+    pieces = split_for_streams(B, chunk, 1 if engine is not None else None)
+    finished = queue.Queue()
+    lock = threading.Lock()
+
+    def piece_done(i, rc):
+        (lo, hi), (r, c) = pieces[i], rc
+        for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
+            out[key][lo:hi] = r[key]
+        with lock:
+            out["launches"] += c["launches"]
+            out["rounds"] += c["rounds"]
+        finished.put(i)
 
     def work():
         try:
-            pieces = split_for_streams(B, chunk, 1 if engine is not None else None)
             jobs = [dict(X=X, Y=Y[lo:hi], table=[prog], P=P, lik_name=lik_name, lik_param=lik_param,
                          specialize=specialize) for lo, hi in pieces]
-            for (lo, hi), (r, c) in zip(pieces, run_fit_jobs(jobs, engine=engine, **lbfgs_opts)):
-                for key in ("x", "f", "lml", "n_iter", "n_eval", "status"):
-                    out[key][lo:hi] = r[key]
-                out["launches"] += c["launches"]
-                out["rounds"] += c["rounds"]
+            run_fit_jobs(jobs, engine=engine, on_done=piece_done, **lbfgs_opts)
         except BaseException as e:      # re-raised on the calling thread
             err.append(e)
+        finally:
+            finished.put(None)          # no more pieces will arrive
 
     t = threading.Thread(target=work)
     t.start()
     try:
         models = make_models() if make_models is not None else [K.deepcopy(template) for _ in range(B)]
         packed = [packed_parameters(m) for m in models]        # still behind the device fit
+        template_params = packed_parameters(template)
+        while True:
+            i = finished.get()
+            if i is None:
+                break
+            lo, hi = pieces[i]
+            # fitted values: the bijector of every packed position applied to its whole column (all copies share the
+            # template's transforms), then plain stores into the models' Parameter objects
+            values = np.empty((hi - lo, len(template_params)))
+            for j, p in enumerate(template_params):
+                values[:, j] = p.transform_fn(np.ascontiguousarray(out["x"][lo:hi, j]))
+            lml, lpd = out["lml"][lo:hi].tolist(), (-out["f"][lo:hi]).tolist()
+            nit, nev, st = out["n_iter"][lo:hi].tolist(), out["n_eval"][lo:hi].tolist(), out["status"][lo:hi].tolist()
+            for b, (m, ps, row) in enumerate(zip(models[lo:hi], packed[lo:hi], values.tolist())):
+                for p, v in zip(ps, row):
+                    p._value = v
+                m.log_marginal_likelihood_value = lml[b]
+                m.log_posterior_density_value = lpd[b]
+                m.fit_info = dict(n_iter=nit[b], n_eval=nev[b], status=st[b])
+            if post is not None and not err:
+                post(lo, hi, models[lo:hi])
     finally:
         t.join()
     if err:
         raise err[0]
-    # fitted values: the bijector of every packed position applied to its whole column (all copies share the template's
-    # transforms), then plain stores into the models' Parameter objects
-    values = np.empty((B, len(packed[0]) if packed else 0))
-    for j, p in enumerate(packed_parameters(template)):
-        values[:, j] = p.transform_fn(np.ascontiguousarray(out["x"][:, j]))
-    lml, lpd = out["lml"].tolist(), (-out["f"]).tolist()
-    nit, nev, st = out["n_iter"].tolist(), out["n_eval"].tolist(), out["status"].tolist()
-    for b, (m, ps, row) in enumerate(zip(models, packed, values.tolist())):
-        for p, v in zip(ps, row):
-            p._value = v
-        m.log_marginal_likelihood_value = lml[b]
-        m.log_posterior_density_value = lpd[b]
-        m.fit_info = dict(n_iter=nit[b], n_eval=nev[b], status=st[b])
     return out, models
 
 

@@ -140,6 +140,7 @@ class GPSearch:
         # outcomes, not this rank's shard) is large enough to pay for their compilation
         from .engine import SPECIALIZE_MIN_MODELS
         self._specialize = len(self.out_names) >= SPECIALIZE_MIN_MODELS
+        post_done = np.zeros(len(names), bool)        # outcomes whose post-fit work was done behind the fit
         if penalization_factor is None:
             res, models = self._iterated_factor_fit(full_kernel, mean_function, names, Xn, Yn, num_factor_iter, num_opt_iter,
                                                     verbose and rank == 0)
@@ -164,15 +165,36 @@ class GPSearch:
             for m, xb in zip(models, res["x"]):
                 m.program().assign(xb[: len(m.trainable_parameters)])
         else:
-            # one structure for every outcome: the device fit overlaps the construction of the model objects
-            res, models = fit_replicated(Xn, Yn, template, make_models=make_models, maxiter=num_opt_iter,
-                                         maxfun=num_opt_iter, specialize=self._specialize)
-        for m in models:
-            m.cut_kernel_components(Xn)
-            m.update_kernel_name()
-        # get_feature_importances of every model (model_search.py:383-387) as one more engine batch
-        for m, fi in zip(models, feature_importances_batch(Xn, Yn, models)):
-            m.feature_importances = fi
+            # one structure for every outcome: the device fit overlaps the construction of the model objects, and the
+            # post-fit work of a piece of outcomes (pruning, importances -- on an engine of its own) runs behind the
+            # pieces that are still being fitted
+            from .model_fitting import lease_engine, release_engine
+            side = {}
+
+            def post(lo, hi, ms):
+                if not side:                                   # an engine of its own, taken when the first piece is done
+                    side["engine"], side["lease"] = lease_engine()
+                for m in ms:
+                    m.cut_kernel_components(Xn)
+                    m.update_kernel_name()
+                for m, fi in zip(ms, feature_importances_batch(Xn, Yn[lo:hi], ms, engine=side["engine"])):
+                    m.feature_importances = fi
+                post_done[lo:hi] = True
+            try:
+                res, models = fit_replicated(Xn, Yn, template, make_models=make_models, maxiter=num_opt_iter,
+                                             maxfun=num_opt_iter, specialize=self._specialize, post=post)
+            finally:
+                if side:
+                    release_engine(side["lease"])
+        todo = [b for b in range(len(models)) if not post_done[b]]
+        if todo:
+            rest = [models[b] for b in todo]
+            for m in rest:
+                m.cut_kernel_components(Xn)
+                m.update_kernel_name()
+            # get_feature_importances of every model (model_search.py:383-387) as one more engine batch
+            for m, fi in zip(rest, feature_importances_batch(Xn, Yn[todo], rest)):
+                m.feature_importances = fi
         local = dict(zip(names, models))
         report = dict(n_models=len(names), seconds=time.time() - t0, n_eval=int(np.sum(res["n_eval"])),
                       status=np.asarray(res["status"]).copy(), n_fits_per_model=n_fits)
